@@ -1,0 +1,94 @@
+"""ctypes binding of ``libfeddat_sm100.so`` (C ABI declared in ``include/feddat_b200.h``).
+
+The library is the product: if it cannot be loaded the import fails loudly -- there is no
+PyTorch/CPU fallback behind these entry points.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import POINTER, c_char_p, c_float, c_int, c_int64, c_uint32, c_void_p
+from pathlib import Path
+
+_LIB_PATH = Path(__file__).resolve().parent / "lib" / "libfeddat_sm100.so"
+_lib = None
+
+# every symbol include/feddat_b200.h declares (tests check the built library exports all of them)
+EXPORTED_SYMBOLS = (
+    "feddat_last_error",
+    "feddat_abi_version",
+    "feddat_dat_fwd",
+    "feddat_dat_bwd_dgrad",
+    "feddat_dat_bwd_wgrad",
+    "feddat_pack_weights",
+    "feddat_mkd_loss",
+    "feddat_fedavg",
+    "feddat_probe_gemm",
+)
+
+
+class FeddatError(RuntimeError):
+    pass
+
+
+def lib_path() -> Path:
+    return _LIB_PATH
+
+
+def load() -> ctypes.CDLL:
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not _LIB_PATH.exists():
+        if os.environ.get("FEDDAT_NO_AUTOBUILD"):
+            raise FeddatError(f"{_LIB_PATH} is missing; run `python -m feddat_b200.build`")
+        from .build import build_library
+        build_library()
+    lib = ctypes.CDLL(str(_LIB_PATH))
+    lib.feddat_last_error.restype = c_char_p
+    lib.feddat_last_error.argtypes = []
+    lib.feddat_abi_version.restype = c_int
+    lib.feddat_abi_version.argtypes = []
+
+    lib.feddat_dat_fwd.restype = c_int
+    lib.feddat_dat_fwd.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                   c_void_p, c_int64, c_int, c_int, c_float, c_int, c_int, c_void_p]
+    lib.feddat_dat_bwd_dgrad.restype = c_int
+    lib.feddat_dat_bwd_dgrad.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                         c_void_p, c_void_p, c_void_p, c_int, c_int, c_int64, c_int,
+                                         c_int, c_float, c_int, c_int, c_int, c_void_p]
+    lib.feddat_dat_bwd_wgrad.restype = c_int
+    lib.feddat_dat_bwd_wgrad.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                         c_void_p, c_void_p, c_int64, c_int, c_int, c_float, c_int,
+                                         c_void_p]
+    lib.feddat_pack_weights.restype = c_int
+    lib.feddat_pack_weights.argtypes = [POINTER(c_void_p), POINTER(c_void_p), POINTER(c_void_p),
+                                        POINTER(c_void_p), c_int, c_int, c_int, c_void_p, c_void_p,
+                                        c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]
+    lib.feddat_mkd_loss.restype = c_int
+    lib.feddat_mkd_loss.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int,
+                                    c_float, c_float, c_float, c_float, c_int64, c_void_p]
+    lib.feddat_fedavg.restype = c_int
+    lib.feddat_fedavg.argtypes = [POINTER(c_void_p), POINTER(c_float), c_int, c_void_p, c_int64,
+                                  c_void_p]
+    lib.feddat_probe_gemm.restype = c_int
+    lib.feddat_probe_gemm.argtypes = [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
+                                      POINTER(c_uint32), c_void_p]
+    _lib = lib
+    return lib
+
+
+def check(rc: int, what: str = "") -> None:
+    if rc != 0:
+        msg = load().feddat_last_error().decode("utf-8", "replace")
+        raise FeddatError(f"{what or 'libfeddat_sm100'} failed (code {rc}): {msg}")
+
+
+def ptr(t) -> c_void_p:
+    """Device pointer of a torch tensor (or None -> NULL)."""
+    return c_void_p(0 if t is None else t.data_ptr())
+
+
+def stream_ptr() -> c_void_p:
+    import torch
+    return c_void_p(torch.cuda.current_stream().cuda_stream)

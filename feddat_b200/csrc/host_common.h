@@ -1,0 +1,45 @@
+// Host-side helpers shared by the C-ABI entry points: thread-local last-error string, CUDA error
+// checks that never throw / exit, and TMA tensor-map construction through the driver entry point
+// (resolved at run time, so the library links against cudart only).
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdint.h>
+#include <stdio.h>
+
+namespace fd {
+
+enum : int {
+  FD_OK = 0,
+  FD_ERR_INVALID = -1,      // bad argument (shape / alignment / null pointer)
+  FD_ERR_UNSUPPORTED = -2,  // configuration the sm_100a kernels do not cover (no fallback exists)
+  FD_ERR_CUDA = -3,         // CUDA runtime / driver failure
+  FD_ERR_NO_DEVICE = -4,    // not an sm_100 device
+};
+
+char* last_error_buf();  // thread-local, 512 bytes
+int set_error(int code, const char* fmt, ...);
+
+#define FD_CHECK_CUDA(expr)                                                                   \
+  do {                                                                                        \
+    cudaError_t _e = (expr);                                                                  \
+    if (_e != cudaSuccess)                                                                    \
+      return fd::set_error(fd::FD_ERR_CUDA, "%s failed: %s (%s:%d)", #expr,                   \
+                           cudaGetErrorString(_e), __FILE__, __LINE__);                       \
+  } while (0)
+
+#define FD_REQUIRE(cond, code, ...)                      \
+  do {                                                   \
+    if (!(cond)) return fd::set_error((code), __VA_ARGS__); \
+  } while (0)
+
+// 2-D row-major bf16 tensor [rows, cols] (cols contiguous) -> tensor map with a
+// [box_rows x box_cols] box and 128-byte swizzle (box_cols * 2 bytes must be 128).
+int make_tmap_bf16_2d(CUtensorMap* out, const void* gptr, uint64_t rows, uint64_t cols,
+                      uint64_t row_stride_elems, uint32_t box_rows, uint32_t box_cols);
+
+int device_sm_count(int* out);
+int check_device_sm100();
+
+}  // namespace fd

@@ -1,0 +1,171 @@
+// Bring-up probe: one CTA, one 128 x N x K bf16 GEMM on tcgen05 with every operand source the
+// production kernels rely on (K-major smem, MN-major smem, A from TMEM).  The descriptor strides can
+// be overridden from the host so a single GPU call can sweep encodings.  Test infrastructure for
+// tests/test_probe_gpu.py; not part of the hot path.
+#include "host_common.h"
+#include "ptx_sm100.cuh"
+
+namespace fd {
+
+struct ProbeParams {
+  int N, K;
+  int a_mode;  // 0 = smem K-major, 1 = smem MN-major, 2 = TMEM
+  int b_mode;  // 0 = smem K-major, 1 = smem MN-major
+  uint32_t a_lbo, a_sbo, b_lbo, b_sbo;  // 0 = default
+  uint32_t a_kstep, b_kstep;            // descriptor advance in bytes per UMMA_K=16 (0 = default)
+  const __nv_bfloat16* A;               // used by a_mode == 2: row-major [128, K]
+  float* D;                             // [128, N] fp32
+};
+
+__global__ void __launch_bounds__(128, 1)
+probe_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                  ProbeParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~uintptr_t(1023));
+  __shared__ __align__(8) uint64_t bar_full, bar_done;
+  __shared__ uint32_t tmem_base_smem;
+
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int N = p.N, K = p.K;
+  const uint32_t a_base = smem_u32(smem);
+  const uint32_t a_bytes = 128u * K * 2u;
+  const uint32_t b_base = a_base + ((a_bytes + 1023u) & ~1023u);
+  const uint32_t b_bytes = static_cast<uint32_t>(N) * K * 2u;
+
+  if (tid == 0) {
+    mbar_init(smem_u32(&bar_full), 1);
+    mbar_init(smem_u32(&bar_done), 1);
+    fence_mbar_init();
+  }
+  if (warp == 0) tmem_alloc(smem_u32(&tmem_base_smem), 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_base_smem;
+
+  if (tid == 0) {
+    uint32_t tx = b_bytes + (p.a_mode == 2 ? 0u : a_bytes);
+    mbar_arrive_expect_tx(smem_u32(&bar_full), tx);
+    if (p.a_mode == 0) {
+      for (int kc = 0; kc < K / 64; ++kc)
+        tma_load_2d(a_base + kc * 128 * 128, &tmA, smem_u32(&bar_full), kc * 64, 0);
+    } else if (p.a_mode == 1) {
+      for (int mb = 0; mb < 2; ++mb)
+        tma_load_2d(a_base + mb * K * 128, &tmA, smem_u32(&bar_full), mb * 64, 0);
+    }
+    if (p.b_mode == 0) {
+      for (int kc = 0; kc < K / 64; ++kc)
+        tma_load_2d(b_base + kc * N * 128, &tmB, smem_u32(&bar_full), kc * 64, 0);
+    } else {
+      for (int nb = 0; nb < N / 64; ++nb)
+        tma_load_2d(b_base + nb * K * 128, &tmB, smem_u32(&bar_full), nb * 64, 0);
+    }
+  }
+  if (p.a_mode == 2) {
+    // A tile into TMEM columns [256, 256 + K/2): thread = row, bf16 pairs packed per column
+    const uint32_t lane_base = static_cast<uint32_t>(warp * 32) << 16;
+    const uint4* arow = reinterpret_cast<const uint4*>(p.A + static_cast<size_t>(tid) * K);
+    for (int c = 0; c < K / 16; ++c) {
+      uint4 v0 = arow[2 * c], v1 = arow[2 * c + 1];
+      uint32_t v[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+      tmem_st8(tmem + lane_base + 256 + c * 8, v);
+    }
+    tmem_st_wait();
+    tc_fence_before();
+  }
+  __syncthreads();
+
+  if (tid == 0) {
+    mbar_wait(smem_u32(&bar_full), 0);
+    tc_fence_after();
+    const uint32_t idesc = make_idesc_bf16(128, N, p.a_mode == 1, p.b_mode == 1);
+    for (int kk = 0; kk < K / 16; ++kk) {
+      uint64_t bdesc;
+      if (p.b_mode == 0) {
+        uint32_t step = p.b_kstep ? p.b_kstep * kk : (kk / 4) * N * 128 + (kk % 4) * 32;
+        bdesc = make_smem_desc(b_base + step, p.b_lbo ? p.b_lbo : 16, p.b_sbo ? p.b_sbo : 1024,
+                               kLayoutSw128);
+      } else {
+        uint32_t step = (p.b_kstep ? p.b_kstep : 2048u) * kk;
+        bdesc = make_smem_desc(b_base + step, p.b_lbo ? p.b_lbo : K * 128,
+                               p.b_sbo ? p.b_sbo : 1024, kLayoutSw128);
+      }
+      if (p.a_mode == 2) {
+        umma_ts(tmem, tmem + 256 + kk * 8, bdesc, idesc, kk > 0);
+      } else {
+        uint64_t adesc;
+        if (p.a_mode == 0) {
+          uint32_t step = p.a_kstep ? p.a_kstep * kk : (kk / 4) * 128 * 128 + (kk % 4) * 32;
+          adesc = make_smem_desc(a_base + step, p.a_lbo ? p.a_lbo : 16, p.a_sbo ? p.a_sbo : 1024,
+                                 kLayoutSw128);
+        } else {
+          uint32_t step = (p.a_kstep ? p.a_kstep : 2048u) * kk;
+          adesc = make_smem_desc(a_base + step, p.a_lbo ? p.a_lbo : K * 128,
+                                 p.a_sbo ? p.a_sbo : 1024, kLayoutSw128);
+        }
+        umma_ss(tmem, adesc, bdesc, idesc, kk > 0);
+      }
+    }
+    umma_commit(smem_u32(&bar_done));
+  }
+  __syncwarp();
+  mbar_wait(smem_u32(&bar_done), 0);
+  tc_fence_after();
+
+  const uint32_t lane_base = static_cast<uint32_t>(warp * 32) << 16;
+  float* drow = p.D + static_cast<size_t>(tid) * N;
+  for (int c = 0; c < N / 16; ++c) {
+    uint32_t v[16];
+    tmem_ld16(tmem + lane_base + c * 16, v);
+    tmem_ld_wait();
+#pragma unroll
+    for (int i = 0; i < 16; i += 4)
+      *reinterpret_cast<float4*>(drow + c * 16 + i) =
+          make_float4(__uint_as_float(v[i]), __uint_as_float(v[i + 1]), __uint_as_float(v[i + 2]),
+                      __uint_as_float(v[i + 3]));
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, 512);
+}
+
+}  // namespace fd
+
+// A: a_mode 0/2 -> row-major [128, K]; a_mode 1 -> row-major [K, 128].
+// B: b_mode 0 -> row-major [N, K];     b_mode 1 -> row-major [K, N].   D = A * B^T, [128, N] fp32.
+extern "C" int feddat_probe_gemm(const void* A, const void* B, float* D, int N, int K, int a_mode,
+                                 int b_mode, const uint32_t* overrides /* 6 values or NULL */,
+                                 void* stream) {
+  using namespace fd;
+  int rc = check_device_sm100();
+  if (rc) return rc;
+  FD_REQUIRE(N % 16 == 0 && N >= 16 && N <= 256 && K % 64 == 0 && K >= 64 && K <= 192 &&
+                 (b_mode == 0 || N % 64 == 0),
+             FD_ERR_INVALID, "probe: N=%d K=%d out of range", N, K);
+  CUtensorMap tmA, tmB;
+  if (a_mode == 1)
+    rc = make_tmap_bf16_2d(&tmA, A, K, 128, 128, K, 64);
+  else
+    rc = make_tmap_bf16_2d(&tmA, A, 128, K, K, 128, 64);
+  if (rc) return rc;
+  if (b_mode == 1)
+    rc = make_tmap_bf16_2d(&tmB, B, K, N, N, K, 64);
+  else
+    rc = make_tmap_bf16_2d(&tmB, B, N, K, K, N, 64);
+  if (rc) return rc;
+  ProbeParams p{};
+  p.N = N; p.K = K; p.a_mode = a_mode; p.b_mode = b_mode;
+  if (overrides) {
+    p.a_lbo = overrides[0]; p.a_sbo = overrides[1]; p.b_lbo = overrides[2]; p.b_sbo = overrides[3];
+    p.a_kstep = overrides[4]; p.b_kstep = overrides[5];
+  }
+  p.A = reinterpret_cast<const __nv_bfloat16*>(A);
+  p.D = D;
+  size_t smem = 1024 + ((128 * K * 2 + 1023) & ~1023) + static_cast<size_t>(N) * K * 2;
+  FD_CHECK_CUDA(cudaFuncSetAttribute(probe_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)smem));
+  probe_gemm_kernel<<<1, 128, smem, static_cast<cudaStream_t>(stream)>>>(tmA, tmB, p);
+  FD_CHECK_CUDA(cudaGetLastError());
+  return FD_OK;
+}

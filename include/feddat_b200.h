@@ -1,0 +1,131 @@
+/* feddat_b200.h -- C ABI of libfeddat_sm100.so
+ *
+ * Drop-in boundary for the FedDAT per-client local-training hot path.  The
+ * reference (HaokunChen245/FedDAT) is pure Python/PyTorch and has no FFI of its own; each entry
+ * point below replaces the PyTorch-eager arithmetic of one reference function, cited per function.
+ * The host side that binds these (ctypes) lives in feddat_b200/_lib.py; INTEGRATION.md shows the
+ * binding a maintainer of the reference would add.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every pointer is a DEVICE pointer unless stated otherwise
+ *   - all buffers are owned by the caller; the library allocates nothing persistent
+ *   - kernels are enqueued on `stream` (a cudaStream_t passed as void*), no internal sync,
+ *     CUDA-graph capturable
+ *   - return 0 on success, a negative FEDDAT_ERR_* otherwise; feddat_last_error() returns a
+ *     thread-local message.  Never throws, never exits.
+ *   - sm_100a only.  Unsupported shapes are an explicit error: there is NO CPU / Triton fallback.
+ */
+#ifndef FEDDAT_B200_H_
+#define FEDDAT_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FEDDAT_OK 0
+#define FEDDAT_ERR_INVALID (-1)
+#define FEDDAT_ERR_UNSUPPORTED (-2)
+#define FEDDAT_ERR_CUDA (-3)
+#define FEDDAT_ERR_NO_DEVICE (-4)
+
+#define FEDDAT_DTYPE_BF16 0
+
+#define FEDDAT_ACT_RELU 0 /* reference default: adapter.py:24 */
+#define FEDDAT_ACT_GELU 1 /* opt-in (BASELINE.json north_star wording) */
+
+const char* feddat_last_error(void);
+int feddat_abi_version(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * DAT bottleneck forward.  Replaces Adapter.forward (src/modeling/models/adapter.py:124-163):
+ *   single mode (:125-131)  Y = Res + up(act(down(X)))                        r_total = r, scale 1
+ *   gating mode (:133-146)  Y = Res + 1.0 * (0.5 * A0(X) + 0.5 * A2(X))       r_total = 2r, scale .5
+ * with the active branches concatenated along the bottleneck dimension:
+ *   Wd_cat [r_total, d] bf16 row-major   (= rows of adapter_i_down.weight, stacked)
+ *   bd_cat [r_total]    fp32
+ *   Wu_cat [d, r_total] bf16 row-major   (= columns of adapter_i_up.weight, side by side)
+ *   bu_cat [d]          fp32             (= sum of the active branches' up biases)
+ *   Y = Res + branch_scale * ( act(X Wd_cat^T + bd_cat) Wu_cat^T + bu_cat )
+ * X, Res, Y: [M, d] bf16 row-major contiguous, 16-byte aligned; Res may alias X; Y must not.
+ * d must be 768; r_total a multiple of 16 in [16, 256].
+ */
+int feddat_dat_fwd(const void* X, const void* Res, void* Y, const void* Wd_cat,
+                   const float* bd_cat, const void* Wu_cat, const float* bu_cat, int64_t M, int d,
+                   int r_total, float branch_scale, int act, int dtype, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * DAT bottleneck backward (autograd of the above; the reference relies on torch autograd of
+ * adapter.py:124-163 with trainability toggled at adapter.py:71-85).
+ *
+ * Stage 1, feddat_dat_bwd_dgrad: recomputes the hidden, then
+ *     dP = (dY Wu_cat) * act'(X Wd_cat^T + bd_cat) * branch_scale
+ *     dX = dP Wd_cat  (+ dY when add_dy != 0, i.e. the residual input IS X: adaptered_output.py:78)
+ *   and, for the trainable slice [r_lo, r_hi) of the bottleneck, writes the bf16 hidden
+ *   H_t [M, r_hi-r_lo] and dP_t [M, r_hi-r_lo] for stage 2 (pass NULL/NULL when nothing trains).
+ *   dX may be NULL (first adapter site: nothing trainable upstream needs it) only if H_t != NULL.
+ *   WuT_cat [r_total, d] and WdT_cat [d, r_total] are the transposes of Wu_cat / Wd_cat (bf16).
+ *
+ * Stage 2, feddat_dat_bwd_wgrad: fp32 accumulate-into (caller zeroes):
+ *     dWu [d, r_t] += branch_scale * dY^T H_t                        dbu [d]   += scale * sum_m dY
+ *     dWd [r_t, d] += dP_t^T X                                       dbd [r_t] += sum_m dP_t
+ *   (dP_t already carries branch_scale.)  r_t = r_hi - r_lo must be a multiple of 16, <= 128.
+ */
+int feddat_dat_bwd_dgrad(const void* X, const void* dY, void* dX, const void* Wd_cat,
+                         const float* bd_cat, const void* WuT_cat, const void* WdT_cat,
+                         void* H_t, void* dP_t, int r_lo, int r_hi, int64_t M, int d, int r_total,
+                         float branch_scale, int act, int add_dy, int dtype, void* stream);
+
+int feddat_dat_bwd_wgrad(const void* X, const void* dY, const void* H_t, const void* dP_t,
+                         float* dWu, float* dbu, float* dWd, float* dbd, int64_t M, int d, int r_t,
+                         float branch_scale, int dtype, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Packing of the fp32 master weights of the active branches into the bf16 operands above.
+ *   down_w[i] : [r, d] fp32, down_b[i] : [r], up_w[i] : [d, r], up_b[i] : [d]   (nn.Linear layout,
+ *   adapter.py:35,41), n_branch in {1, 2}.  Outputs: Wd_cat [n*r, d], WdT_cat [d, n*r],
+ *   Wu_cat [d, n*r], WuT_cat [n*r, d] (bf16), bd_cat [n*r], bu_cat [d] (fp32).  Any output may be
+ *   NULL to skip it.
+ */
+int feddat_pack_weights(const float* const* down_w, const float* const* down_b,
+                        const float* const* up_w, const float* const* up_b, int n_branch, int r,
+                        int d, void* Wd_cat, void* WdT_cat, void* Wu_cat, void* WuT_cat,
+                        float* bd_cat, float* bu_cat, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * MKD head.  Replaces kl_loss (src/train/visionlanguage_tasks/task_trainer.py:506-516) plus the
+ * ViLT task loss BCEWithLogits('mean') * C (task_trainer.py:299,319; train_vqa_crossvqa.py:237)
+ * and the (task + kl) / 2 combination (task_trainer.py:300-301,320-321), forward and backward in
+ * one pass:
+ *     kl   = T^2 / batchmean_div * sum_rows KL( softmax(teacher/T) || softmax(logits/T) )
+ *     task = task_scale * sum_{rows,c} bce_with_logits(logits, target)    (target may be NULL)
+ *     loss_out[0] = kl_weight * kl + task_weight * task, loss_out[1] = kl, loss_out[2] = task
+ *     dlogits = d loss_out[0] / d logits          (dlogits may be NULL: forward only)
+ * logits/teacher/target/dlogits: [rows, C] fp32 row-major.  loss_out: 3 floats, device memory,
+ * overwritten.  For the reference's ViLT path: batchmean_div = rows, task_scale = 1/rows
+ * (mean over rows*C, times C), kl_weight = task_weight = 0.5.
+ */
+int feddat_mkd_loss(const float* logits, const float* teacher, const float* target,
+                    float* loss_out, float* dlogits, int64_t rows, int C, float temp,
+                    float kl_weight, float task_weight, float task_scale, int64_t batchmean_div,
+                    void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * FedAvg of the flat communicated buffer.  Replaces get_average_net (src/train/main.py:50-65):
+ *     out[i] = sum_c weights[c] * clients[c][i]      (fp32; weights are HOST floats, n_clients<=64)
+ * Used for clients that share a GPU; across GPUs the flat buffer goes through one NCCL allreduce.
+ */
+int feddat_fedavg(const float* const* clients /* host array of device ptrs */,
+                  const float* weights /* host */, int n_clients, float* out, int64_t n,
+                  void* stream);
+
+/* Bring-up probe (tests only): one 128 x N x K tcgen05 GEMM, see csrc/probe.cu. */
+int feddat_probe_gemm(const void* A, const void* B, float* D, int N, int K, int a_mode,
+                      int b_mode, const uint32_t* overrides, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FEDDAT_B200_H_ */
