@@ -1,0 +1,49 @@
+"""Oracle: the MKD loss head (reference src/train/visionlanguage_tasks/task_trainer.py).  TEST ONLY."""
+from __future__ import annotations
+
+import numpy as np
+
+
+def _log_softmax(x, axis):
+    m = x.max(axis=axis, keepdims=True)
+    z = x - m
+    return z - np.log(np.exp(z).sum(axis=axis, keepdims=True))
+
+
+def kl_loss(output, target, temp=3.0, with_grad=False):
+    """task_trainer.py:506-516.  softmax over the LAST dim when it is > 3000 wide (:507-509), else
+    over dim=1 (:510-512); F.kl_div(p_log, q, 'batchmean') divides by output.shape[0] (:514); times
+    temp**2 (:515)."""
+    out = np.asarray(output, np.float64)
+    tgt = np.asarray(target, np.float64)
+    axis = -1 if out.shape[-1] > 3000 else 1
+    p_log = _log_softmax(out / temp, axis)
+    q_log = _log_softmax(tgt / temp, axis)
+    q = np.exp(q_log)
+    point = np.where(q > 0, q * (q_log - p_log), 0.0)
+    loss = point.sum() / out.shape[0] * temp ** 2
+    if not with_grad:
+        return loss
+    grad = (np.exp(p_log) - q) * temp / out.shape[0]
+    return loss, grad
+
+
+def bce_with_logits_times_c(logits, target, with_grad=False):
+    """task_trainer.py:299 -- nn.BCEWithLogitsLoss(reduction='mean')(logits, target) * target.shape[1]
+    (criterion built at train_vqa_crossvqa.py:237)."""
+    x = np.asarray(logits, np.float64)
+    t = np.asarray(target, np.float64)
+    l = np.maximum(x, 0) - x * t + np.log1p(np.exp(-np.abs(x)))
+    loss = l.mean() * t.shape[1]
+    if not with_grad:
+        return loss
+    sig = 1.0 / (1.0 + np.exp(-x))
+    return loss, (sig - t) / x.shape[0]
+
+
+def mkd_total(logits, teacher, target, temp=3.0):
+    """task_trainer.py:299-301 / :319-321:  L = (task + kl_loss(logits, teacher.detach())) / 2.
+    Returns (L, kl, task, dL/dlogits)."""
+    kl, gkl = kl_loss(logits, teacher, temp, with_grad=True)
+    task, gtask = bce_with_logits_times_c(logits, target, with_grad=True)
+    return (task + kl) / 2.0, kl, task, (gkl + gtask) / 2.0

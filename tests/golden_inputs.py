@@ -1,0 +1,56 @@
+"""Regenerates the seeded inputs of tests/golden/op_golden.npz (same PCG64 streams as
+tests/golden/make_golden.py, so the fixture only has to carry the reference's OUTPUTS)."""
+import numpy as np
+
+NAMES = ("adapter_0", "adapter_1", "adapter_2")
+
+
+def rng_weights(rng, r, d=768):
+    w = {}
+    for n in NAMES:
+        w[f"{n}_down.weight"] = (rng.standard_normal((r, d)) * 0.05).astype(np.float32)
+        w[f"{n}_down.bias"] = (rng.standard_normal((r,)) * 0.1).astype(np.float32)
+        w[f"{n}_up.weight"] = (rng.standard_normal((d, r)) * 0.05).astype(np.float32)
+        w[f"{n}_up.bias"] = (rng.standard_normal((d,)) * 0.1).astype(np.float32)
+    return w
+
+
+def branch(w, name):
+    return (w[f"{name}_down.weight"], w[f"{name}_down.bias"], w[f"{name}_up.weight"], w[f"{name}_up.bias"])
+
+
+def adapter_inputs(meta, d=768):
+    seed, r, b, s, gating = (int(v) for v in meta)
+    rng = np.random.default_rng(seed)
+    w = rng_weights(rng, r, d)
+    x = rng.standard_normal((b, s, d)).astype(np.float32)
+    g = rng.standard_normal((b, s, d)).astype(np.float32)
+    return w, x, g, r, bool(gating)
+
+
+def bert_inputs(meta, d=768):
+    seed, r, b, s, gating = (int(v) for v in meta)
+    rng = np.random.default_rng(seed)
+    w = rng_weights(rng, r, d)
+    ffn = rng.standard_normal((b, s, d)).astype(np.float32)
+    x = rng.standard_normal((b, s, d)).astype(np.float32)
+    lnw = (1.0 + 0.1 * rng.standard_normal(d)).astype(np.float32)
+    lnb = (0.1 * rng.standard_normal(d)).astype(np.float32)
+    return w, ffn, x, lnw, lnb, r
+
+
+def kl_inputs(meta):
+    seed, temp, shape = int(meta[0]), float(meta[1]), tuple(int(v) for v in meta[2:])
+    rng = np.random.default_rng(seed)
+    a = (rng.standard_normal(shape) * 2).astype(np.float32)
+    b = (rng.standard_normal(shape) * 2).astype(np.float32)
+    return a, b, temp
+
+
+def fedavg_inputs(meta):
+    seed, nums = int(meta[0]), [int(v) for v in meta[1:]]
+    rng = np.random.default_rng(seed)
+    keys = ["a.adapter_1_down.weight", "a.adapter_1_up.bias"]
+    clients = [{k: rng.standard_normal(257 if "bias" in k else (16, 33)).astype(np.float32) for k in keys}
+               for _ in nums]
+    return keys, clients, nums
