@@ -59,8 +59,8 @@ def load() -> ctypes.CDLL:
                                          c_int, c_float, c_int, c_int, c_int, c_void_p]
     lib.feddat_dat_bwd_wgrad.restype = c_int
     lib.feddat_dat_bwd_wgrad.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
-                                         c_void_p, c_void_p, c_int64, c_int, c_int, c_float, c_int,
-                                         c_void_p]
+                                         c_void_p, c_void_p, c_int64, c_int, c_int, c_int, c_int,
+                                         c_float, c_int, c_void_p]
     lib.feddat_pack_weights.restype = c_int
     lib.feddat_pack_weights.argtypes = [POINTER(c_void_p), POINTER(c_void_p), POINTER(c_void_p),
                                         POINTER(c_void_p), c_int, c_int, c_int, c_void_p, c_void_p,

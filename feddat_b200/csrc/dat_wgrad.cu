@@ -1,0 +1,265 @@
+// DAT bottleneck backward, weight gradients of the trainable branch (autograd of reference
+// adapter.py:124-163; trainability per adapter.py:71-85).  Inputs are the activations X, dY and the
+// bf16 hidden H_t / pre-activation gradient dP_t slices written by feddat_dat_bwd_dgrad:
+//
+//   dWu [768, r_t] += scale * dY^T H_t        dbu [768] += scale * sum_m dY
+//   dWd [r_t, 768] += dP_t^T  X               dbd [r_t] += sum_m dP_t
+//
+// Both products contract over the token dimension, so every operand is MN-major for tcgen05:
+// the TMA box is [64 rows x 64 columns] of the row-major activation and the UMMA descriptors walk
+// K = rows (128 B apart), MN = columns (contiguous), 64-column blocks `LBO` apart.
+//
+// Grid = 6 column chunks (128 of the 768 model columns) x row splits.  A CTA accumulates
+//   D1 [r_t(<=128 lanes) x 128] = H_t^T  dY[:, chunk]     (= dWu^T chunk)
+//   D2 [r_t          x 128]    = dP_t^T X [:, chunk]     (= dWd chunk)
+// in TMEM over all its 64-row blocks, and reduces into the fp32 gradients with red.global.add at
+// the end (fp32 atomics: summation order across row splits is not deterministic).  The bias
+// gradients are column sums taken from the same smem stages by the otherwise idle epilogue warps.
+#include "feddat_b200.h"
+#include "host_common.h"
+#include "ptx_sm100.cuh"
+
+namespace fd {
+namespace {
+
+constexpr int kD = 768;
+constexpr int KB = 64;                   // rows (GEMM K) per pipeline stage
+constexpr int NCW = 128;                 // model columns per CTA
+constexpr int NCHUNK = kD / NCW;         // 6
+constexpr int BLK = KB * 128;            // one [64 rows x 64 cols] bf16 block = 8 KB
+constexpr int OPER = 2 * BLK;            // one operand (two 64-column blocks) = 16 KB
+constexpr int STAGE = 4 * OPER;          // H, dP, dY, X
+constexpr int WG_STAGES = 3;
+constexpr int NUM_THREADS = 192;
+
+struct WgradParams {
+  int M, rt, n_splits, n_rowblocks, a_blocks;
+  int ld_dwu;
+  float scale;
+  float* dWu;
+  float* dbu;
+  float* dWd;
+  float* dbd;
+};
+
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+dat_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmDY,
+                 const __grid_constant__ CUtensorMap tmH, const __grid_constant__ CUtensorMap tmDP,
+                 const WgradParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t bars[2 * WG_STAGES + 1];
+  __shared__ uint32_t tmem_base_smem;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int chunk = blockIdx.x % NCHUNK, split = blockIdx.x / NCHUNK;
+  const int col0 = chunk * NCW;
+  const uint32_t smem0 = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar0 = smem_u32(bars);
+  auto bar_full = [&](int s) { return bar0 + 8u * s; };
+  auto bar_empty = [&](int s) { return bar0 + 8u * (WG_STAGES + s); };
+  const uint32_t bar_acc = bar0 + 8u * (2 * WG_STAGES);
+
+  if (tid == 0) {
+    for (int s = 0; s < WG_STAGES; ++s) {
+      mbar_init(bar_full(s), 1);
+      mbar_init(bar_empty(s), 1 + 4);  // MMA commit + one arrive per aux warp
+    }
+    mbar_init(bar_acc, 1);
+    fence_mbar_init();
+    tma_prefetch_desc(&tmX);
+    tma_prefetch_desc(&tmDY);
+    tma_prefetch_desc(&tmH);
+    tma_prefetch_desc(&tmDP);
+  }
+  if (warp == 1) tmem_alloc(smem_u32(&tmem_base_smem), 256);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_base_smem;
+  const int ablk = p.a_blocks;  // 1 when r_t <= 64 (second 64-column block of H/dP never loaded)
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int rb = split; rb < p.n_rowblocks; rb += p.n_splits) {
+        const int m0 = rb * KB;
+        mbar_wait(bar_empty(stage), phase ^ 1);
+        const uint32_t base = smem0 + stage * STAGE;
+        mbar_arrive_expect_tx(bar_full(stage), 2 * ablk * BLK + 2 * OPER);
+        for (int b = 0; b < ablk; ++b) {
+          tma_load_2d(base + b * BLK, &tmH, bar_full(stage), b * 64, m0);
+          tma_load_2d(base + OPER + b * BLK, &tmDP, bar_full(stage), b * 64, m0);
+        }
+        for (int b = 0; b < 2; ++b) {
+          tma_load_2d(base + 2 * OPER + b * BLK, &tmDY, bar_full(stage), col0 + b * 64, m0);
+          tma_load_2d(base + 3 * OPER + b * BLK, &tmX, bar_full(stage), col0 + b * 64, m0);
+        }
+        if (++stage == WG_STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      const uint32_t idesc = make_idesc_bf16(128, NCW, 1, 1);
+      const uint32_t a_lbo = ablk == 2 ? BLK : 0;  // r_t <= 64: lanes 64..127 alias block 0 (ignored)
+      bool first = true;
+      for (int rb = split; rb < p.n_rowblocks; rb += p.n_splits) {
+        mbar_wait(bar_full(stage), phase);
+        tc_fence_after();
+        const uint32_t base = smem0 + stage * STAGE;
+#pragma unroll
+        for (int kk = 0; kk < KB / 16; ++kk) {
+          const uint32_t ko = kk * 16 * 128;
+          umma_ss(tmem, desc_mnmajor_sw128(base + ko, a_lbo),
+                  desc_mnmajor_sw128(base + 2 * OPER + ko, BLK), idesc, !(first && kk == 0));
+          umma_ss(tmem + NCW, desc_mnmajor_sw128(base + OPER + ko, a_lbo),
+                  desc_mnmajor_sw128(base + 3 * OPER + ko, BLK), idesc, !(first && kk == 0));
+        }
+        first = false;
+        umma_commit(bar_empty(stage));
+        if (++stage == WG_STAGES) { stage = 0; phase ^= 1; }
+      }
+      umma_commit(bar_acc);
+    }
+    __syncwarp();
+  } else {
+    // aux: bias-gradient column sums from the staged tiles; then the reduction epilogue
+    const uint32_t q = warp & 3;
+    const uint32_t j = q * 32 + lane;  // column within the chunk == TMEM lane
+    const uint32_t jb = j >> 6, jc = j & 63;
+    float sum_dy = 0.f, sum_dp = 0.f;
+    const bool do_dbd = (chunk == 0) && (static_cast<int>(j) < p.rt) && p.dbd != nullptr;
+    const bool do_dbu = p.dbu != nullptr;
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int rb = split; rb < p.n_rowblocks; rb += p.n_splits) {
+      mbar_wait(bar_full(stage), phase);
+      const uint32_t base = smem0 + stage * STAGE;
+      const uint32_t dy_col = base + 2 * OPER + jb * BLK + (jc & 7) * 2;
+      const uint32_t dp_col = base + OPER + jb * BLK + (jc & 7) * 2;
+      if (do_dbu) {
+#pragma unroll 8
+        for (uint32_t k = 0; k < KB; ++k) {
+          uint16_t v;
+          asm volatile("ld.shared.u16 %0, [%1];"
+                       : "=h"(v)
+                       : "r"(dy_col + k * 128 + (((jc >> 3) ^ (k & 7)) << 4)));
+          sum_dy += __bfloat162float(__ushort_as_bfloat16(v));
+        }
+      }
+      if (do_dbd) {
+#pragma unroll 8
+        for (uint32_t k = 0; k < KB; ++k) {
+          uint16_t v;
+          asm volatile("ld.shared.u16 %0, [%1];"
+                       : "=h"(v)
+                       : "r"(dp_col + k * 128 + (((jc >> 3) ^ (k & 7)) << 4)));
+          sum_dp += __bfloat162float(__ushort_as_bfloat16(v));
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_empty(stage));
+      if (++stage == WG_STAGES) { stage = 0; phase ^= 1; }
+    }
+    if (do_dbu) atomicAdd(p.dbu + col0 + j, p.scale * sum_dy);
+    if (do_dbd) atomicAdd(p.dbd + j, sum_dp);
+
+    if (split < p.n_rowblocks) {  // this CTA accumulated at least one row block
+      mbar_wait(bar_acc, 0);
+      tc_fence_after();
+      const uint32_t lane_addr = (q * 32) << 16;
+      const bool valid = static_cast<int>(j) < p.rt;  // lane j = bottleneck unit j
+#pragma unroll 1
+      for (int c = 0; c < NCW / 32; ++c) {
+        uint32_t v[32];
+        tmem_ld32(tmem + lane_addr + c * 32, v);  // D1: dWu^T
+        tmem_ld_wait();
+        if (valid) {
+          float* dst = p.dWu + static_cast<size_t>(col0 + c * 32) * p.ld_dwu + j;
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            atomicAdd(dst + static_cast<size_t>(i) * p.ld_dwu, p.scale * __uint_as_float(v[i]));
+        }
+        tmem_ld32(tmem + lane_addr + NCW + c * 32, v);  // D2: dWd
+        tmem_ld_wait();
+        if (valid) {
+          float* dst = p.dWd + static_cast<size_t>(j) * kD + col0 + c * 32;
+#pragma unroll
+          for (int i = 0; i < 32; i += 4)
+            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + i),
+                         "f"(__uint_as_float(v[i])), "f"(__uint_as_float(v[i + 1])),
+                         "f"(__uint_as_float(v[i + 2])), "f"(__uint_as_float(v[i + 3]))
+                         : "memory");
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem, 256);
+}
+
+}  // namespace
+}  // namespace fd
+
+extern "C" int feddat_dat_bwd_wgrad(const void* X, const void* dY, const void* H_t,
+                                    const void* dP_t, float* dWu, float* dbu, float* dWd, float* dbd,
+                                    int64_t M, int d, int r_t, int ld_ht, int ld_dwu,
+                                    float branch_scale, int dtype, void* stream) {
+  using namespace fd;
+  int rc = check_device_sm100();
+  if (rc) return rc;
+  FD_REQUIRE(X && dY && H_t && dP_t && dWu && dWd, FD_ERR_INVALID,
+             "dat_bwd_wgrad: null pointer argument");
+  FD_REQUIRE(dtype == FEDDAT_DTYPE_BF16, FD_ERR_UNSUPPORTED,
+             "dat_bwd_wgrad: only bf16 activations are implemented (dtype=%d)", dtype);
+  FD_REQUIRE(d == kD, FD_ERR_UNSUPPORTED, "dat_bwd_wgrad: model_dim must be 768 (got %d)", d);
+  FD_REQUIRE(r_t >= 16 && r_t <= 128 && r_t % 16 == 0, FD_ERR_UNSUPPORTED,
+             "dat_bwd_wgrad: r_t must be a multiple of 16 in [16, 128] (got %d); call once per "
+             "128-wide slice for wider bottlenecks", r_t);
+  FD_REQUIRE(ld_ht >= r_t && ld_ht % 8 == 0 && ld_dwu >= r_t, FD_ERR_INVALID,
+             "dat_bwd_wgrad: bad leading dimensions ld_ht=%d ld_dwu=%d", ld_ht, ld_dwu);
+  FD_REQUIRE((reinterpret_cast<uintptr_t>(dWd) & 15) == 0, FD_ERR_INVALID,
+             "dat_bwd_wgrad: dWd must be 16-byte aligned");
+  FD_REQUIRE(M >= 0 && M < (1ll << 31) - 256, FD_ERR_INVALID, "dat_bwd_wgrad: bad row count %lld",
+             (long long)M);
+  if (M == 0) return FD_OK;
+
+  WgradParams p{};
+  p.M = static_cast<int>(M);
+  p.rt = r_t;
+  p.n_rowblocks = static_cast<int>((M + KB - 1) / KB);
+  p.a_blocks = r_t > 64 ? 2 : 1;
+  p.ld_dwu = ld_dwu;
+  p.scale = branch_scale;
+  p.dWu = dWu; p.dbu = dbu; p.dWd = dWd; p.dbd = dbd;
+  int sms = 0;
+  if ((rc = device_sm_count(&sms))) return rc;
+  int splits = sms / NCHUNK;
+  if (splits > p.n_rowblocks) splits = p.n_rowblocks;
+  if (splits < 1) splits = 1;
+  p.n_splits = splits;
+
+  CUtensorMap tmX, tmDY, tmH, tmDP;
+  if ((rc = make_tmap_bf16_2d(&tmX, X, M, kD, kD, KB, 64))) return rc;
+  if ((rc = make_tmap_bf16_2d(&tmDY, dY, M, kD, kD, KB, 64))) return rc;
+  if ((rc = make_tmap_bf16_2d(&tmH, H_t, M, r_t, ld_ht, KB, 64))) return rc;
+  if ((rc = make_tmap_bf16_2d(&tmDP, dP_t, M, r_t, ld_ht, KB, 64))) return rc;
+
+  const size_t smem = 1024 + static_cast<size_t>(WG_STAGES) * STAGE;
+  static bool configured[64] = {false};
+  int dev = 0;
+  FD_CHECK_CUDA(cudaGetDevice(&dev));
+  if (dev >= 64 || !configured[dev]) {
+    FD_CHECK_CUDA(cudaFuncSetAttribute(dat_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)smem));
+    if (dev < 64) configured[dev] = true;
+  }
+  dat_wgrad_kernel<<<NCHUNK * splits, NUM_THREADS, smem, static_cast<cudaStream_t>(stream)>>>(
+      tmX, tmDY, tmH, tmDP, p);
+  FD_CHECK_CUDA(cudaGetLastError());
+  return FD_OK;
+}

@@ -71,7 +71,10 @@ int feddat_dat_fwd(const void* X, const void* Res, void* Y, const void* Wd_cat,
  * Stage 2, feddat_dat_bwd_wgrad: fp32 accumulate-into (caller zeroes):
  *     dWu [d, r_t] += branch_scale * dY^T H_t                        dbu [d]   += scale * sum_m dY
  *     dWd [r_t, d] += dP_t^T X                                       dbd [r_t] += sum_m dP_t
- *   (dP_t already carries branch_scale.)  r_t = r_hi - r_lo must be a multiple of 16, <= 128.
+ *   (dP_t already carries branch_scale.)  r_t must be a multiple of 16, <= 128; wider trainable
+ *   slices are covered by one call per 128 columns: ld_ht is the row stride (elements) of H_t/dP_t,
+ *   ld_dwu the row stride of dWu, so a call can address a column slice of wider arrays.  dbu / dbd
+ *   may be NULL (skipped).
  */
 int feddat_dat_bwd_dgrad(const void* X, const void* dY, void* dX, const void* Wd_cat,
                          const float* bd_cat, const void* WuT_cat, const void* WdT_cat,
@@ -80,7 +83,7 @@ int feddat_dat_bwd_dgrad(const void* X, const void* dY, void* dX, const void* Wd
 
 int feddat_dat_bwd_wgrad(const void* X, const void* dY, const void* H_t, const void* dP_t,
                          float* dWu, float* dbu, float* dWd, float* dbd, int64_t M, int d, int r_t,
-                         float branch_scale, int dtype, void* stream);
+                         int ld_ht, int ld_dwu, float branch_scale, int dtype, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Packing of the fp32 master weights of the active branches into the bf16 operands above.
@@ -114,8 +117,10 @@ int feddat_mkd_loss(const float* logits, const float* teacher, const float* targ
 
 /* ---------------------------------------------------------------------------------------------
  * FedAvg of the flat communicated buffer.  Replaces get_average_net (src/train/main.py:50-65):
- *     out[i] = sum_c weights[c] * clients[c][i]      (fp32; weights are HOST floats, n_clients<=64)
- * Used for clients that share a GPU; across GPUs the flat buffer goes through one NCCL allreduce.
+ *     out[i] = sum_c (clients[c][i] * weights[c]) / sum(weights)      in client order, fp32
+ * i.e. the reference's `temp += net[key] * num / total` with weights = nums (HOST floats,
+ * n_clients <= 64), bit-identical to the PyTorch expression.  Used for clients that share a GPU;
+ * across GPUs the flat buffer goes through one NCCL allreduce.  All buffers 16-byte aligned.
  */
 int feddat_fedavg(const float* const* clients /* host array of device ptrs */,
                   const float* weights /* host */, int n_clients, float* out, int64_t n,

@@ -1,0 +1,248 @@
+"""Parity of the sm_100a kernels (called through the C ABI via feddat_b200.ops) against the numpy
+oracle and the reference-generated golden vectors.  GPU only.
+
+Tolerances (BASELINE.json north_star): bf16 paths 1e-2 relative (max-norm), fp32 paths 1e-3; FedAvg
+bit-exact.  bf16 kernels are additionally checked against the oracle evaluated on the SAME
+bf16-rounded inputs, where only accumulation order and the bf16 hidden/output rounding differ.
+"""
+import numpy as np
+import pytest
+import torch
+
+import oracle
+from tests.golden_inputs import adapter_inputs, branch, fedavg_inputs, kl_inputs
+
+pytestmark = pytest.mark.gpu
+
+BF16_TOL = 1e-2
+FP32_TOL = 1e-3
+
+
+def relerr(a, b):
+    a = np.asarray(a, np.float64)
+    b = np.asarray(b, np.float64)
+    return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-30))
+
+
+def bf16_round(x):
+    return torch.from_numpy(np.asarray(x, np.float32)).to(torch.bfloat16).float().numpy()
+
+
+def to_dev(x, dtype=torch.float32):
+    return torch.from_numpy(np.ascontiguousarray(x)).to("cuda").to(dtype).contiguous()
+
+
+def dev_branches(brs):
+    return [[to_dev(t) for t in b] for b in brs]
+
+
+def rounded_branches(brs):
+    # the kernels consume bf16 weights and fp32 biases
+    return [(bf16_round(b[0]), b[1], bf16_round(b[2]), b[3]) for b in brs]
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from feddat_b200 import ops as _ops
+    return _ops
+
+
+# ------------------------------------------------------------------------------------------ probe
+@pytest.mark.parametrize("a_mode,b_mode", [(0, 0), (0, 1), (1, 0), (1, 1), (2, 0)])
+def test_tcgen05_probe(a_mode, b_mode):
+    import ctypes
+    from feddat_b200 import _lib
+    lib = _lib.load()
+    N, K = 128, 128
+    torch.manual_seed(0)
+    A = torch.randn(128, K, device="cuda").to(torch.bfloat16)
+    B = torch.randn(N, K, device="cuda").to(torch.bfloat16)
+    ref = A.float() @ B.float().t()
+    A_in = A.t().contiguous() if a_mode == 1 else A
+    B_in = B.t().contiguous() if b_mode == 1 else B
+    D = torch.zeros(128, N, device="cuda")
+    _lib.check(lib.feddat_probe_gemm(_lib.ptr(A_in), _lib.ptr(B_in), _lib.ptr(D), N, K, a_mode, b_mode,
+                                     None, _lib.stream_ptr()))
+    torch.cuda.synchronize()
+    assert (D - ref).abs().max().item() < 1e-3
+
+
+# ---------------------------------------------------------------------------------- DAT fwd / bwd
+ADAPTER_CASES = ["single_r16", "gating_r16", "single_r48", "gating_r48", "gating_r128"]
+
+
+def _case_branches(w, gating):
+    return [branch(w, "adapter_0"), branch(w, "adapter_2")] if gating else [branch(w, "adapter_1")]
+
+
+@pytest.mark.parametrize("case", ADAPTER_CASES)
+def test_dat_forward_matches_reference_golden(golden, ops, case):
+    w, x, g, r, gating = adapter_inputs(golden[f"adapter/{case}/meta"])
+    brs = _case_branches(w, gating)
+    pk = ops.pack_weights(dev_branches(brs))
+    x2 = to_dev(x.reshape(-1, 768), torch.bfloat16)
+    y = ops.dat_forward(x2, x2, pk, 0.5 if gating else 1.0)
+    torch.cuda.synchronize()
+    y = y.float().cpu().numpy()
+    # (1) against the reference's own fp32 output: bf16 tolerance
+    assert relerr(y, golden[f"adapter/{case}/y"].reshape(-1, 768)) < BF16_TOL
+    # (2) against the oracle on identical bf16-rounded operands
+    y_or = oracle.adapter_forward(bf16_round(x.reshape(-1, 768)), bf16_round(x.reshape(-1, 768)),
+                                  rounded_branches(brs), gating)
+    assert relerr(y, y_or) < 6e-3
+
+
+@pytest.mark.parametrize("case", ADAPTER_CASES)
+def test_dat_backward_matches_reference_golden(golden, ops, case):
+    w, x, g, r, gating = adapter_inputs(golden[f"adapter/{case}/meta"])
+    brs = _case_branches(w, gating)
+    pk = ops.pack_weights(dev_branches(brs))
+    x2 = to_dev(x.reshape(-1, 768), torch.bfloat16)
+    g2 = to_dev(g.reshape(-1, 768), torch.bfloat16)
+    dx, grads = ops.dat_backward(x2, g2, pk, 0.5 if gating else 1.0, train_slice=(0, r), need_dx=True,
+                                 add_dy=True)
+    torch.cuda.synchronize()
+    assert relerr(dx.float().cpu().numpy(), golden[f"adapter/{case}/dx"].reshape(-1, 768)) < BF16_TOL
+    d_down_w, d_down_b, d_up_w, d_up_b = [t.cpu().numpy() for t in grads]
+    assert relerr(d_down_b, golden[f"adapter/{case}/d_down_b"]) < 2 * BF16_TOL
+    assert relerr(d_up_b, golden[f"adapter/{case}/d_up_b"]) < BF16_TOL
+    if f"adapter/{case}/d_down_w" in golden:
+        assert relerr(d_down_w, golden[f"adapter/{case}/d_down_w"]) < 2 * BF16_TOL
+        assert relerr(d_up_w, golden[f"adapter/{case}/d_up_w"]) < BF16_TOL
+    # oracle on identical bf16-rounded operands (all four gradients, every case)
+    xr, gr = bf16_round(x.reshape(-1, 768)), bf16_round(g.reshape(-1, 768))
+    dx_or, grads_or = oracle.adapter_backward(xr, gr, rounded_branches(brs), gating, residual_is_input=True)
+    assert relerr(dx.float().cpu().numpy(), dx_or) < BF16_TOL
+    for got, want in zip((d_down_w, d_down_b, d_up_w, d_up_b), grads_or[0]):
+        assert relerr(got, want) < 2 * BF16_TOL
+
+
+@pytest.mark.parametrize("R,M,gating,act", [
+    (48, 164, False, "relu"),      # cfg0-sized (B=2, S=82), the reference's r = 768 // 16
+    (96, 5920, True, "relu"),      # reference rank in gating mode at the cfg1 token count
+    (256, 5920, True, "relu"),     # cfg1: r = 128 gating
+    (128, 1000, False, "relu"),    # r = 128 single (pass B)
+    (64, 130, True, "gelu"),       # opt-in GELU, ragged tail (M % 128 = 2)
+    (16, 1, False, "relu"),        # single row
+    (256, 129, True, "relu"),
+])
+def test_dat_fwd_bwd_full_size_vs_oracle(ops, R, M, gating, act):
+    rng = np.random.default_rng(R * 7919 + M)
+    nb = 2 if gating else 1
+    r = R // nb
+    brs = [((rng.standard_normal((r, 768)) * 0.05).astype(np.float32),
+            (rng.standard_normal(r) * 0.1).astype(np.float32),
+            (rng.standard_normal((768, r)) * 0.05).astype(np.float32),
+            (rng.standard_normal(768) * 0.1).astype(np.float32)) for _ in range(nb)]
+    x = rng.standard_normal((M, 768)).astype(np.float32)
+    res = rng.standard_normal((M, 768)).astype(np.float32)
+    g = rng.standard_normal((M, 768)).astype(np.float32)
+    pk = ops.pack_weights(dev_branches(brs))
+    scale = 0.5 if gating else 1.0
+    xd, rd, gd = (to_dev(t, torch.bfloat16) for t in (x, res, g))
+    y = ops.dat_forward(xd, rd, pk, scale, act)
+    dx, grads = ops.dat_backward(xd, gd, pk, scale, act, train_slice=(0, r), need_dx=True, add_dy=False)
+    torch.cuda.synchronize()
+    xr, rr, gr = bf16_round(x), bf16_round(res), bf16_round(g)
+    rb = rounded_branches(brs)
+    y_or = oracle.adapter_forward(xr, rr, rb, gating, act=act)
+    assert relerr(y.float().cpu().numpy(), y_or) < 6e-3
+    dx_or, grads_or = oracle.adapter_backward(xr, gr, rb, gating, residual_is_input=False, act=act)
+    assert relerr(dx.float().cpu().numpy(), dx_or) < BF16_TOL
+    for got, want in zip(grads, grads_or[0]):
+        assert relerr(got.cpu().numpy(), want) < 2 * BF16_TOL
+
+
+def test_dat_backward_without_dx_and_frozen_only(ops):
+    """First adapter site needs no dX; a fully frozen mode (no trainable slice) needs only dX."""
+    rng = np.random.default_rng(5)
+    r, M = 32, 300
+    brs = [((rng.standard_normal((r, 768)) * 0.05).astype(np.float32), np.zeros(r, np.float32),
+            (rng.standard_normal((768, r)) * 0.05).astype(np.float32), np.zeros(768, np.float32))
+           for _ in range(2)]
+    pk = ops.pack_weights(dev_branches(brs))
+    x = to_dev(rng.standard_normal((M, 768)).astype(np.float32), torch.bfloat16)
+    g = to_dev(rng.standard_normal((M, 768)).astype(np.float32), torch.bfloat16)
+    dx_full, grads_full = ops.dat_backward(x, g, pk, 0.5, train_slice=(0, r), need_dx=True, add_dy=True)
+    dx_none, grads_only = ops.dat_backward(x, g, pk, 0.5, train_slice=(0, r), need_dx=False)
+    dx_only, grads_none = ops.dat_backward(x, g, pk, 0.5, train_slice=None, need_dx=True, add_dy=True)
+    torch.cuda.synchronize()
+    assert dx_none is None and grads_none is None
+    assert torch.equal(dx_only, dx_full)
+    for a, b in zip(grads_only, grads_full):
+        assert relerr(a.cpu().numpy(), b.cpu().numpy()) < 1e-5   # fp32 atomics: order only
+
+
+def test_unsupported_shapes_fail_loudly(ops):
+    from feddat_b200._lib import FeddatError
+    x = torch.zeros(4, 768, device="cuda", dtype=torch.float32)
+    with pytest.raises(FeddatError):
+        ops.dat_forward(x, x, None, 1.0)                      # fp32 activations: no fallback
+    w = [[torch.zeros(24, 768, device="cuda"), torch.zeros(24, device="cuda"),
+          torch.zeros(768, 24, device="cuda"), torch.zeros(768, device="cuda")]]
+    pk = ops.pack_weights(w)
+    xb = torch.zeros(4, 768, device="cuda", dtype=torch.bfloat16)
+    with pytest.raises(FeddatError, match="multiple of 16"):
+        ops.dat_forward(xb, xb, pk, 1.0)                      # r = 24 is not a multiple of 16
+
+
+# --------------------------------------------------------------------------------------- MKD head
+@pytest.mark.parametrize("case", ["vilt_T3", "vilt_T2"])
+def test_mkd_loss_matches_reference_golden(golden, ops, case):
+    a, b, temp = kl_inputs(golden[f"kl/{case}/meta"])
+    tgt = golden[f"mkd/{case}/target"]
+    loss3, dlog = ops.mkd_loss(to_dev(a), to_dev(b), to_dev(tgt), temp)
+    torch.cuda.synchronize()
+    loss3 = loss3.cpu().numpy()
+    assert abs(loss3[0] - golden[f"mkd/{case}/total"]) / abs(golden[f"mkd/{case}/total"]) < FP32_TOL
+    assert abs(loss3[1] - golden[f"kl/{case}/loss"]) / abs(golden[f"kl/{case}/loss"]) < FP32_TOL
+    assert abs(loss3[2] - golden[f"mkd/{case}/task"]) / abs(golden[f"mkd/{case}/task"]) < FP32_TOL
+    assert relerr(dlog.cpu().numpy(), golden[f"mkd/{case}/grad"]) < FP32_TOL
+
+
+def test_kl_only_wide_vocab_matches_reference_golden(golden, ops):
+    a, b, temp = kl_inputs(golden["kl/wide_T3/meta"])       # (2, 3, 3001): softmax over last dim
+    loss3, dlog = ops.mkd_loss(to_dev(a), to_dev(b), None, temp, kl_weight=1.0, task_weight=0.0)
+    torch.cuda.synchronize()
+    assert abs(loss3[1].item() - golden["kl/wide_T3/loss"]) / abs(golden["kl/wide_T3/loss"]) < FP32_TOL
+    assert relerr(dlog.cpu().numpy(), golden["kl/wide_T3/grad"]) < FP32_TOL
+
+
+@pytest.mark.parametrize("rows,C", [(32, 100), (1, 100), (7, 3129), (5, 30522), (256, 30522)])
+def test_mkd_loss_vs_oracle_sizes(ops, rows, C):
+    rng = np.random.default_rng(rows * 31 + C)
+    a = (rng.standard_normal((rows, C)) * 3).astype(np.float32)
+    b = (rng.standard_normal((rows, C)) * 3).astype(np.float32)
+    t = (rng.random((rows, C)) < 0.02).astype(np.float32) * 0.6
+    loss3, dlog = ops.mkd_loss(to_dev(a), to_dev(b), to_dev(t), 2.0)
+    torch.cuda.synchronize()
+    total, kl, task, grad = oracle.mkd_total(a, b, t, 2.0)
+    got = loss3.cpu().numpy()
+    assert abs(got[0] - total) / abs(total) < FP32_TOL
+    assert abs(got[1] - kl) / abs(kl) < FP32_TOL
+    assert abs(got[2] - task) / abs(task) < FP32_TOL
+    assert relerr(dlog.cpu().numpy(), grad) < FP32_TOL
+
+
+# ----------------------------------------------------------------------------------------- FedAvg
+@pytest.mark.parametrize("case", ["equal3", "weighted3", "equal8"])
+def test_fedavg_bit_exact_vs_reference_golden(golden, ops, case):
+    keys, clients, nums = fedavg_inputs(golden[f"fedavg/{case}/meta"])
+    flat = [np.concatenate([c[k].ravel() for k in keys]) for c in clients]
+    pad = (-flat[0].size) % 4
+    bufs = [to_dev(np.pad(f, (0, pad))) for f in flat]
+    out = torch.empty_like(bufs[0])
+    ops.fedavg(bufs, nums, out)
+    torch.cuda.synchronize()
+    want = np.concatenate([golden[f"fedavg/{case}/{k}"].ravel() for k in keys])
+    assert np.array_equal(out.cpu().numpy()[: want.size], want)
+
+
+def test_fedavg_large_and_ragged(ops):
+    rng = np.random.default_rng(9)
+    n = 2_370_048 + 3                      # ViLT r=128 communicated floats (+ ragged tail)
+    cl = [rng.standard_normal(n).astype(np.float32) for _ in range(8)]
+    out = torch.empty(n, device="cuda")
+    ops.fedavg([to_dev(c) for c in cl], [1] * 8, out)
+    torch.cuda.synchronize()
+    assert np.array_equal(out.cpu().numpy(), oracle.get_average_net(cl, [1] * 8))
