@@ -69,8 +69,8 @@ def load() -> ctypes.CDLL:
     lib.feddat_mkd_loss.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int,
                                     c_float, c_float, c_float, c_float, c_int64, c_void_p]
     lib.feddat_fedavg.restype = c_int
-    lib.feddat_fedavg.argtypes = [POINTER(c_void_p), POINTER(c_float), c_int, c_void_p, c_int64,
-                                  c_void_p]
+    lib.feddat_fedavg.argtypes = [POINTER(c_void_p), POINTER(c_float), c_int, c_float, c_void_p,
+                                  c_int64, c_void_p]
     lib.feddat_probe_gemm.restype = c_int
     lib.feddat_probe_gemm.argtypes = [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
                                       POINTER(c_uint32), c_void_p]

@@ -48,7 +48,7 @@ __global__ void __launch_bounds__(256) fedavg_kernel(const __grid_constant__ Fed
 }  // namespace fd
 
 extern "C" int feddat_fedavg(const float* const* clients, const float* weights, int n_clients,
-                             float* out, int64_t n, void* stream) {
+                             float total_weight, float* out, int64_t n, void* stream) {
   using namespace fd;
   int rc = check_device_sm100();
   if (rc) return rc;
@@ -69,6 +69,7 @@ extern "C" int feddat_fedavg(const float* const* clients, const float* weights, 
   }
   FD_REQUIRE((reinterpret_cast<uintptr_t>(out) & 15) == 0, FD_ERR_INVALID,
              "fedavg: out is not 16-byte aligned");
+  if (total_weight > 0.f) total = total_weight;  // partial sum of a rank: divide by the GLOBAL total
   FD_REQUIRE(total != 0.f, FD_ERR_INVALID, "fedavg: weights sum to zero");
   p.total = total; p.n_clients = n_clients; p.out = out; p.n = n;
   int sms = 0;

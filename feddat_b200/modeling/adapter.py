@@ -1,0 +1,299 @@
+"""Drop-in ``Adapter`` (mirror of reference src/modeling/models/adapter.py) whose forward/backward
+run as hand-written sm_100a kernels behind the C ABI.
+
+Kept from the reference: constructor signature, the ``adapter_{i}_down`` /
+``adapter_{i}_up`` ``nn.Linear`` sub-modules (same state-dict keys and shapes, so main.py's
+substring selection of 'adapter_0' / 'adapter_1' / 'adapter_2' keeps working), ``set_active_adapter``
+with its ``requires_grad`` toggling (adapter.py:66-95), ``activate_gating`` / ``deactivate_gating``,
+``forward(hidden_states, input_tensor)``, ``adapter_layer_forward_bert``, attributes ``gating``,
+``scaling``, ``actv``.  New, optional: ``rank=`` (the reference parses --adapter_reduction_factor but
+never forwards it) and ``activation=`` ('relu' = reference, adapter.py:24).
+
+There is no PyTorch fallback: CPU tensors raise.
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+import torch.nn as nn
+
+from .. import ops
+from .._lib import FeddatError
+
+
+def init_bert_weights(module):
+    """adapter.py:5-14: N(0, 0.02) weights, zero biases, unit LayerNorm."""
+    if isinstance(module, (nn.Linear, nn.Embedding)):
+        module.weight.data.normal_(mean=0.0, std=0.02)
+    elif isinstance(module, nn.LayerNorm):
+        module.bias.data.zero_()
+        module.weight.data.fill_(1.0)
+    if isinstance(module, nn.Linear) and module.bias is not None:
+        module.bias.data.zero_()
+
+
+class _DatFunction(torch.autograd.Function):
+    """y = res + scale * (act(x Wd^T + bd) Wu^T + bu) over the concatenated active branches.
+
+    inputs: x [M, 768] bf16, res (same tensor object as x when the residual IS the input), then the
+    fp32 master parameters (down_w, down_b, up_w, up_b) of every active branch.
+    """
+
+    @staticmethod
+    def forward(ctx, adapter: "Adapter", x, res, *params):
+        segs = adapter._segments(params)
+        same = res is x
+        y = None
+        for i, (pk, _, _) in enumerate(segs):
+            y = ops.dat_forward(x, res if i == 0 else y, pk, adapter._scale(), adapter._act_code)
+        ctx.adapter = adapter
+        ctx.segs = segs
+        ctx.same = same
+        ctx.n_params = len(params)
+        ctx.param_needs = [p.requires_grad for p in params]
+        ctx.save_for_backward(x)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        (x,) = ctx.saved_tensors
+        adapter = ctx.adapter
+        dy = dy.contiguous()
+        need_dx = ctx.needs_input_grad[1]
+        need_dres = ctx.needs_input_grad[2] and not ctx.same
+        r = adapter.rank
+        nb = ctx.n_params // 4
+        # which branches train (adapter.py:71-85 toggles requires_grad per mode)
+        branch_trains = [any(ctx.param_needs[4 * b: 4 * b + 4]) for b in range(nb)]
+        grads: List[Optional[torch.Tensor]] = [None] * ctx.n_params
+        dx_total = None
+        for si, (pk, col0, width) in enumerate(ctx.segs):
+            # trainable slice of this segment in concatenated-bottleneck coordinates
+            lo, hi = None, None
+            for b in range(nb):
+                b0, b1 = max(b * r, col0), min((b + 1) * r, col0 + width)
+                if branch_trains[b] and b0 < b1:
+                    lo = b0 if lo is None else min(lo, b0)
+                    hi = b1 if hi is None else max(hi, b1)
+            ts = None if lo is None else (lo - col0, hi - col0)
+            dx, g = ops.dat_backward(x, dy, pk, adapter._scale(), adapter._act_code, train_slice=ts,
+                                     need_dx=need_dx, add_dy=(ctx.same and si == 0))
+            if dx is not None:
+                dx_total = dx if dx_total is None else dx_total + dx
+            if g is not None:
+                d_down_w, d_down_b, d_up_w, d_up_b = g
+                for b in range(nb):
+                    b0, b1 = max(b * r, lo), min((b + 1) * r, hi)
+                    if not branch_trains[b] or b0 >= b1:
+                        continue
+                    s0, s1 = b0 - lo, b1 - lo          # rows/cols inside the slice gradients
+                    p0, p1 = b0 - b * r, b1 - b * r    # rows/cols inside the branch parameters
+                    full = (p0 == 0 and p1 == r)
+
+                    def put(idx, piece, shape, sl):
+                        if full:
+                            grads[idx] = piece.contiguous() if grads[idx] is None else grads[idx] + piece
+                        else:
+                            if grads[idx] is None:
+                                grads[idx] = torch.zeros(shape, device=x.device, dtype=torch.float32)
+                            grads[idx][sl] += piece
+
+                    put(4 * b + 0, d_down_w[s0:s1], (r, adapter.model_dim), slice(p0, p1))
+                    put(4 * b + 1, d_down_b[s0:s1], (r,), slice(p0, p1))
+                    put(4 * b + 2, d_up_w[:, s0:s1], (adapter.model_dim, r), (slice(None), slice(p0, p1)))
+                    if si == 0 or grads[4 * b + 3] is None:
+                        # d_up_b is the same column sum of dY for every segment: take it once
+                        if grads[4 * b + 3] is None:
+                            grads[4 * b + 3] = d_up_b.contiguous()
+        for i, needs in enumerate(ctx.param_needs):
+            if not needs:
+                grads[i] = None
+        dres = dy if need_dres else None
+        return (None, dx_total if need_dx else None, dres, *grads)
+
+
+class Adapter(nn.Module):
+    """The DAT bottleneck operator (reference adapter.py:16-163)."""
+
+    def __init__(self, names, device, model_dim=768, adapter_reduction_factor=16, rank=None,
+                 activation="relu"):
+        super().__init__()
+        if activation not in ("relu", "gelu"):
+            raise ValueError(f"activation must be 'relu' (reference) or 'gelu', got {activation!r}")
+        self.actv = nn.ReLU() if activation == "relu" else nn.GELU()
+        self._act_code = ops.act_code(activation)
+        self.scaling = 1.0
+        self.gating = False
+        self.model_dim = model_dim
+        self.rank = int(rank) if rank is not None else model_dim // adapter_reduction_factor
+        if model_dim != 768:
+            raise FeddatError(f"the sm_100a DAT kernels are built for model_dim=768 (got {model_dim})")
+        if self.rank % 16 != 0 or self.rank < 16:
+            raise FeddatError(f"adapter rank must be a multiple of 16 (got {self.rank}); "
+                              "there is no fallback path for other ranks")
+
+        if isinstance(names, str):
+            names = [names]
+        self.adapter_dict = {}
+        for name in names:
+            if "adapter" in name:
+                for part, (fan_in, fan_out) in (("down", (model_dim, self.rank)), ("up", (self.rank, model_dim))):
+                    n = f"{name}_{part}"
+                    setattr(self, n, nn.Linear(fan_in, fan_out).to(device))
+                    m = getattr(self, n)
+                    m.apply(init_bert_weights)
+                    for p in m.parameters():
+                        p.requires_grad = True
+            elif name in ["gating"]:
+                # kept for state-dict compatibility; the learned gate is commented out upstream
+                # (adapter.py:143) and never used in forward
+                setattr(self, f"{name}_module", nn.Linear(model_dim, 2).to(device))
+                m = getattr(self, f"{name}_module")
+                m.apply(init_bert_weights)
+
+        if hasattr(self, "adapter_2_down"):                      # adapter.py:55-58
+            for m in [self.adapter_2_down, self.adapter_2_up]:
+                for p in m.parameters():
+                    p.requires_grad = False
+        self._active_name: Optional[str] = None
+        self._pack_cache = {}
+
+    # ------------------------------------------------------------------ mode switches (reference API)
+    def deactivate_gating(self):
+        self.gating = False
+
+    def activate_gating(self):
+        self.gating = True
+
+    def set_active_adapter(self, name):
+        """adapter.py:66-95, including the requires_grad side effects."""
+        if isinstance(name, str):
+            self.active_adapter_down = getattr(self, f"{name}_down")
+            self.active_adapter_up = getattr(self, f"{name}_up")
+            self._active_name = name
+
+        if name == "adapter_0":
+            self._set_grad(("adapter_0",), True)
+            self._set_grad(("adapter_1",), False)
+        elif name == "adapter_1":
+            self._set_grad(("adapter_1",), True)
+            self._set_grad(("adapter_0",), False)
+        elif isinstance(name, list):
+            self._set_grad(name, True)
+        return
+
+    def _set_grad(self, names: Sequence[str], flag: bool):
+        for n in names:
+            for part in ("down", "up"):
+                m = getattr(self, f"{n}_{part}", None)
+                if m is not None:
+                    for p in m.parameters():
+                        p.requires_grad = flag
+
+    # ------------------------------------------------------------------ kernel plumbing
+    def _scale(self) -> float:
+        return 0.5 * self.scaling if self.gating else 1.0      # adapter.py:144-146 / :131
+
+    def _active_branch_names(self) -> Tuple[str, ...]:
+        if not self.gating:
+            if self._active_name is None:
+                raise AttributeError("set_active_adapter() was never called")  # reference: adapter.py:127
+            return (self._active_name,)
+        if hasattr(self, "adapter_2_down"):
+            return ("adapter_0", "adapter_2")                   # adapter.py:135
+        return ("adapter_0", "adapter_1")                       # adapter.py:151
+
+    def _branch_params(self, names):
+        out = []
+        for n in names:
+            d, u = getattr(self, f"{n}_down"), getattr(self, f"{n}_up")
+            out += [d.weight, d.bias, u.weight, u.bias]
+        return out
+
+    def _segments(self, params):
+        """Packed bf16 operands of the active branches, split into <=256-wide launches; cached until
+        a parameter changes (optimizer step, FedAvg copy, load_state_dict all bump ``_version``)."""
+        key = (self.gating, self._active_name if not self.gating else None)
+        stamp = tuple((p.data_ptr(), p._version) for p in params)
+        hit = self._pack_cache.get(key)
+        if hit is not None and hit[0] == stamp:
+            return hit[1]
+        for p in params:
+            if not (p.is_cuda and p.dtype == torch.float32):
+                raise FeddatError("adapter parameters must be fp32 CUDA tensors (fp32 masters; the "
+                                  "kernels consume a packed bf16 copy)")
+        nb = len(params) // 4
+        r = self.rank
+        with torch.no_grad():
+            branches = [[params[4 * b + i].detach().contiguous() for i in range(4)] for b in range(nb)]
+            R = nb * r
+            if R <= ops.MAX_R_TOTAL:
+                segs = [(ops.pack_weights(branches), 0, R)]
+            else:
+                segs = []
+                col = 0
+                first = True
+                for b in range(nb):
+                    dw, db, uw, ub = branches[b]
+                    for j0 in range(0, r, ops.MAX_R_TOTAL):
+                        j1 = min(r, j0 + ops.MAX_R_TOTAL)
+                        # bu_cat is the SUM of all branches' up biases: put it on the first segment only
+                        ub_seg = ub if first else torch.zeros_like(ub)
+                        if first and nb == 2:
+                            ub_seg = ub + branches[1][3]
+                        seg = [[dw[j0:j1].contiguous(), db[j0:j1].contiguous(),
+                                uw[:, j0:j1].contiguous(), ub_seg.contiguous()]]
+                        segs.append((ops.pack_weights(seg), col, j1 - j0))
+                        col += j1 - j0
+                        first = False
+        self._pack_cache[key] = (stamp, segs)
+        return segs
+
+    # ------------------------------------------------------------------ forward (reference API)
+    def forward(self, hidden_states, input_tensor):
+        """adapter.py:124-163."""
+        if not hidden_states.is_cuda:
+            raise FeddatError("Adapter.forward: CPU tensors are not supported -- the DAT operator exists "
+                              "only as sm_100a CUDA kernels (no fallback)")
+        names = self._active_branch_names()
+        params = self._branch_params(names)
+        shape = hidden_states.shape
+        out_dtype = hidden_states.dtype
+        same = input_tensor is hidden_states
+        x = hidden_states.reshape(-1, shape[-1])
+        if x.dtype != torch.bfloat16:
+            x = x.to(torch.bfloat16)
+        x = x.contiguous()
+        if same:
+            res = x
+        else:
+            res = input_tensor.reshape(-1, shape[-1])
+            if res.dtype != torch.bfloat16:
+                res = res.to(torch.bfloat16)
+            res = res.contiguous()
+        y = _DatFunction.apply(self, x, res, *params)
+        y = y.view(shape)
+        return y if out_dtype == torch.bfloat16 else y.to(out_dtype)
+
+    # ------------------------------------------------------------------ BERT-site wrapper (reference API)
+    def adapter_layer_forward_bert(self, hidden_states, input_tensor, layer_norm):
+        hidden_states, residual = self.pre_forward(hidden_states, input_tensor, layer_norm)
+        hidden_states = self.forward(hidden_states, residual)
+        hidden_states = self.post_forward(hidden_states, input_tensor, layer_norm)
+        return hidden_states
+
+    def pre_forward(self, hidden_states, input_tensor, layer_norm):
+        residual = hidden_states                                # adapter.py:104 residual_before_ln
+        if layer_norm:
+            hidden_states = layer_norm(hidden_states + input_tensor)
+        else:
+            hidden_states = hidden_states + input_tensor
+        return hidden_states, residual
+
+    def post_forward(self, hidden_states, input_tensor, layer_norm):
+        if layer_norm:
+            hidden_states = layer_norm(hidden_states + input_tensor)
+        else:
+            hidden_states = hidden_states + input_tensor
+        return hidden_states

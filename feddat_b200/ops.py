@@ -183,8 +183,10 @@ def mkd_loss(logits: torch.Tensor, teacher: torch.Tensor, target: Optional[torch
     return loss3, dlogits
 
 
-def fedavg(client_bufs: Sequence[torch.Tensor], nums: Sequence[float], out: torch.Tensor) -> torch.Tensor:
-    """out = sum_c client_c * num_c / sum(nums), reference operation order (main.py:57-64)."""
+def fedavg(client_bufs: Sequence[torch.Tensor], nums: Sequence[float], out: torch.Tensor,
+           total: float = 0.0) -> torch.Tensor:
+    """out = sum_c client_c * num_c / total, reference operation order (main.py:57-64);
+    total defaults to sum(nums) (pass the global total for a per-rank partial sum)."""
     lib = _lib.load()
     n = out.numel()
     for t in list(client_bufs) + [out]:
@@ -193,7 +195,7 @@ def fedavg(client_bufs: Sequence[torch.Tensor], nums: Sequence[float], out: torc
     nc = len(client_bufs)
     ptrs = (ctypes.c_void_p * nc)(*[t.data_ptr() for t in client_bufs])
     w = (ctypes.c_float * nc)(*[float(v) for v in nums])
-    rc = lib.feddat_fedavg(ptrs, w, nc, _lib.ptr(out), n, _lib.stream_ptr())
+    rc = lib.feddat_fedavg(ptrs, w, nc, float(total), _lib.ptr(out), n, _lib.stream_ptr())
     _lib.check(rc, "feddat_fedavg")
     _count()
     return out

@@ -1,0 +1,186 @@
+"""Per-client trainer (mirror of reference src/train/visionlanguage_tasks/task_trainer.py).
+
+``TaskTrainer.train`` (task_trainer.py:24-111), ``forward_pass`` (:248-264), the ``dat`` branch of
+``train_step`` (:280-330, the 3-forward / 2-backward MKD schedule), ``create_optimizer``
+(:477-504) and the module-level ``kl_loss`` (:506-516) keep their names, arguments and ordering of
+side effects (detach points, requires_grad toggles, optimizer / scheduler stepped twice per batch,
+``zero_grad`` -> None grads).  The loss arithmetic runs in the fused sm_100a MKD kernel.
+"""
+from __future__ import annotations
+
+import os
+from typing import Dict
+
+import torch
+import torch.nn as nn
+from torch.optim import AdamW
+
+from .. import ops
+
+
+class _MkdLossFunction(torch.autograd.Function):
+    """(task_weight * task + kl_weight * kl) with d/dlogits from the same kernel launch."""
+
+    @staticmethod
+    def forward(ctx, logits, teacher, target, temp, kl_weight, task_weight):
+        shape = logits.shape
+        lg = logits.contiguous().float()
+        loss3, dlogits = ops.mkd_loss(lg, teacher.contiguous().float(),
+                                      None if target is None else target.contiguous().float(),
+                                      temp, kl_weight, task_weight, need_grad=True)
+        ctx.save_for_backward(dlogits)
+        ctx.shape, ctx.in_dtype = shape, logits.dtype
+        ctx.mark_non_differentiable(loss3)
+        return loss3[0], loss3
+
+    @staticmethod
+    def backward(ctx, g_total, _g3):
+        (dlogits,) = ctx.saved_tensors
+        g = (dlogits * g_total).view(ctx.shape)
+        return g.to(ctx.in_dtype), None, None, None, None, None
+
+
+def kl_loss(output, target, temp=3):
+    """task_trainer.py:506-516: T^2 * KL(softmax(target/T) || softmax(output/T)), 'batchmean'."""
+    total, _ = _MkdLossFunction.apply(output, target, None, float(temp), 1.0, 0.0)
+    return total
+
+
+def mkd_objective(logits, teacher, target, temp=3):
+    """(BCEWithLogits('mean')(logits, target) * C + kl_loss(logits, teacher.detach(), temp)) / 2
+    (task_trainer.py:299-301) in one fused launch.  Returns (L, loss3 = [L, kl, task])."""
+    return _MkdLossFunction.apply(logits, teacher.detach(), target, float(temp), 0.5, 0.5)
+
+
+def get_polynomial_decay_schedule_with_warmup(optimizer, num_warmup_steps, num_training_steps, lr_end=0.0,
+                                              power=1.0):
+    from transformers import get_polynomial_decay_schedule_with_warmup as hf
+    return hf(optimizer, num_warmup_steps=num_warmup_steps, num_training_steps=num_training_steps,
+              lr_end=lr_end, power=power)
+
+
+class TaskTrainer(nn.Module):
+
+    def __init__(self, **kwargs):
+        super().__init__()
+        self.kl_criterion = kl_loss                      # task_trainer.py:15
+        self.kl_temp = 3                                 # kl_loss default; BASELINE cfg1 uses 2.0
+
+    # ------------------------------------------------------------------ train (task_trainer.py:24-111)
+    def train(self, model, er=None, ewc=None, der=None, derpp=None, pnn=None, hat=None):
+        sd = model.state_dict()
+        for name in sd.keys():                           # :36-41  adapter_2 <- adapter_1
+            if "adapter_1" in name:
+                name_tgt = name.replace("adapter_1", "adapter_2")
+                if name_tgt in sd:
+                    sd[name_tgt].data.copy_(sd[name].data)
+        for n, p in model.named_parameters():            # :43-45
+            if "adapter_2" in n:
+                p.requires_grad = False
+        if getattr(self, "task_output_dir", None) and not os.path.isdir(self.task_output_dir):
+            os.makedirs(self.task_output_dir, exist_ok=True)
+
+        model = self.accelerator.prepare(model)
+        optimizer = self.create_optimizer(model, self.args.optimizer_mode)
+        scheduler = get_polynomial_decay_schedule_with_warmup(
+            optimizer, num_warmup_steps=int(self.max_steps * self.warmup_ratio),
+            num_training_steps=self.max_steps, lr_end=0, power=1)
+        model.zero_grad()
+        optimizer, scheduler = self.accelerator.prepare(optimizer, scheduler)
+        loader = self.vqa_train_dataloader
+
+        loss = None
+        for epoch in range(self.local_epochs):
+            model.train()
+            for step, batch in enumerate(loader):
+                if getattr(self.args, "debug", 0) > 0 and step > self.args.debug:
+                    break
+                if "vilt" not in self.args.encoder_name:
+                    batch = self.add_alpha(epoch, batch, step)
+                loss = self.train_step(model, step, batch, optimizer, scheduler, hooks=None, epoch=epoch)
+        self.accelerator.wait_for_everyone()
+        self.last_loss = loss
+        del optimizer, scheduler
+        unwrapped_model = self.accelerator.unwrap_model(model)
+        self.accelerator.free_memory()
+        return 0.0, unwrapped_model
+
+    # ------------------------------------------------------------------ forward_pass (:248-264)
+    def forward_pass(self, model, batch, do_eval: bool = False):
+        inputs = self.batch2inputs_converter(batch)
+        if "albef" in self.args.encoder_name and not do_eval:
+            inputs["train"] = True
+        vilt_like = self.args.encoder_name in ["vilt", "viltbert"]
+        if do_eval is True:
+            with torch.no_grad():
+                return model(task_key=self.task_key, **inputs) if vilt_like else model(self.task_key, inputs)
+        return model(task_key=self.task_key, **inputs) if vilt_like else model(self.task_key, inputs)
+
+    # ------------------------------------------------------------------ train_step (:266-330)
+    def _objective(self, logits, teacher, target, task_loss):
+        """(L, task) with L = (task + kl(logits, teacher.detach())) / 2.  Fused BCE+KL launch for the ViLT criterion
+        (BCEWithLogits 'mean' * C, train_vqa_crossvqa.py:237); KL kernel + given task loss otherwise."""
+        fused = (task_loss is None and isinstance(self.loss_criterion, nn.BCEWithLogitsLoss)
+                 and self.loss_criterion.reduction == "mean" and self.kl_criterion is kl_loss
+                 and self.loss_criterion.weight is None and self.loss_criterion.pos_weight is None)
+        if fused:
+            total, loss3 = mkd_objective(logits, teacher, target, self.kl_temp)
+            return total, loss3[2]
+        if task_loss is None:
+            task_loss = self.loss_criterion(logits, target) * target.shape[1]
+        if self.kl_criterion is kl_loss:
+            loss_kl = kl_loss(logits, teacher.clone().detach(), self.kl_temp)
+        else:
+            loss_kl = self.kl_criterion(logits, teacher.clone().detach())
+        return (task_loss + loss_kl) / 2, task_loss.detach()
+
+    def train_step(self, model, step, batch, optimizer=None, scheduler=None, hooks=None, epoch=None):
+        target = None
+        if isinstance(batch, dict) and "target_scores" in batch.keys():
+            target = batch["target_scores"].to(self.device)
+        if "dat" not in self.args.optimizer_mode:
+            raise NotImplementedError("only optimizer_mode='dat' is on the FedDAT hot path")
+        albef = "albef" in self.args.encoder_name
+
+        with torch.no_grad():                                        # (A) :283-287
+            model.module.activate_gating()
+            _, logits_all = self.forward_pass(model, batch, do_eval=False)
+
+        model.module.deactivate_gating()                             # (B) :290-308
+        model.module.set_active_adapter("adapter_1")
+        output_1_0, logits_1 = self.forward_pass(model, batch, do_eval=False)
+        L_1, _ = self._objective(logits_1, logits_all, target, output_1_0 if albef else None)
+        self.accelerator.backward(L_1)
+        if optimizer is not None:
+            optimizer.step()
+            if scheduler is not None:
+                scheduler.step()
+            optimizer.zero_grad()
+
+        model.module.activate_gating()                               # (C) :311-328
+        model.module.set_active_adapter("adapter_0")
+        output_0_0, logits_0 = self.forward_pass(model, batch, do_eval=False)
+        L_0, loss_0 = self._objective(logits_0, logits_1, target, output_0_0 if albef else None)
+        self.accelerator.backward(L_0)
+        if optimizer is not None:
+            optimizer.step()
+            if scheduler is not None:
+                scheduler.step()
+            optimizer.zero_grad()
+        self.last_logits = (logits_all, logits_1, logits_0)
+        self.last_objectives = (L_1.detach(), L_0.detach())
+        return loss_0          # the task term, as the reference does (task_trainer.py:319,330)
+
+    # ------------------------------------------------------------------ create_optimizer (:477-504)
+    def create_optimizer(self, model, mode="full"):
+        no_decay = ["bias", "LayerNorm.weight"]
+        groups = [
+            {"params": [p for n, p in model.named_parameters()
+                        if (not any(nd in n for nd in no_decay)) and p.requires_grad],
+             "weight_decay": self.weight_decay},
+            {"params": [p for n, p in model.named_parameters()
+                        if (any(nd in n for nd in no_decay)) and p.requires_grad],
+             "weight_decay": 0.0},
+        ]
+        on_cuda = any(p.is_cuda for g in groups for p in g["params"])
+        return AdamW(groups, lr=self.lr, eps=self.adam_epsilon, betas=(0.9, 0.98), fused=on_cuda)

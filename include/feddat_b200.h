@@ -123,8 +123,10 @@ int feddat_mkd_loss(const float* logits, const float* teacher, const float* targ
  * across GPUs the flat buffer goes through one NCCL allreduce.  All buffers 16-byte aligned.
  */
 int feddat_fedavg(const float* const* clients /* host array of device ptrs */,
-                  const float* weights /* host */, int n_clients, float* out, int64_t n,
-                  void* stream);
+                  const float* weights /* host */, int n_clients,
+                  float total_weight /* <= 0: sum(weights); > 0: the global total when this call
+                                        only sums the clients of one rank before the allreduce */,
+                  float* out, int64_t n, void* stream);
 
 /* Bring-up probe (tests only): one 128 x N x K tcgen05 GEMM, see csrc/probe.cu. */
 int feddat_probe_gemm(const void* A, const void* B, float* D, int N, int K, int a_mode,
