@@ -1,0 +1,92 @@
+"""Step-level parity: this repo's TaskTrainer.train_step (bf16 backbone, sm_100a DAT / MKD kernels)
+against the golden produced by the REFERENCE's own TaskTrainer.train_step + Adapter in fp32
+(tests/golden/make_step_golden.py), same seeded init, same batches.  GPU only."""
+from types import SimpleNamespace
+
+import numpy as np
+import pytest
+import torch
+import torch.nn as nn
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def step_golden():
+    from pathlib import Path
+    return np.load(Path(__file__).resolve().parent / "golden" / "step_golden.npz")
+
+
+def build_trainer(model, lr, max_steps, task, temp=3):
+    from feddat_b200.modeling.vilt import convert_batch_to_vilt_input_dict
+    from feddat_b200.train.accelerator import Accelerator
+    from feddat_b200.train.task_trainer import TaskTrainer
+    tr = TaskTrainer()
+    tr.args = SimpleNamespace(optimizer_mode="dat", encoder_name="vilt", debug=0)
+    tr.accelerator = Accelerator(device="cuda")
+    tr.device = torch.device("cuda")
+    tr.task_key = task
+    tr.batch2inputs_converter = convert_batch_to_vilt_input_dict
+    tr.loss_criterion = nn.BCEWithLogitsLoss(reduction="mean")
+    tr.weight_decay, tr.lr, tr.adam_epsilon = 1e-2, lr, 1e-8
+    tr.kl_temp = temp
+    tr.max_steps, tr.warmup_ratio = max_steps, 0.1
+    return tr
+
+
+def test_train_step_matches_reference_trainer(step_golden):
+    from feddat_b200 import ops
+    from feddat_b200.synthetic import make_vilt_batch, to_device
+    from feddat_b200.train.prepare import default_args, place_on_gpu, prepare_model
+    from feddat_b200.train.task_trainer import get_polynomial_decay_schedule_with_warmup
+
+    seed, rank, steps, max_steps, B, T, H, C = (int(v) for v in step_golden["meta"])
+    lr = float(step_golden["lr"])
+    torch.manual_seed(seed)
+    args = default_args(ordered_cl_tasks=["art"], adapter_rank=rank)
+    model = prepare_model(args, place=False)                       # same CPU RNG stream as the golden
+    sd0 = {k: v.clone() for k, v in model.state_dict().items() if "adapter" in k or "task_layer" in k}
+    place_on_gpu(model)
+
+    tr = build_trainer(model, lr, max_steps, "art")
+    # TaskTrainer.train prologue (task_trainer.py:36-45)
+    sd = model.state_dict()
+    for name in sd:
+        if "adapter_1" in name:
+            sd[name.replace("adapter_1", "adapter_2")].data.copy_(sd[name].data)
+    for n, p in model.named_parameters():
+        if "adapter_2" in n:
+            p.requires_grad = False
+    wrapped = tr.accelerator.prepare(model)
+    opt = tr.create_optimizer(wrapped)
+    assert sum(len(g["params"]) for g in opt.param_groups) == int(step_golden["n_optimizer_tensors"])
+    sched = get_polynomial_decay_schedule_with_warmup(opt, int(max_steps * 0.1), max_steps, lr_end=0, power=1)
+
+    launches0 = ops.launch_count
+    wrapped.train()
+    for step in range(steps):
+        batch = to_device(make_vilt_batch(B, T, H, C, seed=seed + step), "cuda")
+        loss_0 = tr.train_step(wrapped, step, batch, opt, sched)
+        torch.cuda.synchronize()
+        got = {n: t.float().cpu().numpy() for n, t in zip(("logits_all", "logits_1", "logits_0"), tr.last_logits)}
+        for n in got:
+            want = step_golden[f"step{step}/{n}"]
+            err = np.abs(got[n] - want).max() / np.abs(want).max()
+            assert err < 2e-2, f"step {step} {n}: rel err {err:.4f}"
+        want_loss = float(step_golden[f"step{step}/loss_0"])
+        assert abs(loss_0.item() - want_loss) / want_loss < 1e-2, (step, loss_0.item(), want_loss)
+    assert ops.launch_count > launches0, "the CUDA kernels did not run"
+
+    # parameter movement after 3 steps (AdamW + poly schedule, lr = 0 on the very first optimizer step)
+    sd1 = model.state_dict()
+    rel = []
+    for k in sd0:
+        if "adapter_2" in k:
+            continue
+        want = float(step_golden[f"delta_norm/{k}"])
+        got_d = (sd1[k].float().cpu() - sd0[k]).double().norm().item()
+        if want > 1e-6:
+            rel.append(abs(got_d - want) / want)
+        else:
+            assert got_d < 1e-5
+    assert np.median(rel) < 5e-2 and max(rel) < 0.25, (np.median(rel), max(rel))
