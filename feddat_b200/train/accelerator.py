@@ -33,6 +33,8 @@ class Accelerator:
             device = torch.device("cuda", self.local_process_index) if torch.cuda.is_available() else torch.device("cpu")
         self.device = torch.device(device)
         if self.device.type == "cuda":
+            if self.device.index is None:
+                self.device = torch.device("cuda", torch.cuda.current_device())
             torch.cuda.set_device(self.device)
 
     @property

@@ -111,22 +111,26 @@ def test_dat_backward_matches_reference_golden(golden, ops, case):
     dx, grads = ops.dat_backward(x2, g2, pk, 0.5 if gating else 1.0, train_slice=(0, r), need_dx=True,
                                  add_dy=True)
     torch.cuda.synchronize()
-    # (1) against the reference's fp32 gradients.  Rounding X / W to bf16 flips the ReLU mask of the
-    # few pre-activations within ~2^-9 of zero; with only tens of rows one flip moves d_down_b by
-    # several percent (the numpy oracle fed the same bf16-rounded operands shows the same 1.5e-2 /
-    # 4e-2 deviation from these goldens), so this link is loose and link (2) below is the strict one.
-    GOLD_TOL = 5e-2
-    assert relerr_fro(dx.float().cpu().numpy(), golden[f"adapter/{case}/dx"].reshape(-1, 768)) < 2e-2
     d_down_w, d_down_b, d_up_w, d_up_b = [t.cpu().numpy() for t in grads]
-    assert relerr_fro(d_down_b, golden[f"adapter/{case}/d_down_b"]) < GOLD_TOL
-    assert relerr_fro(d_up_b, golden[f"adapter/{case}/d_up_b"]) < BF16_TOL
-    if f"adapter/{case}/d_down_w" in golden:
-        assert relerr_fro(d_down_w, golden[f"adapter/{case}/d_down_w"]) < GOLD_TOL
-        assert relerr_fro(d_up_w, golden[f"adapter/{case}/d_up_w"]) < BF16_TOL
-    # (2) oracle (pinned to the reference at 1e-4 by tests/test_oracle_golden.py) on identical
-    # bf16-rounded operands: all four gradients, every case, max-norm
     xr, gr = bf16_round(x.reshape(-1, 768)), bf16_round(g.reshape(-1, 768))
     dx_or, grads_or = oracle.adapter_backward(xr, gr, rounded_branches(brs), gating, residual_is_input=True)
+    # (1) against the reference's fp32 gradients.  Rounding X / W to bf16 flips the ReLU mask of the
+    # few pre-activations within ~2^-9 of zero; with only tens of rows one flip moves a bias/weight
+    # gradient by several percent.  That deviation belongs to the bf16 operands, not to the kernel:
+    # exact arithmetic (the oracle) on the same bf16-rounded operands shows it too.  So the kernel
+    # must be no further from the reference than the oracle-on-bf16 is, plus the bf16 tolerance.
+    gold = {"dx": golden[f"adapter/{case}/dx"].reshape(-1, 768), "d_down_b": golden[f"adapter/{case}/d_down_b"],
+            "d_up_b": golden[f"adapter/{case}/d_up_b"]}
+    got = {"dx": dx.float().cpu().numpy(), "d_down_b": d_down_b, "d_up_b": d_up_b}
+    exact = {"dx": dx_or, "d_down_b": grads_or[0][1], "d_up_b": grads_or[0][3]}
+    if f"adapter/{case}/d_down_w" in golden:
+        gold.update(d_down_w=golden[f"adapter/{case}/d_down_w"], d_up_w=golden[f"adapter/{case}/d_up_w"])
+        got.update(d_down_w=d_down_w, d_up_w=d_up_w)
+        exact.update(d_down_w=grads_or[0][0], d_up_w=grads_or[0][2])
+    for k in gold:
+        assert relerr_fro(got[k], gold[k]) < relerr_fro(exact[k], gold[k]) + BF16_TOL, k
+    # (2) oracle (pinned to the reference at 1e-4 by tests/test_oracle_golden.py) on identical
+    # bf16-rounded operands: all four gradients, every case, max-norm
     assert relerr(dx.float().cpu().numpy(), dx_or) < BF16_TOL
     for got, want in zip((d_down_w, d_down_b, d_up_w, d_up_b), grads_or[0]):
         assert relerr(got, want) < 2 * BF16_TOL
