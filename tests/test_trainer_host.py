@@ -1,0 +1,89 @@
+"""Host logic of TaskTrainer.train_step (the MKD schedule of reference task_trainer.py:280-330) on
+CPU with a stand-in model; the fused loss kernel is replaced by the oracle for this test only."""
+from types import SimpleNamespace
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+import oracle
+from feddat_b200.train import task_trainer as tt
+from feddat_b200.train.accelerator import Accelerator
+
+
+def _oracle_mkd(logits, teacher, target, temp, kl_weight=0.5, task_weight=0.5, need_grad=True):
+    lg, te = logits.detach().numpy(), teacher.detach().numpy()
+    kl, gkl = oracle.kl_loss(lg, te, temp, with_grad=True)
+    task, gtask = (0.0, 0.0) if target is None else oracle.bce_with_logits_times_c(lg, target.numpy(), with_grad=True)
+    loss3 = torch.tensor([kl_weight * kl + task_weight * task, kl, task], dtype=torch.float32)
+    return loss3, torch.from_numpy(np.asarray(kl_weight * gkl + task_weight * gtask, np.float32))
+
+
+class FakeLearner(nn.Module):
+    """Two 'adapters' + head; records the hook calls the trainer makes."""
+
+    def __init__(self):
+        super().__init__()
+        self.adapter_0 = nn.Linear(6, 6)
+        self.adapter_1 = nn.Linear(6, 6)
+        self.adapter_2 = nn.Linear(6, 6)
+        self.task_head = nn.Linear(6, 5)
+        self.gating, self.active, self.log = False, None, []
+
+    def activate_gating(self):
+        self.gating = True; self.log.append("gate_on")
+
+    def deactivate_gating(self):
+        self.gating = False; self.log.append("gate_off")
+
+    def set_active_adapter(self, name):
+        self.active = name; self.log.append(name)
+        for p in self.adapter_0.parameters():
+            p.requires_grad = name == "adapter_0"
+        for p in self.adapter_1.parameters():
+            p.requires_grad = name == "adapter_1"
+
+    def forward(self, task_key, x):
+        self.log.append("fwd")
+        if self.gating:
+            h = x + 0.5 * self.adapter_0(x) + 0.5 * self.adapter_2(x)
+        else:
+            h = x + getattr(self, self.active)(x)
+        return h, self.task_head(h)
+
+
+def test_dat_schedule_and_losses(monkeypatch):
+    monkeypatch.setattr(tt.ops, "mkd_loss", _oracle_mkd)
+    torch.manual_seed(0)
+    m = FakeLearner()
+    for p in m.adapter_2.parameters():
+        p.requires_grad = False
+    tr = tt.TaskTrainer()
+    tr.args = SimpleNamespace(optimizer_mode="dat", encoder_name="vilt")
+    tr.accelerator = Accelerator(device="cpu")
+    tr.device, tr.task_key = torch.device("cpu"), "t"
+    tr.batch2inputs_converter = lambda b: {"x": b["x"]}
+    tr.loss_criterion = nn.BCEWithLogitsLoss(reduction="mean")
+    tr.weight_decay, tr.lr, tr.adam_epsilon, tr.kl_temp = 1e-2, 1e-2, 1e-8, 3
+    wrapped = tr.accelerator.prepare(m)
+    opt = tr.create_optimizer(wrapped)
+    steps = []
+    orig = opt.step
+    opt.step = lambda *a, **k: (steps.append(len(m.log)), orig(*a, **k))[1]
+    x = torch.randn(4, 6)
+    target = (torch.rand(4, 5) < 0.3).float() * 0.6
+    w0 = {n: p.detach().clone() for n, p in m.named_parameters()}
+    loss_0 = tr.train_step(wrapped, 0, {"x": x, "target_scores": target}, opt, None)
+    # hook order of task_trainer.py:283-315
+    assert m.log == ["gate_on", "fwd", "gate_off", "adapter_1", "fwd", "gate_on", "adapter_0", "fwd"]
+    assert len(steps) == 2                                     # optimizer stepped once per pass B and C
+    moved = {n: not torch.equal(p, w0[n]) for n, p in m.named_parameters()}
+    assert moved["adapter_1.weight"] and moved["adapter_0.weight"] and moved["task_head.weight"]
+    assert not moved["adapter_2.weight"]
+    # loss_0 is the TASK term of pass C (reference returns loss_0, not L_0)
+    logits_0 = tr.last_logits[2].detach().numpy()
+    assert abs(loss_0.item() - oracle.bce_with_logits_times_c(logits_0, target.numpy())) < 1e-4
+    # pass C distils from pass B's logits: L_0 = (task + kl(logits_0, logits_1)) / 2
+    want_L0 = oracle.mkd_total(logits_0, tr.last_logits[1].detach().numpy(), target.numpy(), 3)[0]
+    assert abs(tr.last_objectives[1].item() - want_L0) < 1e-4
+    assert all(p.grad is None for p in m.parameters())         # zero_grad -> None (torch >= 2 contract)
