@@ -167,7 +167,7 @@ class TaskTrainer(nn.Module):
             if scheduler is not None:
                 scheduler.step()
             optimizer.zero_grad()
-        self.last_logits = (logits_all, logits_1, logits_0)
+        self.last_logits = (logits_all.detach(), logits_1.detach(), logits_0.detach())
         self.last_objectives = (L_1.detach(), L_0.detach())
         return loss_0          # the task term, as the reference does (task_trainer.py:319,330)
 
