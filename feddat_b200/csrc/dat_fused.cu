@@ -5,23 +5,30 @@
 // "cat" = the active branches concatenated along the bottleneck dimension: one branch
 // (adapter.py:125-131, scale 1) or the two gating branches adapter_0 | adapter_2
 // (adapter.py:133-146, scale 0.5 each), so the dual adapter is ONE GEMM pair with hidden width
-// R = r_total.  One persistent CTA per SM walks 128-row tiles:
+// R = r_total.  One persistent CTA per SM walks 128-row tiles; 12 warps, every hand-off an mbarrier:
 //
-//   warp 0      TMA producer   X k-chunks + Wd_cat k-chunks, then Wu_cat (n-chunk, k-chunk) tiles
-//   warp 1      tcgen05.mma issuer: GEMM1 (128 x R x 768) -> TMEM, GEMM2 (128 x 768 x R) in N2-wide
-//               chunks -> TMEM, accumulators in a 2 x 256-column ring
-//   warps 2-5   epilogue: (1) TMEM -> +bias, act -> bf16 hidden tile in swizzled smem (the A operand
-//               of GEMM2, it never goes to HBM); (2) TMEM -> scale, +bias, +residual (residual tile
-//               brought in by TMA) -> bf16 -> smem -> TMA store
+//   warp 0      TMA producer: one ring of uniform 16 KB slots carries, in consumption order, the X
+//               k-chunks [128 x 64], the Wd_cat k-chunks (one or two 128-row boxes) and the Wu_cat
+//               [128 x 64] tiles; it runs ahead across tiles as far as the ring allows
+//   warp 1      tcgen05.mma issuer.  GEMM1 P = X Wd^T (SS, K-major SW128 smem operands) into TMEM
+//               columns [0, R); GEMM2 in six 128-column chunks, A operand = the hidden tile IN TMEM
+//               (bf16 pairs packed over P's own columns, "TS" MMA), accumulators in a two-buffer
+//               ring in TMEM columns [256, 512)
+//   warp 2      residual producer: TMA loads of the residual [128 x 64] chunks into the staging ring
+//   warp 3      store issuer: TMA stores of finished staging buffers, recycles them
+//   warps 4-7   epilogue group A: (1) P -> +bias, act -> bf16 pairs -> tcgen05.st over P's columns
+//               (the hidden never leaves the SM); (2) even output chunks
+//   warps 8-11  epilogue group B: odd output chunks.  An output chunk = tcgen05.ld, scale, +bias,
+//               +residual (from the staging buffer), bf16 back into the same staging buffer
 //
-// HBM traffic per row: read X (1536 B) + write Y (1536 B); the residual re-read hits L2.
+// HBM traffic per row: read X (1536 B) + write Y (1536 B); the residual re-read and all weights hit L2.
 //
-// The same kernel template, instantiated with kBwd = true, is the backward data-gradient pass
-// (what torch autograd derives from adapter.py:124-163):
-//   GEMM1  P  = X  * Wd_cat^T            (recompute, never stored)
-//   GEMM1b dH = dY * Wu_cat              (B operand: WuT_cat, K-major)
-//   epilogue 1: dP = scale * dH * act'(P + bd) -> bf16 tile in smem (A operand of GEMM3); for the
-//               trainable slice [r_lo, r_hi) also H = act(P + bd) and dP to HBM for the wgrad kernel
+// The same template with kBwd = true is the backward data-gradient pass (what torch autograd derives
+// from adapter.py:124-163):
+//   GEMM1  P  = X  * Wd_cat^T            (recompute, never stored)          -> TMEM [0, R)
+//   GEMM1b dH = dY * Wu_cat              (B operand: WuT_cat, K-major)      -> TMEM [256, 256 + R)
+//   epilogue 1: dP = scale * dH * act'(P + bd) -> bf16 pairs over P's columns (A operand of GEMM3);
+//               for the trainable slice [r_lo, r_hi) also H = act(P + bd) and dP to HBM (wgrad kernel)
 //   GEMM3  dX = dP * Wd_cat              (B operand: WdT_cat, K-major), + dY when the residual
 //               input is X itself (adaptered_output.py:78), -> bf16 -> TMA store
 #include "feddat_b200.h"
@@ -35,16 +42,18 @@ namespace {
 constexpr int kD = 768;
 constexpr int BM = 128;
 constexpr int BK = 64;
-constexpr int KC1 = kD / BK;  // 12 k-chunks for GEMM1
-constexpr int A_SLOT = BM * 128;
-constexpr int STG_BYTES = BM * 128;  // 128 rows x 64 bf16
-constexpr int NSTG = 3;
-constexpr int MAX_STAGES = 4;
-constexpr int NUM_THREADS = 192;
+constexpr int KC1 = kD / BK;          // 12 k-chunks for GEMM1
+constexpr int SLOT = BM * 128;        // 16 KB: [128 rows x 64 bf16], 128-byte swizzle
+constexpr int N2 = 128;               // GEMM2 / GEMM3 output chunk width
+constexpr int NC2 = kD / N2;          // 6 chunks
+constexpr int MAX_SLOTS = 12;
+constexpr int MAX_STG = 4;
+constexpr int NUM_THREADS = 384;
+constexpr uint32_t TM_P = 0;          // TMEM column of P (and of the packed hidden aliasing it)
+constexpr uint32_t TM_D = 256;        // TMEM column of the output ring (and of dH in backward)
 
 struct FusedParams {
-  int M, R, num_tiles, stages, n2, act;
-  uint32_t b_slot_bytes;
+  int M, R, num_tiles, n_slots, n_stg, act;
   float scale;
   const float* bd;
   const float* bu;        // fwd only
@@ -80,43 +89,51 @@ dat_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
                  const __grid_constant__ CUtensorMap tmW2, const __grid_constant__ CUtensorMap tmW1b,
                  const FusedParams p) {
   extern __shared__ uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t bars[2 * MAX_STAGES + 2 + 2 + 2 + NSTG];
+  // barriers: slot full/empty, P full, dH full, hidden full, D full/empty x2, staging res/out/empty
+  __shared__ __align__(8) uint64_t bars[2 * MAX_SLOTS + 3 + 4 + 3 * MAX_STG];
   __shared__ uint32_t tmem_base_smem;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int R = p.R, S = p.stages, N2 = p.n2;
+  const int R = p.R, NS = p.n_slots, NSTG = p.n_stg;
   const int KC2 = (R + 63) / 64;
-  const int NC2 = (kBwd && !p.has_out) ? 0 : kD / N2;
-  const int chunks_per_tile = NC2 * (N2 / 64);
+  const int nc2 = (kBwd && !p.has_out) ? 0 : NC2;
+  const int w_boxes = R > 128 ? 2 : 1;               // 128-row boxes per Wd / WuT k-chunk
+  const uint32_t w_box_bytes = static_cast<uint32_t>(R > 128 ? 128 : R) * 128u;
 
   const uint32_t smem0 = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t stage_bytes = A_SLOT + p.b_slot_bytes;
-  const uint32_t h_base = smem0 + S * stage_bytes;
-  const uint32_t stg_base = h_base + KC2 * A_SLOT;
-  const uint32_t bias_base = stg_base + NSTG * STG_BYTES;
+  const uint32_t stg_base = smem0 + NS * SLOT;
+  const uint32_t bias_base = stg_base + NSTG * SLOT;
   float* bias_smem = reinterpret_cast<float*>(smem_raw + (bias_base - smem_u32(smem_raw)));
 
   const uint32_t bar0 = smem_u32(bars);
-  auto bar_full = [&](int s) { return bar0 + 8u * s; };
-  auto bar_empty = [&](int s) { return bar0 + 8u * (MAX_STAGES + s); };
-  auto bar_acc_full = [&](int b) { return bar0 + 8u * (2 * MAX_STAGES + b); };
-  auto bar_acc_empty = [&](int b) { return bar0 + 8u * (2 * MAX_STAGES + 2 + b); };
-  const uint32_t bar_h_full = bar0 + 8u * (2 * MAX_STAGES + 4);
-  const uint32_t bar_h_empty = bar0 + 8u * (2 * MAX_STAGES + 5);
-  auto bar_res_full = [&](int b) { return bar0 + 8u * (2 * MAX_STAGES + 6 + b); };
+  auto bar_slot_full = [&](int s) { return bar0 + 8u * s; };
+  auto bar_slot_empty = [&](int s) { return bar0 + 8u * (MAX_SLOTS + s); };
+  const uint32_t bar_p_full = bar0 + 8u * (2 * MAX_SLOTS);
+  const uint32_t bar_g_full = bar0 + 8u * (2 * MAX_SLOTS + 1);
+  const uint32_t bar_h_full = bar0 + 8u * (2 * MAX_SLOTS + 2);
+  auto bar_d_full = [&](int b) { return bar0 + 8u * (2 * MAX_SLOTS + 3 + b); };
+  auto bar_d_empty = [&](int b) { return bar0 + 8u * (2 * MAX_SLOTS + 5 + b); };
+  auto bar_res_full = [&](int b) { return bar0 + 8u * (2 * MAX_SLOTS + 7 + b); };
+  auto bar_out_full = [&](int b) { return bar0 + 8u * (2 * MAX_SLOTS + 7 + MAX_STG + b); };
+  auto bar_stg_empty = [&](int b) { return bar0 + 8u * (2 * MAX_SLOTS + 7 + 2 * MAX_STG + b); };
 
   if (tid == 0) {
-    for (int s = 0; s < S; ++s) {
-      mbar_init(bar_full(s), 1);
-      mbar_init(bar_empty(s), 1);
+    for (int s = 0; s < NS; ++s) {
+      mbar_init(bar_slot_full(s), 1);
+      mbar_init(bar_slot_empty(s), 1);
     }
-    for (int b = 0; b < 2; ++b) {
-      mbar_init(bar_acc_full(b), 1);
-      mbar_init(bar_acc_empty(b), 128);
-    }
+    mbar_init(bar_p_full, 1);
+    mbar_init(bar_g_full, 1);
     mbar_init(bar_h_full, 128);
-    mbar_init(bar_h_empty, 1);
-    for (int b = 0; b < NSTG; ++b) mbar_init(bar_res_full(b), 1);
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(bar_d_full(b), 1);
+      mbar_init(bar_d_empty(b), 128);
+    }
+    for (int b = 0; b < NSTG; ++b) {
+      mbar_init(bar_res_full(b), 1);
+      mbar_init(bar_out_full(b), 128);
+      mbar_init(bar_stg_empty(b), 1);
+    }
     fence_mbar_init();
     tma_prefetch_desc(&tmX);
     tma_prefetch_desc(&tmRes);
@@ -125,8 +142,7 @@ dat_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
     tma_prefetch_desc(&tmW2);
     if (kBwd) tma_prefetch_desc(&tmW1b);
   }
-  if (warp == 1) tmem_alloc(smem_u32(&tmem_base_smem), 512);
-  // biases -> smem (broadcast reads in the epilogues)
+  if (warp == 2) tmem_alloc(smem_u32(&tmem_base_smem), 512);
   for (int i = tid; i < R; i += NUM_THREADS) bias_smem[i] = p.bd[i];
   if (!kBwd)
     for (int i = tid; i < kD; i += NUM_THREADS) bias_smem[R + i] = p.bu[i];
@@ -134,208 +150,238 @@ dat_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = tmem_base_smem;
+  const int my_tiles = (p.num_tiles - static_cast<int>(blockIdx.x) + gridDim.x - 1) / gridDim.x;
+  const uint32_t total_chunks = static_cast<uint32_t>(my_tiles) * nc2 * 2;  // 64-column staging chunks
 
   if (warp == 0) {
-    // ------------------------------------------------------------------ TMA producer
+    // ------------------------------------------------------------------ ring producer
     if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
+      uint32_t n = 0;  // slots issued so far
+      auto acquire = [&](uint32_t bytes) -> uint32_t {
+        const uint32_t s = n % NS, par = (n / NS) & 1;
+        mbar_wait(bar_slot_empty(s), par ^ 1);
+        mbar_arrive_expect_tx(bar_slot_full(s), bytes);
+        ++n;
+        return s;
+      };
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
         const int m0 = tile * BM;
-        for (int kc = 0; kc < KC1; ++kc) {
-          mbar_wait(bar_empty(stage), phase ^ 1);
-          const uint32_t a_dst = smem0 + stage * stage_bytes;
-          mbar_arrive_expect_tx(bar_full(stage), A_SLOT + R * 128);
-          tma_load_2d_hint(a_dst, &tmX, bar_full(stage), kc * BK, m0, kEvictNormal);
-          tma_load_2d_hint(a_dst + A_SLOT, &tmWd, bar_full(stage), kc * BK, 0, kEvictLast);
-          if (++stage == S) { stage = 0; phase ^= 1; }
-        }
-        if (kBwd) {
+        for (int pass = 0; pass < (kBwd ? 2 : 1); ++pass) {
+          const CUtensorMap* ta = pass == 0 ? &tmX : &tmRes;
+          const CUtensorMap* tw = pass == 0 ? &tmWd : &tmW1b;
           for (int kc = 0; kc < KC1; ++kc) {
-            mbar_wait(bar_empty(stage), phase ^ 1);
-            const uint32_t a_dst = smem0 + stage * stage_bytes;
-            mbar_arrive_expect_tx(bar_full(stage), A_SLOT + R * 128);
-            tma_load_2d_hint(a_dst, &tmRes, bar_full(stage), kc * BK, m0, kEvictNormal);
-            tma_load_2d_hint(a_dst + A_SLOT, &tmW1b, bar_full(stage), kc * BK, 0, kEvictLast);
-            if (++stage == S) { stage = 0; phase ^= 1; }
+            uint32_t s = acquire(SLOT);
+            tma_load_2d_hint(smem0 + s * SLOT, ta, bar_slot_full(s), kc * BK, m0, kEvictNormal);
+            for (int b = 0; b < w_boxes; ++b) {
+              s = acquire(w_box_bytes);
+              tma_load_2d_hint(smem0 + s * SLOT, tw, bar_slot_full(s), kc * BK, b * 128, kEvictLast);
+            }
           }
         }
-        for (int nc = 0; nc < NC2; ++nc) {
+        for (int c = 0; c < nc2; ++c)
           for (int kc = 0; kc < KC2; ++kc) {
-            mbar_wait(bar_empty(stage), phase ^ 1);
-            const uint32_t b_dst = smem0 + stage * stage_bytes + A_SLOT;
-            mbar_arrive_expect_tx(bar_full(stage), N2 * 128);
-            tma_load_2d_hint(b_dst, &tmW2, bar_full(stage), kc * BK, nc * N2, kEvictLast);
-            if (++stage == S) { stage = 0; phase ^= 1; }
+            const uint32_t s = acquire(SLOT);
+            tma_load_2d_hint(smem0 + s * SLOT, &tmW2, bar_slot_full(s), kc * BK, c * N2, kEvictLast);
           }
-        }
       }
     }
     __syncwarp();
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
     if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0, acc_it = 0, tile_it = 0;
-      const uint32_t idesc1 = make_idesc_bf16(BM, R);
+      uint32_t n = 0, tile_it = 0;
+      uint32_t de[2] = {0, 0};  // uses of each D buffer so far (parity of its "empty" barrier)
+      const uint32_t n_lo = R > 128 ? 128 : R;
+      const uint32_t idesc_lo = make_idesc_bf16(BM, n_lo);
+      const uint32_t idesc_hi = make_idesc_bf16(BM, R > 128 ? R - 128 : 16);
       const uint32_t idesc2 = make_idesc_bf16(BM, N2);
+      auto wait_slot = [&]() -> uint32_t {
+        const uint32_t s = n % NS, par = (n / NS) & 1;
+        mbar_wait(bar_slot_full(s), par);
+        ++n;
+        return s;
+      };
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++tile_it) {
-        for (int g1 = 0; g1 < (kBwd ? 2 : 1); ++g1) {  // GEMM1: P = X Wd_cat^T  (bwd: + dH = dY Wu_cat)
-          const uint32_t buf = acc_it & 1, par = (acc_it >> 1) & 1;
-          mbar_wait(bar_acc_empty(buf), par ^ 1);
-          tc_fence_after();
-          const uint32_t d_tmem = tmem + buf * 256;
-          for (int kc = 0; kc < KC1; ++kc) {
-            mbar_wait(bar_full(stage), phase);
+        for (int pass = 0; pass < (kBwd ? 2 : 1); ++pass) {
+          // pass 0: P = X Wd_cat^T -> [TM_P, +R);  pass 1 (bwd): dH = dY Wu_cat -> [TM_D, +R)
+          const uint32_t d_tmem = tmem + (pass == 0 ? TM_P : TM_D);
+          if (pass == 1) {  // dH overlays the output ring: both buffers must have been drained
+            for (int b = 0; b < 2; ++b) {
+              mbar_wait(bar_d_empty(b), (de[b] & 1) ^ 1);
+              ++de[b];
+            }
             tc_fence_after();
-            const uint32_t a_src = smem0 + stage * stage_bytes;
-#pragma unroll
-            for (int k = 0; k < 4; ++k)
-              umma_ss(d_tmem, desc_kmajor_sw128(a_src + k * 32),
-                      desc_kmajor_sw128(a_src + A_SLOT + k * 32), idesc1, (kc | k) != 0);
-            umma_commit(bar_empty(stage));
-            if (++stage == S) { stage = 0; phase ^= 1; }
           }
-          umma_commit(bar_acc_full(buf));
-          ++acc_it;
+          for (int kc = 0; kc < KC1; ++kc) {
+            const uint32_t sa = wait_slot();
+            const uint32_t sb0 = wait_slot();
+            const uint32_t sb1 = w_boxes == 2 ? wait_slot() : 0;
+            tc_fence_after();
+            const uint32_t a_src = smem0 + sa * SLOT;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const uint64_t adesc = desc_kmajor_sw128(a_src + k * 32);
+              umma_ss(d_tmem, adesc, desc_kmajor_sw128(smem0 + sb0 * SLOT + k * 32), idesc_lo,
+                      (kc | k) != 0);
+              if (w_boxes == 2)
+                umma_ss(d_tmem + 128, adesc, desc_kmajor_sw128(smem0 + sb1 * SLOT + k * 32),
+                        idesc_hi, (kc | k) != 0);
+            }
+            umma_commit(bar_slot_empty(sa));
+            umma_commit(bar_slot_empty(sb0));
+            if (w_boxes == 2) umma_commit(bar_slot_empty(sb1));
+          }
+          umma_commit(pass == 0 ? bar_p_full : bar_g_full);
         }
+        // epilogue 1 done: the packed hidden (dP) is in TMEM [TM_P, TM_P + R/2) and P may be
+        // overwritten by the next tile's GEMM1 (waited even when no GEMM2/3 follows)
         mbar_wait(bar_h_full, tile_it & 1);
         tc_fence_after();
-        for (int nc = 0; nc < NC2; ++nc) {  // GEMM2: Y[:, nc] = H * Wu_cat[nc]^T
-          const uint32_t buf = acc_it & 1, par = (acc_it >> 1) & 1;
-          mbar_wait(bar_acc_empty(buf), par ^ 1);
+        for (int c = 0; c < nc2; ++c) {
+          const int b = c & 1;
+          mbar_wait(bar_d_empty(b), (de[b] & 1) ^ 1);
+          ++de[b];
           tc_fence_after();
-          const uint32_t d_tmem = tmem + buf * 256;
+          const uint32_t d_tmem = tmem + TM_D + b * N2;
           for (int kc = 0; kc < KC2; ++kc) {
-            mbar_wait(bar_full(stage), phase);
+            const uint32_t s = wait_slot();
             tc_fence_after();
-            const uint32_t b_src = smem0 + stage * stage_bytes + A_SLOT;
             const int ksteps = min(4, (R - kc * 64) / 16);
             for (int k = 0; k < ksteps; ++k)
-              umma_ss(d_tmem, desc_kmajor_sw128(h_base + kc * A_SLOT + k * 32),
-                      desc_kmajor_sw128(b_src + k * 32), idesc2, (kc | k) != 0);
-            umma_commit(bar_empty(stage));
-            if (++stage == S) { stage = 0; phase ^= 1; }
+              umma_ts(d_tmem, tmem + TM_P + (kc * 4 + k) * 8,
+                      desc_kmajor_sw128(smem0 + s * SLOT + k * 32), idesc2, (kc | k) != 0);
+            umma_commit(bar_slot_empty(s));
           }
-          umma_commit(bar_acc_full(buf));
-          ++acc_it;
+          umma_commit(bar_d_full(b));
         }
-        umma_commit(bar_h_empty);
+      }
+    }
+    __syncwarp();
+  } else if (warp == 2) {
+    // ------------------------------------------------------------------ residual producer
+    if (lane == 0) {
+      const uint32_t per_tile = nc2 * 2;
+      for (uint32_t g = 0; g < total_chunks; ++g) {
+        const uint32_t sb = g % NSTG, par = (g / NSTG) & 1;
+        mbar_wait(bar_stg_empty(sb), par ^ 1);
+        if (p.has_res) {
+          const int tile = blockIdx.x + (g / per_tile) * gridDim.x;
+          const int c64 = g % per_tile;
+          mbar_arrive_expect_tx(bar_res_full(sb), SLOT);
+          tma_load_2d(stg_base + sb * SLOT, &tmRes, bar_res_full(sb), c64 * 64, tile * BM);
+        } else {
+          mbar_arrive(bar_res_full(sb));
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 3) {
+    // ------------------------------------------------------------------ store issuer
+    if (lane == 0) {
+      const uint32_t per_tile = nc2 * 2;
+      for (uint32_t g = 0; g < total_chunks; ++g) {
+        const uint32_t sb = g % NSTG, par = (g / NSTG) & 1;
+        mbar_wait(bar_out_full(sb), par);
+        const int tile = blockIdx.x + (g / per_tile) * gridDim.x;
+        const int c64 = g % per_tile;
+        tma_store_2d(&tmY, stg_base + sb * SLOT, c64 * 64, tile * BM);
+        tma_store_commit();
+        if (g > 0) {  // the previous store has finished reading its buffer: recycle it
+          tma_store_wait_read<1>();
+          mbar_arrive(bar_stg_empty((g - 1) % NSTG));
+        }
+      }
+      if (total_chunks > 0) {
+        tma_store_wait_read<0>();
+        mbar_arrive(bar_stg_empty((total_chunks - 1) % NSTG));
+        tma_store_wait_all<0>();
       }
     }
     __syncwarp();
   } else {
-    // ------------------------------------------------------------------ epilogue warps
+    // ------------------------------------------------------------------ epilogue groups A / B
+    const int group = (warp - 4) >> 2;      // 0: warps 4-7, 1: warps 8-11
     const uint32_t q = warp & 3;            // TMEM lane quarter this warp may touch
     const uint32_t row = q * 32 + lane;     // tile row == TMEM lane
     const uint32_t lane_addr = (q * 32) << 16;
-    const bool leader = (warp == 2 && lane == 0);
     const float scale = p.scale;
     const int act = p.act;
     const bool has_res = p.has_res != 0;
-    const int my_tiles = (p.num_tiles - static_cast<int>(blockIdx.x) + gridDim.x - 1) / gridDim.x;
-    const uint32_t total_chunks = static_cast<uint32_t>(my_tiles) * chunks_per_tile;
+    uint32_t tile_it = 0;
+    uint32_t df = 0;  // chunk fills of this group's D buffer so far
 
-    auto issue_res_load = [&](uint32_t g) {
-      if (!has_res || g >= total_chunks) return;
-      const int tile = blockIdx.x + (g / chunks_per_tile) * gridDim.x;
-      const int c = g % chunks_per_tile;
-      const uint32_t sb = g % NSTG;
-      mbar_arrive_expect_tx(bar_res_full(sb), STG_BYTES);
-      tma_load_2d(stg_base + sb * STG_BYTES, &tmRes, bar_res_full(sb), c * 64, tile * BM);
-    };
-    if (leader)
-      for (uint32_t g = 0; g < NSTG - 1; ++g) issue_res_load(g);
-
-    uint32_t acc_it = 0, tile_it = 0, chunk_g = 0;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++tile_it) {
       const int m0 = tile * BM;
-      if constexpr (!kBwd) {  // epilogue 1 (forward): hidden tile H = act(P + bd)
-        const uint32_t buf = acc_it & 1, par = (acc_it >> 1) & 1;
-        mbar_wait(bar_acc_full(buf), par);
-        mbar_wait(bar_h_empty, (tile_it & 1) ^ 1);
+      if (group == 0) {
+        // ---------------- epilogue 1: P (and dH) -> packed bf16 hidden over P's own columns
+        mbar_wait(bar_p_full, tile_it & 1);
+        if (kBwd) mbar_wait(bar_g_full, tile_it & 1);
         tc_fence_after();
-        const uint32_t t_src = tmem + lane_addr + buf * 256;
-        for (int c = 0; c < R / 16; ++c) {
-          uint32_t v[16];
-          tmem_ld16(t_src + c * 16, v);
-          tmem_ld_wait();
-          uint32_t w[8];
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            float a = apply_act(__uint_as_float(v[2 * i]) + bias_smem[c * 16 + 2 * i], act);
-            float b = apply_act(__uint_as_float(v[2 * i + 1]) + bias_smem[c * 16 + 2 * i + 1], act);
-            w[i] = pack_bf16x2(a, b);
-          }
-          const uint32_t kc = c >> 2, j0 = (c & 3) * 2;
-          st_shared_v4(h_base + kc * A_SLOT + sw128_offset(row, j0), w[0], w[1], w[2], w[3]);
-          st_shared_v4(h_base + kc * A_SLOT + sw128_offset(row, j0 + 1), w[4], w[5], w[6], w[7]);
-        }
-        tc_fence_before();
-        fence_proxy_async_smem();
-        mbar_arrive(bar_acc_empty(buf));
-        mbar_arrive(bar_h_full);
-        ++acc_it;
-      } else {  // epilogue 1 (backward): dP = scale * dH * act'(P + bd); H_t / dP_t slices to HBM
-        const uint32_t buf_p = acc_it & 1, par_p = (acc_it >> 1) & 1;
-        const uint32_t buf_g = (acc_it + 1) & 1, par_g = ((acc_it + 1) >> 1) & 1;
-        mbar_wait(bar_acc_full(buf_p), par_p);
-        mbar_wait(bar_acc_full(buf_g), par_g);
-        mbar_wait(bar_h_empty, (tile_it & 1) ^ 1);
-        tc_fence_after();
-        const uint32_t t_p = tmem + lane_addr + buf_p * 256;
-        const uint32_t t_g = tmem + lane_addr + buf_g * 256;
+        const uint32_t t_p = tmem + lane_addr + TM_P;
+        const uint32_t t_g = tmem + lane_addr + TM_D;
         const int grow = m0 + static_cast<int>(row);
         const int rt = p.r_hi - p.r_lo;
         for (int c = 0; c < R / 16; ++c) {
-          uint32_t v[16], u[16];
+          uint32_t v[16], u[16], w[8];
           tmem_ld16(t_p + c * 16, v);
-          tmem_ld16(t_g + c * 16, u);
+          if (kBwd) tmem_ld16(t_g + c * 16, u);
           tmem_ld_wait();
-          uint32_t w[8], hh[8];
+          if constexpr (!kBwd) {
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const float p0 = __uint_as_float(v[2 * i]) + bias_smem[c * 16 + 2 * i];
-            const float p1 = __uint_as_float(v[2 * i + 1]) + bias_smem[c * 16 + 2 * i + 1];
-            w[i] = pack_bf16x2(scale * __uint_as_float(u[2 * i]) * act_grad(p0, act),
-                               scale * __uint_as_float(u[2 * i + 1]) * act_grad(p1, act));
-            hh[i] = pack_bf16x2(apply_act(p0, act), apply_act(p1, act));
+            for (int i = 0; i < 8; ++i)
+              w[i] = pack_bf16x2(
+                  apply_act(__uint_as_float(v[2 * i]) + bias_smem[c * 16 + 2 * i], act),
+                  apply_act(__uint_as_float(v[2 * i + 1]) + bias_smem[c * 16 + 2 * i + 1], act));
+          } else {
+            uint32_t hh[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const float p0 = __uint_as_float(v[2 * i]) + bias_smem[c * 16 + 2 * i];
+              const float p1 = __uint_as_float(v[2 * i + 1]) + bias_smem[c * 16 + 2 * i + 1];
+              w[i] = pack_bf16x2(scale * __uint_as_float(u[2 * i]) * act_grad(p0, act),
+                                 scale * __uint_as_float(u[2 * i + 1]) * act_grad(p1, act));
+              hh[i] = pack_bf16x2(apply_act(p0, act), apply_act(p1, act));
+            }
+            const int col = c * 16;
+            if (p.H_t != nullptr && col >= p.r_lo && col < p.r_hi && grow < p.M) {
+              const size_t off = static_cast<size_t>(grow) * rt + (col - p.r_lo);
+              uint4* hd = reinterpret_cast<uint4*>(p.H_t + off);
+              uint4* gd = reinterpret_cast<uint4*>(p.dP_t + off);
+              hd[0] = make_uint4(hh[0], hh[1], hh[2], hh[3]);
+              hd[1] = make_uint4(hh[4], hh[5], hh[6], hh[7]);
+              gd[0] = make_uint4(w[0], w[1], w[2], w[3]);
+              gd[1] = make_uint4(w[4], w[5], w[6], w[7]);
+            }
           }
-          const uint32_t kc = c >> 2, j0 = (c & 3) * 2;
-          st_shared_v4(h_base + kc * A_SLOT + sw128_offset(row, j0), w[0], w[1], w[2], w[3]);
-          st_shared_v4(h_base + kc * A_SLOT + sw128_offset(row, j0 + 1), w[4], w[5], w[6], w[7]);
-          const int col = c * 16;
-          if (p.H_t != nullptr && col >= p.r_lo && col < p.r_hi && grow < p.M) {
-            const size_t off = static_cast<size_t>(grow) * rt + (col - p.r_lo);
-            uint4* hd = reinterpret_cast<uint4*>(p.H_t + off);
-            uint4* gd = reinterpret_cast<uint4*>(p.dP_t + off);
-            hd[0] = make_uint4(hh[0], hh[1], hh[2], hh[3]);
-            hd[1] = make_uint4(hh[4], hh[5], hh[6], hh[7]);
-            gd[0] = make_uint4(w[0], w[1], w[2], w[3]);
-            gd[1] = make_uint4(w[4], w[5], w[6], w[7]);
-          }
+          // columns [8c, 8c+8) were read (as fp32 P columns) in an earlier iteration: safe to reuse
+          tmem_st8(t_p + c * 8, w);
         }
+        tmem_st_wait();
         tc_fence_before();
-        fence_proxy_async_smem();
-        mbar_arrive(bar_acc_empty(buf_p));
-        mbar_arrive(bar_acc_empty(buf_g));
+        if (kBwd) {  // dH (which overlays the output ring) is consumed
+          mbar_arrive(bar_d_empty(0));
+          mbar_arrive(bar_d_empty(1));
+        }
         mbar_arrive(bar_h_full);
-        acc_it += 2;
       }
-      for (int nc = 0; nc < NC2; ++nc) {  // epilogue 2: output chunks
-        const uint32_t buf = acc_it & 1, par = (acc_it >> 1) & 1;
-        mbar_wait(bar_acc_full(buf), par);
+      // ---------------- epilogue 2: this group's output chunks (c = group, group + 2, group + 4)
+      for (int c = group; c < nc2; c += 2) {
+        const int b = c & 1;
+        mbar_wait(bar_d_full(b), df & 1);
+        ++df;
         tc_fence_after();
-        for (int j = 0; j < N2 / 64; ++j, ++chunk_g) {
-          const uint32_t sb = chunk_g % NSTG, rpar = (chunk_g / NSTG) & 1;
-          const int col0 = nc * N2 + j * 64;
-          const uint32_t t_src = tmem + lane_addr + buf * 256 + j * 64;
+#pragma unroll 1
+        for (int j = 0; j < 2; ++j) {
+          const uint32_t g = (tile_it * nc2 + c) * 2 + j;
+          const uint32_t sb = g % NSTG, rpar = (g / NSTG) & 1;
+          const int col0 = c * N2 + j * 64;
+          const uint32_t t_src = tmem + lane_addr + TM_D + b * N2 + j * 64;
           uint32_t v0[32], v1[32];
           tmem_ld32(t_src, v0);
           tmem_ld32(t_src + 32, v1);
-          if (has_res) mbar_wait(bar_res_full(sb), rpar);
+          mbar_wait(bar_res_full(sb), rpar);
           tmem_ld_wait();
-          const uint32_t sbuf = stg_base + sb * STG_BYTES;
+          const uint32_t sbuf = stg_base + sb * SLOT;
           const float* bu = bias_smem + R + col0;
 #pragma unroll
           for (int c8 = 0; c8 < 8; ++c8) {
@@ -358,31 +404,17 @@ dat_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
             st_shared_v4(addr, o[0], o[1], o[2], o[3]);
           }
           fence_proxy_async_smem();
-          named_bar_sync(1, 128);
-          if (leader) {
-            tma_store_2d(&tmY, sbuf, col0, m0);
-            tma_store_commit();
-            tma_store_wait_read<1>();
-            issue_res_load(chunk_g + NSTG - 1);
-          }
-          if (!has_res) {
-            // no residual barrier paces the staging ring: the buffer about to be rewritten
-            // ((chunk_g + 1) % NSTG) was last stored from NSTG - 1 chunks ago, which the leader's
-            // wait_group.read<1> above has retired; make that visible to the other 127 threads.
-            named_bar_sync(2, 128);
-          }
+          mbar_arrive(bar_out_full(sb));
         }
         tc_fence_before();
-        mbar_arrive(bar_acc_empty(buf));
-        ++acc_it;
+        mbar_arrive(bar_d_empty(b));
       }
     }
-    if (leader) tma_store_wait_all<0>();
   }
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem, 512);
+  if (warp == 2) tmem_dealloc(tmem, 512);
 }
 
 int launch_fused(bool bwd, const void* X, const void* Res, void* Out, const void* Wd_cat,
@@ -392,27 +424,22 @@ int launch_fused(bool bwd, const void* X, const void* Res, void* Out, const void
   p.M = static_cast<int>(M);
   p.R = r_total;
   p.num_tiles = static_cast<int>((M + BM - 1) / BM);
-  p.n2 = r_total > 128 ? 256 : 128;
-  p.b_slot_bytes = static_cast<uint32_t>(p.n2 * 128);
-  const int kc2 = (r_total + 63) / 64;
-  const size_t fixed = 1024 + static_cast<size_t>(kc2) * A_SLOT + NSTG * STG_BYTES +
-                       (r_total + kD) * sizeof(float);
-  const size_t max_smem = 227 * 1024 - 512;  // static smem (barriers) lives in the same budget
-  const size_t stage_bytes = A_SLOT + p.b_slot_bytes;
-  int stages = static_cast<int>((max_smem - fixed) / stage_bytes);
-  if (stages > MAX_STAGES) stages = MAX_STAGES;
-  FD_REQUIRE(stages >= 2, FD_ERR_UNSUPPORTED, "%s: shared-memory budget exceeded (R=%d)", who,
+  p.n_slots = 10;
+  p.n_stg = 3;
+  const size_t max_smem = 227 * 1024 - 1024;  // static smem (barriers) lives in the same budget
+  const size_t smem = 1024 + static_cast<size_t>(p.n_slots + p.n_stg) * SLOT +
+                      (r_total + kD) * sizeof(float);
+  FD_REQUIRE(smem <= max_smem, FD_ERR_UNSUPPORTED, "%s: shared-memory budget exceeded (R=%d)", who,
              r_total);
-  p.stages = stages;
-  const size_t smem = fixed + stages * stage_bytes;
 
   CUtensorMap tmX, tmRes, tmY, tmWd, tmW2, tmW1b;
   if ((rc = make_tmap_bf16_2d(&tmX, X, M, kD, kD, BM, 64))) return rc;
   if ((rc = make_tmap_bf16_2d(&tmRes, Res, M, kD, kD, BM, 64))) return rc;
   if ((rc = make_tmap_bf16_2d(&tmY, Out ? Out : X, M, kD, kD, BM, 64))) return rc;
-  if ((rc = make_tmap_bf16_2d(&tmWd, Wd_cat, r_total, kD, kD, r_total, 64))) return rc;
-  if ((rc = make_tmap_bf16_2d(&tmW2, W2, kD, r_total, r_total, p.n2, 64))) return rc;
-  if ((rc = make_tmap_bf16_2d(&tmW1b, W1b ? W1b : Wd_cat, r_total, kD, kD, r_total, 64))) return rc;
+  const uint32_t w_box_rows = r_total > 128 ? 128 : r_total;
+  if ((rc = make_tmap_bf16_2d(&tmWd, Wd_cat, r_total, kD, kD, w_box_rows, 64))) return rc;
+  if ((rc = make_tmap_bf16_2d(&tmW2, W2, kD, r_total, r_total, N2, 64))) return rc;
+  if ((rc = make_tmap_bf16_2d(&tmW1b, W1b ? W1b : Wd_cat, r_total, kD, kD, w_box_rows, 64))) return rc;
 
   int sms = 0;
   if ((rc = device_sm_count(&sms))) return rc;
