@@ -24,6 +24,8 @@ EXPORTED_SYMBOLS = (
     "feddat_mkd_loss",
     "feddat_fedavg",
     "feddat_probe_gemm",
+    "feddat_debug_set_trace",
+    "feddat_probe_l2bw",
 )
 
 
@@ -74,6 +76,10 @@ def load() -> ctypes.CDLL:
     lib.feddat_probe_gemm.restype = c_int
     lib.feddat_probe_gemm.argtypes = [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
                                       POINTER(c_uint32), c_void_p]
+    lib.feddat_probe_l2bw.restype = c_int
+    lib.feddat_probe_l2bw.argtypes = [c_void_p, c_int, c_int, c_int, c_int, c_void_p]
+    lib.feddat_debug_set_trace.restype = c_int
+    lib.feddat_debug_set_trace.argtypes = [c_void_p]
     _lib = lib
     return lib
 

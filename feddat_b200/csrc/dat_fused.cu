@@ -63,14 +63,26 @@ struct FusedParams {
   int r_lo, r_hi;         // trainable slice of the bottleneck
   __nv_bfloat16* H_t;     // [M, r_hi - r_lo] or null
   __nv_bfloat16* dP_t;    // [M, r_hi - r_lo] or null
+  unsigned long long* trace;  // debug: globaltimer stamps of CTA 0's pipeline events (or null)
 };
 
-__device__ __forceinline__ float apply_act(float x, int act) {
-  if (act == 0) return fmaxf(x, 0.f);
+// debug timeline (scripts/trace_kernel.py): event e of CTA 0's tile `t` (t < 2) -> trace[t * 128 + e]
+#define FD_TRACE(ev, t)                                                             \
+  do {                                                                              \
+    if (p.trace != nullptr && blockIdx.x == 0 && (t) < 2)                           \
+      p.trace[(t) * 128 + (ev)] = globaltimer_ns();                                 \
+  } while (0)
+
+// activation is a template parameter: a run-time switch makes ptxas keep the erff path live in the
+// epilogue-1 inner loop (measured: 6.8 us instead of ~1.5 us per 128 x 256 tile)
+template <bool kGelu>
+__device__ __forceinline__ float apply_act(float x) {
+  if constexpr (!kGelu) return fmaxf(x, 0.f);
   return 0.5f * x * (1.f + erff(x * 0.70710678118654752f));
 }
-__device__ __forceinline__ float act_grad(float x, int act) {
-  if (act == 0) return x > 0.f ? 1.f : 0.f;
+template <bool kGelu>
+__device__ __forceinline__ float act_grad(float x) {
+  if constexpr (!kGelu) return x > 0.f ? 1.f : 0.f;
   return 0.5f * (1.f + erff(x * 0.70710678118654752f)) +
          x * 0.3989422804014327f * __expf(-0.5f * x * x);
 }
@@ -82,7 +94,7 @@ __device__ __forceinline__ float act_grad(float x, int act) {
 //   tmWd  [R, 768]       Wd_cat                       Wd_cat
 //   tmW2  [768, R]       Wu_cat                       WdT_cat
 //   tmW1b [R, 768]       (unused)                     WuT_cat
-template <bool kBwd>
+template <bool kBwd, bool kGelu>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 dat_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmRes,
                  const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmWd,
@@ -150,6 +162,7 @@ dat_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = tmem_base_smem;
+  if (tid == 0) FD_TRACE(0, 0);
   const int my_tiles = (p.num_tiles - static_cast<int>(blockIdx.x) + gridDim.x - 1) / gridDim.x;
   const uint32_t total_chunks = static_cast<uint32_t>(my_tiles) * nc2 * 2;  // 64-column staging chunks
 
@@ -164,8 +177,10 @@ dat_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
         ++n;
         return s;
       };
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      uint32_t tile_it = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++tile_it) {
         const int m0 = tile * BM;
+        FD_TRACE(110, tile_it);
         for (int pass = 0; pass < (kBwd ? 2 : 1); ++pass) {
           const CUtensorMap* ta = pass == 0 ? &tmX : &tmRes;
           const CUtensorMap* tw = pass == 0 ? &tmWd : &tmW1b;
@@ -178,11 +193,13 @@ dat_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
             }
           }
         }
+        FD_TRACE(111, tile_it);
         for (int c = 0; c < nc2; ++c)
           for (int kc = 0; kc < KC2; ++kc) {
             const uint32_t s = acquire(SLOT);
             tma_load_2d_hint(smem0 + s * SLOT, &tmW2, bar_slot_full(s), kc * BK, c * N2, kEvictLast);
           }
+        FD_TRACE(112, tile_it);
       }
     }
     __syncwarp();
@@ -217,6 +234,7 @@ dat_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
             const uint32_t sb0 = wait_slot();
             const uint32_t sb1 = w_boxes == 2 ? wait_slot() : 0;
             tc_fence_after();
+            if (pass == 0) FD_TRACE(10 + kc, tile_it);
             const uint32_t a_src = smem0 + sa * SLOT;
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
@@ -232,16 +250,19 @@ dat_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
             if (w_boxes == 2) umma_commit(bar_slot_empty(sb1));
           }
           umma_commit(pass == 0 ? bar_p_full : bar_g_full);
+          FD_TRACE(22 + pass, tile_it);
         }
         // epilogue 1 done: the packed hidden (dP) is in TMEM [TM_P, TM_P + R/2) and P may be
         // overwritten by the next tile's GEMM1 (waited even when no GEMM2/3 follows)
         mbar_wait(bar_h_full, tile_it & 1);
         tc_fence_after();
+        FD_TRACE(24, tile_it);
         for (int c = 0; c < nc2; ++c) {
           const int b = c & 1;
           mbar_wait(bar_d_empty(b), (de[b] & 1) ^ 1);
           ++de[b];
           tc_fence_after();
+          FD_TRACE(25 + c, tile_it);
           const uint32_t d_tmem = tmem + TM_D + b * N2;
           for (int kc = 0; kc < KC2; ++kc) {
             const uint32_t s = wait_slot();
@@ -253,6 +274,7 @@ dat_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
             umma_commit(bar_slot_empty(s));
           }
           umma_commit(bar_d_full(b));
+          FD_TRACE(31 + c, tile_it);
         }
       }
     }
@@ -269,6 +291,7 @@ dat_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
           const int c64 = g % per_tile;
           mbar_arrive_expect_tx(bar_res_full(sb), SLOT);
           tma_load_2d(stg_base + sb * SLOT, &tmRes, bar_res_full(sb), c64 * 64, tile * BM);
+          if (lane == 0) FD_TRACE(90 + c64, g / per_tile);
         } else {
           mbar_arrive(bar_res_full(sb));
         }
@@ -286,6 +309,7 @@ dat_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
         const int c64 = g % per_tile;
         tma_store_2d(&tmY, stg_base + sb * SLOT, c64 * 64, tile * BM);
         tma_store_commit();
+        FD_TRACE(104 + (c64 >> 1), g / per_tile);
         if (g > 0) {  // the previous store has finished reading its buffer: recycle it
           tma_store_wait_read<1>();
           mbar_arrive(bar_stg_empty((g - 1) % NSTG));
@@ -305,7 +329,6 @@ dat_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
     const uint32_t row = q * 32 + lane;     // tile row == TMEM lane
     const uint32_t lane_addr = (q * 32) << 16;
     const float scale = p.scale;
-    const int act = p.act;
     const bool has_res = p.has_res != 0;
     uint32_t tile_it = 0;
     uint32_t df = 0;  // chunk fills of this group's D buffer so far
@@ -317,6 +340,7 @@ dat_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
         mbar_wait(bar_p_full, tile_it & 1);
         if (kBwd) mbar_wait(bar_g_full, tile_it & 1);
         tc_fence_after();
+        if (tid == 128) FD_TRACE(40, tile_it);
         const uint32_t t_p = tmem + lane_addr + TM_P;
         const uint32_t t_g = tmem + lane_addr + TM_D;
         const int grow = m0 + static_cast<int>(row);
@@ -330,17 +354,17 @@ dat_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
 #pragma unroll
             for (int i = 0; i < 8; ++i)
               w[i] = pack_bf16x2(
-                  apply_act(__uint_as_float(v[2 * i]) + bias_smem[c * 16 + 2 * i], act),
-                  apply_act(__uint_as_float(v[2 * i + 1]) + bias_smem[c * 16 + 2 * i + 1], act));
+                  apply_act<kGelu>(__uint_as_float(v[2 * i]) + bias_smem[c * 16 + 2 * i]),
+                  apply_act<kGelu>(__uint_as_float(v[2 * i + 1]) + bias_smem[c * 16 + 2 * i + 1]));
           } else {
             uint32_t hh[8];
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
               const float p0 = __uint_as_float(v[2 * i]) + bias_smem[c * 16 + 2 * i];
               const float p1 = __uint_as_float(v[2 * i + 1]) + bias_smem[c * 16 + 2 * i + 1];
-              w[i] = pack_bf16x2(scale * __uint_as_float(u[2 * i]) * act_grad(p0, act),
-                                 scale * __uint_as_float(u[2 * i + 1]) * act_grad(p1, act));
-              hh[i] = pack_bf16x2(apply_act(p0, act), apply_act(p1, act));
+              w[i] = pack_bf16x2(scale * __uint_as_float(u[2 * i]) * act_grad<kGelu>(p0),
+                                 scale * __uint_as_float(u[2 * i + 1]) * act_grad<kGelu>(p1));
+              hh[i] = pack_bf16x2(apply_act<kGelu>(p0), apply_act<kGelu>(p1));
             }
             const int col = c * 16;
             if (p.H_t != nullptr && col >= p.r_lo && col < p.r_hi && grow < p.M) {
@@ -363,6 +387,7 @@ dat_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
           mbar_arrive(bar_d_empty(1));
         }
         mbar_arrive(bar_h_full);
+        if (tid == 128) FD_TRACE(41, tile_it);
       }
       // ---------------- epilogue 2: this group's output chunks (c = group, group + 2, group + 4)
       for (int c = group; c < nc2; c += 2) {
@@ -370,6 +395,7 @@ dat_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
         mbar_wait(bar_d_full(b), df & 1);
         ++df;
         tc_fence_after();
+        if (lane == 0 && q == 0) FD_TRACE(42 + 4 * c, tile_it);
 #pragma unroll 1
         for (int j = 0; j < 2; ++j) {
           const uint32_t g = (tile_it * nc2 + c) * 2 + j;
@@ -381,6 +407,7 @@ dat_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
           tmem_ld32(t_src + 32, v1);
           mbar_wait(bar_res_full(sb), rpar);
           tmem_ld_wait();
+          if (lane == 0 && q == 0) FD_TRACE(43 + 4 * c + j, tile_it);
           const uint32_t sbuf = stg_base + sb * SLOT;
           const float* bu = bias_smem + R + col0;
 #pragma unroll
@@ -408,6 +435,7 @@ dat_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
         }
         tc_fence_before();
         mbar_arrive(bar_d_empty(b));
+        if (lane == 0 && q == 0) FD_TRACE(45 + 4 * c, tile_it);
       }
     }
   }
@@ -417,6 +445,8 @@ dat_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
   if (warp == 2) tmem_dealloc(tmem, 512);
 }
 
+unsigned long long* g_trace = nullptr;
+
 int launch_fused(bool bwd, const void* X, const void* Res, void* Out, const void* Wd_cat,
                  const void* W2, const void* W1b, FusedParams p, int64_t M, int r_total,
                  cudaStream_t st, const char* who) {
@@ -424,6 +454,7 @@ int launch_fused(bool bwd, const void* X, const void* Res, void* Out, const void
   p.M = static_cast<int>(M);
   p.R = r_total;
   p.num_tiles = static_cast<int>((M + BM - 1) / BM);
+  p.trace = g_trace;
   p.n_slots = 10;
   p.n_stg = 3;
   const size_t max_smem = 227 * 1024 - 1024;  // static smem (barriers) lives in the same budget
@@ -444,22 +475,21 @@ int launch_fused(bool bwd, const void* X, const void* Res, void* Out, const void
   int sms = 0;
   if ((rc = device_sm_count(&sms))) return rc;
   const int grid = p.num_tiles < sms ? p.num_tiles : sms;
-  static bool configured[2][64] = {{false}};
+  using KernelFn = void (*)(const CUtensorMap, const CUtensorMap, const CUtensorMap,
+                            const CUtensorMap, const CUtensorMap, const CUtensorMap,
+                            const FusedParams);
+  const bool gelu = p.act == FEDDAT_ACT_GELU;
+  KernelFn fn = bwd ? (gelu ? dat_fused_kernel<true, true> : dat_fused_kernel<true, false>)
+                    : (gelu ? dat_fused_kernel<false, true> : dat_fused_kernel<false, false>);
+  static bool configured[2][2][64] = {{{false}}};
   int dev = 0;
   FD_CHECK_CUDA(cudaGetDevice(&dev));
-  if (dev >= 64 || !configured[bwd][dev]) {
-    if (bwd)
-      FD_CHECK_CUDA(cudaFuncSetAttribute(dat_fused_kernel<true>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem));
-    else
-      FD_CHECK_CUDA(cudaFuncSetAttribute(dat_fused_kernel<false>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem));
-    if (dev < 64) configured[bwd][dev] = true;
+  if (dev >= 64 || !configured[bwd][gelu][dev]) {
+    FD_CHECK_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)max_smem));
+    if (dev < 64) configured[bwd][gelu][dev] = true;
   }
-  if (bwd)
-    dat_fused_kernel<true><<<grid, NUM_THREADS, smem, st>>>(tmX, tmRes, tmY, tmWd, tmW2, tmW1b, p);
-  else
-    dat_fused_kernel<false><<<grid, NUM_THREADS, smem, st>>>(tmX, tmRes, tmY, tmWd, tmW2, tmW1b, p);
+  fn<<<grid, NUM_THREADS, smem, st>>>(tmX, tmRes, tmY, tmWd, tmW2, tmW1b, p);
   FD_CHECK_CUDA(cudaGetLastError());
   return FD_OK;
 }
@@ -539,4 +569,10 @@ extern "C" int feddat_dat_bwd_dgrad(const void* X, const void* dY, void* dX, con
   p.dP_t = static_cast<__nv_bfloat16*>(dP_t);
   return launch_fused(true, X, dY, dX, Wd_cat, WdT_cat, WuT_cat, p, M, r_total,
                       static_cast<cudaStream_t>(stream), "dat_bwd_dgrad");
+}
+
+// debug: device buffer of 256 uint64 receiving CTA 0's pipeline timestamps (NULL disables)
+extern "C" int feddat_debug_set_trace(void* dev_buf) {
+  fd::g_trace = static_cast<unsigned long long*>(dev_buf);
+  return 0;
 }

@@ -169,3 +169,88 @@ extern "C" int feddat_probe_gemm(const void* A, const void* B, float* D, int N, 
   FD_CHECK_CUDA(cudaGetLastError());
   return FD_OK;
 }
+
+// ------------------------------------------------------------------------------------------------
+// L2 -> SM streaming bandwidth probe: every CTA TMA-loads [128 x 64] bf16 boxes (16 KB) from a small
+// (L2-resident) matrix through an 8-slot ring and discards them.  cluster > 1: each CTA fetches
+// 1/cluster of every box and multicasts it to the whole cluster, so L2 is read once per cluster.
+// ------------------------------------------------------------------------------------------------
+namespace fd {
+
+__global__ void __launch_bounds__(64, 1)
+probe_l2bw_kernel(const __grid_constant__ CUtensorMap tm, int n_boxes, int iters, int cluster) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t bars[16];
+  constexpr int NS = 8;
+  const uint32_t smem0 = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar0 = smem_u32(bars);
+  const uint32_t rank = cluster > 1 ? cluster_ctarank() : 0;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < NS; ++s) {
+      mbar_init(bar0 + 8 * s, 1);                 // full
+      mbar_init(bar0 + 8 * (NS + s), cluster);    // empty: one arrive per CTA of the cluster
+    }
+    fence_mbar_init();
+  }
+  if (cluster > 1) cluster_sync_all(); else __syncthreads();
+  const int rows_per = 128 / cluster;
+  if (threadIdx.x == 0) {          // producer
+    for (int i = 0; i < iters; ++i) {
+      const int s = i % NS;
+      const uint32_t par = (i / NS) & 1;
+      mbar_wait(bar0 + 8 * (NS + s), par ^ 1);
+      mbar_arrive_expect_tx(bar0 + 8 * s, 16384);
+      const int box = (i * 7 + blockIdx.x / cluster * 3) % n_boxes;
+      if (cluster > 1)
+        tma_load_2d_mcast(smem0 + s * 16384 + rank * rows_per * 128, &tm, bar0 + 8 * s, 0,
+                          box * 128 + rank * rows_per, (uint16_t)((1u << cluster) - 1), kEvictLast);
+      else
+        tma_load_2d_hint(smem0 + s * 16384, &tm, bar0 + 8 * s, 0, box * 128, kEvictLast);
+    }
+  } else if (threadIdx.x == 32) {  // consumer
+    for (int i = 0; i < iters; ++i) {
+      const int s = i % NS;
+      const uint32_t par = (i / NS) & 1;
+      mbar_wait(bar0 + 8 * s, par);
+      if (cluster > 1) {
+        for (int r = 0; r < cluster; ++r) mbar_arrive_remote(bar0 + 8 * (NS + s), r);
+      } else {
+        mbar_arrive(bar0 + 8 * (NS + s));
+      }
+    }
+  }
+  if (cluster > 1) cluster_sync_all(); else __syncthreads();
+}
+
+}  // namespace fd
+
+// buf: bf16 [n_boxes * 128, 64] row-major.  Returns after enqueueing `grid` CTAs x `iters` boxes.
+extern "C" int feddat_probe_l2bw(const void* buf, int n_boxes, int iters, int grid, int cluster,
+                                 void* stream) {
+  using namespace fd;
+  int rc = check_device_sm100();
+  if (rc) return rc;
+  FD_REQUIRE(cluster == 1 || cluster == 2 || cluster == 4 || cluster == 8, FD_ERR_INVALID,
+             "probe_l2bw: cluster must be 1, 2, 4 or 8");
+  FD_REQUIRE(grid % cluster == 0, FD_ERR_INVALID, "probe_l2bw: grid must be a multiple of cluster");
+  CUtensorMap tm;
+  rc = make_tmap_bf16_2d(&tm, buf, static_cast<uint64_t>(n_boxes) * 128, 64, 64, 128 / cluster, 64);
+  if (rc) return rc;
+  const size_t smem = 1024 + 8 * 16384;
+  FD_CHECK_CUDA(cudaFuncSetAttribute(probe_l2bw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)smem));
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(64);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = static_cast<cudaStream_t>(stream);
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = cluster;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  FD_CHECK_CUDA(cudaLaunchKernelEx(&cfg, probe_l2bw_kernel, tm, n_boxes, iters, cluster));
+  return FD_OK;
+}

@@ -300,3 +300,41 @@ __device__ __forceinline__ uint32_t sw128_offset(uint32_t row, uint32_t chunk16)
 }
 
 }  // namespace fd
+
+// ----------------------------------------------------------------------------------------------
+// thread-block clusters: rank, barrier, remote mbarrier arrive, multicast TMA
+// ----------------------------------------------------------------------------------------------
+namespace fd {
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// arrive on the mbarrier at the same smem offset in CTA `rank` of this cluster
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t local_bar, uint32_t rank) {
+  asm volatile(
+      "{\n"
+      ".reg .b32 ra;\n"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n"
+      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n"
+      "}\n"
+      ::"r"(local_bar), "r"(rank)
+      : "memory");
+}
+// 2-D tile load delivered to the same smem offset (and signalling the same mbarrier offset) in
+// every CTA of `cta_mask`
+__device__ __forceinline__ void tma_load_2d_mcast(uint32_t dst_smem, const CUtensorMap* tm,
+                                                  uint32_t bar, int c0, int c1, uint16_t cta_mask,
+                                                  uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes"
+      ".multicast::cluster.L2::cache_hint [%0], [%1, {%3, %4}], [%2], %5, %6;"
+      ::"r"(dst_smem), "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar), "r"(c0), "r"(c1),
+      "h"(cta_mask), "l"(policy)
+      : "memory");
+}
+}  // namespace fd

@@ -132,6 +132,13 @@ int feddat_fedavg(const float* const* clients /* host array of device ptrs */,
 int feddat_probe_gemm(const void* A, const void* B, float* D, int N, int K, int a_mode,
                       int b_mode, const uint32_t* overrides, void* stream);
 
+/* L2 -> SM TMA streaming bandwidth probe (optionally multicast across a cluster), csrc/probe.cu. */
+int feddat_probe_l2bw(const void* buf, int n_boxes, int iters, int grid, int cluster, void* stream);
+
+/* Debug (scripts/trace_kernel.py): device buffer of 256 uint64 that receives globaltimer stamps of
+ * CTA 0's pipeline events in feddat_dat_fwd / feddat_dat_bwd_dgrad; NULL disables. */
+int feddat_debug_set_trace(void* dev_buf);
+
 #ifdef __cplusplus
 }
 #endif

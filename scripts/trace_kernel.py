@@ -1,0 +1,62 @@
+"""Timeline of CTA 0's pipeline events inside dat_fused_kernel (debug aid).
+    python scripts/trace_kernel.py [R] [M] [fwd|bwd]"""
+import sys
+from pathlib import Path
+
+import torch
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT))
+from feddat_b200 import _lib, ops  # noqa: E402
+
+R = int(sys.argv[1]) if len(sys.argv) > 1 else 256
+M = int(sys.argv[2]) if len(sys.argv) > 2 else 71040
+mode = sys.argv[3] if len(sys.argv) > 3 else "fwd"
+dev = torch.device("cuda", 0)
+g = torch.Generator(device=dev).manual_seed(0)
+nb = 2 if R > 128 else 1
+r = R // nb
+pk = ops.pack_weights([[torch.randn(r, 768, device=dev, generator=g) * 0.02, torch.zeros(r, device=dev),
+                        torch.randn(768, r, device=dev, generator=g) * 0.02, torch.zeros(768, device=dev)]
+                       for _ in range(nb)])
+x = torch.randn(M, 768, device=dev, generator=g).to(torch.bfloat16)
+dy = torch.randn(M, 768, device=dev, generator=g).to(torch.bfloat16)
+lib = _lib.load()
+
+
+def run():
+    if mode == "fwd":
+        ops.dat_forward(x, x, pk, 0.5)
+    else:
+        ops.dat_backward(x, dy, pk, 0.5, train_slice=None, need_dx=True)
+
+
+for _ in range(3):
+    run()
+buf = torch.zeros(256, dtype=torch.int64, device=dev)
+lib.feddat_debug_set_trace(_lib.ptr(buf))
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record(); run(); e1.record()
+torch.cuda.synchronize()
+lib.feddat_debug_set_trace(None)
+t = buf.cpu().tolist()
+t0 = t[0]
+names = {0: "start", 22: "G1 issued", 23: "G1b issued", 24: "h_full passed", 40: "epiA: P full", 41: "epiA: E1 done",
+         110: "prod: tile start", 111: "prod: G1 slots issued", 112: "prod: all slots issued"}
+for k in range(12):
+    names[10 + k] = f"mma: G1 kc{k} slots ready"
+for c in range(6):
+    names[25 + c] = f"mma: chunk{c} D buffer free"
+    names[31 + c] = f"mma: chunk{c} issued"
+    names[42 + 4 * c] = f"epi{c & 1}: chunk{c} D full"
+    names[43 + 4 * c] = f"epi{c & 1}: chunk{c}.0 res ready"
+    names[44 + 4 * c] = f"epi{c & 1}: chunk{c}.1 res ready"
+    names[45 + 4 * c] = f"epi{c & 1}: chunk{c} done"
+    names[104 + c] = f"store: chunk{c}.x issued"
+for k in range(12):
+    names[90 + k] = f"res: load c64={k} issued"
+print(f"kernel {e0.elapsed_time(e1) * 1e3:.1f} us, R={R} M={M} {mode}")
+for tile in range(2):
+    ev = [(t[tile * 128 + e] - t0, e) for e in range(128) if t[tile * 128 + e] != 0]
+    for dt, e in sorted(ev):
+        print(f"tile{tile} {dt / 1e3:9.2f} us  {names.get(e, e)}")
