@@ -26,6 +26,7 @@ EXPORTED_SYMBOLS = (
     "feddat_probe_gemm",
     "feddat_debug_set_trace",
     "feddat_probe_l2bw",
+    "feddat_probe_pair",
 )
 
 
@@ -78,6 +79,9 @@ def load() -> ctypes.CDLL:
                                       POINTER(c_uint32), c_void_p]
     lib.feddat_probe_l2bw.restype = c_int
     lib.feddat_probe_l2bw.argtypes = [c_void_p, c_int, c_int, c_int, c_int, c_void_p]
+    lib.feddat_probe_pair.restype = c_int
+    lib.feddat_probe_pair.argtypes = [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p,
+                                      c_void_p]
     lib.feddat_debug_set_trace.restype = c_int
     lib.feddat_debug_set_trace.argtypes = [c_void_p]
     _lib = lib

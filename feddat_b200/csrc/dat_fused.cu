@@ -5,12 +5,16 @@
 // "cat" = the active branches concatenated along the bottleneck dimension: one branch
 // (adapter.py:125-131, scale 1) or the two gating branches adapter_0 | adapter_2
 // (adapter.py:133-146, scale 0.5 each), so the dual adapter is ONE GEMM pair with hidden width
-// R = r_total.  One persistent CTA per SM walks 128-row tiles; 12 warps, every hand-off an mbarrier:
+// R = r_total.  Persistent CTA PAIRS (cluster of 2, tcgen05 cta_group::2): a pair walks 256-row
+// super-tiles, each CTA owning 128 rows (its X chunks, its TMEM accumulators, its epilogues, its
+// output) and HALF of every weight tile -- the pair's tensor cores read both halves, so each SM
+// ingests only half the weight bytes (L2->SM traffic is what bounds this kernel: measured 8.95 TB/s
+// chip-wide, scripts/l2bw.py).  12 warps per CTA, every hand-off an mbarrier:
 //
 //   warp 0      TMA producer: one ring of uniform 16 KB slots carries, in consumption order, the X
 //               k-chunks [128 x 64], the Wd_cat k-chunks (one or two 128-row boxes) and the Wu_cat
 //               [128 x 64] tiles; it runs ahead across tiles as far as the ring allows
-//   warp 1      tcgen05.mma issuer.  GEMM1 P = X Wd^T (SS, K-major SW128 smem operands) into TMEM
+//   warp 1      tcgen05.mma issuer (leader CTA of the pair only; M = 256 across the pair).  GEMM1 P = X Wd^T (SS, K-major SW128 smem operands) into TMEM
 //               columns [0, R); GEMM2 in six 128-column chunks, A operand = the hidden tile IN TMEM
 //               (bf16 pairs packed over P's own columns, "TS" MMA), accumulators in a two-buffer
 //               ring in TMEM columns [256, 512)
@@ -47,7 +51,7 @@ constexpr int SLOT = BM * 128;        // 16 KB: [128 rows x 64 bf16], 128-byte s
 constexpr int N2 = 128;               // GEMM2 / GEMM3 output chunk width
 constexpr int NC2 = kD / N2;          // 6 chunks
 constexpr int MAX_SLOTS = 12;
-constexpr int MAX_STG = 4;
+constexpr int MAX_STG = 8;
 constexpr int NUM_THREADS = 384;
 constexpr uint32_t TM_P = 0;          // TMEM column of P (and of the packed hidden aliasing it)
 constexpr uint32_t TM_D = 256;        // TMEM column of the output ring (and of dH in backward)
@@ -109,8 +113,10 @@ dat_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
   const int R = p.R, NS = p.n_slots, NSTG = p.n_stg;
   const int KC2 = (R + 63) / 64;
   const int nc2 = (kBwd && !p.has_out) ? 0 : NC2;
-  const int w_boxes = R > 128 ? 2 : 1;               // 128-row boxes per Wd / WuT k-chunk
-  const uint32_t w_box_bytes = static_cast<uint32_t>(R > 128 ? 128 : R) * 128u;
+  const uint32_t rank = cluster_ctarank();            // 0 = leader of the CTA pair
+  const int RH = R / 2;                               // rows of a Wd / WuT k-chunk this CTA holds
+  const uint32_t w_half_bytes = static_cast<uint32_t>(RH) * 128u;
+  constexpr uint32_t W2_HALF_BYTES = (N2 / 2) * 128u;  // 64 rows of a Wu / WdT tile
 
   const uint32_t smem0 = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t stg_base = smem0 + NS * SLOT;
@@ -136,10 +142,10 @@ dat_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
     }
     mbar_init(bar_p_full, 1);
     mbar_init(bar_g_full, 1);
-    mbar_init(bar_h_full, 128);
+    mbar_init(bar_h_full, 256);          // both CTAs' epilogue-1 threads arrive at the leader
     for (int b = 0; b < 2; ++b) {
       mbar_init(bar_d_full(b), 1);
-      mbar_init(bar_d_empty(b), 128);
+      mbar_init(bar_d_empty(b), 256);    // both CTAs' epilogue-2 threads arrive at the leader
     }
     for (int b = 0; b < NSTG; ++b) {
       mbar_init(bar_res_full(b), 1);
@@ -154,71 +160,79 @@ dat_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
     tma_prefetch_desc(&tmW2);
     if (kBwd) tma_prefetch_desc(&tmW1b);
   }
-  if (warp == 2) tmem_alloc(smem_u32(&tmem_base_smem), 512);
+  if (warp == 2) tmem_alloc_pair(smem_u32(&tmem_base_smem), 512);
   for (int i = tid; i < R; i += NUM_THREADS) bias_smem[i] = p.bd[i];
   if (!kBwd)
     for (int i = tid; i < kD; i += NUM_THREADS) bias_smem[R + i] = p.bu[i];
   tc_fence_before();
-  __syncthreads();
+  cluster_sync_all();   // barrier inits + TMEM allocation visible to both CTAs of the pair
   tc_fence_after();
   const uint32_t tmem = tmem_base_smem;
   if (tid == 0) FD_TRACE(0, 0);
-  const int my_tiles = (p.num_tiles - static_cast<int>(blockIdx.x) + gridDim.x - 1) / gridDim.x;
-  const uint32_t total_chunks = static_cast<uint32_t>(my_tiles) * nc2 * 2;  // 64-column staging chunks
+  const int num_pairs = (p.num_tiles + 1) / 2, pair0 = blockIdx.x >> 1, pair_stride = gridDim.x >> 1;
+  const int my_tiles = (num_pairs - pair0 + pair_stride - 1) / pair_stride;   // super-tiles of this pair
+  const uint32_t total_chunks = static_cast<uint32_t>(my_tiles) * nc2 * 2;    // 64-column staging chunks
+  // this CTA's tile of super-tile `it`: may lie beyond the tensor (odd tile count) -- TMA then
+  // zero-fills the loads and clips the stores, so no role needs a special case
+  auto tile_of = [&](int it) { return 2 * (pair0 + it * pair_stride) + static_cast<int>(rank); };
 
   if (warp == 0) {
     // ------------------------------------------------------------------ ring producer
     if (lane == 0) {
       uint32_t n = 0;  // slots issued so far
+      // the leader's "full" barrier collects the bytes of BOTH CTAs' loads for a slot
       auto acquire = [&](uint32_t bytes) -> uint32_t {
         const uint32_t s = n % NS, par = (n / NS) & 1;
         mbar_wait(bar_slot_empty(s), par ^ 1);
-        mbar_arrive_expect_tx(bar_slot_full(s), bytes);
+        if (rank == 0) mbar_arrive_expect_tx(bar_slot_full(s), 2 * bytes);
         ++n;
         return s;
       };
-      uint32_t tile_it = 0;
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++tile_it) {
-        const int m0 = tile * BM;
+      for (int it = 0; it < my_tiles; ++it) {
+        const uint32_t tile_it = it;
+        const int m0 = tile_of(it) * BM;
         FD_TRACE(110, tile_it);
         for (int pass = 0; pass < (kBwd ? 2 : 1); ++pass) {
           const CUtensorMap* ta = pass == 0 ? &tmX : &tmRes;
           const CUtensorMap* tw = pass == 0 ? &tmWd : &tmW1b;
           for (int kc = 0; kc < KC1; ++kc) {
             uint32_t s = acquire(SLOT);
-            tma_load_2d_hint(smem0 + s * SLOT, ta, bar_slot_full(s), kc * BK, m0, kEvictNormal);
-            for (int b = 0; b < w_boxes; ++b) {
-              s = acquire(w_box_bytes);
-              tma_load_2d_hint(smem0 + s * SLOT, tw, bar_slot_full(s), kc * BK, b * 128, kEvictLast);
-            }
+            tma_load_2d_pair(smem0 + s * SLOT, ta, mapa_u32(bar_slot_full(s), 0), kc * BK, m0,
+                             kEvictNormal);
+            s = acquire(w_half_bytes);
+            tma_load_2d_pair(smem0 + s * SLOT, tw, mapa_u32(bar_slot_full(s), 0), kc * BK,
+                             static_cast<int>(rank) * RH, kEvictLast);
           }
         }
         FD_TRACE(111, tile_it);
         for (int c = 0; c < nc2; ++c)
-          for (int kc = 0; kc < KC2; ++kc) {
-            const uint32_t s = acquire(SLOT);
-            tma_load_2d_hint(smem0 + s * SLOT, &tmW2, bar_slot_full(s), kc * BK, c * N2, kEvictLast);
+          for (int kc = 0; kc < KC2; kc += 2) {   // two 8 KB half tiles share one 16 KB slot
+            const int nk = min(2, KC2 - kc);
+            const uint32_t s = acquire(W2_HALF_BYTES * nk);
+            for (int j = 0; j < nk; ++j)
+              tma_load_2d_pair(smem0 + s * SLOT + j * W2_HALF_BYTES, &tmW2,
+                               mapa_u32(bar_slot_full(s), 0), (kc + j) * BK,
+                               c * N2 + static_cast<int>(rank) * (N2 / 2), kEvictLast);
           }
         FD_TRACE(112, tile_it);
       }
     }
     __syncwarp();
   } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
-      uint32_t n = 0, tile_it = 0;
+    // ------------------------------------------------------------------ MMA issuer (leader CTA)
+    if (lane == 0 && rank == 0) {
+      uint32_t n = 0;
       uint32_t de[2] = {0, 0};  // uses of each D buffer so far (parity of its "empty" barrier)
-      const uint32_t n_lo = R > 128 ? 128 : R;
-      const uint32_t idesc_lo = make_idesc_bf16(BM, n_lo);
-      const uint32_t idesc_hi = make_idesc_bf16(BM, R > 128 ? R - 128 : 16);
-      const uint32_t idesc2 = make_idesc_bf16(BM, N2);
+      const uint32_t idesc1 = make_idesc_bf16(2 * BM, R);
+      const uint32_t idesc2 = make_idesc_bf16(2 * BM, N2);
       auto wait_slot = [&]() -> uint32_t {
         const uint32_t s = n % NS, par = (n / NS) & 1;
         mbar_wait(bar_slot_full(s), par);
         ++n;
         return s;
       };
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++tile_it) {
+      for (int it = 0; it < my_tiles; ++it) {
+        const uint32_t tile_it = it;
         for (int pass = 0; pass < (kBwd ? 2 : 1); ++pass) {
           // pass 0: P = X Wd_cat^T -> [TM_P, +R);  pass 1 (bwd): dH = dY Wu_cat -> [TM_D, +R)
           const uint32_t d_tmem = tmem + (pass == 0 ? TM_P : TM_D);
@@ -231,29 +245,21 @@ dat_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
           }
           for (int kc = 0; kc < KC1; ++kc) {
             const uint32_t sa = wait_slot();
-            const uint32_t sb0 = wait_slot();
-            const uint32_t sb1 = w_boxes == 2 ? wait_slot() : 0;
+            const uint32_t sb = wait_slot();
             tc_fence_after();
             if (pass == 0) FD_TRACE(10 + kc, tile_it);
-            const uint32_t a_src = smem0 + sa * SLOT;
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              const uint64_t adesc = desc_kmajor_sw128(a_src + k * 32);
-              umma_ss(d_tmem, adesc, desc_kmajor_sw128(smem0 + sb0 * SLOT + k * 32), idesc_lo,
-                      (kc | k) != 0);
-              if (w_boxes == 2)
-                umma_ss(d_tmem + 128, adesc, desc_kmajor_sw128(smem0 + sb1 * SLOT + k * 32),
-                        idesc_hi, (kc | k) != 0);
-            }
-            umma_commit(bar_slot_empty(sa));
-            umma_commit(bar_slot_empty(sb0));
-            if (w_boxes == 2) umma_commit(bar_slot_empty(sb1));
+            for (int k = 0; k < 4; ++k)
+              umma_ss_pair(d_tmem, desc_kmajor_sw128(smem0 + sa * SLOT + k * 32),
+                           desc_kmajor_sw128(smem0 + sb * SLOT + k * 32), idesc1, (kc | k) != 0);
+            umma_commit_pair(bar_slot_empty(sa), 0b11);
+            umma_commit_pair(bar_slot_empty(sb), 0b11);
           }
-          umma_commit(pass == 0 ? bar_p_full : bar_g_full);
+          umma_commit_pair(pass == 0 ? bar_p_full : bar_g_full, 0b11);
           FD_TRACE(22 + pass, tile_it);
         }
-        // epilogue 1 done: the packed hidden (dP) is in TMEM [TM_P, TM_P + R/2) and P may be
-        // overwritten by the next tile's GEMM1 (waited even when no GEMM2/3 follows)
+        // epilogue 1 done in BOTH CTAs: the packed hidden (dP) is in TMEM [TM_P, TM_P + R/2) and P
+        // may be overwritten by the next tile's GEMM1 (waited even when no GEMM2/3 follows)
         mbar_wait(bar_h_full, tile_it & 1);
         tc_fence_after();
         FD_TRACE(24, tile_it);
@@ -264,16 +270,20 @@ dat_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
           tc_fence_after();
           FD_TRACE(25 + c, tile_it);
           const uint32_t d_tmem = tmem + TM_D + b * N2;
-          for (int kc = 0; kc < KC2; ++kc) {
+          for (int kc = 0; kc < KC2; kc += 2) {
             const uint32_t s = wait_slot();
             tc_fence_after();
-            const int ksteps = min(4, (R - kc * 64) / 16);
-            for (int k = 0; k < ksteps; ++k)
-              umma_ts(d_tmem, tmem + TM_P + (kc * 4 + k) * 8,
-                      desc_kmajor_sw128(smem0 + s * SLOT + k * 32), idesc2, (kc | k) != 0);
-            umma_commit(bar_slot_empty(s));
+            const int nk = min(2, KC2 - kc);
+            for (int j = 0; j < nk; ++j) {
+              const int ksteps = min(4, (R - (kc + j) * 64) / 16);
+              for (int k = 0; k < ksteps; ++k)
+                umma_ts_pair(d_tmem, tmem + TM_P + ((kc + j) * 4 + k) * 8,
+                             desc_kmajor_sw128(smem0 + s * SLOT + j * (N2 / 2) * 128 + k * 32),
+                             idesc2, (kc | j | k) != 0);
+            }
+            umma_commit_pair(bar_slot_empty(s), 0b11);
           }
-          umma_commit(bar_d_full(b));
+          umma_commit_pair(bar_d_full(b), 0b11);
           FD_TRACE(31 + c, tile_it);
         }
       }
@@ -287,7 +297,7 @@ dat_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
         const uint32_t sb = g % NSTG, par = (g / NSTG) & 1;
         mbar_wait(bar_stg_empty(sb), par ^ 1);
         if (p.has_res) {
-          const int tile = blockIdx.x + (g / per_tile) * gridDim.x;
+          const int tile = tile_of(g / per_tile);
           const int c64 = g % per_tile;
           mbar_arrive_expect_tx(bar_res_full(sb), SLOT);
           tma_load_2d(stg_base + sb * SLOT, &tmRes, bar_res_full(sb), c64 * 64, tile * BM);
@@ -305,7 +315,7 @@ dat_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
       for (uint32_t g = 0; g < total_chunks; ++g) {
         const uint32_t sb = g % NSTG, par = (g / NSTG) & 1;
         mbar_wait(bar_out_full(sb), par);
-        const int tile = blockIdx.x + (g / per_tile) * gridDim.x;
+        const int tile = tile_of(g / per_tile);
         const int c64 = g % per_tile;
         tma_store_2d(&tmY, stg_base + sb * SLOT, c64 * 64, tile * BM);
         tma_store_commit();
@@ -330,11 +340,14 @@ dat_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
     const uint32_t lane_addr = (q * 32) << 16;
     const float scale = p.scale;
     const bool has_res = p.has_res != 0;
-    uint32_t tile_it = 0;
     uint32_t df = 0;  // chunk fills of this group's D buffer so far
+    // the MMA issuer lives in the leader CTA: "hidden ready" / "D buffer drained" go to ITS barriers
+    const uint32_t leader_h_full = mapa_u32(bar_h_full, 0);
+    const uint32_t leader_d_empty[2] = {mapa_u32(bar_d_empty(0), 0), mapa_u32(bar_d_empty(1), 0)};
 
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++tile_it) {
-      const int m0 = tile * BM;
+    for (int it = 0; it < my_tiles; ++it) {
+      const uint32_t tile_it = it;
+      const int m0 = tile_of(it) * BM;
       if (group == 0) {
         // ---------------- epilogue 1: P (and dH) -> packed bf16 hidden over P's own columns
         mbar_wait(bar_p_full, tile_it & 1);
@@ -383,10 +396,10 @@ dat_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
         tmem_st_wait();
         tc_fence_before();
         if (kBwd) {  // dH (which overlays the output ring) is consumed
-          mbar_arrive(bar_d_empty(0));
-          mbar_arrive(bar_d_empty(1));
+          mbar_arrive_cluster_addr(leader_d_empty[0]);
+          mbar_arrive_cluster_addr(leader_d_empty[1]);
         }
-        mbar_arrive(bar_h_full);
+        mbar_arrive_cluster_addr(leader_h_full);
         if (tid == 128) FD_TRACE(41, tile_it);
       }
       // ---------------- epilogue 2: this group's output chunks (c = group, group + 2, group + 4)
@@ -409,13 +422,19 @@ dat_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
           tmem_ld_wait();
           if (lane == 0 && q == 0) FD_TRACE(43 + 4 * c + j, tile_it);
           const uint32_t sbuf = stg_base + sb * SLOT;
-          const float* bu = bias_smem + R + col0;
+          const float4* bu4 = reinterpret_cast<const float4*>(bias_smem + R + col0);
 #pragma unroll
           for (int c8 = 0; c8 < 8; ++c8) {
             const uint32_t addr = sbuf + sw128_offset(row, c8);
             uint4 rv = make_uint4(0u, 0u, 0u, 0u);
             if (has_res) rv = ld_shared_v4(addr);
             const uint32_t rr[4] = {rv.x, rv.y, rv.z, rv.w};
+            float bb[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+            if constexpr (!kBwd) {
+              const float4 b0 = bu4[2 * c8], b1 = bu4[2 * c8 + 1];
+              bb[0] = b0.x; bb[1] = b0.y; bb[2] = b0.z; bb[3] = b0.w;
+              bb[4] = b1.x; bb[5] = b1.y; bb[6] = b1.z; bb[7] = b1.w;
+            }
             uint32_t o[4];
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
@@ -425,8 +444,8 @@ dat_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
               const float2 r2 = unpack_bf16x2(rr[i]);
               if constexpr (kBwd)
                 o[i] = pack_bf16x2(r2.x + a0, r2.y + a1);
-              else
-                o[i] = pack_bf16x2(r2.x + scale * (a0 + bu[e]), r2.y + scale * (a1 + bu[e + 1]));
+              else   // res + scale * (acc + bias)
+                o[i] = pack_bf16x2(fmaf(scale, a0 + bb[2 * i], r2.x), fmaf(scale, a1 + bb[2 * i + 1], r2.y));
             }
             st_shared_v4(addr, o[0], o[1], o[2], o[3]);
           }
@@ -434,15 +453,15 @@ dat_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
           mbar_arrive(bar_out_full(sb));
         }
         tc_fence_before();
-        mbar_arrive(bar_d_empty(b));
+        mbar_arrive_cluster_addr(leader_d_empty[b]);
         if (lane == 0 && q == 0) FD_TRACE(45 + 4 * c, tile_it);
       }
     }
   }
 
   tc_fence_before();
-  __syncthreads();
-  if (warp == 2) tmem_dealloc(tmem, 512);
+  cluster_sync_all();   // the partner's smem / barriers / TMEM stay valid until both CTAs are done
+  if (warp == 2) tmem_dealloc_pair(tmem, 512);
 }
 
 unsigned long long* g_trace = nullptr;
@@ -455,8 +474,8 @@ int launch_fused(bool bwd, const void* X, const void* Res, void* Out, const void
   p.R = r_total;
   p.num_tiles = static_cast<int>((M + BM - 1) / BM);
   p.trace = g_trace;
-  p.n_slots = 10;
-  p.n_stg = 3;
+  p.n_slots = 7;    // 16 KB TMA ring slots (X chunks, weight half-chunks)
+  p.n_stg = 6;      // 16 KB residual-in / output staging buffers
   const size_t max_smem = 227 * 1024 - 1024;  // static smem (barriers) lives in the same budget
   const size_t smem = 1024 + static_cast<size_t>(p.n_slots + p.n_stg) * SLOT +
                       (r_total + kD) * sizeof(float);
@@ -467,14 +486,15 @@ int launch_fused(bool bwd, const void* X, const void* Res, void* Out, const void
   if ((rc = make_tmap_bf16_2d(&tmX, X, M, kD, kD, BM, 64))) return rc;
   if ((rc = make_tmap_bf16_2d(&tmRes, Res, M, kD, kD, BM, 64))) return rc;
   if ((rc = make_tmap_bf16_2d(&tmY, Out ? Out : X, M, kD, kD, BM, 64))) return rc;
-  const uint32_t w_box_rows = r_total > 128 ? 128 : r_total;
+  const uint32_t w_box_rows = r_total / 2;   // each CTA of a pair holds half of every weight tile
   if ((rc = make_tmap_bf16_2d(&tmWd, Wd_cat, r_total, kD, kD, w_box_rows, 64))) return rc;
-  if ((rc = make_tmap_bf16_2d(&tmW2, W2, kD, r_total, r_total, N2, 64))) return rc;
+  if ((rc = make_tmap_bf16_2d(&tmW2, W2, kD, r_total, r_total, N2 / 2, 64))) return rc;
   if ((rc = make_tmap_bf16_2d(&tmW1b, W1b ? W1b : Wd_cat, r_total, kD, kD, w_box_rows, 64))) return rc;
 
   int sms = 0;
   if ((rc = device_sm_count(&sms))) return rc;
-  const int grid = p.num_tiles < sms ? p.num_tiles : sms;
+  const int num_pairs = (p.num_tiles + 1) / 2;
+  const int grid = 2 * (num_pairs < sms / 2 ? num_pairs : sms / 2);
   using KernelFn = void (*)(const CUtensorMap, const CUtensorMap, const CUtensorMap,
                             const CUtensorMap, const CUtensorMap, const CUtensorMap,
                             const FusedParams);
@@ -489,7 +509,19 @@ int launch_fused(bool bwd, const void* X, const void* Res, void* Out, const void
                                        (int)max_smem));
     if (dev < 64) configured[bwd][gelu][dev] = true;
   }
-  fn<<<grid, NUM_THREADS, smem, st>>>(tmX, tmRes, tmY, tmWd, tmW2, tmW1b, p);
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(NUM_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  FD_CHECK_CUDA(cudaLaunchKernelEx(&cfg, fn, tmX, tmRes, tmY, tmWd, tmW2, tmW1b, p));
   FD_CHECK_CUDA(cudaGetLastError());
   return FD_OK;
 }

@@ -254,3 +254,132 @@ extern "C" int feddat_probe_l2bw(const void* buf, int n_boxes, int iters, int gr
   FD_CHECK_CUDA(cudaLaunchKernelEx(&cfg, probe_l2bw_kernel, tm, n_boxes, iters, cluster));
   return FD_OK;
 }
+
+// ------------------------------------------------------------------------------------------------
+// cta_group::2 bring-up: one CTA pair, D[256 x N] = A[256 x K] * B[N x K]^T.  Each CTA holds its
+// 128 rows of A (smem, or TMEM when a_tmem) and N/2 rows of B; the leader CTA issues the MMAs.
+// ------------------------------------------------------------------------------------------------
+namespace fd {
+
+__global__ void __launch_bounds__(128, 1)
+probe_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                  const __nv_bfloat16* A, float* D, int N, int K, int a_tmem, int reps,
+                  unsigned long long* ns_out) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t bar_full, bar_done;
+  __shared__ uint32_t tmem_base_smem;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const uint32_t rank = cluster_ctarank();
+  const uint32_t smem0 = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t a_base = smem0;
+  const uint32_t a_bytes = 128u * K * 2u;
+  const uint32_t b_base = a_base + a_bytes;
+  const int NH = N / 2;
+  const uint32_t b_bytes = static_cast<uint32_t>(NH) * K * 2u;
+
+  if (tid == 0) {
+    mbar_init(smem_u32(&bar_full), 1);
+    mbar_init(smem_u32(&bar_done), 1);
+    fence_mbar_init();
+  }
+  if (warp == 0) tmem_alloc_pair(smem_u32(&tmem_base_smem), 512);
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem = tmem_base_smem;
+  const uint32_t lane_base = static_cast<uint32_t>(warp * 32) << 16;
+
+  if (tid == 0) {
+    const uint32_t leader_full = mapa_u32(smem_u32(&bar_full), 0);
+    if (rank == 0)
+      mbar_arrive_expect_tx(smem_u32(&bar_full), 2 * (b_bytes + (a_tmem ? 0u : a_bytes)));
+    if (!a_tmem)
+      for (int kc = 0; kc < K / 64; ++kc)
+        tma_load_2d_pair(a_base + kc * 128 * 128, &tmA, leader_full, kc * 64, rank * 128,
+                         kEvictNormal);
+    for (int kc = 0; kc < K / 64; ++kc)
+      tma_load_2d_pair(b_base + kc * NH * 128, &tmB, leader_full, kc * 64, rank * NH, kEvictNormal);
+  }
+  if (a_tmem) {
+    const uint4* arow =
+        reinterpret_cast<const uint4*>(A + static_cast<size_t>(rank * 128 + tid) * K);
+    for (int c = 0; c < K / 16; ++c) {
+      uint4 v0 = arow[2 * c], v1 = arow[2 * c + 1];
+      uint32_t v[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+      tmem_st8(tmem + lane_base + 256 + c * 8, v);
+    }
+    tmem_st_wait();
+    tc_fence_before();
+  }
+  cluster_sync_all();  // both CTAs' TMEM A operands are written before the leader issues
+
+  if (rank == 0 && tid == 0) {
+    mbar_wait(smem_u32(&bar_full), 0);
+    tc_fence_after();
+    const uint32_t idesc = make_idesc_bf16(256, N);
+    const uint64_t t0 = globaltimer_ns();
+    for (int rep = 0; rep < reps; ++rep)   // reps > 1: MMA-throughput timing (D is then reps * A B^T)
+      for (int kk = 0; kk < K / 16; ++kk) {
+        const uint64_t bdesc = desc_kmajor_sw128(b_base + (kk / 4) * NH * 128 + (kk % 4) * 32);
+        if (a_tmem)
+          umma_ts_pair(tmem, tmem + 256 + kk * 8, bdesc, idesc, (rep | kk) > 0);
+        else
+          umma_ss_pair(tmem, desc_kmajor_sw128(a_base + (kk / 4) * 128 * 128 + (kk % 4) * 32),
+                       bdesc, idesc, (rep | kk) > 0);
+      }
+    umma_commit_pair(smem_u32(&bar_done), 0b11);
+    mbar_wait(smem_u32(&bar_done), 0);
+    if (ns_out) *ns_out = globaltimer_ns() - t0;
+  }
+  __syncwarp();
+  mbar_wait(smem_u32(&bar_done), 0);
+  tc_fence_after();
+  float* drow = D + static_cast<size_t>(rank * 128 + tid) * N;
+  for (int c = 0; c < N / 16; ++c) {
+    uint32_t v[16];
+    tmem_ld16(tmem + lane_base + c * 16, v);
+    tmem_ld_wait();
+#pragma unroll
+    for (int i = 0; i < 16; i += 4)
+      *reinterpret_cast<float4*>(drow + c * 16 + i) =
+          make_float4(__uint_as_float(v[i]), __uint_as_float(v[i + 1]), __uint_as_float(v[i + 2]),
+                      __uint_as_float(v[i + 3]));
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 0) tmem_dealloc_pair(tmem, 512);
+}
+
+}  // namespace fd
+
+// A: bf16 [256, K] row-major; B: bf16 [N, K] row-major; D: fp32 [256, N].
+extern "C" int feddat_probe_pair(const void* A, const void* B, float* D, int N, int K, int a_tmem,
+                                 int reps, unsigned long long* ns_out, void* stream) {
+  using namespace fd;
+  int rc = check_device_sm100();
+  if (rc) return rc;
+  FD_REQUIRE(N % 32 == 0 && N >= 32 && N <= 256 && K % 64 == 0 && K >= 64 && K <= 256,
+             FD_ERR_INVALID, "probe_pair: N=%d K=%d out of range", N, K);
+  CUtensorMap tmA, tmB;
+  if ((rc = make_tmap_bf16_2d(&tmA, A, 256, K, K, 128, 64))) return rc;
+  if ((rc = make_tmap_bf16_2d(&tmB, B, N, K, K, N / 2, 64))) return rc;
+  const size_t smem = 1024 + 128 * K * 2 + static_cast<size_t>(N / 2) * K * 2;
+  FD_CHECK_CUDA(cudaFuncSetAttribute(probe_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)smem));
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(2);
+  cfg.blockDim = dim3(128);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = static_cast<cudaStream_t>(stream);
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  FD_CHECK_CUDA(cudaLaunchKernelEx(&cfg, probe_pair_kernel, tmA, tmB,
+                                   static_cast<const __nv_bfloat16*>(A), D, N, K, a_tmem,
+                                   reps < 1 ? 1 : reps, ns_out));
+  return FD_OK;
+}

@@ -132,6 +132,10 @@ int feddat_fedavg(const float* const* clients /* host array of device ptrs */,
 int feddat_probe_gemm(const void* A, const void* B, float* D, int N, int K, int a_mode,
                       int b_mode, const uint32_t* overrides, void* stream);
 
+/* cta_group::2 bring-up probe (tests only): D[256,N] = A[256,K] B[N,K]^T on one CTA pair. */
+int feddat_probe_pair(const void* A, const void* B, float* D, int N, int K, int a_tmem, int reps,
+                      unsigned long long* ns_out /* device, nullable: MMA loop time */, void* stream);
+
 /* L2 -> SM TMA streaming bandwidth probe (optionally multicast across a cluster), csrc/probe.cu. */
 int feddat_probe_l2bw(const void* buf, int n_boxes, int iters, int grid, int cluster, void* stream);
 

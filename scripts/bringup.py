@@ -39,6 +39,29 @@ def run_probe(a_mode, b_mode, N, K, overrides=None):
     return {"max_abs_err": err, "ref_absmax": ref.abs().max().item(), "ok": bool(err < 1e-2)}
 
 
+def run_pair(N, K, a_tmem, reps=1):
+    import torch
+    from feddat_b200 import _lib
+    lib = _lib.load()
+    torch.manual_seed(0)
+    A = torch.randn(256, K, device="cuda").to(torch.bfloat16)
+    B = torch.randn(N, K, device="cuda").to(torch.bfloat16)
+    ref = A.float() @ B.float().t()
+    D = torch.full((256, N), float("nan"), device="cuda", dtype=torch.float32)
+    ns = torch.zeros(1, dtype=torch.int64, device="cuda")
+    _lib.check(lib.feddat_probe_pair(_lib.ptr(A), _lib.ptr(B), _lib.ptr(D), N, K, a_tmem, reps, _lib.ptr(ns),
+                                     _lib.stream_ptr()))
+    torch.cuda.synchronize()
+    if reps > 1:
+        n_mma = reps * K // 16
+        t = ns.item()
+        return {"n_mma": n_mma, "ns_per_mma": t / n_mma, "tflops_pair": 2 * 256 * N * 16 * n_mma / t / 1e3,
+                "ok": True}
+    err = (D - ref).abs()
+    return {"max_abs_err": err.max().item(), "err_top": err[:128].max().item(), "err_bot": err[128:].max().item(),
+            "nan": int(torch.isnan(D).sum().item()), "ok": bool(err.max().item() < 1e-2)}
+
+
 def run_fwd(R, M, scale, act=0, alias=True):
     import torch
     from feddat_b200 import _lib
@@ -94,6 +117,8 @@ def run_case(case: str):
         a, b, N, K = map(int, parts[1:5])
         ov = list(map(int, parts[5:11])) if len(parts) >= 11 else None
         return run_probe(a, b, N, K, ov)
+    if parts[0] == "pair":
+        return run_pair(int(parts[1]), int(parts[2]), int(parts[3]), int(parts[4]) if len(parts) > 4 else 1)
     if parts[0] == "fwd":
         R, M = int(parts[1]), int(parts[2])
         scale = float(parts[3])
