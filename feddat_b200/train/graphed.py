@@ -1,0 +1,115 @@
+"""CUDA-graph replay of ``TaskTrainer.train_step`` (dat mode).
+
+One train step is ~1000 kernel launches (three ViLT forwards, two backwards, two fused-AdamW steps);
+launched eagerly from Python the GPU idles a third of the time.  The whole step -- including the
+autograd backward, the sm_100a DAT / MKD kernels (enqueued through the C ABI on the capturing stream)
+and both optimizer steps -- is captured once and replayed per batch.
+
+What stays outside the graph, per step: one H2D copy of the batch into static tensors and one tiny H2D
+copy of the three learning-rate values the step needs (the reference steps its scheduler twice per
+batch: task_trainer.py:303-308, 323-328), computed on the host by the scheduler's own lambda.
+Semantics are those of ``train_step`` (same call order, same detach points, grads set to None).
+"""
+from __future__ import annotations
+
+from typing import Dict
+
+import torch
+
+
+class _ReplayScheduler:
+    """Stands in for the LR scheduler inside the captured region: each ``step()`` copies the next
+    pre-staged learning rate into the optimizer's (tensor) lr."""
+
+    def __init__(self, optimizer, lr_buf):
+        self.optimizer, self.lr_buf, self.i = optimizer, lr_buf, 0
+
+    def load(self, idx):
+        for g in self.optimizer.param_groups:
+            g["lr"].copy_(self.lr_buf[idx])
+
+    def step(self):
+        self.i += 1
+        self.load(self.i)
+
+
+class GraphedTrainStep:
+    def __init__(self, trainer, wrapped_model, optimizer, scheduler, example_batch: Dict, warmup: int = 2):
+        for g in optimizer.param_groups:
+            if not (isinstance(g["lr"], torch.Tensor) and g["lr"].is_cuda and g.get("capturable", False)):
+                raise ValueError("GraphedTrainStep needs an optimizer built by TaskTrainer.create_optimizer on "
+                                 "CUDA (capturable fused AdamW with a tensor lr)")
+        self.trainer, self.model, self.opt, self.sched = trainer, wrapped_model, optimizer, scheduler
+        dev = example_batch["target_scores"].device
+        self.static = {"encodings": {k: (v.clone() if isinstance(v, torch.Tensor) else v)
+                                     for k, v in example_batch["encodings"].items()},
+                       "target_scores": example_batch["target_scores"].clone()}
+        self.lr_buf = torch.zeros(3, device=dev, dtype=torch.float32)
+        self.base_lrs = [float(b) for b in scheduler.base_lrs]
+        self.lmbda = scheduler.lr_lambdas[0]
+        self.graph = None
+        self.loss = None
+        self.launches_per_step = 0
+        # eager warm-up steps on a side stream (real training steps: state advances exactly as eager)
+        self._warm = warmup
+
+    # ------------------------------------------------------------------
+    def _stage_lrs(self):
+        e = self.sched.last_epoch
+        vals = [self.base_lrs[0] * self.lmbda(e + i) for i in range(3)]
+        host = torch.tensor(vals, dtype=torch.float32).pin_memory()
+        self.lr_buf.copy_(host, non_blocking=True)
+
+    def _advance_scheduler(self):
+        self.sched.last_epoch += 2
+        self.sched._last_lr = [b * self.lmbda(self.sched.last_epoch) for b in self.base_lrs]
+
+    def _load_batch(self, batch):
+        for k, v in batch["encodings"].items():
+            if isinstance(v, torch.Tensor):
+                self.static["encodings"][k].copy_(v, non_blocking=True)
+        self.static["target_scores"].copy_(batch["target_scores"], non_blocking=True)
+
+    def _clear_caches(self):
+        inner = self.model.module
+        for a in inner._adapters():
+            a._pack_cache.clear()
+        inner.vilt_encoder._embed_cache = None
+
+    def _body(self):
+        rs = _ReplayScheduler(self.opt, self.lr_buf)
+        rs.load(0)
+        return self.trainer.train_step(self.model, 0, self.static, self.opt, rs)
+
+    def _capture(self):
+        from .. import ops
+        self._clear_caches()
+        torch.cuda.synchronize()
+        self.graph = torch.cuda.CUDAGraph()
+        n0 = ops.launch_count
+        with torch.cuda.graph(self.graph):
+            self.loss = self._body()
+        self.launches_per_step = ops.launch_count - n0
+        self._clear_caches()          # cached packs now live in the graph's private pool: never reuse eagerly
+
+    # ------------------------------------------------------------------
+    def __call__(self, batch: Dict) -> torch.Tensor:
+        """Runs one train step on ``batch`` (host-pinned or device tensors); returns the task loss
+        (device scalar, valid until the next call)."""
+        self._load_batch(batch)
+        if self._warm > 0:
+            self._warm -= 1
+            s = torch.cuda.Stream()
+            s.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(s):
+                loss = self.trainer.train_step(self.model, 0, self.static, self.opt, self.sched)
+            torch.cuda.current_stream().wait_stream(s)
+            return loss
+        self._stage_lrs()
+        if self.graph is None:
+            self._capture()
+        self.graph.replay()
+        self._advance_scheduler()
+        from .. import ops
+        ops.launch_count += self.launches_per_step
+        return self.loss

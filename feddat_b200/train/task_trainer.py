@@ -182,5 +182,10 @@ class TaskTrainer(nn.Module):
                         if (any(nd in n for nd in no_decay)) and p.requires_grad],
              "weight_decay": 0.0},
         ]
-        on_cuda = any(p.is_cuda for g in groups for p in g["params"])
-        return AdamW(groups, lr=self.lr, eps=self.adam_epsilon, betas=(0.9, 0.98), fused=on_cuda)
+        dev = next((p.device for g in groups for p in g["params"] if p.is_cuda), None)
+        if dev is None:
+            return AdamW(groups, lr=self.lr, eps=self.adam_epsilon, betas=(0.9, 0.98))
+        # fused + capturable with a device-tensor lr: same arithmetic, and the two optimizer steps of
+        # a train step can live inside a CUDA graph (feddat_b200/train/graphed.py)
+        return AdamW(groups, lr=torch.tensor(float(self.lr), device=dev), eps=self.adam_epsilon,
+                     betas=(0.9, 0.98), fused=True, capturable=True)

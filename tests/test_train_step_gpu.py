@@ -111,3 +111,38 @@ def test_train_step_matches_reference_trainer(step_golden):
             assert got_d < 1e-5
     print("parameter-movement norms vs reference: median rel err %.4f, max %.4f" % (np.median(rel), max(rel)))
     assert np.median(rel) < 5e-2 and max(rel) < 0.25, (np.median(rel), max(rel))
+
+
+def test_graphed_train_step_equals_eager():
+    """CUDA-graph replay of train_step == the eager train_step (same kernels, same order)."""
+    from feddat_b200.synthetic import make_vilt_batch, to_device
+    from feddat_b200.train.graphed import GraphedTrainStep
+    from feddat_b200.train.prepare import default_args, place_on_gpu, prepare_model
+    from feddat_b200.train.task_trainer import get_polynomial_decay_schedule_with_warmup
+
+    def build():
+        torch.manual_seed(7)
+        model = prepare_model(default_args(ordered_cl_tasks=["art"], adapter_rank=32), place=False)
+        place_on_gpu(model)
+        tr = build_trainer(model, 1e-3, 20, "art", temp=2.0)
+        for n, p in model.named_parameters():
+            if "adapter_2" in n:
+                p.requires_grad = False
+        wrapped = tr.accelerator.prepare(model)
+        opt = tr.create_optimizer(wrapped)
+        sched = get_polynomial_decay_schedule_with_warmup(opt, 2, 20, lr_end=0, power=1)
+        wrapped.train()
+        return model, tr, wrapped, opt, sched
+
+    batches = [to_device(make_vilt_batch(2, 16, 224, 100, seed=50 + i), "cuda") for i in range(5)]
+    m1, tr1, w1, o1, s1 = build()
+    eager = [tr1.train_step(w1, i, batches[i], o1, s1).item() for i in range(5)]
+    m2, tr2, w2, o2, s2 = build()
+    g = GraphedTrainStep(tr2, w2, o2, s2, batches[0], warmup=2)
+    graphed = [g(batches[i]).item() for i in range(5)]
+    assert g.graph is not None and g.launches_per_step > 0
+    np.testing.assert_allclose(graphed, eager, rtol=2e-3)
+    assert s2.last_epoch == s1.last_epoch == 10
+    for (n1, p1), (_, p2) in zip(m1.named_parameters(), m2.named_parameters()):
+        if "adapter_0" in n1 or "adapter_1" in n1 or "task_layer" in n1:
+            assert torch.allclose(p1, p2, rtol=2e-2, atol=2e-5), n1
