@@ -187,5 +187,11 @@ class TaskTrainer(nn.Module):
             return AdamW(groups, lr=self.lr, eps=self.adam_epsilon, betas=(0.9, 0.98))
         # fused + capturable with a device-tensor lr: same arithmetic, and the two optimizer steps of
         # a train step can live inside a CUDA graph (feddat_b200/train/graphed.py)
-        return AdamW(groups, lr=torch.tensor(float(self.lr), device=dev), eps=self.adam_epsilon,
-                     betas=(0.9, 0.98), fused=True, capturable=True)
+        opt = AdamW(groups, lr=float(self.lr), eps=self.adam_epsilon, betas=(0.9, 0.98), fused=True,
+                    capturable=True)
+        # per-group lr tensors are installed AFTER construction: ``defaults["lr"]`` must stay a float,
+        # the HF polynomial schedule divides by it (lr_init) -- if it aliased the live lr tensor, the
+        # warm-up step that sets lr = 0 would turn every later factor into 0/0
+        for g in opt.param_groups:
+            g["lr"] = torch.tensor(float(g["lr"]), device=dev)
+        return opt
