@@ -48,6 +48,7 @@ class _DatFunction(torch.autograd.Function):
         for i, (pk, _, _) in enumerate(segs):
             y = ops.dat_forward(x, res if i == 0 else y, pk, adapter._scale(), adapter._act_code)
         ctx.adapter = adapter
+        ctx.scale = adapter._scale()        # mode at FORWARD time (backward may run after a mode switch)
         ctx.segs = segs
         ctx.same = same
         ctx.n_params = len(params)
@@ -77,7 +78,7 @@ class _DatFunction(torch.autograd.Function):
                     lo = b0 if lo is None else min(lo, b0)
                     hi = b1 if hi is None else max(hi, b1)
             ts = None if lo is None else (lo - col0, hi - col0)
-            dx, g = ops.dat_backward(x, dy, pk, adapter._scale(), adapter._act_code, train_slice=ts,
+            dx, g = ops.dat_backward(x, dy, pk, ctx.scale, adapter._act_code, train_slice=ts,
                                      need_dx=need_dx, add_dy=(ctx.same and si == 0))
             if dx is not None:
                 dx_total = dx if dx_total is None else dx_total + dx

@@ -189,12 +189,27 @@ class ViltContinualLearner(nn.Module):
 
     def forward_single_image(self, task_key: str, images=None, texts=None, **encodings):
         """vilt.py:244-264: (pooler_output, logits)."""
+        encoder_output = self.encode(images, texts, **encodings)
+        return encoder_output, self.classify(task_key, encoder_output)
+
+    def encode(self, images=None, texts=None, **encodings):
+        """The encoder half of ``forward_single_image`` (vilt.py:257-259): pooled output (batch, hidden)."""
         if images is not None:
             encodings = dict(self.vilt_encoder.process_inputs(images, texts))
-        encoder_output = self.vilt_encoder(**encodings)
+        return self.vilt_encoder(**encodings)
+
+    def classify(self, task_key: str, encoder_output):
+        """The task-head half of ``forward_single_image`` (vilt.py:261-262)."""
         head = self.task_layer[task_key]
-        output_logits = head(encoder_output.to(head.clf_fc0.weight.dtype))
-        return encoder_output, output_logits
+        return head(encoder_output.to(head.clf_fc0.weight.dtype))
+
+    def gating_forward_is_reusable(self) -> bool:
+        """True when the encoder is a deterministic function of (inputs, adapter_0, adapter_2, frozen
+        backbone): every ViLT dropout probability is 0 (HF ViltConfig defaults).  The MKD
+        schedule's passes A and C then share one encoder forward (TaskTrainer.train_step)."""
+        cfg = self.vilt_encoder.vilt.config
+        return (float(getattr(cfg, "hidden_dropout_prob", 0.0)) == 0.0
+                and float(getattr(cfg, "attention_probs_dropout_prob", 0.0)) == 0.0)
 
     # ------------------------------------------------------------------ adapter hooks (vilt.py:356-382)
     def add_adapter(self):

@@ -65,6 +65,10 @@ class TaskTrainer(nn.Module):
         super().__init__()
         self.kl_criterion = kl_loss                      # task_trainer.py:15
         self.kl_temp = 3                                 # kl_loss default; BASELINE cfg1 uses 2.0
+        # passes A and C of the MKD schedule run the SAME encoder function (gating: adapter_0 +
+        # adapter_2 + frozen backbone; step B only updates adapter_1 and the head) whenever the
+        # encoder has no dropout (ViLT): one grad-enabled forward serves both
+        self.reuse_gating_forward = True
 
     # ------------------------------------------------------------------ train (task_trainer.py:24-111)
     def train(self, model, er=None, ewc=None, der=None, derpp=None, pnn=None, hat=None):
@@ -142,9 +146,19 @@ class TaskTrainer(nn.Module):
             raise NotImplementedError("only optimizer_mode='dat' is on the FedDAT hot path")
         albef = "albef" in self.args.encoder_name
 
-        with torch.no_grad():                                        # (A) :283-287
-            model.module.activate_gating()
-            _, logits_all = self.forward_pass(model, batch, do_eval=False)
+        inner = model.module
+        reuse = (self.reuse_gating_forward and not albef
+                 and getattr(inner, "gating_forward_is_reusable", lambda: False)())
+        if reuse:                                                    # (A) + encoder half of (C)
+            inner.activate_gating()
+            inner.set_active_adapter("adapter_0")
+            enc_all = inner.encode(**self.batch2inputs_converter(batch))
+            with torch.no_grad():
+                logits_all = inner.classify(self.task_key, enc_all)
+        else:
+            with torch.no_grad():                                    # (A) :283-287
+                model.module.activate_gating()
+                _, logits_all = self.forward_pass(model, batch, do_eval=False)
 
         model.module.deactivate_gating()                             # (B) :290-308
         model.module.set_active_adapter("adapter_1")
@@ -159,7 +173,10 @@ class TaskTrainer(nn.Module):
 
         model.module.activate_gating()                               # (C) :311-328
         model.module.set_active_adapter("adapter_0")
-        output_0_0, logits_0 = self.forward_pass(model, batch, do_eval=False)
+        if reuse:       # same pooled output as a fresh forward (bit-identical), head re-applied after step B
+            output_0_0, logits_0 = enc_all, inner.classify(self.task_key, enc_all)
+        else:
+            output_0_0, logits_0 = self.forward_pass(model, batch, do_eval=False)
         L_0, loss_0 = self._objective(logits_0, logits_1, target, output_0_0 if albef else None)
         self.accelerator.backward(L_0)
         if optimizer is not None:

@@ -87,3 +87,55 @@ def test_dat_schedule_and_losses(monkeypatch):
     want_L0 = oracle.mkd_total(logits_0, tr.last_logits[1].detach().numpy(), target.numpy(), 3)[0]
     assert abs(tr.last_objectives[1].item() - want_L0) < 1e-4
     assert all(p.grad is None for p in m.parameters())         # zero_grad -> None (torch >= 2 contract)
+
+
+class ReusableLearner(FakeLearner):
+    """FakeLearner with the encode / classify split the ViLT learner exposes (no dropout)."""
+
+    def encode(self, x):
+        self.log.append("enc")
+        assert self.gating
+        return x + 0.5 * self.adapter_0(x) + 0.5 * self.adapter_2(x)
+
+    def classify(self, task_key, h):
+        return self.task_head(h)
+
+    def gating_forward_is_reusable(self):
+        return True
+
+
+def _one_step(learner_cls, reuse):
+    torch.manual_seed(0)
+    m = learner_cls()
+    for p in m.adapter_2.parameters():
+        p.requires_grad = False
+    tr = tt.TaskTrainer()
+    tr.reuse_gating_forward = reuse
+    tr.args = SimpleNamespace(optimizer_mode="dat", encoder_name="vilt")
+    tr.accelerator = Accelerator(device="cpu")
+    tr.device, tr.task_key = torch.device("cpu"), "t"
+    tr.batch2inputs_converter = lambda b: {"x": b["x"]}
+    tr.loss_criterion = nn.BCEWithLogitsLoss(reduction="mean")
+    tr.weight_decay, tr.lr, tr.adam_epsilon, tr.kl_temp = 1e-2, 1e-2, 1e-8, 3
+    wrapped = tr.accelerator.prepare(m)
+    opt = tr.create_optimizer(wrapped)
+    g = torch.Generator().manual_seed(1)
+    losses = []
+    for i in range(3):
+        x = torch.randn(4, 6, generator=g)
+        target = (torch.rand(4, 5, generator=g) < 0.3).float() * 0.6
+        losses.append(tr.train_step(wrapped, i, {"x": x, "target_scores": target}, opt, None).item())
+    return m, losses, tr
+
+
+def test_shared_gating_forward_equals_three_forward_schedule(monkeypatch):
+    """Passes A and C share one encoder forward -- same losses, same parameters, same
+    final requires_grad state as the reference's three-forward schedule."""
+    monkeypatch.setattr(tt.ops, "mkd_loss", _oracle_mkd)
+    m_ref, l_ref, _ = _one_step(ReusableLearner, reuse=False)
+    m_new, l_new, _ = _one_step(ReusableLearner, reuse=True)
+    assert m_ref.log.count("fwd") == 9 and m_new.log.count("fwd") == 3 and m_new.log.count("enc") == 3
+    np.testing.assert_allclose(l_new, l_ref, rtol=1e-6)
+    for (n, p), (_, q) in zip(m_ref.named_parameters(), m_new.named_parameters()):
+        assert torch.allclose(p, q, rtol=1e-6, atol=1e-7), n
+        assert p.requires_grad == q.requires_grad, n
