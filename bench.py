@@ -200,13 +200,24 @@ def run_ours(args):
     dev_batches = [to_device(b, device) for b in host]
     torch.cuda.synchronize()
 
+    if args.eager:
+        def run_step(batch):
+            return c.trainer.train_step(c.wrapped, 0, batch, c.opt, c.sched)
+    else:
+        # the public graphed step (feddat_b200/train/graphed.py): two eager steps, then one capture of
+        # the whole train_step (3 fwd / 2 bwd / 2 AdamW), replayed per batch
+        from feddat_b200.train.graphed import GraphedTrainStep
+        run_step = GraphedTrainStep(c.trainer, c.wrapped, c.opt, c.sched, dev_batches[0], warmup=2)
+
     def step_resident(i):
-        return c.trainer.train_step(c.wrapped, i, dev_batches[i % len(dev_batches)], c.opt, c.sched)
+        return run_step(dev_batches[i % len(dev_batches)])
 
     def step_e2e(i):
-        batch = to_device(host[i % len(host)], device)         # H2D from pinned memory, every step
-        loss = c.trainer.train_step(c.wrapped, i, batch, c.opt, c.sched)
-        return loss.item()                                     # D2H read of the step's result
+        if args.eager:
+            batch = to_device(host[i % len(host)], device)     # H2D from pinned memory, every step
+        else:
+            batch = host[i % len(host)]                        # H2D into the graph's static tensors
+        return run_step(batch).item()                          # D2H read of the step's result
 
     def round_boundary():
         if world > 1:
@@ -265,6 +276,7 @@ def run_ours(args):
             "warmup": W, "ms_per_step": round(ms / K, 3), "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": WORKLOAD, "global_batch": B * world, "clients": world,
+                       "step_launch": "eager" if args.eager else "cuda-graph replay of train_step",
                        "l2": "per-step working set (222 MB bf16 backbone weights + >1 GB activations) exceeds the 126 MB L2; kernel micro-timings flush L2 (256 MB write) between launches",
                        "init": "seeded random ViLT-B/32 (no pretrained weights on the box)"},
             "clocks": clocks,
@@ -340,6 +352,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cpu-batch", type=int, default=4, help="batch of the bounded CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--eager", action="store_true", help="launch train_step eagerly instead of replaying its CUDA graph")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3

@@ -42,7 +42,8 @@ class _DatFunction(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, adapter: "Adapter", x, res, *params):
-        segs = adapter._segments(params)
+        need_bwd = any(ctx.needs_input_grad[1:])
+        segs = adapter._segments(params, need_bwd=need_bwd)
         same = res is x
         y = None
         for i, (pk, _, _) in enumerate(segs):
@@ -158,7 +159,6 @@ class Adapter(nn.Module):
                 for p in m.parameters():
                     p.requires_grad = False
         self._active_name: Optional[str] = None
-        self._pack_cache = {}
 
     # ------------------------------------------------------------------ mode switches (reference API)
     def deactivate_gating(self):
@@ -212,14 +212,14 @@ class Adapter(nn.Module):
             out += [d.weight, d.bias, u.weight, u.bias]
         return out
 
-    def _segments(self, params):
-        """Packed bf16 operands of the active branches, split into <=256-wide launches; cached until
-        a parameter changes (optimizer step, FedAvg copy, load_state_dict all bump ``_version``)."""
-        key = (self.gating, self._active_name if not self.gating else None)
-        stamp = tuple((p.data_ptr(), p._version) for p in params)
-        hit = self._pack_cache.get(key)
-        if hit is not None and hit[0] == stamp:
-            return hit[1]
+    def _segments(self, params, need_bwd: bool = True):
+        """Packed bf16 operands of the active branches, split into <=256-wide launches.
+
+        Packed afresh on EVERY forward (one ~3 us launch per site): nothing observable from Python
+        tells reliably that a parameter's values changed -- ``torch._fused_adamw_`` does not bump
+        ``Tensor._version`` and neither does the ``state_dict()[k].data.copy_(...)`` idiom the
+        reference round loop uses (main.py:446-450, task_trainer.py:36-41) -- so a cached copy would
+        silently go stale.  Backward reuses the forward's packs through ``ctx.segs``."""
         for p in params:
             if not (p.is_cuda and p.dtype == torch.float32):
                 raise FeddatError("adapter parameters must be fp32 CUDA tensors (fp32 masters; the "
@@ -230,7 +230,7 @@ class Adapter(nn.Module):
             branches = [[params[4 * b + i].detach().contiguous() for i in range(4)] for b in range(nb)]
             R = nb * r
             if R <= ops.MAX_R_TOTAL:
-                segs = [(ops.pack_weights(branches), 0, R)]
+                segs = [(ops.pack_weights(branches, need_bwd=need_bwd), 0, R)]
             else:
                 segs = []
                 col = 0
@@ -245,10 +245,9 @@ class Adapter(nn.Module):
                             ub_seg = ub + branches[1][3]
                         seg = [[dw[j0:j1].contiguous(), db[j0:j1].contiguous(),
                                 uw[:, j0:j1].contiguous(), ub_seg.contiguous()]]
-                        segs.append((ops.pack_weights(seg), col, j1 - j0))
+                        segs.append((ops.pack_weights(seg, need_bwd=need_bwd), col, j1 - j0))
                         col += j1 - j0
                         first = False
-        self._pack_cache[key] = (stamp, segs)
         return segs
 
     # ------------------------------------------------------------------ forward (reference API)

@@ -70,11 +70,15 @@ class GraphedTrainStep:
                 self.static["encodings"][k].copy_(v, non_blocking=True)
         self.static["target_scores"].copy_(batch["target_scores"], non_blocking=True)
 
+    def accepts(self, batch) -> bool:
+        """True when ``batch`` has the captured shapes (a ragged last batch must run eagerly)."""
+        if batch["target_scores"].shape != self.static["target_scores"].shape:
+            return False
+        return all(not isinstance(v, torch.Tensor) or v.shape == self.static["encodings"][k].shape
+                   for k, v in batch["encodings"].items())
+
     def _clear_caches(self):
-        inner = self.model.module
-        for a in inner._adapters():
-            a._pack_cache.clear()
-        inner.vilt_encoder._embed_cache = None
+        self.model.module.vilt_encoder._embed_cache = None
 
     def _body(self):
         rs = _ReplayScheduler(self.opt, self.lr_buf)
@@ -90,7 +94,7 @@ class GraphedTrainStep:
         with torch.cuda.graph(self.graph):
             self.loss = self._body()
         self.launches_per_step = ops.launch_count - n0
-        self._clear_caches()          # cached packs now live in the graph's private pool: never reuse eagerly
+        self._clear_caches()          # the cached embedding now lives in the graph's private pool: never reuse eagerly
 
     # ------------------------------------------------------------------
     def __call__(self, batch: Dict) -> torch.Tensor:

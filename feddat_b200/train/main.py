@@ -69,6 +69,8 @@ def build_parser():
     p.add_argument("--adapter_activation", default="relu", choices=["relu", "gelu"])
     p.add_argument("--kl_temp", type=float, default=3.0, help="MKD temperature (reference kl_loss default 3)")
     p.add_argument("--synthetic_batches", type=int, default=8, help="train batches per client per epoch")
+    p.add_argument("--cuda_graph", action="store_true",
+                   help="replay the captured train_step (feddat_b200/train/graphed.py) for full-shape batches")
     p.add_argument("--image_size", type=int, default=384)
     p.add_argument("--text_len", type=int, default=40)
     p.add_argument("--fix_adapter0_optimizer", action="store_true",

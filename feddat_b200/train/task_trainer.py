@@ -94,6 +94,7 @@ class TaskTrainer(nn.Module):
         loader = self.vqa_train_dataloader
 
         loss = None
+        graphed = None          # --cuda_graph: replay the captured step for every full-shape batch
         for epoch in range(self.local_epochs):
             model.train()
             for step, batch in enumerate(loader):
@@ -101,6 +102,13 @@ class TaskTrainer(nn.Module):
                     break
                 if "vilt" not in self.args.encoder_name:
                     batch = self.add_alpha(epoch, batch, step)
+                if getattr(self.args, "cuda_graph", False) and "encodings" in batch:
+                    from .graphed import GraphedTrainStep
+                    if graphed is None:
+                        graphed = GraphedTrainStep(self, model, optimizer, scheduler, batch, warmup=1)
+                    if graphed.accepts(batch):
+                        loss = graphed(batch)
+                        continue
                 loss = self.train_step(model, step, batch, optimizer, scheduler, hooks=None, epoch=epoch)
         self.accelerator.wait_for_everyone()
         self.last_loss = loss

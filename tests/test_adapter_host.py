@@ -58,3 +58,4 @@ def test_forward_without_active_adapter_raises_like_reference():
     ad = Adapter(NAMES, "cpu")
     with pytest.raises((AttributeError, FeddatError)):
         ad(torch.zeros(1, 1, 768), torch.zeros(1, 1, 768))
+

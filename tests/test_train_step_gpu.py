@@ -146,3 +146,41 @@ def test_graphed_train_step_equals_eager():
     for (n1, p1), (_, p2) in zip(m1.named_parameters(), m2.named_parameters()):
         if "adapter_0" in n1 or "adapter_1" in n1 or "task_layer" in n1:
             assert torch.allclose(p1, p2, rtol=2e-2, atol=2e-5), n1
+
+
+def test_adapter_forward_sees_every_kind_of_parameter_update():
+    """Regression: the packed bf16 operands must follow the fp32 masters through updates that do NOT
+    bump Tensor._version -- fused AdamW and the reference's ``state_dict()[k].data.copy_`` idiom."""
+    from feddat_b200.modeling.adapter import Adapter
+
+    def ref(a, name, x):
+        d, u = getattr(a, f"{name}_down"), getattr(a, f"{name}_up")
+        bf = lambda t: t.detach().to(torch.bfloat16).float()                     # noqa: E731
+        h = torch.relu(x.float() @ bf(d.weight).T + d.bias.detach()).to(torch.bfloat16).float()
+        return x.float() + h @ bf(u.weight).T + u.bias.detach()
+
+    torch.manual_seed(3)
+    a = Adapter(names=["adapter_0", "adapter_1", "adapter_2"], device="cuda", rank=32)
+    for p in a.parameters():
+        p.data.normal_(0, 0.05)
+    a.set_active_adapter("adapter_1")
+    x = torch.randn(300, 768, device="cuda").to(torch.bfloat16)
+    params = a._branch_params(("adapter_1",))
+    opt = torch.optim.AdamW(params, lr=5e-2, fused=True)
+
+    def check(tag):
+        y = a(x, x).float()
+        want = ref(a, "adapter_1", x)
+        err = ((y - want).abs().max() / want.abs().max()).item()
+        assert err < 1e-2, (tag, err)
+        return y
+
+    y0 = check("initial")
+    a(x, x).float().square().mean().backward()
+    opt.step()                                                                   # no _version bump
+    y1 = check("after fused AdamW step")
+    assert (y1 - y0).abs().max().item() > 1e-2                                  # the update is visible
+    sd = a.state_dict()
+    sd["adapter_1_up.weight"].data.copy_(torch.randn_like(sd["adapter_1_up.weight"]) * 0.05)
+    y2 = check("after state_dict().data.copy_")
+    assert (y2 - y1).abs().max().item() > 1e-2
