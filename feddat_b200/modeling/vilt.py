@@ -93,13 +93,22 @@ class ViltEncoderWrapper(nn.Module):
         emb = self.vilt.embeddings
         cfg = self.vilt.config
         text = emb.text_embeddings(input_ids=input_ids, token_type_ids=token_type_ids)
-        x = emb.patch_embeddings(pixel_values.to(emb.cls_token.dtype))          # (B, C, h, w)
-        b, c, h, w = x.shape
+        # patch embedding = Conv2d(3, 768, kernel 32, stride 32): non-overlapping patches, so it is ONE
+        # [B*h*w, 3072] x [3072, 768] GEMM (cuDNN's generic fprop + NCHW<->NHWC transposes took
+        # 0.86 ms per step for this 22 GFLOP product, profiles/r1_summary.md)
+        proj = emb.patch_embeddings.projection
+        ps = proj.kernel_size[0]
+        b, cin, hh, ww = pixel_values.shape
+        h, w = hh // ps, ww // ps
+        px = pixel_values.to(proj.weight.dtype)[:, :, :h * ps, :w * ps]
+        patches = px.reshape(b, cin, h, ps, w, ps).permute(0, 2, 4, 1, 3, 5).reshape(b * h * w, cin * ps * ps)
+        x = F.linear(patches, proj.weight.view(proj.out_channels, -1), proj.bias).view(b, h * w, -1)
+        c = x.shape[-1]
         pd = cfg.image_size // cfg.patch_size
         spatial = emb.position_embeddings[:, 1:, :].transpose(1, 2).view(1, c, pd, pd)
         if (h, w) != (pd, pd):
             spatial = F.interpolate(spatial.float(), size=(h, w), mode="bilinear", align_corners=True).to(x.dtype)
-        x = (x + spatial).flatten(2).transpose(1, 2)
+        x = x + spatial.flatten(2).transpose(1, 2)
         cls = emb.cls_token.expand(b, -1, -1) + emb.position_embeddings[:, 0, :][:, None, :]
         img = emb.dropout(torch.cat((cls, x), dim=1))
         tt = emb.token_type_embeddings.weight
