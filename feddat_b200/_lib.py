@@ -27,6 +27,7 @@ EXPORTED_SYMBOLS = (
     "feddat_debug_set_trace",
     "feddat_probe_l2bw",
     "feddat_probe_pair",
+    "feddat_probe_ingest",
 )
 
 
@@ -79,6 +80,9 @@ def load() -> ctypes.CDLL:
                                       POINTER(c_uint32), c_void_p]
     lib.feddat_probe_l2bw.restype = c_int
     lib.feddat_probe_l2bw.argtypes = [c_void_p, c_int, c_int, c_int, c_int, c_void_p]
+    lib.feddat_probe_ingest.restype = c_int
+    lib.feddat_probe_ingest.argtypes = [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p,
+                                        c_void_p]
     lib.feddat_probe_pair.restype = c_int
     lib.feddat_probe_pair.argtypes = [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p,
                                       c_void_p]

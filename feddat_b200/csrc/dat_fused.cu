@@ -8,22 +8,26 @@
 // R = r_total.  Persistent CTA PAIRS (cluster of 2, tcgen05 cta_group::2): a pair walks 256-row
 // super-tiles, each CTA owning 128 rows (its X chunks, its TMEM accumulators, its epilogues, its
 // output) and HALF of every weight tile -- the pair's tensor cores read both halves, so each SM
-// ingests only half the weight bytes (L2->SM traffic is what bounds this kernel: measured 8.95 TB/s
-// chip-wide, scripts/l2bw.py).  12 warps per CTA, every hand-off an mbarrier:
+// ingests only half the weight bytes.  12 warps per CTA, every hand-off an mbarrier:
 //
-//   warp 0      TMA producer: one ring of uniform 16 KB slots carries, in consumption order, the X
-//               k-chunks [128 x 64], the Wd_cat k-chunks (one or two 128-row boxes) and the Wu_cat
-//               [128 x 64] tiles; it runs ahead across tiles as far as the ring allows
-//   warp 1      tcgen05.mma issuer (leader CTA of the pair only; M = 256 across the pair).  GEMM1 P = X Wd^T (SS, K-major SW128 smem operands) into TMEM
-//               columns [0, R); GEMM2 in six 128-column chunks, A operand = the hidden tile IN TMEM
-//               (bf16 pairs packed over P's own columns, "TS" MMA), accumulators in a two-buffer
-//               ring in TMEM columns [256, 512)
-//   warp 2      residual producer: TMA loads of the residual [128 x 64] chunks into the staging ring
-//   warp 3      store issuer: TMA stores of finished staging buffers, recycles them
-//   warps 4-7   epilogue group A: (1) P -> +bias, act -> bf16 pairs -> tcgen05.st over P's columns
-//               (the hidden never leaves the SM); (2) even output chunks
-//   warps 8-11  epilogue group B: odd output chunks.  An output chunk = tcgen05.ld, scale, +bias,
-//               +residual (from the staging buffer), bf16 back into the same staging buffer
+//   ring        NS = 4 stages of 32 KB.  GEMM1 stage kc = [X k-chunk 128 x 64 | Wd_cat half k-chunk
+//               R/2 x 64]; GEMM2 stage c = this CTA's half [64 x R] of the Wu_cat tile of output chunk c
+//               (one 3-D TMA box when R % 64 == 0).  Producers run ahead across tiles.
+//   warp 0      ring producers: lane 0 issues the activation TMA (X, and dY in backward), lane 1 the
+//               weight TMA of every GEMM1 stage and the GEMM2 tiles, in one converged loop
+//               (a single issuing thread sustains one TMA per ~170 ns, scripts/ingest_probe.py: the
+//               v3 kernel's one-thread / 16 KB-slot ring capped the SM at 62 GB/s of a possible 130+)
+//   warp 1      tcgen05.mma issuer (leader CTA of the pair only; M = 256 across the pair).  GEMM1
+//               P = X Wd^T (SS, K-major SW128 smem operands) into TMEM columns [0, R); GEMM2 in six
+//               128-column chunks, A operand = the hidden tile IN TMEM (bf16 pairs packed over P's own
+//               columns, "TS" MMA), accumulators in a two-buffer ring in TMEM columns [256, 512)
+//   warp 3      residual producer: TMA loads of the residual [128 x 64] chunks into the staging ring
+//   warp 2      store issuer: TMA stores of finished staging buffers, recycles them
+//   warps 4-7   epilogue group A, warps 8-11 group B.  (1) each group packs HALF of P's columns ->
+//               +bias, act -> bf16 pairs -> tcgen05.st over its own half of P (the hidden never leaves
+//               the SM); (2) group A drains even output chunks, group B odd ones: tcgen05.ld, scale,
+//               +bias, +residual (from the staging buffer), bf16 back into the same staging buffer.
+//               One elected lane per warp signals each barrier.
 //
 // HBM traffic per row: read X (1536 B) + write Y (1536 B); the residual re-read and all weights hit L2.
 //
@@ -48,16 +52,18 @@ constexpr int BM = 128;
 constexpr int BK = 64;
 constexpr int KC1 = kD / BK;          // 12 k-chunks for GEMM1
 constexpr int SLOT = BM * 128;        // 16 KB: [128 rows x 64 bf16], 128-byte swizzle
+constexpr int STAGE = 2 * SLOT;       // 32 KB ring stage
 constexpr int N2 = 128;               // GEMM2 / GEMM3 output chunk width
 constexpr int NC2 = kD / N2;          // 6 chunks
-constexpr int MAX_SLOTS = 12;
-constexpr int MAX_STG = 8;
+constexpr int NS = 4;                 // ring stages (power of two)
+constexpr int NSTG = 5;               // 16 KB residual-in / output staging buffers
 constexpr int NUM_THREADS = 384;
+constexpr uint32_t W2_KB_BYTES = (N2 / 2) * 128u;  // one k-block [64 rows x 64] of a half W2 tile
 constexpr uint32_t TM_P = 0;          // TMEM column of P (and of the packed hidden aliasing it)
 constexpr uint32_t TM_D = 256;        // TMEM column of the output ring (and of dH in backward)
 
 struct FusedParams {
-  int M, R, num_tiles, n_slots, n_stg, act;
+  int M, R, num_tiles, w2_3d, act;
   float scale;
   const float* bd;
   const float* bu;        // fwd only
@@ -96,44 +102,51 @@ __device__ __forceinline__ float act_grad(float x) {
 //   tmRes [M, 768]       residual input               dY  (GEMM1b A operand and the optional +dY)
 //   tmY   [M, 768]       Y                            dX
 //   tmWd  [R, 768]       Wd_cat                       Wd_cat
-//   tmW2  [768, R]       Wu_cat                       WdT_cat
+//   tmW2  [768, R]       Wu_cat                       WdT_cat      (2-D, one [64 x 64] k-block per box)
+//   tmW2k [768, R]       the same tensor as a 3-D (64, 768, R/64) view: box = all k-blocks of 64 rows
 //   tmW1b [R, 768]       (unused)                     WuT_cat
 template <bool kBwd, bool kGelu>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 dat_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmRes,
                  const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmWd,
-                 const __grid_constant__ CUtensorMap tmW2, const __grid_constant__ CUtensorMap tmW1b,
-                 const FusedParams p) {
+                 const __grid_constant__ CUtensorMap tmW2, const __grid_constant__ CUtensorMap tmW2k,
+                 const __grid_constant__ CUtensorMap tmW1b, const FusedParams p) {
   extern __shared__ uint8_t smem_raw[];
-  // barriers: slot full/empty, P full, dH full, hidden full, D full/empty x2, staging res/out/empty
-  __shared__ __align__(8) uint64_t bars[2 * MAX_SLOTS + 3 + 4 + 3 * MAX_STG];
+  // barriers: stage full/empty, P full, dH full, hidden full, D full/empty x2, staging res/out/empty
+  __shared__ __align__(8) uint64_t bars[2 * NS + 3 + 4 + 3 * NSTG];
   __shared__ uint32_t tmem_base_smem;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int R = p.R, NS = p.n_slots, NSTG = p.n_stg;
+  const int R = p.R;
   const int KC2 = (R + 63) / 64;
   const int nc2 = (kBwd && !p.has_out) ? 0 : NC2;
   const uint32_t rank = cluster_ctarank();            // 0 = leader of the CTA pair
   const int RH = R / 2;                               // rows of a Wd / WuT k-chunk this CTA holds
   const uint32_t w_half_bytes = static_cast<uint32_t>(RH) * 128u;
-  constexpr uint32_t W2_HALF_BYTES = (N2 / 2) * 128u;  // 64 rows of a Wu / WdT tile
+  // epilogue 1 is split between the two epilogue groups by 16-column chunks of P: group A packs
+  // chunks [0, nA), group B chunks [nA, n16).  Each packs IN PLACE over its own columns, so the
+  // hidden's k-step k (16 bottleneck units = 8 packed columns) sits at hidden_col(k)
+  const int n16 = R / 16, nA = (n16 + 1) / 2;
+  auto hidden_col = [&](int k) -> uint32_t {
+    return TM_P + static_cast<uint32_t>(k < nA ? 8 * k : 16 * nA + 8 * (k - nA));
+  };
 
   const uint32_t smem0 = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t stg_base = smem0 + NS * SLOT;
+  const uint32_t stg_base = smem0 + NS * STAGE;
   const uint32_t bias_base = stg_base + NSTG * SLOT;
   float* bias_smem = reinterpret_cast<float*>(smem_raw + (bias_base - smem_u32(smem_raw)));
 
   const uint32_t bar0 = smem_u32(bars);
-  auto bar_slot_full = [&](int s) { return bar0 + 8u * s; };
-  auto bar_slot_empty = [&](int s) { return bar0 + 8u * (MAX_SLOTS + s); };
-  const uint32_t bar_p_full = bar0 + 8u * (2 * MAX_SLOTS);
-  const uint32_t bar_g_full = bar0 + 8u * (2 * MAX_SLOTS + 1);
-  const uint32_t bar_h_full = bar0 + 8u * (2 * MAX_SLOTS + 2);
-  auto bar_d_full = [&](int b) { return bar0 + 8u * (2 * MAX_SLOTS + 3 + b); };
-  auto bar_d_empty = [&](int b) { return bar0 + 8u * (2 * MAX_SLOTS + 5 + b); };
-  auto bar_res_full = [&](int b) { return bar0 + 8u * (2 * MAX_SLOTS + 7 + b); };
-  auto bar_out_full = [&](int b) { return bar0 + 8u * (2 * MAX_SLOTS + 7 + MAX_STG + b); };
-  auto bar_stg_empty = [&](int b) { return bar0 + 8u * (2 * MAX_SLOTS + 7 + 2 * MAX_STG + b); };
+  auto bar_slot_full = [&](uint32_t s) { return bar0 + 8u * s; };
+  auto bar_slot_empty = [&](uint32_t s) { return bar0 + 8u * (NS + s); };
+  const uint32_t bar_p_full = bar0 + 8u * (2 * NS);
+  const uint32_t bar_g_full = bar0 + 8u * (2 * NS + 1);
+  const uint32_t bar_h_full = bar0 + 8u * (2 * NS + 2);
+  auto bar_d_full = [&](int b) { return bar0 + 8u * (2 * NS + 3 + b); };
+  auto bar_d_empty = [&](int b) { return bar0 + 8u * (2 * NS + 5 + b); };
+  auto bar_res_full = [&](uint32_t b) { return bar0 + 8u * (2 * NS + 7 + b); };
+  auto bar_out_full = [&](uint32_t b) { return bar0 + 8u * (2 * NS + 7 + NSTG + b); };
+  auto bar_stg_empty = [&](uint32_t b) { return bar0 + 8u * (2 * NS + 7 + 2 * NSTG + b); };
 
   if (tid == 0) {
     for (int s = 0; s < NS; ++s) {
@@ -142,14 +155,14 @@ dat_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
     }
     mbar_init(bar_p_full, 1);
     mbar_init(bar_g_full, 1);
-    mbar_init(bar_h_full, 256);          // both CTAs' epilogue-1 threads arrive at the leader
+    mbar_init(bar_h_full, 16);           // one lane of each of the 8 epilogue warps, both CTAs
     for (int b = 0; b < 2; ++b) {
       mbar_init(bar_d_full(b), 1);
-      mbar_init(bar_d_empty(b), 256);    // both CTAs' epilogue-2 threads arrive at the leader
+      mbar_init(bar_d_empty(b), 8);      // the 4 warps of the group that drains buffer b, both CTAs
     }
     for (int b = 0; b < NSTG; ++b) {
       mbar_init(bar_res_full(b), 1);
-      mbar_init(bar_out_full(b), 128);
+      mbar_init(bar_out_full(b), 4);     // the 4 warps of one epilogue group
       mbar_init(bar_stg_empty(b), 1);
     }
     fence_mbar_init();
@@ -158,6 +171,7 @@ dat_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
     tma_prefetch_desc(&tmY);
     tma_prefetch_desc(&tmWd);
     tma_prefetch_desc(&tmW2);
+    tma_prefetch_desc(&tmW2k);
     if (kBwd) tma_prefetch_desc(&tmW1b);
   }
   if (warp == 2) tmem_alloc_pair(smem_u32(&tmem_base_smem), 512);
@@ -172,49 +186,65 @@ dat_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
   const int num_pairs = (p.num_tiles + 1) / 2, pair0 = blockIdx.x >> 1, pair_stride = gridDim.x >> 1;
   const int my_tiles = (num_pairs - pair0 + pair_stride - 1) / pair_stride;   // super-tiles of this pair
   const uint32_t total_chunks = static_cast<uint32_t>(my_tiles) * nc2 * 2;    // 64-column staging chunks
+  constexpr int G1_STAGES = KC1 * (kBwd ? 2 : 1);
   // this CTA's tile of super-tile `it`: may lie beyond the tensor (odd tile count) -- TMA then
   // zero-fills the loads and clips the stores, so no role needs a special case
   auto tile_of = [&](int it) { return 2 * (pair0 + it * pair_stride) + static_cast<int>(rank); };
+  // every TMA of the pair credits its bytes to the LEADER's stage barrier
+  const uint32_t leader_full0 = mapa_u32(bar_slot_full(0), 0);
 
   if (warp == 0) {
-    // ------------------------------------------------------------------ ring producer
-    if (lane == 0) {
-      uint32_t n = 0;  // slots issued so far
-      // the leader's "full" barrier collects the bytes of BOTH CTAs' loads for a slot
-      auto acquire = [&](uint32_t bytes) -> uint32_t {
-        const uint32_t s = n % NS, par = (n / NS) & 1;
-        mbar_wait(bar_slot_empty(s), par ^ 1);
-        if (rank == 0) mbar_arrive_expect_tx(bar_slot_full(s), 2 * bytes);
-        ++n;
-        return s;
-      };
+    // ------------------------------------------------------------------ ring producers
+    // lane 0 = activations (X, dY), lane 1 = weights: the SAME loop, so the warp stays converged;
+    // each lane issues its own TMA (a lone thread sustains only one TMA per ~170 ns)
+    if (lane < 2) {
+      uint32_t n = 0;  // ring stages consumed so far (all roles count the same sequence)
       for (int it = 0; it < my_tiles; ++it) {
         const uint32_t tile_it = it;
         const int m0 = tile_of(it) * BM;
-        FD_TRACE(110, tile_it);
+        if (lane == 0) FD_TRACE(110, tile_it);
         for (int pass = 0; pass < (kBwd ? 2 : 1); ++pass) {
-          const CUtensorMap* ta = pass == 0 ? &tmX : &tmRes;
-          const CUtensorMap* tw = pass == 0 ? &tmWd : &tmW1b;
-          for (int kc = 0; kc < KC1; ++kc) {
-            uint32_t s = acquire(SLOT);
-            tma_load_2d_pair(smem0 + s * SLOT, ta, mapa_u32(bar_slot_full(s), 0), kc * BK, m0,
-                             kEvictNormal);
-            s = acquire(w_half_bytes);
-            tma_load_2d_pair(smem0 + s * SLOT, tw, mapa_u32(bar_slot_full(s), 0), kc * BK,
-                             static_cast<int>(rank) * RH, kEvictLast);
+          const CUtensorMap* tm = lane == 0 ? (pass == 0 ? &tmX : &tmRes) : (pass == 0 ? &tmWd : &tmW1b);
+          const int c1 = lane == 0 ? m0 : static_cast<int>(rank) * RH;
+          const uint64_t pol = lane == 0 ? kEvictNormal : kEvictLast;
+          for (int kc = 0; kc < KC1; ++kc, ++n) {
+            const uint32_t s = n & (NS - 1), par = (n / NS) & 1;
+            mbar_wait(bar_slot_empty(s), par ^ 1);
+            // the leader's "full" barrier collects the bytes of BOTH CTAs' loads (X and W) for a
+            // stage.  Lane 1's bytes may land before lane 0's expect_tx: the phase cannot complete
+            // before that arrival, and a transiently negative tx-count is legal.
+            if (lane == 0 && rank == 0) mbar_arrive_expect_tx(bar_slot_full(s), 2 * (SLOT + w_half_bytes));
+            tma_load_2d_pair(smem0 + s * STAGE + lane * SLOT, tm, leader_full0 + 8u * s, kc * BK, c1, pol);
           }
         }
-        FD_TRACE(111, tile_it);
-        for (int c = 0; c < nc2; ++c)
-          for (int kc = 0; kc < KC2; kc += 2) {   // two 8 KB half tiles share one 16 KB slot
-            const int nk = min(2, KC2 - kc);
-            const uint32_t s = acquire(W2_HALF_BYTES * nk);
-            for (int j = 0; j < nk; ++j)
-              tma_load_2d_pair(smem0 + s * SLOT + j * W2_HALF_BYTES, &tmW2,
-                               mapa_u32(bar_slot_full(s), 0), (kc + j) * BK,
-                               c * N2 + static_cast<int>(rank) * (N2 / 2), kEvictLast);
+        if (lane == 0) FD_TRACE(111, tile_it);
+        // Next tile's activations -> L2 now, so that its GEMM1 streams from L2 instead of waiting on
+        // HBM in lock-step with every other SM
+        if (lane == 0 && it + 1 < my_tiles) {
+          const int m1 = tile_of(it + 1) * BM;
+          for (int kc = 0; kc < KC1; ++kc) {
+            tma_prefetch_l2_2d(&tmX, kc * BK, m1);
+            if (kBwd) tma_prefetch_l2_2d(&tmRes, kc * BK, m1);
           }
-        FD_TRACE(112, tile_it);
+        }
+        // GEMM2 stages: this CTA's half [64 x R] of the W2 tile of output chunk c (lane 1); lane 0
+        // waits along (a parity wait is only meaningful within one lap of the ring)
+        for (int c = 0; c < nc2; ++c, ++n) {
+          const uint32_t s = n & (NS - 1), par = (n / NS) & 1;
+          mbar_wait(bar_slot_empty(s), par ^ 1);
+          if (lane == 1) {
+            if (rank == 0) mbar_arrive_expect_tx(bar_slot_full(s), 2 * KC2 * W2_KB_BYTES);
+            const int row0 = c * N2 + static_cast<int>(rank) * (N2 / 2);
+            if (p.w2_3d) {   // all k-blocks of the half tile in one box
+              tma_load_3d_pair(smem0 + s * STAGE, &tmW2k, leader_full0 + 8u * s, 0, row0, 0, kEvictLast);
+            } else {
+              for (int kb = 0; kb < KC2; ++kb)
+                tma_load_2d_pair(smem0 + s * STAGE + kb * W2_KB_BYTES, &tmW2, leader_full0 + 8u * s,
+                                 kb * BK, row0, kEvictLast);
+            }
+          }
+        }
+        if (lane == 1) FD_TRACE(112, tile_it);
       }
     }
     __syncwarp();
@@ -225,104 +255,104 @@ dat_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
       uint32_t de[2] = {0, 0};  // uses of each D buffer so far (parity of its "empty" barrier)
       const uint32_t idesc1 = make_idesc_bf16(2 * BM, R);
       const uint32_t idesc2 = make_idesc_bf16(2 * BM, N2);
-      auto wait_slot = [&]() -> uint32_t {
-        const uint32_t s = n % NS, par = (n / NS) & 1;
-        mbar_wait(bar_slot_full(s), par);
-        ++n;
-        return s;
-      };
       for (int it = 0; it < my_tiles; ++it) {
         const uint32_t tile_it = it;
         for (int pass = 0; pass < (kBwd ? 2 : 1); ++pass) {
           // pass 0: P = X Wd_cat^T -> [TM_P, +R);  pass 1 (bwd): dH = dY Wu_cat -> [TM_D, +R)
           const uint32_t d_tmem = tmem + (pass == 0 ? TM_P : TM_D);
-          if (pass == 1) {  // dH overlays the output ring: both buffers must have been drained
-            for (int b = 0; b < 2; ++b) {
-              mbar_wait(bar_d_empty(b), (de[b] & 1) ^ 1);
-              ++de[b];
-            }
+          if (pass == 1) {
+            // dH overlays the output ring: the previous tile's last chunks must have been drained.
+            // No new "use" is registered: dH's own readers are covered by bar_h_full below.
+            for (int b = 0; b < 2; ++b) mbar_wait(bar_d_empty(b), (de[b] & 1) ^ 1);
             tc_fence_after();
           }
-          for (int kc = 0; kc < KC1; ++kc) {
-            const uint32_t sa = wait_slot();
-            const uint32_t sb = wait_slot();
+          for (int kc = 0; kc < KC1; ++kc, ++n) {
+            const uint32_t s = n & (NS - 1), par = (n / NS) & 1;
+            mbar_wait(bar_slot_full(s), par);
             tc_fence_after();
             if (pass == 0) FD_TRACE(10 + kc, tile_it);
+            // descriptors differ only in the start-address field (bits [0,14) of addr >> 4, no
+            // carry below 256 KB): one build per stage, +2 per 32-byte k-step
+            const uint64_t adesc = desc_kmajor_sw128(smem0 + s * STAGE);
+            const uint64_t bdesc = adesc + (SLOT >> 4);
+            umma_ss_pair(d_tmem, adesc, bdesc, idesc1, kc != 0);
 #pragma unroll
-            for (int k = 0; k < 4; ++k)
-              umma_ss_pair(d_tmem, desc_kmajor_sw128(smem0 + sa * SLOT + k * 32),
-                           desc_kmajor_sw128(smem0 + sb * SLOT + k * 32), idesc1, (kc | k) != 0);
-            umma_commit_pair(bar_slot_empty(sa), 0b11);
-            umma_commit_pair(bar_slot_empty(sb), 0b11);
+            for (int k = 1; k < 4; ++k) umma_ss_pair(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc1, 1);
+            umma_commit_pair(bar_slot_empty(s), 0b11);
           }
           umma_commit_pair(pass == 0 ? bar_p_full : bar_g_full, 0b11);
           FD_TRACE(22 + pass, tile_it);
         }
-        // epilogue 1 done in BOTH CTAs: the packed hidden (dP) is in TMEM [TM_P, TM_P + R/2) and P
-        // may be overwritten by the next tile's GEMM1 (waited even when no GEMM2/3 follows)
+        // epilogue 1 done in BOTH CTAs: the packed hidden (dP) is in TMEM and P may be overwritten
+        // by the next tile's GEMM1 (waited even when no GEMM2/3 follows)
         mbar_wait(bar_h_full, tile_it & 1);
         tc_fence_after();
         FD_TRACE(24, tile_it);
-        for (int c = 0; c < nc2; ++c) {
+        for (int c = 0; c < nc2; ++c, ++n) {
           const int b = c & 1;
           mbar_wait(bar_d_empty(b), (de[b] & 1) ^ 1);
           ++de[b];
+          const uint32_t s = n & (NS - 1), par = (n / NS) & 1;
+          mbar_wait(bar_slot_full(s), par);
           tc_fence_after();
           FD_TRACE(25 + c, tile_it);
           const uint32_t d_tmem = tmem + TM_D + b * N2;
-          for (int kc = 0; kc < KC2; kc += 2) {
-            const uint32_t s = wait_slot();
-            tc_fence_after();
-            const int nk = min(2, KC2 - kc);
-            for (int j = 0; j < nk; ++j) {
-              const int ksteps = min(4, (R - (kc + j) * 64) / 16);
-              for (int k = 0; k < ksteps; ++k)
-                umma_ts_pair(d_tmem, tmem + TM_P + ((kc + j) * 4 + k) * 8,
-                             desc_kmajor_sw128(smem0 + s * SLOT + j * (N2 / 2) * 128 + k * 32),
-                             idesc2, (kc | j | k) != 0);
-            }
-            umma_commit_pair(bar_slot_empty(s), 0b11);
+          // fully unrolled and predicated: a single thread issues every MMA, and the rolled loop's
+          // address arithmetic cost ~70 ns per instruction against 33 ns of tensor time (N = 128)
+          const uint64_t bdesc = desc_kmajor_sw128(smem0 + s * STAGE);
+          const uint32_t a0 = tmem + TM_P, a_hi = static_cast<uint32_t>(8 * nA);
+#pragma unroll
+          for (int kk = 0; kk < 16; ++kk) {
+            if (kk < n16)
+              umma_ts_pair(d_tmem, a0 + 8 * kk + (kk >= nA ? a_hi : 0u),
+                           bdesc + (((kk >> 2) * W2_KB_BYTES + (kk & 3) * 32) >> 4), idesc2,
+                           kk != 0 ? 1u : 0u);
           }
+          umma_commit_pair(bar_slot_empty(s), 0b11);
           umma_commit_pair(bar_d_full(b), 0b11);
           FD_TRACE(31 + c, tile_it);
         }
       }
     }
     __syncwarp();
-  } else if (warp == 2) {
+  } else if (warp == 3) {
     // ------------------------------------------------------------------ residual producer
     if (lane == 0) {
       const uint32_t per_tile = nc2 * 2;
-      for (uint32_t g = 0; g < total_chunks; ++g) {
-        const uint32_t sb = g % NSTG, par = (g / NSTG) & 1;
-        mbar_wait(bar_stg_empty(sb), par ^ 1);
-        if (p.has_res) {
-          const int tile = tile_of(g / per_tile);
-          const int c64 = g % per_tile;
-          mbar_arrive_expect_tx(bar_res_full(sb), SLOT);
-          tma_load_2d(stg_base + sb * SLOT, &tmRes, bar_res_full(sb), c64 * 64, tile * BM);
-          if (lane == 0) FD_TRACE(90 + c64, g / per_tile);
-        } else {
-          mbar_arrive(bar_res_full(sb));
+      uint32_t g = 0;
+      for (int it = 0; it < my_tiles; ++it) {
+        const int m0 = tile_of(it) * BM;
+        for (uint32_t c64 = 0; c64 < per_tile; ++c64, ++g) {
+          const uint32_t sb = g % NSTG, par = (g / NSTG) & 1;
+          mbar_wait(bar_stg_empty(sb), par ^ 1);
+          if (p.has_res) {
+            mbar_arrive_expect_tx(bar_res_full(sb), SLOT);
+            tma_load_2d(stg_base + sb * SLOT, &tmRes, bar_res_full(sb), c64 * 64, m0);
+            FD_TRACE(90 + c64, it);
+          } else {
+            mbar_arrive(bar_res_full(sb));
+          }
         }
       }
     }
     __syncwarp();
-  } else if (warp == 3) {
+  } else if (warp == 2) {
     // ------------------------------------------------------------------ store issuer
     if (lane == 0) {
       const uint32_t per_tile = nc2 * 2;
-      for (uint32_t g = 0; g < total_chunks; ++g) {
-        const uint32_t sb = g % NSTG, par = (g / NSTG) & 1;
-        mbar_wait(bar_out_full(sb), par);
-        const int tile = tile_of(g / per_tile);
-        const int c64 = g % per_tile;
-        tma_store_2d(&tmY, stg_base + sb * SLOT, c64 * 64, tile * BM);
-        tma_store_commit();
-        FD_TRACE(104 + (c64 >> 1), g / per_tile);
-        if (g > 0) {  // the previous store has finished reading its buffer: recycle it
-          tma_store_wait_read<1>();
-          mbar_arrive(bar_stg_empty((g - 1) % NSTG));
+      uint32_t g = 0;
+      for (int it = 0; it < my_tiles; ++it) {
+        const int m0 = tile_of(it) * BM;
+        for (uint32_t c64 = 0; c64 < per_tile; ++c64, ++g) {
+          const uint32_t sb = g % NSTG, par = (g / NSTG) & 1;
+          mbar_wait(bar_out_full(sb), par);
+          tma_store_2d(&tmY, stg_base + sb * SLOT, c64 * 64, m0);
+          tma_store_commit();
+          FD_TRACE(104 + (c64 >> 1), it);
+          if (g > 0) {  // the previous store has finished reading its buffer: recycle it
+            tma_store_wait_read<1>();
+            mbar_arrive(bar_stg_empty((g - 1) % NSTG));
+          }
         }
       }
       if (total_chunks > 0) {
@@ -343,13 +373,15 @@ dat_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
     uint32_t df = 0;  // chunk fills of this group's D buffer so far
     // the MMA issuer lives in the leader CTA: "hidden ready" / "D buffer drained" go to ITS barriers
     const uint32_t leader_h_full = mapa_u32(bar_h_full, 0);
-    const uint32_t leader_d_empty[2] = {mapa_u32(bar_d_empty(0), 0), mapa_u32(bar_d_empty(1), 0)};
+    const uint32_t leader_d_empty = mapa_u32(bar_d_empty(group), 0);
+    const int c_lo = group == 0 ? 0 : nA, c_hi = group == 0 ? nA : n16;
+    const uint32_t w_base = group == 0 ? 0u : static_cast<uint32_t>(16 * nA);   // where its hidden goes
 
     for (int it = 0; it < my_tiles; ++it) {
       const uint32_t tile_it = it;
       const int m0 = tile_of(it) * BM;
-      if (group == 0) {
-        // ---------------- epilogue 1: P (and dH) -> packed bf16 hidden over P's own columns
+      {
+        // ---------------- epilogue 1: this group's half of P (and dH) -> packed bf16 hidden
         mbar_wait(bar_p_full, tile_it & 1);
         if (kBwd) mbar_wait(bar_g_full, tile_it & 1);
         tc_fence_after();
@@ -358,7 +390,7 @@ dat_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
         const uint32_t t_g = tmem + lane_addr + TM_D;
         const int grow = m0 + static_cast<int>(row);
         const int rt = p.r_hi - p.r_lo;
-        for (int c = 0; c < R / 16; ++c) {
+        for (int c = c_lo; c < c_hi; ++c) {
           uint32_t v[16], u[16], w[8];
           tmem_ld16(t_p + c * 16, v);
           if (kBwd) tmem_ld16(t_g + c * 16, u);
@@ -390,21 +422,18 @@ dat_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
               gd[1] = make_uint4(w[4], w[5], w[6], w[7]);
             }
           }
-          // columns [8c, 8c+8) were read (as fp32 P columns) in an earlier iteration: safe to reuse
-          tmem_st8(t_p + c * 8, w);
+          // the target columns lie inside a P chunk of THIS group that it has already read
+          tmem_st8(t_p + w_base + (c - c_lo) * 8, w);
         }
         tmem_st_wait();
         tc_fence_before();
-        if (kBwd) {  // dH (which overlays the output ring) is consumed
-          mbar_arrive_cluster_addr(leader_d_empty[0]);
-          mbar_arrive_cluster_addr(leader_d_empty[1]);
-        }
-        mbar_arrive_cluster_addr(leader_h_full);
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster_addr(leader_h_full);
         if (tid == 128) FD_TRACE(41, tile_it);
       }
       // ---------------- epilogue 2: this group's output chunks (c = group, group + 2, group + 4)
       for (int c = group; c < nc2; c += 2) {
-        const int b = c & 1;
+        const int b = c & 1;   // == group
         mbar_wait(bar_d_full(b), df & 1);
         ++df;
         tc_fence_after();
@@ -416,44 +445,67 @@ dat_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
           const int col0 = c * N2 + j * 64;
           const uint32_t t_src = tmem + lane_addr + TM_D + b * N2 + j * 64;
           uint32_t v0[32], v1[32];
+          const bool tr = (tid == 128) && c == 0 && j == 0;
+          if (tr) FD_TRACE(120, tile_it);
           tmem_ld32(t_src, v0);
           tmem_ld32(t_src + 32, v1);
+          if (tr) FD_TRACE(121, tile_it);
           mbar_wait(bar_res_full(sb), rpar);
+          if (tr) FD_TRACE(122, tile_it);
           tmem_ld_wait();
+          if (tr) FD_TRACE(123, tile_it);
           if (lane == 0 && q == 0) FD_TRACE(43 + 4 * c + j, tile_it);
           const uint32_t sbuf = stg_base + sb * SLOT;
           const float4* bu4 = reinterpret_cast<const float4*>(bias_smem + R + col0);
+          // Two batches of 32 columns: the four residual ld.shared of a batch are issued back to back,
+          // then the math (bias loads included) is free code for the scheduler, then the four
+          // st.shared.  (asm volatile keeps program order: interleaving load / math / store per 16-byte
+          // chunk exposed the full ld.shared latency eight times per half chunk -- 950 clk measured.)
 #pragma unroll
-          for (int c8 = 0; c8 < 8; ++c8) {
-            const uint32_t addr = sbuf + sw128_offset(row, c8);
-            uint4 rv = make_uint4(0u, 0u, 0u, 0u);
-            if (has_res) rv = ld_shared_v4(addr);
-            const uint32_t rr[4] = {rv.x, rv.y, rv.z, rv.w};
-            float bb[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-            if constexpr (!kBwd) {
-              const float4 b0 = bu4[2 * c8], b1 = bu4[2 * c8 + 1];
-              bb[0] = b0.x; bb[1] = b0.y; bb[2] = b0.z; bb[3] = b0.w;
-              bb[4] = b1.x; bb[5] = b1.y; bb[6] = b1.z; bb[7] = b1.w;
-            }
-            uint32_t o[4];
+          for (int hb = 0; hb < 2; ++hb) {
+            uint4 rv[4];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const int e = c8 * 8 + 2 * i;
-              const float a0 = __uint_as_float(e < 32 ? v0[e & 31] : v1[e & 31]);
-              const float a1 = __uint_as_float(e < 32 ? v0[(e + 1) & 31] : v1[(e + 1) & 31]);
-              const float2 r2 = unpack_bf16x2(rr[i]);
-              if constexpr (kBwd)
-                o[i] = pack_bf16x2(r2.x + a0, r2.y + a1);
-              else   // res + scale * (acc + bias)
-                o[i] = pack_bf16x2(fmaf(scale, a0 + bb[2 * i], r2.x), fmaf(scale, a1 + bb[2 * i + 1], r2.y));
+            for (int i4 = 0; i4 < 4; ++i4) {
+              rv[i4] = make_uint4(0u, 0u, 0u, 0u);
+              if (has_res) rv[i4] = ld_shared_v4(sbuf + sw128_offset(row, hb * 4 + i4));
             }
-            st_shared_v4(addr, o[0], o[1], o[2], o[3]);
+            uint32_t o[4][4];
+#pragma unroll
+            for (int i4 = 0; i4 < 4; ++i4) {
+              const uint32_t rr[4] = {rv[i4].x, rv[i4].y, rv[i4].z, rv[i4].w};
+              float bb[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+              if constexpr (!kBwd) {
+                const float4 b0 = bu4[2 * (hb * 4 + i4)], b1 = bu4[2 * (hb * 4 + i4) + 1];
+                bb[0] = b0.x; bb[1] = b0.y; bb[2] = b0.z; bb[3] = b0.w;
+                bb[4] = b1.x; bb[5] = b1.y; bb[6] = b1.z; bb[7] = b1.w;
+              }
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const int e = i4 * 8 + 2 * i;          // column inside this 32-column batch
+                const float a0 = __uint_as_float(hb == 0 ? v0[e] : v1[e]);
+                const float a1 = __uint_as_float(hb == 0 ? v0[e + 1] : v1[e + 1]);
+                const float2 r2 = unpack_bf16x2(rr[i]);
+                if constexpr (kBwd)
+                  o[i4][i] = pack_bf16x2(r2.x + a0, r2.y + a1);
+                else   // res + scale * (acc + bias)
+                  o[i4][i] = pack_bf16x2(fmaf(scale, a0 + bb[2 * i], r2.x),
+                                         fmaf(scale, a1 + bb[2 * i + 1], r2.y));
+              }
+            }
+#pragma unroll
+            for (int i4 = 0; i4 < 4; ++i4)
+              st_shared_v4(sbuf + sw128_offset(row, hb * 4 + i4), o[i4][0], o[i4][1], o[i4][2], o[i4][3]);
           }
+          if (tr) FD_TRACE(124, tile_it);
           fence_proxy_async_smem();
-          mbar_arrive(bar_out_full(sb));
+          if (tr) FD_TRACE(125, tile_it);
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar_out_full(sb));
+          if (tr) FD_TRACE(126, tile_it);
         }
         tc_fence_before();
-        mbar_arrive_cluster_addr(leader_d_empty[b]);
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster_addr(leader_d_empty);
         if (lane == 0 && q == 0) FD_TRACE(45 + 4 * c, tile_it);
       }
     }
@@ -474,21 +526,22 @@ int launch_fused(bool bwd, const void* X, const void* Res, void* Out, const void
   p.R = r_total;
   p.num_tiles = static_cast<int>((M + BM - 1) / BM);
   p.trace = g_trace;
-  p.n_slots = 7;    // 16 KB TMA ring slots (X chunks, weight half-chunks)
-  p.n_stg = 6;      // 16 KB residual-in / output staging buffers
+  p.w2_3d = (r_total % 64 == 0) ? 1 : 0;
   const size_t max_smem = 227 * 1024 - 1024;  // static smem (barriers) lives in the same budget
-  const size_t smem = 1024 + static_cast<size_t>(p.n_slots + p.n_stg) * SLOT +
+  const size_t smem = 1024 + static_cast<size_t>(NS) * STAGE + static_cast<size_t>(NSTG) * SLOT +
                       (r_total + kD) * sizeof(float);
   FD_REQUIRE(smem <= max_smem, FD_ERR_UNSUPPORTED, "%s: shared-memory budget exceeded (R=%d)", who,
              r_total);
 
-  CUtensorMap tmX, tmRes, tmY, tmWd, tmW2, tmW1b;
+  CUtensorMap tmX, tmRes, tmY, tmWd, tmW2, tmW2k, tmW1b;
   if ((rc = make_tmap_bf16_2d(&tmX, X, M, kD, kD, BM, 64))) return rc;
   if ((rc = make_tmap_bf16_2d(&tmRes, Res, M, kD, kD, BM, 64))) return rc;
   if ((rc = make_tmap_bf16_2d(&tmY, Out ? Out : X, M, kD, kD, BM, 64))) return rc;
   const uint32_t w_box_rows = r_total / 2;   // each CTA of a pair holds half of every weight tile
   if ((rc = make_tmap_bf16_2d(&tmWd, Wd_cat, r_total, kD, kD, w_box_rows, 64))) return rc;
   if ((rc = make_tmap_bf16_2d(&tmW2, W2, kD, r_total, r_total, N2 / 2, 64))) return rc;
+  tmW2k = tmW2;
+  if (p.w2_3d && (rc = make_tmap_bf16_kblocks(&tmW2k, W2, kD, r_total, r_total, N2 / 2, r_total / 64))) return rc;
   if ((rc = make_tmap_bf16_2d(&tmW1b, W1b ? W1b : Wd_cat, r_total, kD, kD, w_box_rows, 64))) return rc;
 
   int sms = 0;
@@ -497,7 +550,7 @@ int launch_fused(bool bwd, const void* X, const void* Res, void* Out, const void
   const int grid = 2 * (num_pairs < sms / 2 ? num_pairs : sms / 2);
   using KernelFn = void (*)(const CUtensorMap, const CUtensorMap, const CUtensorMap,
                             const CUtensorMap, const CUtensorMap, const CUtensorMap,
-                            const FusedParams);
+                            const CUtensorMap, const FusedParams);
   const bool gelu = p.act == FEDDAT_ACT_GELU;
   KernelFn fn = bwd ? (gelu ? dat_fused_kernel<true, true> : dat_fused_kernel<true, false>)
                     : (gelu ? dat_fused_kernel<false, true> : dat_fused_kernel<false, false>);
@@ -521,7 +574,7 @@ int launch_fused(bool bwd, const void* X, const void* Res, void* Out, const void
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  FD_CHECK_CUDA(cudaLaunchKernelEx(&cfg, fn, tmX, tmRes, tmY, tmWd, tmW2, tmW1b, p));
+  FD_CHECK_CUDA(cudaLaunchKernelEx(&cfg, fn, tmX, tmRes, tmY, tmWd, tmW2, tmW2k, tmW1b, p));
   FD_CHECK_CUDA(cudaGetLastError());
   return FD_OK;
 }

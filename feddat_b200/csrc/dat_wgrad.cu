@@ -33,7 +33,7 @@ constexpr int WG_STAGES = 3;
 constexpr int NUM_THREADS = 192;
 
 struct WgradParams {
-  int M, rt, n_splits, n_rowblocks, a_blocks;
+  int M, rt, n_splits, n_rowblocks, a_blocks, a_3d;
   int ld_dwu;
   float scale;
   float* dWu;
@@ -43,8 +43,9 @@ struct WgradParams {
 };
 
 __global__ void __launch_bounds__(NUM_THREADS, 1)
-dat_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmDY,
+dat_wgrad_kernel(const __grid_constant__ CUtensorMap tmXk, const __grid_constant__ CUtensorMap tmDYk,
                  const __grid_constant__ CUtensorMap tmH, const __grid_constant__ CUtensorMap tmDP,
+                 const __grid_constant__ CUtensorMap tmHk, const __grid_constant__ CUtensorMap tmDPk,
                  const WgradParams p) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bars[2 * WG_STAGES + 1];
@@ -66,10 +67,12 @@ dat_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
     }
     mbar_init(bar_acc, 1);
     fence_mbar_init();
-    tma_prefetch_desc(&tmX);
-    tma_prefetch_desc(&tmDY);
+    tma_prefetch_desc(&tmXk);
+    tma_prefetch_desc(&tmDYk);
     tma_prefetch_desc(&tmH);
     tma_prefetch_desc(&tmDP);
+    tma_prefetch_desc(&tmHk);
+    tma_prefetch_desc(&tmDPk);
   }
   if (warp == 1) tmem_alloc(smem_u32(&tmem_base_smem), 256);
   tc_fence_before();
@@ -79,21 +82,28 @@ dat_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
   const int ablk = p.a_blocks;  // 1 when r_t <= 64 (second 64-column block of H/dP never loaded)
 
   if (warp == 0) {
-    if (lane == 0) {
+    // four producer lanes, one operand each (H_t, dP_t, dY, X): a lone thread sustains one TMA per
+    // ~170 ns (scripts/ingest_probe.py), and a stage used to be eight 8 KB boxes issued by one thread.
+    // dY / X (and H_t / dP_t when r_t % 64 == 0) arrive as ONE 3-D box covering both 64-column blocks.
+    if (lane < 4) {
       int stage = 0;
       uint32_t phase = 0;
       for (int rb = split; rb < p.n_rowblocks; rb += p.n_splits) {
         const int m0 = rb * KB;
         mbar_wait(bar_empty(stage), phase ^ 1);
-        const uint32_t base = smem0 + stage * STAGE;
-        mbar_arrive_expect_tx(bar_full(stage), 2 * ablk * BLK + 2 * OPER);
-        for (int b = 0; b < ablk; ++b) {
-          tma_load_2d(base + b * BLK, &tmH, bar_full(stage), b * 64, m0);
-          tma_load_2d(base + OPER + b * BLK, &tmDP, bar_full(stage), b * 64, m0);
-        }
-        for (int b = 0; b < 2; ++b) {
-          tma_load_2d(base + 2 * OPER + b * BLK, &tmDY, bar_full(stage), col0 + b * 64, m0);
-          tma_load_2d(base + 3 * OPER + b * BLK, &tmX, bar_full(stage), col0 + b * 64, m0);
+        const uint32_t dst = smem0 + stage * STAGE + lane * OPER;
+        // lanes 1-3 may complete bytes before lane 0's expect_tx: the phase cannot close before lane
+        // 0's arrival, and a transiently negative tx-count is legal
+        if (lane == 0) mbar_arrive_expect_tx(bar_full(stage), 2 * ablk * BLK + 2 * OPER);
+        if (lane < 2) {
+          if (p.a_3d) {
+            tma_load_3d(dst, lane == 0 ? &tmHk : &tmDPk, bar_full(stage), 0, m0, 0);
+          } else {
+            for (int b = 0; b < ablk; ++b)
+              tma_load_2d(dst + b * BLK, lane == 0 ? &tmH : &tmDP, bar_full(stage), b * 64, m0);
+          }
+        } else {
+          tma_load_3d(dst, lane == 2 ? &tmDYk : &tmXk, bar_full(stage), 0, m0, col0 / 64);
         }
         if (++stage == WG_STAGES) { stage = 0; phase ^= 1; }
       }
@@ -243,11 +253,18 @@ extern "C" int feddat_dat_bwd_wgrad(const void* X, const void* dY, const void* H
   if (splits < 1) splits = 1;
   p.n_splits = splits;
 
-  CUtensorMap tmX, tmDY, tmH, tmDP;
-  if ((rc = make_tmap_bf16_2d(&tmX, X, M, kD, kD, KB, 64))) return rc;
-  if ((rc = make_tmap_bf16_2d(&tmDY, dY, M, kD, kD, KB, 64))) return rc;
+  p.a_3d = (r_t % 64 == 0) ? 1 : 0;
+  CUtensorMap tmXk, tmDYk, tmH, tmDP, tmHk, tmDPk;
+  if ((rc = make_tmap_bf16_kblocks(&tmXk, X, M, kD, kD, KB, 2))) return rc;
+  if ((rc = make_tmap_bf16_kblocks(&tmDYk, dY, M, kD, kD, KB, 2))) return rc;
   if ((rc = make_tmap_bf16_2d(&tmH, H_t, M, r_t, ld_ht, KB, 64))) return rc;
   if ((rc = make_tmap_bf16_2d(&tmDP, dP_t, M, r_t, ld_ht, KB, 64))) return rc;
+  tmHk = tmH;
+  tmDPk = tmDP;
+  if (p.a_3d) {
+    if ((rc = make_tmap_bf16_kblocks(&tmHk, H_t, M, r_t, ld_ht, KB, r_t / 64))) return rc;
+    if ((rc = make_tmap_bf16_kblocks(&tmDPk, dP_t, M, r_t, ld_ht, KB, r_t / 64))) return rc;
+  }
 
   const size_t smem = 1024 + static_cast<size_t>(WG_STAGES) * STAGE;
   static bool configured[64] = {false};
@@ -259,7 +276,7 @@ extern "C" int feddat_dat_bwd_wgrad(const void* X, const void* dY, const void* H
     if (dev < 64) configured[dev] = true;
   }
   dat_wgrad_kernel<<<NCHUNK * splits, NUM_THREADS, smem, static_cast<cudaStream_t>(stream)>>>(
-      tmX, tmDY, tmH, tmDP, p);
+      tmXk, tmDYk, tmH, tmDP, tmHk, tmDPk, p);
   FD_CHECK_CUDA(cudaGetLastError());
   return FD_OK;
 }

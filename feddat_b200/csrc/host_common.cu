@@ -63,6 +63,30 @@ int make_tmap_bf16_2d(CUtensorMap* out, const void* gptr, uint64_t rows, uint64_
   return FD_OK;
 }
 
+int make_tmap_bf16_kblocks(CUtensorMap* out, const void* gptr, uint64_t rows, uint64_t cols,
+                           uint64_t row_stride_elems, uint32_t box_rows, uint32_t box_blocks) {
+  PFN_encodeTiled enc = get_encode_fn();
+  FD_REQUIRE(enc != nullptr, FD_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  FD_REQUIRE((reinterpret_cast<uintptr_t>(gptr) & 15) == 0, FD_ERR_INVALID,
+             "tensor base %p is not 16-byte aligned", gptr);
+  FD_REQUIRE(cols % 64 == 0 && cols / 64 >= 1 && cols / 64 <= 256 && (row_stride_elems * 2) % 16 == 0 &&
+                 box_rows >= 1 && box_rows <= 256 && box_blocks >= 1 && box_blocks <= cols / 64,
+             FD_ERR_INVALID, "bad k-block tensor map: cols=%llu stride=%llu box=%u rows x %u blocks",
+             (unsigned long long)cols, (unsigned long long)row_stride_elems, box_rows, box_blocks);
+  cuuint64_t gdim[3] = {64, rows, cols / 64};
+  cuuint64_t gstride[2] = {row_stride_elems * 2, 128};
+  cuuint32_t box[3] = {64, box_rows, box_blocks};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(gptr), gdim, gstride,
+                   box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  FD_REQUIRE(r == CUDA_SUCCESS, FD_ERR_CUDA,
+             "cuTensorMapEncodeTiled (3-D k-block view) failed (%d) rows=%llu cols=%llu stride=%llu",
+             (int)r, (unsigned long long)rows, (unsigned long long)cols,
+             (unsigned long long)row_stride_elems);
+  return FD_OK;
+}
+
 int device_sm_count(int* out) {
   static int cached[64] = {0};
   int dev = 0;

@@ -39,6 +39,12 @@ int set_error(int code, const char* fmt, ...);
 int make_tmap_bf16_2d(CUtensorMap* out, const void* gptr, uint64_t rows, uint64_t cols,
                       uint64_t row_stride_elems, uint32_t box_rows, uint32_t box_cols);
 
+// The same [rows, cols] tensor (cols a multiple of 64) viewed as 3-D (64, rows, cols / 64): one box =
+// [box_rows x 64] of `box_blocks` consecutive 64-column blocks, landing in smem as that many
+// consecutive 128B-swizzled [box_rows x 64] tiles -- a whole MMA operand in one TMA instruction.
+int make_tmap_bf16_kblocks(CUtensorMap* out, const void* gptr, uint64_t rows, uint64_t cols,
+                           uint64_t row_stride_elems, uint32_t box_rows, uint32_t box_blocks);
+
 int device_sm_count(int* out);
 int check_device_sm100();
 

@@ -256,6 +256,88 @@ extern "C" int feddat_probe_l2bw(const void* buf, int n_boxes, int iters, int gr
 }
 
 // ------------------------------------------------------------------------------------------------
+// Per-SM TMA ingest probe: `ns` slots of [box_rows x 64] bf16 boxes (128-byte swizzle) streamed from a
+// [n_rows, row_stride] tensor; n_prod producer threads (slot s belongs to producer s % n_prod), one
+// consumer thread that releases slots in order.  Separates "ring too shallow" (rate grows with ns)
+// from a per-SM or chip-wide bandwidth cap (rate independent of ns; per-SM rate vs grid size).
+// ------------------------------------------------------------------------------------------------
+namespace fd {
+
+__global__ void __launch_bounds__(160, 1)
+probe_ingest_kernel(const __grid_constant__ CUtensorMap tm, int n_rows, int n_colblk, int iters, int ns,
+                    int box_rows, int n_prod, long long* issue_clk) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t bars[32];
+  const uint32_t smem0 = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar0 = smem_u32(bars);
+  const uint32_t slot_bytes = static_cast<uint32_t>(box_rows) * 128u;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < ns; ++s) {
+      mbar_init(bar0 + 8 * s, 1);
+      mbar_init(bar0 + 8 * (16 + s), 1);
+    }
+    fence_mbar_init();
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_rowblk = n_rows / box_rows;
+  if (warp < n_prod && lane == 0) {
+    // all indices advance incrementally: no division on the issue path
+    int s = warp % ns;
+    uint32_t par = 0;
+    int rb = (blockIdx.x * 131 + warp * 7) % n_rowblk, cb = blockIdx.x % n_colblk;
+    long long t_issue = 0;
+    for (int i = warp; i < iters; i += n_prod) {
+      mbar_wait(bar0 + 8 * (16 + s), par ^ 1);
+      const long long c0 = clock64();
+      mbar_arrive_expect_tx(bar0 + 8 * s, slot_bytes);
+      tma_load_2d_hint(smem0 + s * slot_bytes, &tm, bar0 + 8 * s, cb * 64, rb * box_rows, kEvictLast);
+      t_issue += clock64() - c0;
+      s += n_prod;
+      if (s >= ns) { s -= ns; par ^= 1; }
+      rb += 7 * n_prod;
+      if (rb >= n_rowblk) { rb -= n_rowblk; if (++cb == n_colblk) cb = 0; }
+    }
+    if (issue_clk != nullptr && blockIdx.x == 0 && warp == 0)
+      issue_clk[0] = t_issue / ((iters + n_prod - 1) / n_prod);
+  } else if (warp == 4 && lane == 0) {
+    int cs = 0;
+    uint32_t cpar = 0;
+    for (int i = 0; i < iters; ++i) {
+      mbar_wait(bar0 + 8 * cs, cpar);
+      mbar_arrive(bar0 + 8 * (16 + cs));
+      if (++cs == ns) { cs = 0; cpar ^= 1; }
+    }
+  }
+  __syncthreads();
+}
+
+}  // namespace fd
+
+// buf: bf16 [n_rows, row_stride] row-major (row_stride a multiple of 64).
+extern "C" int feddat_probe_ingest(const void* buf, int n_rows, int row_stride, int iters, int grid,
+                                   int ns, int box_rows, int n_prod, long long* issue_clk,
+                                   void* stream) {
+  using namespace fd;
+  int rc = check_device_sm100();
+  if (rc) return rc;
+  FD_REQUIRE(ns >= 1 && ns <= 16 && n_prod >= 1 && n_prod <= 4 && ns % n_prod == 0 && box_rows >= 8 && box_rows <= 256 &&
+                 row_stride % 64 == 0 && n_rows % box_rows == 0,
+             FD_ERR_INVALID, "probe_ingest: bad arguments");
+  const size_t smem = 1024 + static_cast<size_t>(ns) * box_rows * 128;
+  FD_REQUIRE(smem <= 226 * 1024, FD_ERR_INVALID, "probe_ingest: ring does not fit in shared memory");
+  CUtensorMap tm;
+  rc = make_tmap_bf16_2d(&tm, buf, n_rows, row_stride, row_stride, box_rows, 64);
+  if (rc) return rc;
+  FD_CHECK_CUDA(cudaFuncSetAttribute(probe_ingest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     226 * 1024));
+  probe_ingest_kernel<<<grid, 160, smem, static_cast<cudaStream_t>(stream)>>>(
+      tm, n_rows, row_stride / 64, iters, ns, box_rows, n_prod, issue_clk);
+  FD_CHECK_CUDA(cudaGetLastError());
+  return FD_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
 // cta_group::2 bring-up: one CTA pair, D[256 x N] = A[256 x K] * B[N x K]^T.  Each CTA holds its
 // 128 rows of A (smem, or TMEM when a_tmem) and N/2 rows of B; the leader CTA issues the MMAs.
 // ------------------------------------------------------------------------------------------------

@@ -113,6 +113,22 @@ __device__ __forceinline__ void tma_load_2d_hint(uint32_t dst_smem, const CUtens
       "l"(policy)
       : "memory");
 }
+// box -> L2 only (no smem destination, no barrier)
+__device__ __forceinline__ void tma_prefetch_l2_2d(const CUtensorMap* tm, int c0, int c1) {
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];"
+               ::"l"(reinterpret_cast<uint64_t>(tm)), "r"(c0), "r"(c1)
+               : "memory");
+}
+// 3-D tile load for the k-block views of make_tmap_bf16_kblocks: c0 = column inside the 64-wide
+// block, c1 = row, c2 = block
+__device__ __forceinline__ void tma_load_3d(uint32_t dst_smem, const CUtensorMap* tm, uint32_t bar,
+                                            int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(dst_smem), "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* tm, uint32_t src_smem, int c0,
                                              int c1) {
   asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
@@ -349,9 +365,12 @@ __device__ __forceinline__ uint32_t mapa_u32(uint32_t local_smem_addr, uint32_t 
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_smem_addr), "r"(rank));
   return r;
 }
+// Default (.release, .cta-scope) semantics, as CUTLASS's ClusterBarrier::arrive(cta_id): the barriers
+// signalled this way order tcgen05 traffic (already fenced with tcgen05.fence::before_thread_sync),
+// not generic-proxy memory, so the cluster-scope release fence (a ~1 us ERRBAR/MEMBAR stall per
+// arrive in the v3 epilogue, profiles/r1_dat_kernels_v3) is not needed.
 __device__ __forceinline__ void mbar_arrive_cluster_addr(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr)
-               : "memory");
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 // executed by one warp in EACH CTA of the pair, same dst offset in both
 __device__ __forceinline__ void tmem_alloc_pair(uint32_t dst_smem, uint32_t ncols) {
@@ -404,6 +423,18 @@ __device__ __forceinline__ void tma_load_2d_pair(uint32_t dst_smem, const CUtens
       ".L2::cache_hint [%0], [%1, {%3, %4}], [%2], %5;"
       ::"r"(dst_smem), "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar_cluster_addr), "r"(c0),
       "r"(c1), "l"(policy)
+      : "memory");
+}
+// 3-D variant (see make_tmap_bf16_kblocks): c0 = column inside the 64-wide k-block, c1 = row,
+// c2 = k-block
+__device__ __forceinline__ void tma_load_3d_pair(uint32_t dst_smem, const CUtensorMap* tm,
+                                                 uint32_t bar_cluster_addr, int c0, int c1, int c2,
+                                                 uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+      ".L2::cache_hint [%0], [%1, {%3, %4, %5}], [%2], %6;"
+      ::"r"(dst_smem), "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar_cluster_addr), "r"(c0),
+      "r"(c1), "r"(c2), "l"(policy)
       : "memory");
 }
 }  // namespace fd

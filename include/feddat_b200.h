@@ -138,6 +138,9 @@ int feddat_probe_pair(const void* A, const void* B, float* D, int N, int K, int 
 
 /* L2 -> SM TMA streaming bandwidth probe (optionally multicast across a cluster), csrc/probe.cu. */
 int feddat_probe_l2bw(const void* buf, int n_boxes, int iters, int grid, int cluster, void* stream);
+/* Per-SM TMA ingest sweep (ring depth, box height, producer count, grid size); bring-up / profiling only. */
+int feddat_probe_ingest(const void* buf, int n_rows, int row_stride, int iters, int grid, int ns,
+                        int box_rows, int n_prod, long long* issue_clk, void* stream);
 
 /* Debug (scripts/trace_kernel.py): device buffer of 256 uint64 that receives globaltimer stamps of
  * CTA 0's pipeline events in feddat_dat_fwd / feddat_dat_bwd_dgrad; NULL disables. */

@@ -55,6 +55,9 @@ for c in range(6):
     names[104 + c] = f"store: chunk{c}.x issued"
 for k in range(12):
     names[90 + k] = f"res: load c64={k} issued"
+names.update({120: "E2 c0.0: D full seen", 121: "E2 c0.0: tmem_ld issued", 122: "E2 c0.0: residual ready",
+              123: "E2 c0.0: tmem_ld done", 124: "E2 c0.0: math + st.shared done", 125: "E2 c0.0: proxy fence done",
+              126: "E2 c0.0: arrived"})
 print(f"kernel {e0.elapsed_time(e1) * 1e3:.1f} us, R={R} M={M} {mode}")
 for tile in range(2):
     ev = [(t[tile * 128 + e] - t0, e) for e in range(128) if t[tile * 128 + e] != 0]

@@ -144,6 +144,10 @@ def test_dat_backward_matches_reference_golden(golden, ops, case):
     (64, 130, True, "gelu"),       # opt-in GELU, ragged tail (M % 128 = 2)
     (16, 1, False, "relu"),        # single row
     (256, 129, True, "relu"),
+    # persistent CTAs walking SEVERAL tiles each (ring / TMEM / staging hand-offs across tiles):
+    (256, 71117, True, "relu"),    # 12 sites batched (the steady-state bench size) + ragged tail
+    (128, 40001, False, "relu"),
+    (96, 25003, True, "relu"),     # R % 64 != 0: per-k-block 2-D weight loads
 ])
 def test_dat_fwd_bwd_full_size_vs_oracle(ops, R, M, gating, act):
     rng = np.random.default_rng(R * 7919 + M)
@@ -167,7 +171,20 @@ def test_dat_fwd_bwd_full_size_vs_oracle(ops, R, M, gating, act):
     y_or = oracle.adapter_forward(xr, rr, rb, gating, act=act)
     assert relerr(y.float().cpu().numpy(), y_or) < 6e-3
     dx_or, grads_or = oracle.adapter_backward(xr, gr, rb, gating, residual_is_input=False, act=act)
-    assert relerr(dx.float().cpu().numpy(), dx_or) < BF16_TOL
+    dx_np = dx.float().cpu().numpy()
+    # relu' is discontinuous at 0: a pre-activation within fp32 accumulation noise of 0 (a handful
+    # of the M * R units at the large sizes) may legitimately take either gate value, which moves
+    # that ROW of dX by |dH_j * Wd_j| (measured: 1 such unit at M = 40 001 already between numpy
+    # fp32 and fp64).  Rows holding such a unit are exempt from the max-norm bar; every other row,
+    # and all the (token-summed) weight gradients, keep it.
+    near = np.zeros(M, bool)
+    if act == "relu":
+        for (dw, db, _, _) in rb:
+            near |= (np.abs(xr.astype(np.float64) @ dw.T.astype(np.float64) + db) < 2e-5).any(axis=1)
+    assert near.sum() <= 8 + 4e-5 * M * R, near.sum()      # ~3x the expected count for N(0, 1.4) pre-activations
+    row_err = np.abs(dx_np - dx_or).max(axis=1) / np.abs(dx_or).max()
+    bad = np.nonzero(row_err >= BF16_TOL)[0]
+    assert set(bad.tolist()) <= set(np.nonzero(near)[0].tolist()), (bad[:10], row_err[bad[:10]], int(near.sum()))
     for got, want in zip(grads, grads_or[0]):
         assert relerr(got.cpu().numpy(), want) < 2 * BF16_TOL
 
