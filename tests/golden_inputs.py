@@ -54,3 +54,37 @@ def fedavg_inputs(meta):
     clients = [{k: rng.standard_normal(257 if "bias" in k else (16, 33)).astype(np.float32) for k in keys}
                for _ in nums]
     return keys, clients, nums
+
+
+def fill_params(module, seed):
+    """Deterministic fill of every parameter of ``module`` BY NAME (sorted), independent of the
+    construction order and of torch's RNG: adapter weights ~ N(0, .05), backbone weights ~ N(0, .02) (BERT
+    init; larger values make the frozen block amplify the operator's bf16 rounding in d_x), LayerNorm
+    weights 1 + N(0, .1), biases ~ N(0, .1) (backbone: .02).  Used identically by tests/golden/make_albef_site_golden.py (on the reference modules)
+    and by the GPU test (on this repo's modules), so the fixture need not carry 7 M weights."""
+    import zlib
+
+    import torch
+    for name, p in sorted(module.named_parameters(), key=lambda kv: kv[0]):
+        rng = np.random.default_rng([seed, zlib.crc32(name.encode())])
+        ad = "adapter" in name
+        if p.dim() == 1:
+            if "norm" in name.lower() and name.endswith("weight"):
+                v = 1.0 + rng.standard_normal(p.shape) * 0.1
+            else:
+                v = rng.standard_normal(p.shape) * (0.1 if ad else 0.02)
+        else:
+            v = rng.standard_normal(p.shape) * (0.05 if ad else 0.02)
+        with torch.no_grad():
+            p.copy_(torch.from_numpy(v.astype(np.float32)))
+
+
+def albef_site_inputs():
+    rng = np.random.default_rng(2024)
+    return {"vit_x": rng.standard_normal((2, 21, 768)).astype(np.float32),       # 42 rows: one ragged tile
+            "bert_h": rng.standard_normal((2, 13, 3072)).astype(np.float32),
+            "bert_x": rng.standard_normal((2, 13, 768)).astype(np.float32)}
+
+
+def albef_site_gout(shape):
+    return np.random.default_rng(99).standard_normal(tuple(shape)).astype(np.float32)

@@ -1,0 +1,137 @@
+"""ALBEF injection sites: this repo's ``Block`` / ``BertOutput`` with the sm_100a
+DAT operator against the golden produced by executing the reference's own vit.Block /
+xbert.BertOutput in fp32 (tests/golden/make_albef_site_golden.py).  GPU only."""
+import types
+from functools import partial
+from pathlib import Path
+
+import numpy as np
+import pytest
+import torch
+import torch.nn as nn
+
+from tests.golden_inputs import albef_site_gout, albef_site_inputs, fill_params
+
+pytestmark = pytest.mark.gpu
+NAMES = ["adapter_0", "adapter_1", "adapter_2"]
+BF16_TOL = 1e-2          # north_star: 1e-2 relative for bf16 (max-norm)
+
+
+@pytest.fixture(scope="module")
+def golden():
+    return np.load(Path(__file__).resolve().parent / "golden" / "albef_site_golden.npz")
+
+
+def relerr(a, b):
+    return float(np.abs(np.asarray(a, np.float64) - b).max() / np.abs(b).max())
+
+
+def set_mode(adapter, mode):
+    if mode == "gating":
+        adapter.activate_gating(); adapter.set_active_adapter("adapter_0")
+    else:
+        adapter.deactivate_gating(); adapter.set_active_adapter("adapter_1")
+
+
+def rb(t):
+    """bf16 rounding with a straight-through gradient."""
+    return t + (t.to(torch.bfloat16).float() - t).detach()
+
+
+def emulated_forward(self, hidden_states, input_tensor):
+    """The DAT operator in plain torch fp32 with bf16 rounding at the points where the sm_100a path
+    rounds (operands, hidden, adapter output, result, incoming gradient).  relu' is discontinuous: on
+    these small sites (26 / 42 rows) a handful of pre-activations lie within the bf16 rounding of the
+    operator's INPUT of zero, so the fp32 golden cannot discriminate gate-dependent gradients by itself;
+    this emulation shares the kernel's rounding points and therefore its gates."""
+    s = self._scale()
+    x, res = rb(hidden_states.float()), rb(input_tensor.float())
+    up = 0
+    for n in self._active_branch_names():
+        d, u = getattr(self, f"{n}_down"), getattr(self, f"{n}_up")
+        hid = rb(torch.relu(x @ rb(d.weight).t() + d.bias))
+        up = up + hid @ rb(u.weight).t() + u.bias
+    y = rb(res + rb(s * up))
+    if y.requires_grad:
+        y.register_hook(lambda g: g.to(torch.bfloat16).float())
+    return y
+
+
+def relerr_fro(a, b):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    return float(np.linalg.norm(a - b) / np.linalg.norm(b))
+
+
+def run_site(module, call):
+    out, inputs = call(module)
+    out.backward(torch.from_numpy(albef_site_gout(out.shape)).cuda())
+    res = {"out": out.detach().float().cpu().numpy()}
+    for k, t in inputs.items():
+        res[f"d_{k}"] = t.grad.float().cpu().numpy()
+    for n, p in module.named_parameters():
+        if "adapter" in n and p.grad is not None and float(p.grad.abs().max()) > 0.0:
+            res[f"grad/{n}"] = p.grad.float().cpu().numpy()
+    return res
+
+
+def check(golden, prefix, build, call):
+    import types as _t
+    ours = run_site(build(), call)
+    emul_mod = build()
+    emul_mod.adapter.forward = _t.MethodType(emulated_forward, emul_mod.adapter)
+    emul = run_site(emul_mod, call)
+    gold = {k[len(prefix) + 1:]: golden[k] for k in golden.files if k.startswith(prefix + "/")}
+    assert set(ours) == set(gold) == set(emul), (sorted(ours), sorted(gold))
+    assert sum(k.startswith("grad/") for k in ours) == 4            # one trainable branch: 4 tensors
+    for k in ours:
+        tol = 2 * BF16_TOL if k.startswith("grad/") else BF16_TOL
+        # (1) the kernels against the same arithmetic with the same rounding points: max-norm
+        assert relerr(ours[k], emul[k]) < tol, (k, relerr(ours[k], emul[k]))
+        # (2) against the reference's fp32 golden: the forward output at the max-norm bar; gradients no
+        #     further (Frobenius) than the rounding-point emulation is, plus the bar
+        if k == "out":
+            assert relerr(ours[k], gold[k]) < BF16_TOL, (k, relerr(ours[k], gold[k]))
+        else:
+            assert relerr_fro(ours[k], gold[k]) < relerr_fro(emul[k], gold[k]) + BF16_TOL, k
+
+
+@pytest.mark.parametrize("mode", ["single_adapter_1", "gating"])
+def test_vit_block_site_matches_reference(golden, mode):
+    from feddat_b200.modeling.albef_sites import Block
+    rank = int(golden["meta_rank"][0])
+
+    def build():
+        block = Block(dim=768, num_heads=12, mlp_ratio=4, qkv_bias=True, norm_layer=partial(nn.LayerNorm, eps=1e-6),
+                      adapter_config={"names": NAMES, "device": "cuda", "rank": rank}).cuda()
+        fill_params(block, seed=11)
+        set_mode(block.adapter, mode)
+        return block
+
+    def call(block):
+        x = torch.from_numpy(albef_site_inputs()["vit_x"]).cuda().requires_grad_(True)
+        return block(x), {"x": x}
+
+    check(golden, f"vit_block/{mode}", build, call)
+
+
+@pytest.mark.parametrize("mode", ["single_adapter_1", "gating"])
+def test_bert_output_site_matches_reference(golden, mode):
+    from feddat_b200.modeling.albef_sites import BertOutput
+    rank = int(golden["meta_rank"][0])
+
+    def build():
+        cfg = types.SimpleNamespace(intermediate_size=3072, hidden_size=768, layer_norm_eps=1e-12,
+                                    hidden_dropout_prob=0.0,
+                                    adapter_config={"names": NAMES, "device": "cuda", "rank": rank})
+        bout = BertOutput(cfg).cuda()
+        fill_params(bout, seed=12)
+        set_mode(bout.adapter, mode)
+        return bout
+
+    def call(bout):
+        inp = albef_site_inputs()
+        h = torch.from_numpy(inp["bert_h"]).cuda()
+        x = torch.from_numpy(inp["bert_x"]).cuda().requires_grad_(True)
+        return bout(h, x), {"x": x}
+
+    check(golden, f"bert_output/{mode}", build, call)

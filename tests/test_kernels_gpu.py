@@ -282,3 +282,23 @@ def test_fedavg_large_and_ragged(ops):
     ops.fedavg([to_dev(c) for c in cl], [1] * 8, out)
     torch.cuda.synchronize()
     assert np.array_equal(out.cpu().numpy(), oracle.get_average_net(cl, [1] * 8))
+
+
+@pytest.mark.parametrize("r,nb", [(16, 1), (48, 2), (128, 2), (256, 1), (40 * 0 + 80, 1)])
+def test_pack_weights_bit_exact(ops, r, nb):
+    """feddat_pack_weights: bf16 round-to-nearest of the stacked / side-by-side masters and their
+    transposes, bias concatenation and the summed up-bias -- bit-exact against torch."""
+    g = torch.Generator(device="cuda").manual_seed(r * 10 + nb)
+    brs = [[torch.randn(r, 768, device="cuda", generator=g) * 0.05, torch.randn(r, device="cuda", generator=g),
+            torch.randn(768, r, device="cuda", generator=g) * 0.05, torch.randn(768, device="cuda", generator=g)]
+           for _ in range(nb)]
+    pk = ops.pack_weights(brs)
+    torch.cuda.synchronize()
+    wd = torch.cat([b[0] for b in brs], dim=0).to(torch.bfloat16)
+    wu = torch.cat([b[2] for b in brs], dim=1).to(torch.bfloat16)
+    assert torch.equal(pk.wd, wd) and torch.equal(pk.wdT, wd.t().contiguous())
+    assert torch.equal(pk.wu, wu) and torch.equal(pk.wuT, wu.t().contiguous())
+    assert torch.equal(pk.bd, torch.cat([b[1] for b in brs]))
+    assert torch.equal(pk.bu, brs[0][3] + brs[1][3] if nb == 2 else brs[0][3])
+    fwd_only = ops.pack_weights(brs, need_bwd=False)
+    assert fwd_only.wdT is None and torch.equal(fwd_only.wu, wu)
