@@ -26,6 +26,8 @@ EXPORTED_SYMBOLS = (
     "feddat_probe_gemm",
     "feddat_debug_set_trace",
     "feddat_probe_l2bw",
+    "feddat_ln_fwd",
+    "feddat_ln_bwd",
     "feddat_probe_pair",
     "feddat_probe_ingest",
 )
@@ -80,6 +82,12 @@ def load() -> ctypes.CDLL:
                                       POINTER(c_uint32), c_void_p]
     lib.feddat_probe_l2bw.restype = c_int
     lib.feddat_probe_l2bw.argtypes = [c_void_p, c_int, c_int, c_int, c_int, c_void_p]
+    lib.feddat_ln_fwd.restype = c_int
+    lib.feddat_ln_fwd.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                  c_int64, c_int, c_float, c_int, c_void_p]
+    lib.feddat_ln_bwd.restype = c_int
+    lib.feddat_ln_bwd.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64,
+                                  c_int, c_int, c_void_p]
     lib.feddat_probe_ingest.restype = c_int
     lib.feddat_probe_ingest.argtypes = [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p,
                                         c_void_p]

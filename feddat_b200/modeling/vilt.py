@@ -88,6 +88,12 @@ class ViltEncoderWrapper(nn.Module):
             att = layer.attention.attention
             att.forward = types.MethodType(_sdpa_self_attention_forward, att)
 
+    def enable_fused_layernorm(self):
+        """Fused (residual add +) LayerNorm kernels for the frozen blocks (modeling/fused_ln.py)."""
+        from . import fused_ln
+        fused_ln.enable(self.vilt)
+        self.fused_layernorm = True
+
     # ------------------------------------------------------------------ dense fast path
     def _dense_embeddings(self, input_ids, token_type_ids, pixel_values):
         emb = self.vilt.embeddings
@@ -126,8 +132,8 @@ class ViltEncoderWrapper(nn.Module):
             self._embed_cache = (key, hidden, input_ids, pixel_values)
         for layer in self.vilt.encoder.layer:
             hidden = layer(hidden, None)[0]
-        hidden = self.vilt.layernorm(hidden)
-        return self.vilt.pooler(hidden)
+        # the pooler reads only the CLS row of the final LayerNorm (per-row op): normalise that row alone
+        return self.vilt.pooler(self.vilt.layernorm(hidden[:, 0:1]))
 
     def forward(self, **encodings: Dict) -> torch.FloatTensor:
         """vilt.py:115-129: returns ``pooler_output`` (batch, hidden)."""

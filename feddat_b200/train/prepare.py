@@ -62,6 +62,7 @@ def place_on_gpu(model, device="cuda"):
     model.vilt_encoder.device = torch.device(device)
     model.cast_frozen_backbone(torch.bfloat16)
     model.vilt_encoder.enable_sdpa()
+    model.vilt_encoder.enable_fused_layernorm()
     return model
 
 

@@ -128,6 +128,22 @@ int feddat_fedavg(const float* const* clients /* host array of device ptrs */,
                                         only sums the clients of one rank before the allreduce */,
                   float* out, int64_t n, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Fused (residual add +) LayerNorm over d = 768 for the frozen transformer block around each DAT
+ * site (HF ViltLayer.forward: layernorm_before / first residual + layernorm_after; the tensors the
+ * reference's Adaptered_ViltOutput.forward, src/modeling/adaptered_output.py:73-79, receives).
+ *   s = bf16(x + res) (res, sum_out both NULL: s = x), y = bf16((s - mean) rstd w + b); mean, rstd: fp32 [M]
+ *   dx = rstd (g - mean_c g - xhat mean_c(g xhat)) (+ dsum),  g = dy w,  xhat = (s - mean) rstd
+ * The affine parameters are FROZEN on this path (main.py:138-139): no weight / bias gradients.
+ * x, res, y, sum_out, dy, dsum, s, dx: [M, 768] bf16 contiguous; weight, bias: [768] bf16.
+ */
+int feddat_ln_fwd(const void* x, const void* res, const void* weight, const void* bias, void* y,
+                  void* sum_out, float* mean, float* rstd, int64_t M, int d, float eps, int dtype,
+                  void* stream);
+int feddat_ln_bwd(const void* dy, const void* dsum, const void* s, const void* weight,
+                  const float* mean, const float* rstd, void* dx, int64_t M, int d, int dtype,
+                  void* stream);
+
 /* Bring-up probe (tests only): one 128 x N x K tcgen05 GEMM, see csrc/probe.cu. */
 int feddat_probe_gemm(const void* A, const void* B, float* D, int N, int K, int a_mode,
                       int b_mode, const uint32_t* overrides, void* stream);

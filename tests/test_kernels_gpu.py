@@ -302,3 +302,30 @@ def test_pack_weights_bit_exact(ops, r, nb):
     assert torch.equal(pk.bu, brs[0][3] + brs[1][3] if nb == 2 else brs[0][3])
     fwd_only = ops.pack_weights(brs, need_bwd=False)
     assert fwd_only.wdT is None and torch.equal(fwd_only.wu, wu)
+
+
+@pytest.mark.parametrize("M,with_res", [(5920, True), (5920, False), (13, True), (1, False), (71117, True)])
+def test_fused_layernorm_matches_torch(ops, M, with_res):
+    """feddat_ln_fwd / feddat_ln_bwd (frozen affine) against torch.nn.functional.layer_norm evaluated in
+    fp32 on the same bf16 operands: y, the bf16 residual sum, the saved statistics, and dL/d(input)."""
+    g = torch.Generator(device="cuda").manual_seed(M)
+    x = (torch.randn(M, 768, device="cuda", generator=g) * 2 + 0.3).to(torch.bfloat16)
+    res = torch.randn(M, 768, device="cuda", generator=g).to(torch.bfloat16) if with_res else None
+    w = (1 + 0.2 * torch.randn(768, device="cuda", generator=g)).to(torch.bfloat16)
+    b = (0.1 * torch.randn(768, device="cuda", generator=g)).to(torch.bfloat16)
+    dy = torch.randn(M, 768, device="cuda", generator=g).to(torch.bfloat16)
+    dsum = torch.randn(M, 768, device="cuda", generator=g).to(torch.bfloat16) if with_res else None
+    eps = 1e-12
+    y, s, mean, rstd = ops.layer_norm_fwd(x, res, w, b, eps)
+    dx = ops.layer_norm_bwd(dy, dsum, s, w, mean, rstd)
+    torch.cuda.synchronize()
+    s_ref = (x.float() + res.float()).to(torch.bfloat16) if with_res else x
+    assert torch.equal(s, s_ref)                                           # bf16 sum: bit-exact
+    sf = s_ref.float().requires_grad_(True)
+    y_ref = torch.nn.functional.layer_norm(sf, (768,), w.float(), b.float(), eps)
+    y_ref.backward(dy.float())
+    dx_ref = sf.grad + (dsum.float() if with_res else 0)
+    assert relerr(mean.cpu().numpy(), s_ref.float().mean(-1).cpu().numpy()) < 1e-5
+    assert relerr(rstd.cpu().numpy(), (s_ref.float().var(-1, unbiased=False) + eps).rsqrt().cpu().numpy()) < 1e-5
+    assert relerr(y.float().cpu().numpy(), y_ref.detach().cpu().numpy()) < 4e-3       # one bf16 rounding of the result
+    assert relerr(dx.float().cpu().numpy(), dx_ref.cpu().numpy()) < 4e-3

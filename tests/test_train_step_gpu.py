@@ -188,3 +188,24 @@ def test_adapter_forward_sees_every_kind_of_parameter_update():
     sd["adapter_1_up.weight"].data.copy_(torch.randn_like(sd["adapter_1_up.weight"]) * 0.05)
     y2 = check("after state_dict().data.copy_")
     assert (y2 - y1).abs().max().item() > 1e-2
+
+
+def test_fused_layernorm_layer_equals_stock_hf_layer():
+    """fast_vilt_layer_forward (fused add + LayerNorm kernels) == the stock HF ViltLayer.forward on the
+    same bf16 layer: output and input gradient."""
+    from feddat_b200.train.prepare import default_args, place_on_gpu, prepare_model
+    torch.manual_seed(3)
+    model = prepare_model(default_args(ordered_cl_tasks=["art"], adapter_rank=32), place=False)
+    place_on_gpu(model)
+    model.activate_gating(); model.set_active_adapter("adapter_0")
+    layer = model.vilt_encoder.vilt.encoder.layer[5]
+    h0 = torch.randn(4, 37, 768, device="cuda").to(torch.bfloat16)
+    outs = []
+    for fused in (True, False):
+        h = h0.clone().requires_grad_(True)
+        y = layer(h, None)[0] if fused else type(layer).forward(layer, h, None)[0]
+        y.float().square().mean().backward()
+        outs.append((y.detach().float(), h.grad.float()))
+    (y1, g1), (y2, g2) = outs
+    assert ((y1 - y2).abs().max() / y2.abs().max()).item() < 1e-2
+    assert ((g1 - g2).abs().max() / g2.abs().max()).item() < 2e-2
