@@ -28,6 +28,8 @@ EXPORTED_SYMBOLS = (
     "feddat_probe_l2bw",
     "feddat_ln_fwd",
     "feddat_ln_bwd",
+    "feddat_gelu_fwd",
+    "feddat_gelu_bwd",
     "feddat_probe_pair",
     "feddat_probe_ingest",
 )
@@ -88,6 +90,10 @@ def load() -> ctypes.CDLL:
     lib.feddat_ln_bwd.restype = c_int
     lib.feddat_ln_bwd.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64,
                                   c_int, c_int, c_void_p]
+    lib.feddat_gelu_fwd.restype = c_int
+    lib.feddat_gelu_fwd.argtypes = [c_void_p, c_void_p, c_int64, c_int, c_void_p]
+    lib.feddat_gelu_bwd.restype = c_int
+    lib.feddat_gelu_bwd.argtypes = [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p]
     lib.feddat_probe_ingest.restype = c_int
     lib.feddat_probe_ingest.argtypes = [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p,
                                         c_void_p]

@@ -8,7 +8,7 @@ first residual connection fused:
     ln1        = LN_before(h)                         one launch
     attn       = attention(ln1)                        (HF module, SDPA)
     h2, ln2    = h + attn, LN_after(h + attn)          one launch for the add AND the LayerNorm
-    out        = output(intermediate(ln2), h2)         dense + GELU (torch), then the DAT site
+    out        = output(intermediate(ln2), h2)         dense (cuBLAS) + GELU (feddat_gelu_*), then the DAT site
 
 It applies only where the kernels are defined -- bf16 CUDA activations of width 768, frozen bf16 affine
 parameters (main.py:138-139 freezes the whole backbone), no attention mask / attention maps requested --
@@ -50,6 +50,33 @@ class _AddLayerNorm(torch.autograd.Function):
         return dx, (dx if ctx.has_res else None), None, None, None
 
 
+class _Gelu(torch.autograd.Function):
+    """Exact-erf GELU (HF ViltIntermediate's activation) through feddat_gelu_fwd / feddat_gelu_bwd."""
+
+    @staticmethod
+    def forward(ctx, x):
+        ctx.save_for_backward(x)
+        return ops.gelu_fwd(x)
+
+    @staticmethod
+    def backward(ctx, gy):
+        (x,) = ctx.saved_tensors
+        return ops.gelu_bwd(gy.contiguous(), x)
+
+
+def intermediate(mod, h: torch.Tensor) -> torch.Tensor:
+    """HF ViltIntermediate.forward: dense (cuBLAS) + GELU (this repo's streaming kernel when the module's
+    activation is the exact GELU and the tensor is CUDA bf16)."""
+    act = mod.intermediate_act_fn
+    exact_gelu = type(act).__name__ == "GELUActivation" or (isinstance(act, torch.nn.GELU) and act.approximate == "none")
+    if not exact_gelu:
+        return mod(h)
+    pre = mod.dense(h)
+    if pre.is_cuda and pre.dtype == torch.bfloat16 and pre.is_contiguous() and pre.numel() % 8 == 0:
+        return _Gelu.apply(pre)
+    return act(pre)
+
+
 def _usable(ln: torch.nn.LayerNorm, h: torch.Tensor) -> bool:
     return (h.is_cuda and h.dtype == torch.bfloat16 and h.shape[-1] == 768 and h.is_contiguous()
             and tuple(ln.normalized_shape) == (768,) and ln.weight is not None and ln.bias is not None
@@ -78,7 +105,7 @@ def fast_vilt_layer_forward(self, hidden_states, attention_mask=None, output_att
     ln1 = layer_norm(self.layernorm_before, hidden_states)
     attention_output = self.attention(ln1, None, output_attentions=False)[0]
     hidden_states, ln2 = add_layer_norm(self.layernorm_after, attention_output, hidden_states)   # first residual
-    layer_output = self.intermediate(ln2)
+    layer_output = intermediate(self.intermediate, ln2)
     layer_output = self.output(layer_output, hidden_states)                                     # second residual + DAT
     return (layer_output,)
 

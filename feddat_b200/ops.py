@@ -238,3 +238,26 @@ def layer_norm_bwd(dy: torch.Tensor, dsum: Optional[torch.Tensor], s: torch.Tens
     _lib.check(rc, "feddat_ln_bwd")
     _count()
     return dx
+
+
+def gelu_fwd(x: torch.Tensor) -> torch.Tensor:
+    """Exact-erf GELU of a contiguous CUDA bf16 tensor (feddat_gelu_fwd)."""
+    lib = _lib.load()
+    if not (x.is_cuda and x.dtype == torch.bfloat16 and x.is_contiguous() and x.numel() % 8 == 0):
+        raise _lib.FeddatError("gelu: expected a contiguous CUDA bf16 tensor with a multiple of 8 elements")
+    y = torch.empty_like(x)
+    _lib.check(lib.feddat_gelu_fwd(_lib.ptr(x), _lib.ptr(y), x.numel(), DTYPE_BF16, _lib.stream_ptr()), "feddat_gelu_fwd")
+    _count()
+    return y
+
+
+def gelu_bwd(dy: torch.Tensor, x: torch.Tensor) -> torch.Tensor:
+    lib = _lib.load()
+    for t in (dy, x):
+        if not (t.is_cuda and t.dtype == torch.bfloat16 and t.is_contiguous() and t.shape == x.shape):
+            raise _lib.FeddatError("gelu_bwd: expected contiguous CUDA bf16 tensors of one shape")
+    dx = torch.empty_like(x)
+    _lib.check(lib.feddat_gelu_bwd(_lib.ptr(dy), _lib.ptr(x), _lib.ptr(dx), x.numel(), DTYPE_BF16, _lib.stream_ptr()),
+               "feddat_gelu_bwd")
+    _count()
+    return dx

@@ -144,6 +144,11 @@ int feddat_ln_bwd(const void* dy, const void* dsum, const void* s, const void* w
                   const float* mean, const float* rstd, void* dx, int64_t M, int d, int dtype,
                   void* stream);
 
+/* Exact (erf) GELU of the frozen ViLT intermediate layer (HF ViltIntermediate), bf16 in / out, n a
+ * multiple of 8:  y = 0.5 x (1 + erf(x / sqrt 2));  dx = dy * d/dx of that. */
+int feddat_gelu_fwd(const void* x, void* y, int64_t n, int dtype, void* stream);
+int feddat_gelu_bwd(const void* dy, const void* x, void* dx, int64_t n, int dtype, void* stream);
+
 /* Bring-up probe (tests only): one 128 x N x K tcgen05 GEMM, see csrc/probe.cu. */
 int feddat_probe_gemm(const void* A, const void* B, float* D, int N, int K, int a_mode,
                       int b_mode, const uint32_t* overrides, void* stream);

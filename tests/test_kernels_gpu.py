@@ -329,3 +329,17 @@ def test_fused_layernorm_matches_torch(ops, M, with_res):
     assert relerr(rstd.cpu().numpy(), (s_ref.float().var(-1, unbiased=False) + eps).rsqrt().cpu().numpy()) < 1e-5
     assert relerr(y.float().cpu().numpy(), y_ref.detach().cpu().numpy()) < 4e-3       # one bf16 rounding of the result
     assert relerr(dx.float().cpu().numpy(), dx_ref.cpu().numpy()) < 4e-3
+
+
+@pytest.mark.parametrize("shape", [(5920, 3072), (3, 8), (1, 3072)])
+def test_gelu_matches_torch(ops, shape):
+    g = torch.Generator(device="cuda").manual_seed(shape[0])
+    x = (torch.randn(*shape, device="cuda", generator=g) * 2).to(torch.bfloat16)
+    dy = torch.randn(*shape, device="cuda", generator=g).to(torch.bfloat16)
+    y, dx = ops.gelu_fwd(x), ops.gelu_bwd(dy, x)
+    xf = x.float().requires_grad_(True)
+    y_ref = torch.nn.functional.gelu(xf)
+    y_ref.backward(dy.float())
+    assert relerr(y.float().cpu().numpy(), y_ref.detach().cpu().numpy()) < 4e-3      # one bf16 rounding
+    assert relerr(dx.float().cpu().numpy(), xf.grad.cpu().numpy()) < 4e-3
+    assert torch.equal(y, y_ref.detach().to(torch.bfloat16))                          # same fp32 formula: bit-exact
