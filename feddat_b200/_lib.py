@@ -30,6 +30,7 @@ EXPORTED_SYMBOLS = (
     "feddat_ln_bwd",
     "feddat_gelu_fwd",
     "feddat_gelu_bwd",
+    "feddat_debug_force_fused_fwd",
     "feddat_probe_pair",
     "feddat_probe_ingest",
 )
@@ -94,6 +95,8 @@ def load() -> ctypes.CDLL:
     lib.feddat_gelu_fwd.argtypes = [c_void_p, c_void_p, c_int64, c_int, c_void_p]
     lib.feddat_gelu_bwd.restype = c_int
     lib.feddat_gelu_bwd.argtypes = [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p]
+    lib.feddat_debug_force_fused_fwd.restype = c_int
+    lib.feddat_debug_force_fused_fwd.argtypes = [c_int]
     lib.feddat_probe_ingest.restype = c_int
     lib.feddat_probe_ingest.argtypes = [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p,
                                         c_void_p]

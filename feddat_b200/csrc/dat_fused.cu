@@ -39,6 +39,7 @@
 //               for the trainable slice [r_lo, r_hi) also H = act(P + bd) and dP to HBM (wgrad kernel)
 //   GEMM3  dX = dP * Wd_cat              (B operand: WdT_cat, K-major), + dY when the residual
 //               input is X itself (adaptered_output.py:78), -> bf16 -> TMA store
+#include "dat_kernels.h"
 #include "feddat_b200.h"
 #include "host_common.h"
 #include "ptx_sm100.cuh"
@@ -118,6 +119,7 @@ dat_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
   __shared__ uint32_t tmem_base_smem;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid == 0) FD_TRACE(1, 0);      // kernel entry (before barrier init / TMEM alloc / bias staging)
   const int R = p.R;
   const int KC2 = (R + 63) / 64;
   const int nc2 = (kBwd && !p.has_out) ? 0 : NC2 / p.n_split;   // output chunks THIS pair produces
@@ -540,9 +542,11 @@ dat_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
   tc_fence_before();
   cluster_sync_all();   // the partner's smem / barriers / TMEM stay valid until both CTAs are done
   if (warp == 2) tmem_dealloc_pair(tmem, 512);
+  if (tid == 64) FD_TRACE(2, 0);     // CTA exit
 }
 
-unsigned long long* g_trace = nullptr;
+
+bool g_force_fused = false;
 
 int launch_fused(bool bwd, const void* X, const void* Res, void* Out, const void* Wd_cat,
                  const void* W2, const void* W1b, FusedParams p, int64_t M, int r_total,
@@ -551,7 +555,7 @@ int launch_fused(bool bwd, const void* X, const void* Res, void* Out, const void
   p.M = static_cast<int>(M);
   p.R = r_total;
   p.num_tiles = static_cast<int>((M + BM - 1) / BM);
-  p.trace = g_trace;
+  p.trace = fd::g_trace;
   p.w2_3d = (r_total % 64 == 0) ? 1 : 0;
   const size_t max_smem = 227 * 1024 - 1024;  // static smem (barriers) lives in the same budget
   const size_t smem = 1024 + static_cast<size_t>(NS) * STAGE + static_cast<size_t>(NSTG) * SLOT +
@@ -638,6 +642,15 @@ extern "C" int feddat_dat_fwd(const void* X, const void* Res, void* Y, const voi
              "dat_fwd: null pointer argument");
   if ((rc = check_common("dat_fwd", M, d, r_total, act, dtype))) return rc;
   if (M == 0) return FD_OK;
+  {
+    // more super-tiles than CTA pairs: the tile-pipelined kernel (dat_fwd_pipe.cu)
+    int sms = 0;
+    if ((rc = device_sm_count(&sms))) return rc;
+    const int64_t num_pairs = ((M + BM - 1) / BM + 1) / 2;
+    if (num_pairs > sms / 2 && !g_force_fused)
+      return launch_dat_fwd_pipe(X, Res, Y, Wd_cat, bd_cat, Wu_cat, bu_cat, M, r_total, branch_scale, act,
+                                 2 * (sms / 2), static_cast<cudaStream_t>(stream));
+  }
   FusedParams p{};
   p.act = act;
   p.scale = branch_scale;
@@ -685,6 +698,12 @@ extern "C" int feddat_dat_bwd_dgrad(const void* X, const void* dY, void* dX, con
   p.dP_t = static_cast<__nv_bfloat16*>(dP_t);
   return launch_fused(true, X, dY, dX, Wd_cat, WdT_cat, WuT_cat, p, M, r_total,
                       static_cast<cudaStream_t>(stream), "dat_bwd_dgrad");
+}
+
+// debug / A-B measurement: route every forward through dat_fused_kernel (1) or choose by size (0)
+extern "C" int feddat_debug_force_fused_fwd(int on) {
+  fd::g_force_fused = on != 0;
+  return 0;
 }
 
 // debug: device buffer of 256 uint64 receiving CTA 0's pipeline timestamps (NULL disables)

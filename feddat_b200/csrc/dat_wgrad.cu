@@ -40,6 +40,7 @@ struct WgradParams {
   float* dbu;
   float* dWd;
   float* dbd;
+  unsigned long long* trace;   // debug timeline of CTA 0 (events 200..) or null
 };
 
 __global__ void __launch_bounds__(NUM_THREADS, 1)
@@ -52,6 +53,11 @@ dat_wgrad_kernel(const __grid_constant__ CUtensorMap tmXk, const __grid_constant
   __shared__ uint32_t tmem_base_smem;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+#define WG_TRACE(ev)                                                              \
+  do {                                                                            \
+    if (p.trace != nullptr && blockIdx.x == 0) p.trace[(ev)] = globaltimer_ns();  \
+  } while (0)
+  if (tid == 0) WG_TRACE(200);
   const int chunk = blockIdx.x % NCHUNK, split = blockIdx.x / NCHUNK;
   const int col0 = chunk * NCW;
   const uint32_t smem0 = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -79,6 +85,7 @@ dat_wgrad_kernel(const __grid_constant__ CUtensorMap tmXk, const __grid_constant
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = tmem_base_smem;
+  if (tid == 0) WG_TRACE(201);       // prologue done
   const int ablk = p.a_blocks;  // 1 when r_t <= 64 (second 64-column block of H/dP never loaded)
 
   if (warp == 0) {
@@ -133,6 +140,7 @@ dat_wgrad_kernel(const __grid_constant__ CUtensorMap tmXk, const __grid_constant
         if (++stage == WG_STAGES) { stage = 0; phase ^= 1; }
       }
       umma_commit(bar_acc);
+      WG_TRACE(202);                  // all MMAs issued
     }
     __syncwarp();
   } else {
@@ -180,6 +188,7 @@ dat_wgrad_kernel(const __grid_constant__ CUtensorMap tmXk, const __grid_constant
     if (split < p.n_rowblocks) {  // this CTA accumulated at least one row block
       mbar_wait(bar_acc, 0);
       tc_fence_after();
+      if (tid == 64) WG_TRACE(203);   // accumulators complete
       const uint32_t lane_addr = (q * 32) << 16;
       const bool valid = static_cast<int>(j) < p.rt;  // lane j = bottleneck unit j
 #pragma unroll 1
@@ -207,9 +216,11 @@ dat_wgrad_kernel(const __grid_constant__ CUtensorMap tmXk, const __grid_constant
       }
     }
   }
+  if (tid == 64) WG_TRACE(204);       // reductions issued
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem, 256);
+  if (tid == 0) WG_TRACE(205);
 }
 
 }  // namespace
@@ -246,6 +257,7 @@ extern "C" int feddat_dat_bwd_wgrad(const void* X, const void* dY, const void* H
   p.ld_dwu = ld_dwu;
   p.scale = branch_scale;
   p.dWu = dWu; p.dbu = dbu; p.dWd = dWd; p.dbd = dbd;
+  p.trace = g_trace;
   int sms = 0;
   if ((rc = device_sm_count(&sms))) return rc;
   int splits = sms / NCHUNK;

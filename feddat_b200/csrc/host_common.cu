@@ -87,6 +87,8 @@ int make_tmap_bf16_kblocks(CUtensorMap* out, const void* gptr, uint64_t rows, ui
   return FD_OK;
 }
 
+unsigned long long* g_trace = nullptr;
+
 int device_sm_count(int* out) {
   static int cached[64] = {0};
   int dev = 0;

@@ -45,6 +45,9 @@ int make_tmap_bf16_2d(CUtensorMap* out, const void* gptr, uint64_t rows, uint64_
 int make_tmap_bf16_kblocks(CUtensorMap* out, const void* gptr, uint64_t rows, uint64_t cols,
                            uint64_t row_stride_elems, uint32_t box_rows, uint32_t box_blocks);
 
+// debug: device buffer of 256 uint64 receiving pipeline timestamps of CTA 0 (NULL = off)
+extern unsigned long long* g_trace;
+
 int device_sm_count(int* out);
 int check_device_sm100();
 

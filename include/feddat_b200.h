@@ -149,6 +149,10 @@ int feddat_ln_bwd(const void* dy, const void* dsum, const void* s, const void* w
 int feddat_gelu_fwd(const void* x, void* y, int64_t n, int dtype, void* stream);
 int feddat_gelu_bwd(const void* dy, const void* x, void* dx, int64_t n, int dtype, void* stream);
 
+/* A/B measurement switch (tests / profiling): 1 = always use the single-tile forward kernel, 0 = pick the
+ * tile-pipelined forward kernel when there are more 256-row super-tiles than CTA pairs (default). */
+int feddat_debug_force_fused_fwd(int on);
+
 /* Bring-up probe (tests only): one 128 x N x K tcgen05 GEMM, see csrc/probe.cu. */
 int feddat_probe_gemm(const void* A, const void* B, float* D, int N, int K, int a_mode,
                       int b_mode, const uint32_t* overrides, void* stream);

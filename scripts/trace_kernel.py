@@ -28,7 +28,7 @@ def run():
     if mode == "fwd":
         ops.dat_forward(x, x, pk, 0.5)
     else:
-        ops.dat_backward(x, dy, pk, 0.5, train_slice=None, need_dx=True)
+        ops.dat_backward(x, dy, pk, 0.5, train_slice=(0, r) if mode == "bwdw" else None, need_dx=True)
 
 
 for _ in range(3):
@@ -40,8 +40,8 @@ e0.record(); run(); e1.record()
 torch.cuda.synchronize()
 lib.feddat_debug_set_trace(None)
 t = buf.cpu().tolist()
-t0 = t[0]
-names = {0: "start", 22: "G1 issued", 23: "G1b issued", 24: "h_full passed", 40: "epiA: P full", 41: "epiA: E1 done",
+t0 = t[1] if t[1] else t[0]
+names = {1: "kernel entry", 2: "CTA exit", 0: "start", 22: "G1 issued", 23: "G1b issued", 24: "h_full passed", 40: "epiA: P full", 41: "epiA: E1 done",
          110: "prod: tile start", 111: "prod: G1 slots issued", 112: "prod: all slots issued"}
 for k in range(12):
     names[10 + k] = f"mma: G1 kc{k} slots ready"
@@ -58,7 +58,14 @@ for k in range(12):
 names.update({120: "E2 c0.0: D full seen", 121: "E2 c0.0: tmem_ld issued", 122: "E2 c0.0: residual ready",
               123: "E2 c0.0: tmem_ld done", 124: "E2 c0.0: math + st.shared done", 125: "E2 c0.0: proxy fence done",
               126: "E2 c0.0: arrived"})
+wg = {200: "wgrad: entry", 201: "wgrad: prologue done", 202: "wgrad: all MMAs issued", 203: "wgrad: accumulators complete",
+      204: "wgrad: reductions issued", 205: "wgrad: exit"}
 print(f"kernel {e0.elapsed_time(e1) * 1e3:.1f} us, R={R} M={M} {mode}")
+if any(t[e] for e in wg):
+    w0 = t[200]
+    for e in sorted(wg):
+        print(f"wgrad {(t[e] - w0) / 1e3:9.2f} us  {wg[e]}   (dgrad entry {-(t[1] - w0) / 1e3:.2f} us earlier)" if e == 200 else
+              f"wgrad {(t[e] - w0) / 1e3:9.2f} us  {wg[e]}")
 for tile in range(2):
     ev = [(t[tile * 128 + e] - t0, e) for e in range(128) if t[tile * 128 + e] != 0]
     for dt, e in sorted(ev):
