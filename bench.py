@@ -147,11 +147,11 @@ def kernel_rooflines(peaks, device):
             fn(*sets[i % len(sets)])
         ts = []
         for i in range(iters):
-            x, dy = sets[(3 + i) % len(sets)]
+            args_i = sets[(3 + i) % len(sets)]
             torch.cuda._sleep(200_000)                      # ~100 us: the launch below is queued behind it
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-            fn(x, dy)
+            fn(*args_i)
             e1.record()
             torch.cuda.synchronize()
             ts.append(e0.elapsed_time(e1) * 1e-3)
@@ -159,15 +159,23 @@ def kernel_rooflines(peaks, device):
 
     for M in (B * 185, 12 * B * 185):
         n_sets = max(2, -(-300_000_000 // (2 * M * D * 2)))
-        sets = [(torch.randn(M, D, device=device, generator=g).to(torch.bfloat16),
-                 torch.randn(M, D, device=device, generator=g).to(torch.bfloat16)) for _ in range(n_sets)]
         pk2, pk1 = mk(RANK, 2), mk(RANK, 1)
         r = RANK
+        sets = []
+        for _ in range(n_sets):
+            x = torch.randn(M, D, device=device, generator=g).to(torch.bfloat16)
+            dy = torch.randn(M, D, device=device, generator=g).to(torch.bfloat16)
+            # the hidden the forward saves for the backward (ReLU path: no recompute in dgrad)
+            h2 = ops.dat_forward(x, x, pk2, 0.5, save_hidden=True)[1]
+            h1 = ops.dat_forward(x, x, pk1, 1.0, save_hidden=True)[1]
+            sets.append((x, dy, h2, h1))
         cases = {
-            "fwd_gating": (lambda x, dy: ops.dat_forward(x, x, pk2, 0.5), 8 * D * r * M, 4 * D * M),
-            "fwd_single": (lambda x, dy: ops.dat_forward(x, x, pk1, 1.0), 4 * D * r * M, 4 * D * M),
-            "bwd_gating": (lambda x, dy: ops.dat_backward(x, dy, pk2, 0.5, train_slice=(0, r)), 12 * D * r * M, 6 * D * M),
-            "bwd_single": (lambda x, dy: ops.dat_backward(x, dy, pk1, 1.0, train_slice=(0, r)), 8 * D * r * M, 6 * D * M),
+            "fwd_gating": (lambda x, dy, h2, h1: ops.dat_forward(x, x, pk2, 0.5, save_hidden=True), 8 * D * r * M, 4 * D * M),
+            "fwd_single": (lambda x, dy, h2, h1: ops.dat_forward(x, x, pk1, 1.0, save_hidden=True), 4 * D * r * M, 4 * D * M),
+            "bwd_gating": (lambda x, dy, h2, h1: ops.dat_backward(x, dy, pk2, 0.5, train_slice=(0, r), hidden=h2),
+                           12 * D * r * M, 6 * D * M),
+            "bwd_single": (lambda x, dy, h2, h1: ops.dat_backward(x, dy, pk1, 1.0, train_slice=(0, r), hidden=h1),
+                           8 * D * r * M, 6 * D * M),
         }
         for name, (fn, flops, nbytes) in cases.items():
             t = timeit(fn, sets)

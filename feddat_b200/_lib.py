@@ -61,11 +61,11 @@ def load() -> ctypes.CDLL:
 
     lib.feddat_dat_fwd.restype = c_int
     lib.feddat_dat_fwd.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
-                                   c_void_p, c_int64, c_int, c_int, c_float, c_int, c_int, c_void_p]
+                                   c_void_p, c_void_p, c_int64, c_int, c_int, c_float, c_int, c_int, c_void_p]
     lib.feddat_dat_bwd_dgrad.restype = c_int
     lib.feddat_dat_bwd_dgrad.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
-                                         c_void_p, c_void_p, c_void_p, c_int, c_int, c_int64, c_int,
-                                         c_int, c_float, c_int, c_int, c_int, c_void_p]
+                                         c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int64,
+                                         c_int, c_int, c_float, c_int, c_int, c_int, c_void_p]
     lib.feddat_dat_bwd_wgrad.restype = c_int
     lib.feddat_dat_bwd_wgrad.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                          c_void_p, c_void_p, c_int64, c_int, c_int, c_int, c_int,

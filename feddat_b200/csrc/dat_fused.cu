@@ -73,8 +73,11 @@ struct FusedParams {
   int has_out;            // 0: dX not requested (skip GEMM3 / epilogue 2)
   int has_res;            // add the residual tile (fwd: always; bwd: add_dy)
   int r_lo, r_hi;         // trainable slice of the bottleneck
-  __nv_bfloat16* H_t;     // [M, r_hi - r_lo] or null
-  __nv_bfloat16* dP_t;    // [M, r_hi - r_lo] or null
+  __nv_bfloat16* H_t;     // bwd, recompute mode: hidden of the trainable slice (row stride ld_t) or null
+  __nv_bfloat16* dP_t;    // bwd: pre-activation gradient of the trainable slice (row stride ld_t) or null
+  int ld_t;               // row stride (elements) of H_t / dP_t
+  const __nv_bfloat16* H_in;   // bwd, saved mode: the forward's hidden [M, R] (no P recompute)
+  __nv_bfloat16* H_out;        // fwd: where to save the hidden [M, R] for such a backward, or null
   unsigned long long* trace;  // debug: globaltimer stamps of CTA 0's pipeline events (or null)
 };
 
@@ -107,7 +110,9 @@ __device__ __forceinline__ float act_grad(float x) {
 //   tmW2  [768, R]       Wu_cat                       WdT_cat      (2-D, one [64 x 64] k-block per box)
 //   tmW2k [768, R]       the same tensor as a 3-D (64, 768, R/64) view: box = all k-blocks of 64 rows
 //   tmW1b [R, 768]       (unused)                     WuT_cat
-template <bool kBwd, bool kGelu>
+// kSaved (backward, ReLU only): the hidden saved by the forward replaces the recompute of P -- no X
+// read, no GEMM1 pass 0; relu'(P) is read off the saved hidden (H > 0).
+template <bool kBwd, bool kGelu, bool kSaved = false>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 dat_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmRes,
                  const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmWd,
@@ -179,7 +184,8 @@ dat_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
   }
   if (warp == 2) tmem_alloc_pair(smem_u32(&tmem_base_smem), 512);
   // biases in smem: bd as is; bu PRE-SCALED by the branch scale (epilogue 2 is one FFMA per element)
-  for (int i = tid; i < R; i += NUM_THREADS) bias_smem[i] = p.bd[i];
+  if (!kSaved)
+    for (int i = tid; i < R; i += NUM_THREADS) bias_smem[i] = p.bd[i];
   if (!kBwd)
     for (int i = tid; i < kD; i += NUM_THREADS) bias_smem[R + i] = p.scale * p.bu[i];
   tc_fence_before();
@@ -213,7 +219,7 @@ dat_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
         const uint32_t tile_it = it;
         const int m0 = tile_of(it) * BM;
         if (lane == 0) FD_TRACE(110, tile_it);
-        for (int pass = 0; pass < (kBwd ? 2 : 1); ++pass) {
+        for (int pass = kSaved ? 1 : 0; pass < (kBwd ? 2 : 1); ++pass) {
           const CUtensorMap* tm = lane == 0 ? (pass == 0 ? &tmX : &tmRes) : (pass == 0 ? &tmWd : &tmW1b);
           const int c1 = lane == 0 ? m0 : static_cast<int>(rank) * RH;
           const uint64_t pol = lane == 0 ? kEvictNormal : kEvictLast;
@@ -233,7 +239,7 @@ dat_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
         if (lane == 0 && it + 1 < my_tiles) {
           const int m1 = tile_of(it + 1) * BM;
           for (int kc = 0; kc < KC1; ++kc) {
-            tma_prefetch_l2_2d(&tmX, kc * BK, m1);
+            if (!kSaved) tma_prefetch_l2_2d(&tmX, kc * BK, m1);
             if (kBwd) tma_prefetch_l2_2d(&tmRes, kc * BK, m1);
           }
         }
@@ -270,7 +276,7 @@ dat_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
       const uint32_t idesc2 = make_idesc_bf16(2 * BM, N2);
       for (int it = 0; it < my_tiles; ++it) {
         const uint32_t tile_it = it;
-        for (int pass = 0; pass < (kBwd ? 2 : 1); ++pass) {
+        for (int pass = kSaved ? 1 : 0; pass < (kBwd ? 2 : 1); ++pass) {
           // pass 0: P = X Wd_cat^T -> [TM_P, +R);  pass 1 (bwd): dH = dY Wu_cat -> [TM_D, +R)
           const uint32_t d_tmem = tmem + (pass == 0 ? TM_P : TM_D);
           if (pass == 1) {
@@ -401,53 +407,100 @@ dat_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
       const int m0 = tile_of(it) * BM;
       {
         // ---------------- epilogue 1: this group's half of P (and dH) -> packed bf16 hidden
-        mbar_wait(bar_p_full, tile_it & 1);
+        const int grow = m0 + static_cast<int>(row);
+        uint4 hreg[8][2];     // kSaved: this row's saved hidden, all of the group's chunks
+        uint32_t wall[8][8];  // forward with H_out: the packed hidden, stored to HBM after GEMM2 is released
+        if constexpr (kSaved) {
+          // issued BEFORE the wait on GEMM1b: the global-load latency hides under it
+          const uint4* hrow = reinterpret_cast<const uint4*>(p.H_in + static_cast<size_t>(grow) * R);
+#pragma unroll
+          for (int ci = 0; ci < 8; ++ci) {
+            hreg[ci][0] = hreg[ci][1] = make_uint4(0u, 0u, 0u, 0u);
+            if (c_lo + ci < c_hi && grow < p.M) {
+              hreg[ci][0] = __ldg(hrow + 2 * (c_lo + ci));
+              hreg[ci][1] = __ldg(hrow + 2 * (c_lo + ci) + 1);
+            }
+          }
+        }
+        if (!kSaved) mbar_wait(bar_p_full, tile_it & 1);
         if (kBwd) mbar_wait(bar_g_full, tile_it & 1);
         tc_fence_after();
         if (tid == 128) FD_TRACE(40, tile_it);
         const uint32_t t_p = tmem + lane_addr + TM_P;
         const uint32_t t_g = tmem + lane_addr + TM_D;
-        const int grow = m0 + static_cast<int>(row);
-        const int rt = p.r_hi - p.r_lo;
-        for (int c = c_lo; c < c_hi; ++c) {
-          uint32_t v[16], u[16], w[8];
-          tmem_ld16(t_p + c * 16, v);
-          if (kBwd) tmem_ld16(t_g + c * 16, u);
-          const float* bdv = bias_smem + c * 16;
-          tmem_ld_wait();
-          if constexpr (!kBwd) {
 #pragma unroll
-            for (int i = 0; i < 8; ++i)
-              w[i] = pack_bf16x2(apply_act<kGelu>(__uint_as_float(v[2 * i]) + bdv[2 * i]),
-                                 apply_act<kGelu>(__uint_as_float(v[2 * i + 1]) + bdv[2 * i + 1]));
-          } else {
-            uint32_t hh[8];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const float p0 = __uint_as_float(v[2 * i]) + bdv[2 * i];
-              const float p1 = __uint_as_float(v[2 * i + 1]) + bdv[2 * i + 1];
-              w[i] = pack_bf16x2(scale * __uint_as_float(u[2 * i]) * act_grad<kGelu>(p0),
-                                 scale * __uint_as_float(u[2 * i + 1]) * act_grad<kGelu>(p1));
-              hh[i] = pack_bf16x2(apply_act<kGelu>(p0), apply_act<kGelu>(p1));
-            }
+        for (int ci = 0; ci < 8; ++ci) {
+          const int c = c_lo + ci;
+          if (c < c_hi) {
+            uint32_t v[16], u[16], w[8];
+            if (!kSaved) tmem_ld16(t_p + c * 16, v);
+            if (kBwd) tmem_ld16(t_g + c * 16, u);
+            const float* bdv = bias_smem + c * 16;
+            tmem_ld_wait();
             const int col = c * 16;
-            if (p.H_t != nullptr && c_base == 0 && col >= p.r_lo && col < p.r_hi && grow < p.M) {
-              const size_t off = static_cast<size_t>(grow) * rt + (col - p.r_lo);
-              uint4* hd = reinterpret_cast<uint4*>(p.H_t + off);
-              uint4* gd = reinterpret_cast<uint4*>(p.dP_t + off);
-              hd[0] = make_uint4(hh[0], hh[1], hh[2], hh[3]);
-              hd[1] = make_uint4(hh[4], hh[5], hh[6], hh[7]);
-              gd[0] = make_uint4(w[0], w[1], w[2], w[3]);
-              gd[1] = make_uint4(w[4], w[5], w[6], w[7]);
+            if constexpr (!kBwd) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i)
+                w[i] = pack_bf16x2(apply_act<kGelu>(__uint_as_float(v[2 * i]) + bdv[2 * i]),
+                                   apply_act<kGelu>(__uint_as_float(v[2 * i + 1]) + bdv[2 * i + 1]));
+#pragma unroll
+              for (int i = 0; i < 8; ++i) wall[ci][i] = w[i];
+            } else if constexpr (kSaved) {
+              const uint32_t hb[8] = {hreg[ci][0].x, hreg[ci][0].y, hreg[ci][0].z, hreg[ci][0].w,
+                                      hreg[ci][1].x, hreg[ci][1].y, hreg[ci][1].z, hreg[ci][1].w};
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {      // relu'(P) == (H > 0); H is never negative
+                const float g0 = (hb[i] & 0x00007fffu) ? scale * __uint_as_float(u[2 * i]) : 0.f;
+                const float g1 = (hb[i] & 0x7fff0000u) ? scale * __uint_as_float(u[2 * i + 1]) : 0.f;
+                w[i] = pack_bf16x2(g0, g1);
+              }
+              if (p.dP_t != nullptr && c_base == 0 && col >= p.r_lo && col < p.r_hi && grow < p.M) {
+                uint4* gd = reinterpret_cast<uint4*>(p.dP_t + static_cast<size_t>(grow) * p.ld_t + (col - p.r_lo));
+                gd[0] = make_uint4(w[0], w[1], w[2], w[3]);
+                gd[1] = make_uint4(w[4], w[5], w[6], w[7]);
+              }
+            } else {
+              uint32_t hh[8];
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                const float p0 = __uint_as_float(v[2 * i]) + bdv[2 * i];
+                const float p1 = __uint_as_float(v[2 * i + 1]) + bdv[2 * i + 1];
+                w[i] = pack_bf16x2(scale * __uint_as_float(u[2 * i]) * act_grad<kGelu>(p0),
+                                   scale * __uint_as_float(u[2 * i + 1]) * act_grad<kGelu>(p1));
+                hh[i] = pack_bf16x2(apply_act<kGelu>(p0), apply_act<kGelu>(p1));
+              }
+              if (p.H_t != nullptr && c_base == 0 && col >= p.r_lo && col < p.r_hi && grow < p.M) {
+                const size_t off = static_cast<size_t>(grow) * p.ld_t + (col - p.r_lo);
+                uint4* hd = reinterpret_cast<uint4*>(p.H_t + off);
+                uint4* gd = reinterpret_cast<uint4*>(p.dP_t + off);
+                hd[0] = make_uint4(hh[0], hh[1], hh[2], hh[3]);
+                hd[1] = make_uint4(hh[4], hh[5], hh[6], hh[7]);
+                gd[0] = make_uint4(w[0], w[1], w[2], w[3]);
+                gd[1] = make_uint4(w[4], w[5], w[6], w[7]);
+              }
             }
+            // the target columns lie inside a P chunk of THIS group that it has already read (or, in
+            // saved mode, in the unused P region)
+            tmem_st8(t_p + w_base + (c - c_lo) * 8, w);
           }
-          // the target columns lie inside a P chunk of THIS group that it has already read
-          tmem_st8(t_p + w_base + (c - c_lo) * 8, w);
         }
         tmem_st_wait();
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive_cluster_addr(leader_h_full);
+        if constexpr (!kBwd) {
+          // save the hidden for a kSaved backward AFTER GEMM2 has been released: a row-per-thread store
+          // is 32 L1 transactions per instruction and must not sit on the tensor pipe's critical path
+          if (p.H_out != nullptr && c_base == 0 && grow < p.M) {
+            uint4* hrow = reinterpret_cast<uint4*>(p.H_out + static_cast<size_t>(grow) * R);
+#pragma unroll
+            for (int ci = 0; ci < 8; ++ci)
+              if (c_lo + ci < c_hi) {
+                hrow[2 * (c_lo + ci)] = make_uint4(wall[ci][0], wall[ci][1], wall[ci][2], wall[ci][3]);
+                hrow[2 * (c_lo + ci) + 1] = make_uint4(wall[ci][4], wall[ci][5], wall[ci][6], wall[ci][7]);
+              }
+          }
+        }
         if (tid == 128) FD_TRACE(41, tile_it);
       }
       // ---------------- epilogue 2: this group's output chunks (c = group, group + 2, group + 4)
@@ -587,15 +640,18 @@ int launch_fused(bool bwd, const void* X, const void* Res, void* Out, const void
                             const CUtensorMap, const CUtensorMap, const CUtensorMap,
                             const CUtensorMap, const FusedParams);
   const bool gelu = p.act == FEDDAT_ACT_GELU;
-  KernelFn fn = bwd ? (gelu ? dat_fused_kernel<true, true> : dat_fused_kernel<true, false>)
-                    : (gelu ? dat_fused_kernel<false, true> : dat_fused_kernel<false, false>);
-  static bool configured[2][2][64] = {{{false}}};
+  const bool saved = bwd && p.H_in != nullptr;
+  KernelFn fn = saved ? dat_fused_kernel<true, false, true>
+                : bwd ? (gelu ? dat_fused_kernel<true, true> : dat_fused_kernel<true, false>)
+                      : (gelu ? dat_fused_kernel<false, true> : dat_fused_kernel<false, false>);
+  static bool configured[3][2][64] = {{{false}}};
   int dev = 0;
   FD_CHECK_CUDA(cudaGetDevice(&dev));
-  if (dev >= 64 || !configured[bwd][gelu][dev]) {
+  const int kidx = saved ? 2 : (bwd ? 1 : 0);
+  if (dev >= 64 || !configured[kidx][gelu][dev]) {
     FD_CHECK_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)max_smem));
-    if (dev < 64) configured[bwd][gelu][dev] = true;
+    if (dev < 64) configured[kidx][gelu][dev] = true;
   }
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(grid);
@@ -633,8 +689,8 @@ int check_common(const char* who, int64_t M, int d, int r_total, int act, int dt
 
 extern "C" int feddat_dat_fwd(const void* X, const void* Res, void* Y, const void* Wd_cat,
                               const float* bd_cat, const void* Wu_cat, const float* bu_cat,
-                              int64_t M, int d, int r_total, float branch_scale, int act, int dtype,
-                              void* stream) {
+                              void* H_out, int64_t M, int d, int r_total, float branch_scale, int act,
+                              int dtype, void* stream) {
   using namespace fd;
   int rc = check_device_sm100();
   if (rc) return rc;
@@ -647,8 +703,9 @@ extern "C" int feddat_dat_fwd(const void* X, const void* Res, void* Y, const voi
     int sms = 0;
     if ((rc = device_sm_count(&sms))) return rc;
     const int64_t num_pairs = ((M + BM - 1) / BM + 1) / 2;
+    FD_REQUIRE((reinterpret_cast<uintptr_t>(H_out) & 15) == 0, FD_ERR_INVALID, "dat_fwd: H_out must be 16-byte aligned");
     if (num_pairs > sms / 2 && !g_force_fused)
-      return launch_dat_fwd_pipe(X, Res, Y, Wd_cat, bd_cat, Wu_cat, bu_cat, M, r_total, branch_scale, act,
+      return launch_dat_fwd_pipe(X, Res, Y, Wd_cat, bd_cat, Wu_cat, bu_cat, H_out, M, r_total, branch_scale, act,
                                  2 * (sms / 2), static_cast<cudaStream_t>(stream));
   }
   FusedParams p{};
@@ -658,29 +715,39 @@ extern "C" int feddat_dat_fwd(const void* X, const void* Res, void* Y, const voi
   p.bu = bu_cat;
   p.has_out = 1;
   p.has_res = 1;
+  p.H_out = static_cast<__nv_bfloat16*>(H_out);
   return launch_fused(false, X, Res, Y, Wd_cat, Wu_cat, nullptr, p, M, r_total,
                       static_cast<cudaStream_t>(stream), "dat_fwd");
 }
 
 extern "C" int feddat_dat_bwd_dgrad(const void* X, const void* dY, void* dX, const void* Wd_cat,
                                     const float* bd_cat, const void* WuT_cat, const void* WdT_cat,
-                                    void* H_t, void* dP_t, int r_lo, int r_hi, int64_t M, int d,
-                                    int r_total, float branch_scale, int act, int add_dy, int dtype,
-                                    void* stream) {
+                                    const void* H_in, void* H_t, void* dP_t, int ld_t, int r_lo, int r_hi,
+                                    int64_t M, int d, int r_total, float branch_scale, int act, int add_dy,
+                                    int dtype, void* stream) {
   using namespace fd;
   int rc = check_device_sm100();
   if (rc) return rc;
-  FD_REQUIRE(X && dY && Wd_cat && bd_cat && WuT_cat && WdT_cat, FD_ERR_INVALID,
-             "dat_bwd_dgrad: null pointer argument");
+  FD_REQUIRE(dY && WuT_cat && WdT_cat, FD_ERR_INVALID, "dat_bwd_dgrad: null pointer argument");
   if ((rc = check_common("dat_bwd_dgrad", M, d, r_total, act, dtype))) return rc;
-  FD_REQUIRE((H_t == nullptr) == (dP_t == nullptr), FD_ERR_INVALID,
-             "dat_bwd_dgrad: H_t and dP_t must both be given or both be NULL");
-  FD_REQUIRE(dX != nullptr || H_t != nullptr, FD_ERR_INVALID,
-             "dat_bwd_dgrad: nothing to compute (dX and H_t are both NULL)");
-  if (H_t) {
+  if (H_in != nullptr) {
+    FD_REQUIRE(act == FEDDAT_ACT_RELU, FD_ERR_UNSUPPORTED,
+               "dat_bwd_dgrad: a saved hidden determines act' only for ReLU; pass H_in = NULL (recompute) for GELU");
+    FD_REQUIRE(H_t == nullptr, FD_ERR_INVALID, "dat_bwd_dgrad: H_t is not produced in saved mode (H_in holds it)");
+    FD_REQUIRE((reinterpret_cast<uintptr_t>(H_in) & 15) == 0, FD_ERR_INVALID, "dat_bwd_dgrad: H_in must be 16-byte aligned");
+    FD_REQUIRE(dX != nullptr || dP_t != nullptr, FD_ERR_INVALID, "dat_bwd_dgrad: nothing to compute");
+  } else {
+    FD_REQUIRE(X && Wd_cat && bd_cat, FD_ERR_INVALID, "dat_bwd_dgrad: X, Wd_cat, bd_cat are needed to recompute P");
+    FD_REQUIRE((H_t == nullptr) == (dP_t == nullptr), FD_ERR_INVALID,
+               "dat_bwd_dgrad: H_t and dP_t must both be given or both be NULL");
+    FD_REQUIRE(dX != nullptr || H_t != nullptr, FD_ERR_INVALID,
+               "dat_bwd_dgrad: nothing to compute (dX and H_t are both NULL)");
+  }
+  if (dP_t) {
     FD_REQUIRE(r_lo >= 0 && r_hi > r_lo && r_hi <= r_total && r_lo % 16 == 0 && r_hi % 16 == 0,
                FD_ERR_INVALID, "dat_bwd_dgrad: bad trainable slice [%d, %d) of %d", r_lo, r_hi,
                r_total);
+    FD_REQUIRE(ld_t >= r_hi - r_lo && ld_t % 8 == 0, FD_ERR_INVALID, "dat_bwd_dgrad: bad row stride ld_t=%d", ld_t);
     FD_REQUIRE(((reinterpret_cast<uintptr_t>(H_t) | reinterpret_cast<uintptr_t>(dP_t)) & 15) == 0,
                FD_ERR_INVALID, "dat_bwd_dgrad: H_t / dP_t must be 16-byte aligned");
   }
@@ -688,15 +755,18 @@ extern "C" int feddat_dat_bwd_dgrad(const void* X, const void* dY, void* dX, con
   FusedParams p{};
   p.act = act;
   p.scale = branch_scale;
-  p.bd = bd_cat;
+  p.bd = H_in ? nullptr : bd_cat;
   p.bu = nullptr;
   p.has_out = dX != nullptr;
   p.has_res = (dX != nullptr && add_dy) ? 1 : 0;
-  p.r_lo = H_t ? r_lo : 0;
-  p.r_hi = H_t ? r_hi : 0;
+  p.r_lo = dP_t ? r_lo : 0;
+  p.r_hi = dP_t ? r_hi : 0;
+  p.ld_t = ld_t;
   p.H_t = static_cast<__nv_bfloat16*>(H_t);
   p.dP_t = static_cast<__nv_bfloat16*>(dP_t);
-  return launch_fused(true, X, dY, dX, Wd_cat, WdT_cat, WuT_cat, p, M, r_total,
+  p.H_in = static_cast<const __nv_bfloat16*>(H_in);
+  // saved mode never touches X / Wd_cat: any valid tensor keeps the (unused) tensor maps well formed
+  return launch_fused(true, H_in ? dY : X, dY, dX, H_in ? WuT_cat : Wd_cat, WdT_cat, WuT_cat, p, M, r_total,
                       static_cast<cudaStream_t>(stream), "dat_bwd_dgrad");
 }
 

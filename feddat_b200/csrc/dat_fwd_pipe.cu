@@ -58,6 +58,7 @@ struct PipeParams {
   float scale;
   const float* bd;
   const float* bu;
+  __nv_bfloat16* H_out;     // save the hidden [M, R] for a saved-mode backward, or null
   unsigned long long* trace;
 };
 
@@ -312,6 +313,7 @@ dat_fwd_pipe_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
 
     for (int it = 0; it < my_tiles; ++it) {
       const uint32_t tile_it = it;
+      const int grow = tile_of(it) * BM + static_cast<int>(row);
       {
         // ---------------- epilogue 1: this group's half of P -> packed bf16 hidden in H
         mbar_wait(bar_p_full, tile_it & 1);
@@ -320,21 +322,37 @@ dat_fwd_pipe_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
         if (tid == 128) FDP_TRACE(40, tile_it);
         const uint32_t t_p = tmem + lane_addr + TM_P;
         const uint32_t t_h = tmem + lane_addr + TM_H;
-        for (int c = c_lo; c < c_hi; ++c) {
-          uint32_t v[16], w[8];
-          tmem_ld16(t_p + c * 16, v);
-          tmem_ld_wait();
-          const float* bdv = bias_smem + c * 16;
+        uint32_t wall[8][8];      // the group's packed hidden, kept for the (deferred) global save
 #pragma unroll
-          for (int i = 0; i < 8; ++i)
-            w[i] = pack_bf16x2(apply_act<kGelu>(__uint_as_float(v[2 * i]) + bdv[2 * i]),
-                               apply_act<kGelu>(__uint_as_float(v[2 * i + 1]) + bdv[2 * i + 1]));
-          tmem_st8(t_h + c * 8, w);
+        for (int ci = 0; ci < 8; ++ci) {
+          const int c = c_lo + ci;
+          if (c < c_hi) {
+            uint32_t v[16];
+            tmem_ld16(t_p + c * 16, v);
+            tmem_ld_wait();
+            const float* bdv = bias_smem + c * 16;
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+              wall[ci][i] = pack_bf16x2(apply_act<kGelu>(__uint_as_float(v[2 * i]) + bdv[2 * i]),
+                                        apply_act<kGelu>(__uint_as_float(v[2 * i + 1]) + bdv[2 * i + 1]));
+            tmem_st8(t_h + c * 8, wall[ci]);
+          }
         }
         tmem_st_wait();
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive_cluster_addr(leader_h_full);
+        // the hidden goes to HBM AFTER GEMM2 has been released: a row-per-thread store is 32 L1
+        // transactions per instruction, which would otherwise sit on the tensor pipe's critical path
+        if (p.H_out != nullptr && grow < p.M) {
+          uint4* hrow = reinterpret_cast<uint4*>(p.H_out + static_cast<size_t>(grow) * R);
+#pragma unroll
+          for (int ci = 0; ci < 8; ++ci)
+            if (c_lo + ci < c_hi) {
+              hrow[2 * (c_lo + ci)] = make_uint4(wall[ci][0], wall[ci][1], wall[ci][2], wall[ci][3]);
+              hrow[2 * (c_lo + ci) + 1] = make_uint4(wall[ci][4], wall[ci][5], wall[ci][6], wall[ci][7]);
+            }
+        }
         if (tid == 128) FDP_TRACE(41, tile_it);
       }
       // ---------------- epilogue 2: output chunks c == group (mod 2), 64 columns each
@@ -398,8 +416,8 @@ dat_fwd_pipe_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
 }  // namespace
 
 int launch_dat_fwd_pipe(const void* X, const void* Res, void* Y, const void* Wd_cat, const float* bd_cat,
-                        const void* Wu_cat, const float* bu_cat, int64_t M, int r_total, float scale, int act,
-                        int grid, cudaStream_t st) {
+                        const void* Wu_cat, const float* bu_cat, void* H_out, int64_t M, int r_total, float scale,
+                        int act, int grid, cudaStream_t st) {
   int rc;
   PipeParams p{};
   p.M = static_cast<int>(M);
@@ -409,6 +427,7 @@ int launch_dat_fwd_pipe(const void* X, const void* Res, void* Y, const void* Wd_
   p.scale = scale;
   p.bd = bd_cat;
   p.bu = bu_cat;
+  p.H_out = static_cast<__nv_bfloat16*>(H_out);
   p.trace = g_trace;
   const size_t max_smem = 227 * 1024 - 1024;
   const size_t smem = 1024 + static_cast<size_t>(NG1) * G1STAGE + static_cast<size_t>(NW2 + NSTG) * SLOT +

@@ -8,7 +8,7 @@ namespace fd {
 // dat_fwd_pipe.cu: forward software-pipelined across tiles (every CTA pair owns >= 2 super-tiles).
 // `grid` = 2 x (CTA pairs to launch).
 int launch_dat_fwd_pipe(const void* X, const void* Res, void* Y, const void* Wd_cat, const float* bd_cat,
-                        const void* Wu_cat, const float* bu_cat, int64_t M, int r_total, float scale, int act,
-                        int grid, cudaStream_t st);
+                        const void* Wu_cat, const float* bu_cat, void* H_out, int64_t M, int r_total, float scale,
+                        int act, int grid, cudaStream_t st);
 
 }  // namespace fd

@@ -46,8 +46,16 @@ class _DatFunction(torch.autograd.Function):
         segs = adapter._segments(params, need_bwd=need_bwd)
         same = res is x
         y = None
+        # ReLU: keep the hidden (what autograd would save) so that backward skips the recompute of
+        # x Wd^T; GELU's derivative needs the pre-activation, which the backward kernel recomputes
+        save_h = need_bwd and adapter._act_code == ops.ACT_RELU
+        hs = []
         for i, (pk, _, _) in enumerate(segs):
-            y = ops.dat_forward(x, res if i == 0 else y, pk, adapter._scale(), adapter._act_code)
+            out = ops.dat_forward(x, res if i == 0 else y, pk, adapter._scale(), adapter._act_code,
+                                  save_hidden=save_h)
+            y, h = out if save_h else (out, None)
+            hs.append(h)
+        ctx.hs = hs
         ctx.adapter = adapter
         ctx.scale = adapter._scale()        # mode at FORWARD time (backward may run after a mode switch)
         ctx.segs = segs
@@ -80,7 +88,7 @@ class _DatFunction(torch.autograd.Function):
                     hi = b1 if hi is None else max(hi, b1)
             ts = None if lo is None else (lo - col0, hi - col0)
             dx, g = ops.dat_backward(x, dy, pk, ctx.scale, adapter._act_code, train_slice=ts,
-                                     need_dx=need_dx, add_dy=(ctx.same and si == 0))
+                                     need_dx=need_dx, add_dy=(ctx.same and si == 0), hidden=ctx.hs[si])
             if dx is not None:
                 dx_total = dx if dx_total is None else dx_total + dx
             if g is not None:

@@ -85,8 +85,9 @@ def pack_weights(branches: Sequence[Sequence[torch.Tensor]], need_bwd: bool = Tr
 
 
 def dat_forward(x: torch.Tensor, res: torch.Tensor, w: PackedWeights, scale: float, act=ACT_RELU,
-                out: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """Y = res + scale * (act(x Wd^T + bd) Wu^T + bu)   (adapter.py:124-163)."""
+                out: Optional[torch.Tensor] = None, save_hidden: bool = False):
+    """Y = res + scale * (act(x Wd^T + bd) Wu^T + bu)   (adapter.py:124-163).  With ``save_hidden`` returns
+    (Y, H) where H [M, r_total] bf16 is the hidden, for a backward that does not recompute it."""
     lib = _lib.load()
     _check_act2d(x, "dat_forward x")
     _check_act2d(res, "dat_forward res")
@@ -94,48 +95,70 @@ def dat_forward(x: torch.Tensor, res: torch.Tensor, w: PackedWeights, scale: flo
         raise _lib.FeddatError(f"dat_forward: r_total={w.r_total} > {MAX_R_TOTAL}; the Adapter module "
                                "splits such bottlenecks into several launches")
     y = out if out is not None else torch.empty_like(x)
+    h = torch.empty(x.shape[0], w.r_total, device=x.device, dtype=torch.bfloat16) if save_hidden else None
     rc = lib.feddat_dat_fwd(_lib.ptr(x), _lib.ptr(res), _lib.ptr(y), _lib.ptr(w.wd), _lib.ptr(w.bd),
-                            _lib.ptr(w.wu), _lib.ptr(w.bu), x.shape[0], x.shape[1], w.r_total,
+                            _lib.ptr(w.wu), _lib.ptr(w.bu), _lib.ptr(h), x.shape[0], x.shape[1], w.r_total,
                             float(scale), act_code(act), DTYPE_BF16, _lib.stream_ptr())
     _lib.check(rc, "feddat_dat_fwd")
     _count()
-    return y
+    return (y, h) if save_hidden else y
 
 
-def dat_backward(x: torch.Tensor, dy: torch.Tensor, w: PackedWeights, scale: float, act=ACT_RELU,
-                 train_slice: Optional[tuple] = None, need_dx: bool = True, add_dy: bool = True):
+def dat_backward(x: Optional[torch.Tensor], dy: torch.Tensor, w: PackedWeights, scale: float, act=ACT_RELU,
+                 train_slice: Optional[tuple] = None, need_dx: bool = True, add_dy: bool = True,
+                 hidden: Optional[torch.Tensor] = None):
     """Backward of dat_forward.  Returns (dx | None, grads | None) where grads =
     (d_down_w [rt,d], d_down_b [rt], d_up_w [d,rt], d_up_b [d]) in fp32 for the trainable slice
-    ``train_slice = (r_lo, r_hi)`` of the concatenated bottleneck."""
+    ``train_slice = (r_lo, r_hi)`` of the concatenated bottleneck.  ``hidden`` = the H saved by
+    ``dat_forward(save_hidden=True)`` (ReLU): the dgrad kernel then skips the recompute of x Wd^T
+    (``x`` is still needed by the weight-gradient kernel when something trains)."""
     lib = _lib.load()
-    _check_act2d(x, "dat_backward x")
     _check_act2d(dy, "dat_backward dy")
+    if x is not None:
+        _check_act2d(x, "dat_backward x")
     if w.wdT is None:
         raise _lib.FeddatError("dat_backward: weights were packed with need_bwd=False")
-    M, d = x.shape
-    dev = x.device
-    dx = torch.empty_like(x) if need_dx else None
+    saved = hidden is not None
+    if saved and act_code(act) != ACT_RELU:
+        raise _lib.FeddatError("dat_backward: a saved hidden determines act' only for ReLU")
+    if x is None and (not saved or train_slice is not None):
+        raise _lib.FeddatError("dat_backward: x is required (recompute mode, or weight gradients)")
+    M, d = dy.shape
+    R = w.r_total
+    dev = dy.device
+    dx = torch.empty_like(dy) if need_dx else None
     h_t = dp_t = None
     rt = 0
     if train_slice is not None:
         r_lo, r_hi = train_slice
         rt = r_hi - r_lo
-        h_t = torch.empty(M, rt, device=dev, dtype=torch.bfloat16)
-        dp_t = torch.empty(M, rt, device=dev, dtype=torch.bfloat16)
+        if saved:
+            # full-width scratch: only the trainable columns are written / read (row stride R, like H)
+            dp_full = torch.empty(M, R, device=dev, dtype=torch.bfloat16)
+            dp_t = dp_full[:, r_lo:r_hi]
+            h_t = hidden[:, r_lo:r_hi]
+            ld_t = R
+        else:
+            h_t = torch.empty(M, rt, device=dev, dtype=torch.bfloat16)
+            dp_t = torch.empty(M, rt, device=dev, dtype=torch.bfloat16)
+            ld_t = rt
     else:
         r_lo = r_hi = 0
-    if dx is None and h_t is None:
+        ld_t = 0
+    if dx is None and dp_t is None:
         return None, None
-    rc = lib.feddat_dat_bwd_dgrad(_lib.ptr(x), _lib.ptr(dy), _lib.ptr(dx), _lib.ptr(w.wd), _lib.ptr(w.bd),
-                                  _lib.ptr(w.wuT), _lib.ptr(w.wdT), _lib.ptr(h_t), _lib.ptr(dp_t), r_lo,
-                                  r_hi, M, d, w.r_total, float(scale), act_code(act), int(add_dy),
-                                  DTYPE_BF16, _lib.stream_ptr())
-    _lib.check(rc, "feddat_dat_bwd_dgrad")
-    _count()
     grads = None
     if train_slice is not None:
         f32 = dict(device=dev, dtype=torch.float32)
         g = torch.zeros(2 * d * rt + rt + d, **f32)          # one memset for all four gradients
+    rc = lib.feddat_dat_bwd_dgrad(_lib.ptr(x), _lib.ptr(dy), _lib.ptr(dx), _lib.ptr(w.wd), _lib.ptr(w.bd),
+                                  _lib.ptr(w.wuT), _lib.ptr(w.wdT), _lib.ptr(hidden),
+                                  None if saved else _lib.ptr(h_t), _lib.ptr(dp_t), ld_t, r_lo,
+                                  r_hi, M, d, R, float(scale), act_code(act), int(add_dy),
+                                  DTYPE_BF16, _lib.stream_ptr())
+    _lib.check(rc, "feddat_dat_bwd_dgrad")
+    _count()
+    if train_slice is not None:
         d_down_w = g[: rt * d].view(rt, d)
         d_up_w = g[rt * d: 2 * rt * d].view(d, rt)
         d_down_b = g[2 * rt * d: 2 * rt * d + rt]
@@ -146,7 +169,7 @@ def dat_backward(x: torch.Tensor, dy: torch.Tensor, w: PackedWeights, scale: flo
                 _lib.ptr(x), _lib.ptr(dy), ctypes.c_void_p(h_t.data_ptr() + 2 * j0),
                 ctypes.c_void_p(dp_t.data_ptr() + 2 * j0), ctypes.c_void_p(d_up_w.data_ptr() + 4 * j0),
                 _lib.ptr(d_up_b) if j0 == 0 else None, ctypes.c_void_p(d_down_w.data_ptr() + 4 * j0 * d),
-                ctypes.c_void_p(d_down_b.data_ptr() + 4 * j0), M, d, w_, rt, rt, float(scale), DTYPE_BF16,
+                ctypes.c_void_p(d_down_b.data_ptr() + 4 * j0), M, d, w_, ld_t, rt, float(scale), DTYPE_BF16,
                 _lib.stream_ptr())
             _lib.check(rc, "feddat_dat_bwd_wgrad")
             _count()

@@ -53,8 +53,10 @@ int feddat_abi_version(void);
  * d must be 768; r_total a multiple of 16 in [16, 256].
  */
 int feddat_dat_fwd(const void* X, const void* Res, void* Y, const void* Wd_cat,
-                   const float* bd_cat, const void* Wu_cat, const float* bu_cat, int64_t M, int d,
-                   int r_total, float branch_scale, int act, int dtype, void* stream);
+                   const float* bd_cat, const void* Wu_cat, const float* bu_cat,
+                   void* H_out /* NULL, or [M, r_total] bf16: the hidden act(X Wd_cat^T + bd_cat), saved for a
+                                  backward that does not recompute it (what torch autograd would save) */,
+                   int64_t M, int d, int r_total, float branch_scale, int act, int dtype, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * DAT bottleneck backward (autograd of the above; the reference relies on torch autograd of
@@ -67,6 +69,10 @@ int feddat_dat_fwd(const void* X, const void* Res, void* Y, const void* Wd_cat,
  *   H_t [M, r_hi-r_lo] and dP_t [M, r_hi-r_lo] for stage 2 (pass NULL/NULL when nothing trains).
  *   dX may be NULL (first adapter site: nothing trainable upstream needs it) only if H_t != NULL.
  *   WuT_cat [r_total, d] and WdT_cat [d, r_total] are the transposes of Wu_cat / Wd_cat (bf16).
+ *   Two modes.  RECOMPUTE (H_in == NULL; any activation): as above, H_t and dP_t written with row stride
+ *   ld_t.  SAVED (H_in = the forward's H_out, ReLU only): P is not recomputed -- X, Wd_cat, bd_cat are
+ *   unused (may be NULL), relu'(P) = (H_in > 0), H_t must be NULL (stage 2 reads the slice of H_in
+ *   itself), dP_t [.., ld_t] is written for the trainable slice.
  *
  * Stage 2, feddat_dat_bwd_wgrad: fp32 accumulate-into (caller zeroes):
  *     dWu [d, r_t] += branch_scale * dY^T H_t                        dbu [d]   += scale * sum_m dY
@@ -78,8 +84,9 @@ int feddat_dat_fwd(const void* X, const void* Res, void* Y, const void* Wd_cat,
  */
 int feddat_dat_bwd_dgrad(const void* X, const void* dY, void* dX, const void* Wd_cat,
                          const float* bd_cat, const void* WuT_cat, const void* WdT_cat,
-                         void* H_t, void* dP_t, int r_lo, int r_hi, int64_t M, int d, int r_total,
-                         float branch_scale, int act, int add_dy, int dtype, void* stream);
+                         const void* H_in, void* H_t, void* dP_t, int ld_t, int r_lo, int r_hi,
+                         int64_t M, int d, int r_total, float branch_scale, int act, int add_dy,
+                         int dtype, void* stream);
 
 int feddat_dat_bwd_wgrad(const void* X, const void* dY, const void* H_t, const void* dP_t,
                          float* dWu, float* dbu, float* dWd, float* dbd, int64_t M, int d, int r_t,

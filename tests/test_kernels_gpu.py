@@ -187,6 +187,18 @@ def test_dat_fwd_bwd_full_size_vs_oracle(ops, R, M, gating, act):
     assert set(bad.tolist()) <= set(np.nonzero(near)[0].tolist()), (bad[:10], row_err[bad[:10]], int(near.sum()))
     for got, want in zip(grads, grads_or[0]):
         assert relerr(got.cpu().numpy(), want) < 2 * BF16_TOL
+    if act == "relu":
+        # SAVED mode (the product path for ReLU): the forward keeps the hidden, the dgrad kernel skips the
+        # recompute of X Wd^T and reads relu' off it -- same dP bits, hence the same dX
+        y2, h = ops.dat_forward(xd, rd, pk, scale, act, save_hidden=True)
+        dx2, grads2 = ops.dat_backward(xd, gd, pk, scale, act, train_slice=(0, r), need_dx=True, add_dy=False, hidden=h)
+        torch.cuda.synchronize()
+        assert torch.equal(y2, y)
+        h_or = np.concatenate([np.maximum(xr.astype(np.float64) @ dw.T.astype(np.float64) + db, 0) for (dw, db, _, _) in rb], axis=1)
+        assert relerr(h.float().cpu().numpy(), h_or) < 6e-3
+        assert torch.equal(dx2, dx)
+        for a, b2 in zip(grads2, grads):
+            assert relerr(a.cpu().numpy(), b2.cpu().numpy()) < 1e-5        # fp32 atomics: order only
 
 
 def test_dat_backward_without_dx_and_frozen_only(ops):

@@ -20,7 +20,7 @@ def test_library_exports_every_declared_symbol():
     for n in names:
         assert hasattr(lib, n), f"{n} declared in include/feddat_b200.h but not exported"
     assert set(names) == set(_lib.EXPORTED_SYMBOLS)
-    assert lib.feddat_abi_version() == 1
+    assert lib.feddat_abi_version() == 2
 
 
 def test_entry_points_fail_loudly_without_a_gpu():
