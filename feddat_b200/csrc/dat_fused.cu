@@ -752,6 +752,15 @@ extern "C" int feddat_dat_bwd_dgrad(const void* X, const void* dY, void* dX, con
                FD_ERR_INVALID, "dat_bwd_dgrad: H_t / dP_t must be 16-byte aligned");
   }
   if (M == 0) return FD_OK;
+  if (H_in != nullptr && dX != nullptr && !g_force_fused) {
+    // more super-tiles than CTA pairs: the tile-pipelined kernel (dat_fwd_pipe.cu, kBwd)
+    int sms = 0;
+    if ((rc = device_sm_count(&sms))) return rc;
+    const int64_t num_pairs = ((M + BM - 1) / BM + 1) / 2;
+    if (num_pairs > sms / 2)
+      return launch_dat_bwd_pipe(dY, dX, WuT_cat, WdT_cat, H_in, dP_t, ld_t, r_lo, r_hi, M, r_total, branch_scale,
+                                 add_dy, 2 * (sms / 2), static_cast<cudaStream_t>(stream));
+  }
   FusedParams p{};
   p.act = act;
   p.scale = branch_scale;

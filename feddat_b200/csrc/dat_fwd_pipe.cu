@@ -28,8 +28,13 @@
 //               (2) group b drains the output chunks with parity b: tcgen05.ld, D buffer handed back at
 //               once, y = res + bf16(scale * (acc + bu)) as a packed bf16 add, staging, TMA store
 //
-// Used by feddat_dat_fwd when every CTA pair owns at least two super-tiles; single-site launches keep
-// dat_fused_kernel with its column split.
+// kBwd = true is the SAVED-mode backward data gradient on the same pipeline (ReLU; the forward saved the
+// hidden, see dat_fused.cu): GEMM1 = dH = dY WuT_cat^T into "P", epilogue 1 = dP = scale * dH * (H_in > 0)
+// packed into "H" (the trainable slice also goes to HBM for the weight-gradient kernel), GEMM2 =
+// dX = dP WdT_cat^T, epilogue 2 = (+ dY) -> bf16 -> TMA store.
+//
+// Used by feddat_dat_fwd / feddat_dat_bwd_dgrad when there are more 256-row super-tiles than CTA pairs;
+// single-site launches keep dat_fused_kernel with its column split.
 #include "dat_kernels.h"
 #include "feddat_b200.h"
 #include "host_common.h"
@@ -56,9 +61,14 @@ constexpr uint32_t W2_KB_BYTES = (N2 / 2) * 128u;   // one k-block [32 rows x 64
 struct PipeParams {
   int M, R, num_tiles, w2_3d;
   float scale;
-  const float* bd;
-  const float* bu;
-  __nv_bfloat16* H_out;     // save the hidden [M, R] for a saved-mode backward, or null
+  const float* bd;          // fwd
+  const float* bu;          // fwd
+  __nv_bfloat16* H_out;     // fwd: save the hidden [M, R] for a saved-mode backward, or null
+  // bwd (saved mode)
+  const __nv_bfloat16* H_in;   // the forward's hidden [M, R]
+  __nv_bfloat16* dP_t;         // pre-activation gradient of the trainable slice (row stride ld_t) or null
+  int ld_t, r_lo, r_hi;
+  int has_res;                 // add dY to dX (the residual input was X itself)
   unsigned long long* trace;
 };
 
@@ -74,9 +84,15 @@ __device__ __forceinline__ float apply_act(float x) {
   return 0.5f * x * (1.f + erff(x * 0.70710678118654752f));
 }
 
-template <bool kGelu>
+// Tensor maps:   forward            backward (kBwd)
+//   tmX          X                  dY          (GEMM1 A operand)
+//   tmRes        residual input     dY          (the optional + dY)
+//   tmY          Y                  dX
+//   tmWd         Wd_cat             WuT_cat     (GEMM1 B operand, [R, 768])
+//   tmW2 / k     Wu_cat             WdT_cat     (GEMM2 B operand, [768, R])
+template <bool kBwd, bool kGelu>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
-dat_fwd_pipe_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmRes,
+dat_pipe_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmRes,
                     const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmWd,
                     const __grid_constant__ CUtensorMap tmW2, const __grid_constant__ CUtensorMap tmW2k,
                     const PipeParams p) {
@@ -144,8 +160,10 @@ dat_fwd_pipe_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
     tma_prefetch_desc(&tmW2k);
   }
   if (warp == 2) tmem_alloc_pair(smem_u32(&tmem_base_smem), 512);
-  for (int i = tid; i < R; i += NUM_THREADS) bias_smem[i] = p.bd[i];
-  for (int i = tid; i < kD; i += NUM_THREADS) bias_smem[R + i] = p.scale * p.bu[i];   // pre-scaled
+  if (!kBwd) {
+    for (int i = tid; i < R; i += NUM_THREADS) bias_smem[i] = p.bd[i];
+    for (int i = tid; i < kD; i += NUM_THREADS) bias_smem[R + i] = p.scale * p.bu[i];   // pre-scaled
+  }
   tc_fence_before();
   cluster_sync_all();
   tc_fence_after();
@@ -267,8 +285,12 @@ dat_fwd_pipe_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
           {   // residual chunk c
             const uint32_t sb = g % NSTG, par = (g / NSTG) & 1;
             mbar_wait(bar_stg_empty(sb), par ^ 1);
-            mbar_arrive_expect_tx(bar_res_full(sb), SLOT);
-            tma_load_2d(stg_base + sb * SLOT, &tmRes, bar_res_full(sb), c * N2, m0);
+            if (!kBwd || p.has_res) {
+              mbar_arrive_expect_tx(bar_res_full(sb), SLOT);
+              tma_load_2d(stg_base + sb * SLOT, &tmRes, bar_res_full(sb), c * N2, m0);
+            } else {
+              mbar_arrive(bar_res_full(sb));
+            }
           }
         }
       }
@@ -316,13 +338,25 @@ dat_fwd_pipe_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
       const int grow = tile_of(it) * BM + static_cast<int>(row);
       {
         // ---------------- epilogue 1: this group's half of P -> packed bf16 hidden in H
+        uint4 hreg[8][2];         // kBwd: this row's saved hidden (issued before the wait on GEMM1)
+        if constexpr (kBwd) {
+          const uint4* hrow = reinterpret_cast<const uint4*>(p.H_in + static_cast<size_t>(grow) * R);
+#pragma unroll
+          for (int ci = 0; ci < 8; ++ci) {
+            hreg[ci][0] = hreg[ci][1] = make_uint4(0u, 0u, 0u, 0u);
+            if (c_lo + ci < c_hi && grow < p.M) {
+              hreg[ci][0] = __ldg(hrow + 2 * (c_lo + ci));
+              hreg[ci][1] = __ldg(hrow + 2 * (c_lo + ci) + 1);
+            }
+          }
+        }
         mbar_wait(bar_p_full, tile_it & 1);
         if (it > 0) mbar_wait(bar_h_free, (tile_it - 1) & 1);   // GEMM2 of the previous tile has read H
         tc_fence_after();
         if (tid == 128) FDP_TRACE(40, tile_it);
         const uint32_t t_p = tmem + lane_addr + TM_P;
         const uint32_t t_h = tmem + lane_addr + TM_H;
-        uint32_t wall[8][8];      // the group's packed hidden, kept for the (deferred) global save
+        uint32_t wall[8][8];      // the group's packed hidden / dP, kept for the (deferred) global store
 #pragma unroll
         for (int ci = 0; ci < 8; ++ci) {
           const int c = c_lo + ci;
@@ -330,11 +364,22 @@ dat_fwd_pipe_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
             uint32_t v[16];
             tmem_ld16(t_p + c * 16, v);
             tmem_ld_wait();
-            const float* bdv = bias_smem + c * 16;
+            if constexpr (!kBwd) {
+              const float* bdv = bias_smem + c * 16;
 #pragma unroll
-            for (int i = 0; i < 8; ++i)
-              wall[ci][i] = pack_bf16x2(apply_act<kGelu>(__uint_as_float(v[2 * i]) + bdv[2 * i]),
-                                        apply_act<kGelu>(__uint_as_float(v[2 * i + 1]) + bdv[2 * i + 1]));
+              for (int i = 0; i < 8; ++i)
+                wall[ci][i] = pack_bf16x2(apply_act<kGelu>(__uint_as_float(v[2 * i]) + bdv[2 * i]),
+                                          apply_act<kGelu>(__uint_as_float(v[2 * i + 1]) + bdv[2 * i + 1]));
+            } else {
+              const uint32_t hb[8] = {hreg[ci][0].x, hreg[ci][0].y, hreg[ci][0].z, hreg[ci][0].w,
+                                      hreg[ci][1].x, hreg[ci][1].y, hreg[ci][1].z, hreg[ci][1].w};
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {      // relu'(P) == (H > 0); H is never negative
+                const float g0 = (hb[i] & 0x00007fffu) ? scale * __uint_as_float(v[2 * i]) : 0.f;
+                const float g1 = (hb[i] & 0x7fff0000u) ? scale * __uint_as_float(v[2 * i + 1]) : 0.f;
+                wall[ci][i] = pack_bf16x2(g0, g1);
+              }
+            }
             tmem_st8(t_h + c * 8, wall[ci]);
           }
         }
@@ -342,16 +387,30 @@ dat_fwd_pipe_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive_cluster_addr(leader_h_full);
-        // the hidden goes to HBM AFTER GEMM2 has been released: a row-per-thread store is 32 L1
-        // transactions per instruction, which would otherwise sit on the tensor pipe's critical path
-        if (p.H_out != nullptr && grow < p.M) {
-          uint4* hrow = reinterpret_cast<uint4*>(p.H_out + static_cast<size_t>(grow) * R);
+        // global stores AFTER GEMM2 has been released (a row-per-thread store is 32 L1 transactions per
+        // instruction): forward saves the hidden, backward the trainable slice of dP for the wgrad kernel
+        if constexpr (!kBwd) {
+          if (p.H_out != nullptr && grow < p.M) {
+            uint4* hrow = reinterpret_cast<uint4*>(p.H_out + static_cast<size_t>(grow) * R);
 #pragma unroll
-          for (int ci = 0; ci < 8; ++ci)
-            if (c_lo + ci < c_hi) {
-              hrow[2 * (c_lo + ci)] = make_uint4(wall[ci][0], wall[ci][1], wall[ci][2], wall[ci][3]);
-              hrow[2 * (c_lo + ci) + 1] = make_uint4(wall[ci][4], wall[ci][5], wall[ci][6], wall[ci][7]);
+            for (int ci = 0; ci < 8; ++ci)
+              if (c_lo + ci < c_hi) {
+                hrow[2 * (c_lo + ci)] = make_uint4(wall[ci][0], wall[ci][1], wall[ci][2], wall[ci][3]);
+                hrow[2 * (c_lo + ci) + 1] = make_uint4(wall[ci][4], wall[ci][5], wall[ci][6], wall[ci][7]);
+              }
+          }
+        } else {
+          if (p.dP_t != nullptr && grow < p.M) {
+#pragma unroll
+            for (int ci = 0; ci < 8; ++ci) {
+              const int col = (c_lo + ci) * 16;
+              if (c_lo + ci < c_hi && col >= p.r_lo && col < p.r_hi) {
+                uint4* gd = reinterpret_cast<uint4*>(p.dP_t + static_cast<size_t>(grow) * p.ld_t + (col - p.r_lo));
+                gd[0] = make_uint4(wall[ci][0], wall[ci][1], wall[ci][2], wall[ci][3]);
+                gd[1] = make_uint4(wall[ci][4], wall[ci][5], wall[ci][6], wall[ci][7]);
+              }
             }
+          }
         }
         if (tid == 128) FDP_TRACE(41, tile_it);
       }
@@ -379,20 +438,29 @@ dat_fwd_pipe_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
         for (int hb = 0; hb < 2; ++hb) {
           uint4 rv[4];
 #pragma unroll
-          for (int i4 = 0; i4 < 4; ++i4) rv[i4] = ld_shared_v4(sbuf + sw128_offset(row, hb * 4 + i4));
+          for (int i4 = 0; i4 < 4; ++i4) {
+            rv[i4] = make_uint4(0u, 0u, 0u, 0u);
+            if (!kBwd || p.has_res) rv[i4] = ld_shared_v4(sbuf + sw128_offset(row, hb * 4 + i4));
+          }
           uint32_t o[4][4];
 #pragma unroll
           for (int i4 = 0; i4 < 4; ++i4) {
             const uint32_t rr[4] = {rv[i4].x, rv[i4].y, rv[i4].z, rv[i4].w};
-            const float4 b0 = bu4[2 * (hb * 4 + i4)], b1 = bu4[2 * (hb * 4 + i4) + 1];
-            const float sbv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+            float sbv[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+            if constexpr (!kBwd) {
+              const float4 b0 = bu4[2 * (hb * 4 + i4)], b1 = bu4[2 * (hb * 4 + i4) + 1];
+              sbv[0] = b0.x; sbv[1] = b0.y; sbv[2] = b0.z; sbv[3] = b0.w;
+              sbv[4] = b1.x; sbv[5] = b1.y; sbv[6] = b1.z; sbv[7] = b1.w;
+            }
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
               const int e = i4 * 8 + 2 * i;
               const float a0 = __uint_as_float(hb == 0 ? v0[e] : v1[e]);
               const float a1 = __uint_as_float(hb == 0 ? v0[e + 1] : v1[e + 1]);
-              // y = res + bf16(scale * (acc + bu)): see dat_fused.cu (the reference's autocast arithmetic)
-              o[i4][i] = hadd2_bf16(rr[i], pack_bf16x2(fmaf(scale, a0, sbv[2 * i]), fmaf(scale, a1, sbv[2 * i + 1])));
+              // fwd: y = res + bf16(scale * (acc + bu)) (see dat_fused.cu); bwd: dX = (dY +) bf16(acc)
+              const uint32_t t = kBwd ? pack_bf16x2(a0, a1)
+                                      : pack_bf16x2(fmaf(scale, a0, sbv[2 * i]), fmaf(scale, a1, sbv[2 * i + 1]));
+              o[i4][i] = hadd2_bf16(rr[i], t);
             }
           }
 #pragma unroll
@@ -413,47 +481,40 @@ dat_fwd_pipe_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
   if (tid == 64) FDP_TRACE(2, 0);
 }
 
-}  // namespace
 
-int launch_dat_fwd_pipe(const void* X, const void* Res, void* Y, const void* Wd_cat, const float* bd_cat,
-                        const void* Wu_cat, const float* bu_cat, void* H_out, int64_t M, int r_total, float scale,
-                        int act, int grid, cudaStream_t st) {
+int launch_pipe(bool bwd, const void* A, const void* Res, void* Out, const void* W1, const void* W2, PipeParams p,
+                int64_t M, int r_total, bool gelu, int grid, cudaStream_t st) {
   int rc;
-  PipeParams p{};
   p.M = static_cast<int>(M);
   p.R = r_total;
   p.num_tiles = static_cast<int>((M + BM - 1) / BM);
   p.w2_3d = (r_total % 64 == 0) ? 1 : 0;
-  p.scale = scale;
-  p.bd = bd_cat;
-  p.bu = bu_cat;
-  p.H_out = static_cast<__nv_bfloat16*>(H_out);
   p.trace = g_trace;
   const size_t max_smem = 227 * 1024 - 1024;
   const size_t smem = 1024 + static_cast<size_t>(NG1) * G1STAGE + static_cast<size_t>(NW2 + NSTG) * SLOT +
                       (r_total + kD) * sizeof(float);
-  FD_REQUIRE(smem <= max_smem, FD_ERR_UNSUPPORTED, "dat_fwd: shared-memory budget exceeded (R=%d)", r_total);
+  FD_REQUIRE(smem <= max_smem, FD_ERR_UNSUPPORTED, "dat pipe kernel: shared-memory budget exceeded (R=%d)", r_total);
 
   CUtensorMap tmX, tmRes, tmY, tmWd, tmW2, tmW2k;
-  if ((rc = make_tmap_bf16_2d(&tmX, X, M, kD, kD, BM, 64))) return rc;
+  if ((rc = make_tmap_bf16_2d(&tmX, A, M, kD, kD, BM, 64))) return rc;
   if ((rc = make_tmap_bf16_2d(&tmRes, Res, M, kD, kD, BM, 64))) return rc;
-  if ((rc = make_tmap_bf16_2d(&tmY, Y, M, kD, kD, BM, 64))) return rc;
-  if ((rc = make_tmap_bf16_2d(&tmWd, Wd_cat, r_total, kD, kD, r_total / 2, 64))) return rc;
-  if ((rc = make_tmap_bf16_2d(&tmW2, Wu_cat, kD, r_total, r_total, N2 / 2, 64))) return rc;
+  if ((rc = make_tmap_bf16_2d(&tmY, Out, M, kD, kD, BM, 64))) return rc;
+  if ((rc = make_tmap_bf16_2d(&tmWd, W1, r_total, kD, kD, r_total / 2, 64))) return rc;
+  if ((rc = make_tmap_bf16_2d(&tmW2, W2, kD, r_total, r_total, N2 / 2, 64))) return rc;
   tmW2k = tmW2;
-  if (p.w2_3d && (rc = make_tmap_bf16_kblocks(&tmW2k, Wu_cat, kD, r_total, r_total, N2 / 2, r_total / 64)))
+  if (p.w2_3d && (rc = make_tmap_bf16_kblocks(&tmW2k, W2, kD, r_total, r_total, N2 / 2, r_total / 64)))
     return rc;
 
   using KernelFn = void (*)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap,
                             const CUtensorMap, const CUtensorMap, const PipeParams);
-  const bool gelu = act == FEDDAT_ACT_GELU;
-  KernelFn fn = gelu ? dat_fwd_pipe_kernel<true> : dat_fwd_pipe_kernel<false>;
-  static bool configured[2][64] = {{false}};
+  KernelFn fn = bwd ? dat_pipe_kernel<true, false> : (gelu ? dat_pipe_kernel<false, true> : dat_pipe_kernel<false, false>);
+  static bool configured[3][64] = {{false}};
   int dev = 0;
   FD_CHECK_CUDA(cudaGetDevice(&dev));
-  if (dev >= 64 || !configured[gelu][dev]) {
+  const int kidx = bwd ? 2 : (gelu ? 1 : 0);
+  if (dev >= 64 || !configured[kidx][dev]) {
     FD_CHECK_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem));
-    if (dev < 64) configured[gelu][dev] = true;
+    if (dev < 64) configured[kidx][dev] = true;
   }
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(grid);
@@ -470,6 +531,33 @@ int launch_dat_fwd_pipe(const void* X, const void* Res, void* Y, const void* Wd_
   FD_CHECK_CUDA(cudaLaunchKernelEx(&cfg, fn, tmX, tmRes, tmY, tmWd, tmW2, tmW2k, p));
   FD_CHECK_CUDA(cudaGetLastError());
   return FD_OK;
+}
+
+}  // namespace
+
+int launch_dat_fwd_pipe(const void* X, const void* Res, void* Y, const void* Wd_cat, const float* bd_cat,
+                        const void* Wu_cat, const float* bu_cat, void* H_out, int64_t M, int r_total, float scale,
+                        int act, int grid, cudaStream_t st) {
+  PipeParams p{};
+  p.scale = scale;
+  p.bd = bd_cat;
+  p.bu = bu_cat;
+  p.H_out = static_cast<__nv_bfloat16*>(H_out);
+  return launch_pipe(false, X, Res, Y, Wd_cat, Wu_cat, p, M, r_total, act == FEDDAT_ACT_GELU, grid, st);
+}
+
+int launch_dat_bwd_pipe(const void* dY, void* dX, const void* WuT_cat, const void* WdT_cat, const void* H_in,
+                        void* dP_t, int ld_t, int r_lo, int r_hi, int64_t M, int r_total, float scale, int add_dy,
+                        int grid, cudaStream_t st) {
+  PipeParams p{};
+  p.scale = scale;
+  p.H_in = static_cast<const __nv_bfloat16*>(H_in);
+  p.dP_t = static_cast<__nv_bfloat16*>(dP_t);
+  p.ld_t = ld_t;
+  p.r_lo = dP_t ? r_lo : 0;
+  p.r_hi = dP_t ? r_hi : 0;
+  p.has_res = add_dy ? 1 : 0;
+  return launch_pipe(true, dY, dY, dX, WuT_cat, WdT_cat, p, M, r_total, false, grid, st);
 }
 
 }  // namespace fd

@@ -11,4 +11,9 @@ int launch_dat_fwd_pipe(const void* X, const void* Res, void* Y, const void* Wd_
                         const void* Wu_cat, const float* bu_cat, void* H_out, int64_t M, int r_total, float scale,
                         int act, int grid, cudaStream_t st);
 
+// Saved-mode backward data gradient on the same pipeline (ReLU, dX requested).
+int launch_dat_bwd_pipe(const void* dY, void* dX, const void* WuT_cat, const void* WdT_cat, const void* H_in,
+                        void* dP_t, int ld_t, int r_lo, int r_hi, int64_t M, int r_total, float scale, int add_dy,
+                        int grid, cudaStream_t st);
+
 }  // namespace fd

@@ -199,6 +199,10 @@ def test_dat_fwd_bwd_full_size_vs_oracle(ops, R, M, gating, act):
         assert torch.equal(dx2, dx)
         for a, b2 in zip(grads2, grads):
             assert relerr(a.cpu().numpy(), b2.cpu().numpy()) < 1e-5        # fp32 atomics: order only
+        # residual input == X (adaptered_output.py:78): dX additionally carries dY, one packed bf16 add
+        dx3, _ = ops.dat_backward(xd, gd, pk, scale, act, train_slice=None, need_dx=True, add_dy=True, hidden=h)
+        torch.cuda.synchronize()
+        assert torch.equal(dx3, (dx2.float() + gd.float()).to(torch.bfloat16))
 
 
 def test_dat_backward_without_dx_and_frozen_only(ops):
