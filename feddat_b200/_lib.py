@@ -33,6 +33,7 @@ EXPORTED_SYMBOLS = (
     "feddat_debug_force_fused_fwd",
     "feddat_probe_pair",
     "feddat_probe_ingest",
+    "feddat_probe_tilecopy",
 )
 
 
@@ -97,6 +98,8 @@ def load() -> ctypes.CDLL:
     lib.feddat_gelu_bwd.argtypes = [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p]
     lib.feddat_debug_force_fused_fwd.restype = c_int
     lib.feddat_debug_force_fused_fwd.argtypes = [c_int]
+    lib.feddat_probe_tilecopy.restype = c_int
+    lib.feddat_probe_tilecopy.argtypes = [c_void_p, c_void_p, c_int64, c_int, c_int, c_int, c_void_p]
     lib.feddat_probe_ingest.restype = c_int
     lib.feddat_probe_ingest.argtypes = [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p,
                                         c_void_p]

@@ -338,6 +338,90 @@ extern "C" int feddat_probe_ingest(const void* buf, int n_rows, int row_stride, 
 }
 
 // ------------------------------------------------------------------------------------------------
+// Tile-copy probe: the DAT kernels' HBM access pattern without any compute.  Persistent CTAs walk
+// 128-row tiles of a [M, 768] bf16 tensor; each tile is read as twelve [128 x 64] TMA boxes (k-chunk
+// order, like GEMM1) and written back to a second tensor as twelve [128 x 64] TMA stores (like the
+// output chunks).  Separates "this access pattern cannot reach the copy bandwidth" from "the compute
+// pipeline leaves HBM idle".  mode 1: read only.
+// ------------------------------------------------------------------------------------------------
+namespace fd {
+
+__global__ void __launch_bounds__(96, 1)
+probe_tilecopy_kernel(const __grid_constant__ CUtensorMap tmSrc, const __grid_constant__ CUtensorMap tmDst,
+                      int num_tiles, int ns, int read_only) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t bars[32];
+  const uint32_t smem0 = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar0 = smem_u32(bars);
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < ns; ++s) {
+      mbar_init(bar0 + 8 * s, 1);
+      mbar_init(bar0 + 8 * (16 + s), 1);
+    }
+    fence_mbar_init();
+    tma_prefetch_desc(&tmSrc);
+    tma_prefetch_desc(&tmDst);
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == 0 && lane == 0) {
+    int s = 0;
+    uint32_t par = 0;
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x)
+      for (int kc = 0; kc < 12; ++kc) {
+        mbar_wait(bar0 + 8 * (16 + s), par ^ 1);
+        mbar_arrive_expect_tx(bar0 + 8 * s, 16384);
+        tma_load_2d(smem0 + s * 16384, &tmSrc, bar0 + 8 * s, kc * 64, t * 128);
+        if (++s == ns) { s = 0; par ^= 1; }
+      }
+  } else if (warp == 1 && lane == 0) {
+    int s = 0, prev = -1;
+    uint32_t par = 0;
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x)
+      for (int kc = 0; kc < 12; ++kc) {
+        mbar_wait(bar0 + 8 * s, par);
+        if (read_only) {
+          mbar_arrive(bar0 + 8 * (16 + s));
+        } else {
+          tma_store_2d(&tmDst, smem0 + s * 16384, kc * 64, t * 128);
+          tma_store_commit();
+          if (prev >= 0) {
+            tma_store_wait_read<1>();
+            mbar_arrive(bar0 + 8 * (16 + prev));
+          }
+          prev = s;
+        }
+        if (++s == ns) { s = 0; par ^= 1; }
+      }
+    if (!read_only && prev >= 0) {
+      tma_store_wait_read<0>();
+      mbar_arrive(bar0 + 8 * (16 + prev));
+      tma_store_wait_all<0>();
+    }
+  }
+  __syncthreads();
+}
+
+}  // namespace fd
+
+extern "C" int feddat_probe_tilecopy(const void* src, void* dst, int64_t M, int grid, int ns, int read_only,
+                                     void* stream) {
+  using namespace fd;
+  int rc = check_device_sm100();
+  if (rc) return rc;
+  FD_REQUIRE(ns >= 2 && ns <= 13 && M > 0 && grid > 0, FD_ERR_INVALID, "probe_tilecopy: bad arguments");
+  CUtensorMap tmS, tmD;
+  if ((rc = make_tmap_bf16_2d(&tmS, src, M, 768, 768, 128, 64))) return rc;
+  if ((rc = make_tmap_bf16_2d(&tmD, dst, M, 768, 768, 128, 64))) return rc;
+  const size_t smem = 1024 + static_cast<size_t>(ns) * 16384;
+  FD_CHECK_CUDA(cudaFuncSetAttribute(probe_tilecopy_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
+  probe_tilecopy_kernel<<<grid, 96, smem, static_cast<cudaStream_t>(stream)>>>(
+      tmS, tmD, static_cast<int>((M + 127) / 128), ns, read_only);
+  FD_CHECK_CUDA(cudaGetLastError());
+  return FD_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
 // cta_group::2 bring-up: one CTA pair, D[256 x N] = A[256 x K] * B[N x K]^T.  Each CTA holds its
 // 128 rows of A (smem, or TMEM when a_tmem) and N/2 rows of B; the leader CTA issues the MMAs.
 // ------------------------------------------------------------------------------------------------

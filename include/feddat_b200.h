@@ -170,6 +170,9 @@ int feddat_probe_pair(const void* A, const void* B, float* D, int N, int K, int 
 
 /* L2 -> SM TMA streaming bandwidth probe (optionally multicast across a cluster), csrc/probe.cu. */
 int feddat_probe_l2bw(const void* buf, int n_boxes, int iters, int grid, int cluster, void* stream);
+/* HBM access-pattern probe: tiles of a [M, 768] bf16 tensor read as [128 x 64] TMA boxes and written back
+ * the same way, no compute (profiling only). */
+int feddat_probe_tilecopy(const void* src, void* dst, int64_t M, int grid, int ns, int read_only, void* stream);
 /* Per-SM TMA ingest sweep (ring depth, box height, producer count, grid size); bring-up / profiling only. */
 int feddat_probe_ingest(const void* buf, int n_rows, int row_stride, int iters, int grid, int ns,
                         int box_rows, int n_prod, long long* issue_clk, void* stream);

@@ -26,15 +26,17 @@ pk2, pk1 = mk(2), mk(1)
 for M in Ms:
     x = torch.randn(M, D, device=dev, generator=g).to(torch.bfloat16)
     dy = torch.randn(M, D, device=dev, generator=g).to(torch.bfloat16)
+    # the product path for ReLU: the forward saves the hidden, the backward does not recompute it
     for _ in range(2):
-        ops.dat_forward(x, x, pk2, 0.5)
-        ops.dat_backward(x, dy, pk2, 0.5, train_slice=(0, r))
+        _, h2 = ops.dat_forward(x, x, pk2, 0.5, save_hidden=True)
+        _, h1 = ops.dat_forward(x, x, pk1, 1.0, save_hidden=True)
+        ops.dat_backward(x, dy, pk2, 0.5, train_slice=(0, r), hidden=h2)
     torch.cuda.synchronize()
     torch.cuda.profiler.start()
-    ops.dat_forward(x, x, pk2, 0.5)
-    ops.dat_forward(x, x, pk1, 1.0)
-    ops.dat_backward(x, dy, pk2, 0.5, train_slice=(0, r))
-    ops.dat_backward(x, dy, pk1, 1.0, train_slice=(0, r))
+    ops.dat_forward(x, x, pk2, 0.5, save_hidden=True)
+    ops.dat_forward(x, x, pk1, 1.0, save_hidden=True)
+    ops.dat_backward(x, dy, pk2, 0.5, train_slice=(0, r), hidden=h2)
+    ops.dat_backward(x, dy, pk1, 1.0, train_slice=(0, r), hidden=h1)
     torch.cuda.synchronize()
     torch.cuda.profiler.stop()
 print("done")
