@@ -306,7 +306,12 @@ def run_ours(args):
             "gpu_launches": launches,
             "roofline": {"kernel": "dat_bwd gating r=128 (dgrad + wgrad launches), M=5920 rows/site",
                          "bound": "tensor", "achieved": dom["tflops"], "peak": peak, "unit": "TFLOP/s",
-                         "frac": round(dom["tflops"] / peak, 4), "traffic": None,
+                         "frac": round(dom["tflops"] / peak, 4),
+                         # dram__bytes_read.sum + dram__bytes_write.sum of the two launches, from the round's
+                         # ncu --set full capture (profiles/r1_dat_kernels_v14_raw.csv: dgrad 12.96 MB + wgrad
+                         # 22.05 MB read, 0 written inside the kernels -- the 18 MB of outputs stay dirty in
+                         # L2); algorithmic bytes = 6 d M = 27.3 MB
+                         "traffic": 35.0e6, "traffic_unit": "bytes per dgrad + wgrad launch pair (ncu)",
                          "peak_source": f"{peaks['source']} bf16_tflops (burst: kernel timed alone)",
                          "algorithmic_flops_per_launch": 12 * D * RANK * B * 185,
                          "steady_state_M71040": {"achieved": big["tflops"], "frac": round(big["tflops"] / peak, 4)}},

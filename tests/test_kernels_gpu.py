@@ -358,4 +358,13 @@ def test_gelu_matches_torch(ops, shape):
     y_ref.backward(dy.float())
     assert relerr(y.float().cpu().numpy(), y_ref.detach().cpu().numpy()) < 4e-3      # one bf16 rounding
     assert relerr(dx.float().cpu().numpy(), xf.grad.cpu().numpy()) < 4e-3
-    assert torch.equal(y, y_ref.detach().to(torch.bfloat16))                          # same fp32 formula: bit-exact
+    # Phi comes from the A-S erfc form (|abs error| < 1e-6 before rounding): the same bf16 value as torch's
+    # erff path wherever the output is not a far-tail value (x > -3; boundaries aside), and in the
+    # negative tail -- where 1 + erf cancels catastrophically in fp32 and torch returns e.g. -0.0 at
+    # x = -6.3 -- within 1e-6 absolute of the exact float64 GELU
+    yb = y_ref.detach().to(torch.bfloat16)
+    main = x.float() > -3
+    assert (y[main] == yb[main]).float().mean().item() > 0.999 if main.any() else True
+    exact = 0.5 * x.double() * (1 + torch.erf(x.double() / 2 ** 0.5))
+    d = (y.double() - exact).abs()
+    assert bool((d <= exact.abs() * 2 ** -8 + 1e-6).all())
