@@ -222,7 +222,7 @@ dat_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
         for (int pass = kSaved ? 1 : 0; pass < (kBwd ? 2 : 1); ++pass) {
           const CUtensorMap* tm = lane == 0 ? (pass == 0 ? &tmX : &tmRes) : (pass == 0 ? &tmWd : &tmW1b);
           const int c1 = lane == 0 ? m0 : static_cast<int>(rank) * RH;
-          const uint64_t pol = lane == 0 ? kEvictNormal : kEvictLast;
+          const uint64_t pol = kEvictLast;   // activations too: they are re-read as the residual
           for (int kc = 0; kc < KC1; ++kc, ++n) {
             const uint32_t s = n & (NS - 1), par = (n / NS) & 1;
             mbar_wait(bar_slot_empty(s), par ^ 1);
@@ -371,7 +371,8 @@ dat_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
         for (uint32_t c64 = 0; c64 < per_tile; ++c64, ++g) {
           const uint32_t sb = g % NSTG, par = (g / NSTG) & 1;
           mbar_wait(bar_out_full(sb), par);
-          tma_store_2d(&tmY, stg_base + sb * SLOT, (c_base * 2 + c64) * 64, m0);
+          // outputs are never re-read by this kernel: let them leave L2 first
+          tma_store_2d_hint(&tmY, stg_base + sb * SLOT, (c_base * 2 + c64) * 64, m0, kEvictFirst);
           tma_store_commit();
           FD_TRACE(104 + (c64 >> 1), it);
           if (g > 0) {  // the previous store has finished reading its buffer: recycle it

@@ -19,6 +19,8 @@
 //   G1 ring   3 stages x 32 KB   [X k-chunk 128 x 64 | Wd_cat half k-chunk R/2 x 64]
 //   W2 ring   3 slots  x 16 KB   this CTA's half [32 x R] of the Wu_cat tile of one output chunk
 //   staging   4 slots  x 16 KB   residual in / output out, [128 x 64]
+// (3 / 3 / 4 is the measured optimum of the 208 KB: 4 / 2 / 3 runs 13 % slower, 2 / 3 / 6 5 % slower --
+// every ring wants more bytes in flight than shared memory holds.)
 //
 //   warp 0      lanes 0 / 1: G1 ring producers (activations / weights), + L2 prefetch of the next tile
 //   warp 1      MMA issuer (whole warp, one elected lane issues)
@@ -180,7 +182,7 @@ dat_pipe_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
     if (lane < 2) {
       uint32_t n = 0;
       const CUtensorMap* tm = lane == 0 ? &tmX : &tmWd;
-      const uint64_t pol = lane == 0 ? kEvictNormal : kEvictLast;
+      const uint64_t pol = kEvictLast;
       for (int it = 0; it < my_tiles; ++it) {
         const int m0 = tile_of(it) * BM;
         const int c1 = lane == 0 ? m0 : static_cast<int>(rank) * RH;
@@ -306,7 +308,9 @@ dat_pipe_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
         for (int c = 0; c < NC2; ++c, ++g) {
           const uint32_t sb = g % NSTG, par = (g / NSTG) & 1;
           mbar_wait(bar_out_full(sb), par);
-          tma_store_2d(&tmY, stg_base + sb * SLOT, c * N2, m0);
+          // outputs are never re-read by this kernel: let them leave L2 first, the activations (re-read as the
+          // residual a few microseconds after GEMM1 consumed them) last
+          tma_store_2d_hint(&tmY, stg_base + sb * SLOT, c * N2, m0, kEvictFirst);
           tma_store_commit();
           if (g > 0) {
             tma_store_wait_read<1>();

@@ -145,6 +145,12 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap* tm, uint32_t src
                ::"l"(reinterpret_cast<uint64_t>(tm)), "r"(src_smem), "r"(c0), "r"(c1)
                : "memory");
 }
+__device__ __forceinline__ void tma_store_2d_hint(const CUtensorMap* tm, uint32_t src_smem, int c0, int c1,
+                                                  uint64_t policy) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group.L2::cache_hint [%0, {%2, %3}], [%1], %4;"
+               ::"l"(reinterpret_cast<uint64_t>(tm)), "r"(src_smem), "r"(c0), "r"(c1), "l"(policy)
+               : "memory");
+}
 __device__ __forceinline__ void tma_store_commit() {
   asm volatile("cp.async.bulk.commit_group;" ::: "memory");
 }
