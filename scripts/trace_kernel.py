@@ -60,10 +60,14 @@ names.update({120: "E2 c0.0: D full seen", 121: "E2 c0.0: tmem_ld issued", 122: 
               126: "E2 c0.0: arrived"})
 wg = {200: "wgrad: entry", 201: "wgrad: prologue done", 202: "wgrad: all MMAs issued", 203: "wgrad: accumulators complete",
       204: "wgrad: reductions issued", 205: "wgrad: exit"}
+for i in range(10):
+    wg[210 + i] = f"wgrad: stage {i} loads issued"
+    wg[220 + i] = f"wgrad: stage {i} MMAs issued"
+    wg[230 + i] = f"wgrad: stage {i} bias sums done (warp 2)"
 print(f"kernel {e0.elapsed_time(e1) * 1e3:.1f} us, R={R} M={M} {mode}")
 if any(t[e] for e in wg):
     w0 = t[200]
-    for e in sorted(wg):
+    for e in sorted((e for e in wg if t[e]), key=lambda e: t[e]):
         print(f"wgrad {(t[e] - w0) / 1e3:9.2f} us  {wg[e]}   (dgrad entry {-(t[1] - w0) / 1e3:.2f} us earlier)" if e == 200 else
               f"wgrad {(t[e] - w0) / 1e3:9.2f} us  {wg[e]}")
 for tile in range(2):
