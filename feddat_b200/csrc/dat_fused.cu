@@ -183,11 +183,6 @@ dat_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
     if (kBwd) tma_prefetch_desc(&tmW1b);
   }
   if (warp == 2) tmem_alloc_pair(smem_u32(&tmem_base_smem), 512);
-  // biases in smem: bd as is; bu PRE-SCALED by the branch scale (epilogue 2 is one FFMA per element)
-  if (!kSaved)
-    for (int i = tid; i < R; i += NUM_THREADS) bias_smem[i] = p.bd[i];
-  if (!kBwd)
-    for (int i = tid; i < kD; i += NUM_THREADS) bias_smem[R + i] = p.scale * p.bu[i];
   tc_fence_before();
   cluster_sync_all();   // barrier inits + TMEM allocation visible to both CTAs of the pair
   tc_fence_after();
@@ -382,9 +377,9 @@ dat_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
         }
       }
       if (total_chunks > 0) {
+        // smem has been read; kernel completion covers the visibility of the writes themselves
         tma_store_wait_read<0>();
         mbar_arrive(bar_stg_empty((total_chunks - 1) % NSTG));
-        tma_store_wait_all<0>();
       }
     }
     __syncwarp();
@@ -402,6 +397,17 @@ dat_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
     const uint32_t leader_d_empty = mapa_u32(bar_d_empty(group), 0);
     const int c_lo = group == 0 ? 0 : nA, c_hi = group == 0 ? nA : n16;
     const uint32_t w_base = group == 0 ? 0u : static_cast<uint32_t>(16 * nA);   // where its hidden goes
+    // Biases -> smem by the 256 epilogue threads, AFTER the cluster sync: the (cold) global reads overlap
+    // GEMM1 instead of delaying every role.  bd as is; bu PRE-SCALED by the branch scale (epilogue 2 is
+    // one FFMA per element).
+    {
+      const int et = tid - 128;
+      if (!kSaved)
+        for (int i = et; i < R; i += 256) bias_smem[i] = p.bd[i];
+      if (!kBwd)
+        for (int i = et; i < kD; i += 256) bias_smem[R + i] = p.scale * p.bu[i];
+      named_bar_sync(1, 256);
+    }
 
     for (int it = 0; it < my_tiles; ++it) {
       const uint32_t tile_it = it;

@@ -162,10 +162,6 @@ dat_pipe_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
     tma_prefetch_desc(&tmW2k);
   }
   if (warp == 2) tmem_alloc_pair(smem_u32(&tmem_base_smem), 512);
-  if (!kBwd) {
-    for (int i = tid; i < R; i += NUM_THREADS) bias_smem[i] = p.bd[i];
-    for (int i = tid; i < kD; i += NUM_THREADS) bias_smem[R + i] = p.scale * p.bu[i];   // pre-scaled
-  }
   tc_fence_before();
   cluster_sync_all();
   tc_fence_after();
@@ -319,9 +315,8 @@ dat_pipe_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
         }
       }
       if (total > 0) {
-        tma_store_wait_read<0>();
+        tma_store_wait_read<0>();       // kernel completion covers the visibility of the writes
         mbar_arrive(bar_stg_empty((total - 1) % NSTG));
-        tma_store_wait_all<0>();
       }
     }
     __syncwarp();
@@ -336,6 +331,12 @@ dat_pipe_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
     const uint32_t leader_h_full = mapa_u32(bar_h_full, 0);
     const uint32_t leader_d_empty = mapa_u32(bar_d_empty(group), 0);
     const int c_lo = group == 0 ? 0 : nA, c_hi = group == 0 ? nA : n16;
+    if (!kBwd) {   // biases -> smem after the cluster sync (the cold reads overlap GEMM1); bu pre-scaled
+      const int et = tid - 128;
+      for (int i = et; i < R; i += 256) bias_smem[i] = p.bd[i];
+      for (int i = et; i < kD; i += 256) bias_smem[R + i] = p.scale * p.bu[i];
+      named_bar_sync(1, 256);
+    }
 
     for (int it = 0; it < my_tiles; ++it) {
       const uint32_t tile_it = it;
