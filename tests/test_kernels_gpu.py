@@ -148,6 +148,8 @@ def test_dat_backward_matches_reference_golden(golden, ops, case):
     (256, 71117, True, "relu"),    # 12 sites batched (the steady-state bench size) + ragged tail
     (128, 40001, False, "relu"),
     (96, 25003, True, "relu"),     # R % 64 != 0: per-k-block 2-D weight loads
+    (64, 20011, True, "gelu"),     # tile-pipelined forward with GELU; backward recomputes (no saved mode)
+    (128, 9000, False, "relu"),    # 36 super-tiles: two CTA pairs per super-tile (column split S = 2)
 ])
 def test_dat_fwd_bwd_full_size_vs_oracle(ops, R, M, gating, act):
     rng = np.random.default_rng(R * 7919 + M)
@@ -223,6 +225,16 @@ def test_dat_backward_without_dx_and_frozen_only(ops):
     assert torch.equal(dx_only, dx_full)
     for a, b in zip(grads_only, grads_full):
         assert relerr(a.cpu().numpy(), b.cpu().numpy()) < 1e-5   # fp32 atomics: order only
+    # the same three variants in SAVED mode (what Adapter's autograd uses for ReLU)
+    _, h = ops.dat_forward(x, x, pk, 0.5, save_hidden=True)
+    s_full, sg_full = ops.dat_backward(x, g, pk, 0.5, train_slice=(0, r), need_dx=True, add_dy=True, hidden=h)
+    s_none, sg_only = ops.dat_backward(x, g, pk, 0.5, train_slice=(0, r), need_dx=False, hidden=h)
+    s_only, sg_none = ops.dat_backward(None, g, pk, 0.5, train_slice=None, need_dx=True, add_dy=True, hidden=h)
+    torch.cuda.synchronize()
+    assert s_none is None and sg_none is None
+    assert torch.equal(s_full, dx_full) and torch.equal(s_only, dx_full)
+    for a, b in zip(list(sg_full) + list(sg_only), list(grads_full) + list(grads_full)):
+        assert relerr(a.cpu().numpy(), b.cpu().numpy()) < 1e-5
 
 
 def test_unsupported_shapes_fail_loudly(ops):
