@@ -88,7 +88,7 @@ def load() -> ctypes.CDLL:
     lib.feddat_probe_l2bw.argtypes = [c_void_p, c_int, c_int, c_int, c_int, c_void_p]
     lib.feddat_ln_fwd.restype = c_int
     lib.feddat_ln_fwd.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
-                                  c_int64, c_int, c_float, c_int, c_void_p]
+                                  c_void_p, c_void_p, c_int64, c_int, c_float, c_int, c_void_p]
     lib.feddat_ln_bwd.restype = c_int
     lib.feddat_ln_bwd.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64,
                                   c_int, c_int, c_void_p]

@@ -7,8 +7,11 @@ first residual connection fused:
 
     ln1        = LN_before(h)                         one launch
     attn       = attention(ln1)                        (HF module, SDPA)
-    h2, ln2    = h + attn, LN_after(h + attn)          one launch for the add AND the LayerNorm
-    out        = output(intermediate(ln2), h2)         dense (cuBLAS) + GELU (feddat_gelu_*), then the DAT site
+    h2, ln2    = h + attn, LN_after(h + attn)          one launch for the add AND the LayerNorm (it also
+                                                       emits h2 + b_out, the output dense layer's bias)
+    inter      = GELU(dense(ln2))                      cuBLAS + feddat_gelu_*
+    x          = (h2 + b_out) + inter W_out^T          ONE GEMM with a beta = 1 epilogue (the second residual)
+    out        = adapter(x, x)                         the DAT site
 
 It applies only where the kernels are defined -- bf16 CUDA activations of width 768, frozen bf16 affine
 parameters (main.py:138-139 freezes the whole backbone), no attention mask / attention maps requested --
@@ -24,18 +27,21 @@ from .. import ops
 
 
 class _AddLayerNorm(torch.autograd.Function):
-    """(y, s) = (LayerNorm(x + res), x + res); ``res`` may be None (then s is x and is not returned as
-    a fresh tensor).  Affine parameters are frozen: no gradients for them."""
+    """y = LayerNorm(s), s = x + res (``res`` may be None: s is x).  Returns y alone (no res), (y, s), or --
+    with ``bias2`` -- (y, s + bias2): the residual stream with the next dense layer's bias pre-added, the
+    only form in which it is then consumed.  Affine parameters and bias2 are frozen: no gradients for them."""
 
     @staticmethod
-    def forward(ctx, x, res, weight, bias, eps):
+    def forward(ctx, x, res, weight, bias, eps, bias2):
         shape = x.shape
         x2 = x.reshape(-1, shape[-1])
         r2 = None if res is None else res.reshape(-1, shape[-1])
-        y, s, mean, rstd = ops.layer_norm_fwd(x2, r2, weight, bias, eps)
+        y, s, mean, rstd, s2 = ops.layer_norm_fwd(x2, r2, weight, bias, eps, bias2)
         ctx.save_for_backward(s, weight, mean, rstd)
         ctx.has_res = res is not None
         ctx.shape = shape
+        if bias2 is not None:
+            return y.view(shape), s2.view(shape)
         if res is None:
             return y.view(shape)
         return y.view(shape), s.view(shape)
@@ -47,7 +53,7 @@ class _AddLayerNorm(torch.autograd.Function):
         gy2 = gy.reshape(-1, d).contiguous()
         gs2 = None if gs is None else gs.reshape(-1, d).contiguous()
         dx = ops.layer_norm_bwd(gy2, gs2, s, weight, mean, rstd).view(ctx.shape)
-        return dx, (dx if ctx.has_res else None), None, None, None
+        return dx, (dx if ctx.has_res else None), None, None, None, None
 
 
 class _Gelu(torch.autograd.Function):
@@ -85,17 +91,27 @@ def _usable(ln: torch.nn.LayerNorm, h: torch.Tensor) -> bool:
 
 def layer_norm(ln: torch.nn.LayerNorm, h: torch.Tensor) -> torch.Tensor:
     if _usable(ln, h):
-        return _AddLayerNorm.apply(h, None, ln.weight, ln.bias, ln.eps)
+        return _AddLayerNorm.apply(h, None, ln.weight, ln.bias, ln.eps, None)
     return ln(h)
 
 
-def add_layer_norm(ln: torch.nn.LayerNorm, a: torch.Tensor, b: torch.Tensor):
-    """(a + b, LayerNorm(a + b))."""
+def add_layer_norm(ln: torch.nn.LayerNorm, a: torch.Tensor, b: torch.Tensor, bias2=None):
+    """(a + b [+ bias2], LayerNorm(a + b))."""
     if _usable(ln, a) and b.dtype == a.dtype and b.shape == a.shape and b.is_contiguous():
-        y, s = _AddLayerNorm.apply(a, b, ln.weight, ln.bias, ln.eps)
+        y, s = _AddLayerNorm.apply(a, b, ln.weight, ln.bias, ln.eps, bias2)
         return s, y
     s = a + b
-    return s, ln(s)
+    return (s if bias2 is None else s + bias2), ln(s)
+
+
+def _prebias_ok(out_mod, h: torch.Tensor) -> bool:
+    """The "dense + bias + residual" of Adaptered_ViltOutput can be ONE GEMM (beta = 1 epilogue) when its
+    dense layer is frozen bf16 with a bias and its dropout is the identity."""
+    dense = getattr(getattr(out_mod, "layer", None), "dense", None)
+    drop = getattr(getattr(out_mod, "layer", None), "dropout", None)
+    return (hasattr(out_mod, "adapter") and isinstance(dense, torch.nn.Linear) and dense.bias is not None
+            and dense.weight.dtype == h.dtype and not dense.weight.requires_grad and not dense.bias.requires_grad
+            and dense.bias.is_contiguous() and (drop is None or drop.p == 0.0 or not out_mod.training))
 
 
 def fast_vilt_layer_forward(self, hidden_states, attention_mask=None, output_attentions=False):
@@ -104,6 +120,15 @@ def fast_vilt_layer_forward(self, hidden_states, attention_mask=None, output_att
         return type(self).forward(self, hidden_states, attention_mask, output_attentions)
     ln1 = layer_norm(self.layernorm_before, hidden_states)
     attention_output = self.attention(ln1, None, output_attentions=False)[0]
+    if _prebias_ok(self.output, hidden_states):
+        # first residual + LayerNorm in one launch, which also emits the residual stream with the output
+        # dense layer's bias pre-added; second residual = the GEMM's beta = 1 epilogue; then the DAT site
+        dense = self.output.layer.dense
+        res_b, ln2 = add_layer_norm(self.layernorm_after, attention_output, hidden_states, bias2=dense.bias)
+        inter = intermediate(self.intermediate, ln2)
+        h = torch.addmm(res_b.reshape(-1, res_b.shape[-1]), inter.reshape(-1, inter.shape[-1]), dense.weight.t())
+        h = h.view(res_b.shape)
+        return (self.output.adapter(h, h),)
     hidden_states, ln2 = add_layer_norm(self.layernorm_after, attention_output, hidden_states)   # first residual
     layer_output = intermediate(self.intermediate, ln2)
     layer_output = self.output(layer_output, hidden_states)                                     # second residual + DAT

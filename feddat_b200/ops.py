@@ -225,25 +225,30 @@ def fedavg(client_bufs: Sequence[torch.Tensor], nums: Sequence[float], out: torc
 
 
 def layer_norm_fwd(x: torch.Tensor, res: Optional[torch.Tensor], weight: torch.Tensor, bias: torch.Tensor,
-                   eps: float):
-    """(y, s, mean, rstd): s = bf16(x + res) (s is x itself when res is None), y = LayerNorm(s) over the
-    last dimension (768), statistics in fp32 (feddat_ln_fwd)."""
+                   eps: float, bias2: Optional[torch.Tensor] = None):
+    """(y, s, mean, rstd, s2): s = bf16(x + res) (s is x itself when res is None), y = LayerNorm(s) over the
+    last dimension (768), statistics in fp32; s2 = bf16(s + bias2) when ``bias2`` is given, else None
+    (feddat_ln_fwd)."""
     lib = _lib.load()
     _check_act2d(x, "layer_norm x")
     if res is not None:
         _check_act2d(res, "layer_norm res")
-    for t, n in ((weight, "weight"), (bias, "bias")):
+    for t, n in ((weight, "weight"), (bias, "bias"), (bias2, "bias2")):
+        if t is None:
+            continue
         if not (t.is_cuda and t.dtype == torch.bfloat16 and t.is_contiguous() and t.numel() == x.shape[1]):
             raise _lib.FeddatError(f"layer_norm {n}: expected a contiguous CUDA bf16 [{x.shape[1]}] tensor")
     M, d = x.shape
     y = torch.empty_like(x)
     s = torch.empty_like(x) if res is not None else None
+    s2 = torch.empty_like(x) if bias2 is not None else None
     stats = torch.empty(2, M, device=x.device, dtype=torch.float32)
     rc = lib.feddat_ln_fwd(_lib.ptr(x), _lib.ptr(res), _lib.ptr(weight), _lib.ptr(bias), _lib.ptr(y), _lib.ptr(s),
-                           _lib.ptr(stats[0]), _lib.ptr(stats[1]), M, d, float(eps), DTYPE_BF16, _lib.stream_ptr())
+                           _lib.ptr(bias2), _lib.ptr(s2), _lib.ptr(stats[0]), _lib.ptr(stats[1]), M, d, float(eps),
+                           DTYPE_BF16, _lib.stream_ptr())
     _lib.check(rc, "feddat_ln_fwd")
     _count()
-    return y, (s if s is not None else x), stats[0], stats[1]
+    return y, (s if s is not None else x), stats[0], stats[1], s2
 
 
 def layer_norm_bwd(dy: torch.Tensor, dsum: Optional[torch.Tensor], s: torch.Tensor, weight: torch.Tensor,

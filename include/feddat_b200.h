@@ -140,13 +140,15 @@ int feddat_fedavg(const float* const* clients /* host array of device ptrs */,
  * site (HF ViltLayer.forward: layernorm_before / first residual + layernorm_after; the tensors the
  * reference's Adaptered_ViltOutput.forward, src/modeling/adaptered_output.py:73-79, receives).
  *   s = bf16(x + res) (res, sum_out both NULL: s = x), y = bf16((s - mean) rstd w + b); mean, rstd: fp32 [M]
+ *   s2 = bf16(s + bias2) (bias2, sum2_out both NULL: skipped): the residual stream with the next dense layer's
+ *   bias pre-added (that layer then is one GEMM with a beta = 1 epilogue)
  *   dx = rstd (g - mean_c g - xhat mean_c(g xhat)) (+ dsum),  g = dy w,  xhat = (s - mean) rstd
  * The affine parameters are FROZEN on this path (main.py:138-139): no weight / bias gradients.
  * x, res, y, sum_out, dy, dsum, s, dx: [M, 768] bf16 contiguous; weight, bias: [768] bf16.
  */
 int feddat_ln_fwd(const void* x, const void* res, const void* weight, const void* bias, void* y,
-                  void* sum_out, float* mean, float* rstd, int64_t M, int d, float eps, int dtype,
-                  void* stream);
+                  void* sum_out, const void* bias2, void* sum2_out, float* mean, float* rstd, int64_t M,
+                  int d, float eps, int dtype, void* stream);
 int feddat_ln_bwd(const void* dy, const void* dsum, const void* s, const void* weight,
                   const float* mean, const float* rstd, void* dx, int64_t M, int d, int dtype,
                   void* stream);

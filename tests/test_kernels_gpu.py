@@ -344,11 +344,15 @@ def test_fused_layernorm_matches_torch(ops, M, with_res):
     dy = torch.randn(M, 768, device="cuda", generator=g).to(torch.bfloat16)
     dsum = torch.randn(M, 768, device="cuda", generator=g).to(torch.bfloat16) if with_res else None
     eps = 1e-12
-    y, s, mean, rstd = ops.layer_norm_fwd(x, res, w, b, eps)
+    b2 = (0.1 * torch.randn(768, device="cuda", generator=g)).to(torch.bfloat16)
+    y, s, mean, rstd, s2 = ops.layer_norm_fwd(x, res, w, b, eps, bias2=b2)
+    y_nob2 = ops.layer_norm_fwd(x, res, w, b, eps)
     dx = ops.layer_norm_bwd(dy, dsum, s, w, mean, rstd)
     torch.cuda.synchronize()
     s_ref = (x.float() + res.float()).to(torch.bfloat16) if with_res else x
     assert torch.equal(s, s_ref)                                           # bf16 sum: bit-exact
+    assert torch.equal(s2, (s_ref.float() + b2.float()).to(torch.bfloat16))   # pre-biased residual stream
+    assert y_nob2[4] is None and torch.equal(y_nob2[0], y)
     sf = s_ref.float().requires_grad_(True)
     y_ref = torch.nn.functional.layer_norm(sf, (768,), w.float(), b.float(), eps)
     y_ref.backward(dy.float())

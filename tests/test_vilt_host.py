@@ -54,3 +54,20 @@ def test_learner_keys_and_hooks():
     assert all((not a.gating) and a.adapter_1_up.bias.requires_grad and not a.adapter_0_up.bias.requires_grad
                for a in ads)
     assert len(m.get_param_adapter("adapter_1")) == 24
+
+
+def test_frozen_qkv_backward_equals_autograd():
+    """_FrozenQKV (three frozen projections, data gradients accumulated inside the GEMMs) == plain autograd."""
+    from feddat_b200.modeling.vilt import _FrozenQKV
+    torch.manual_seed(0)
+    lin = [torch.nn.Linear(768, 768) for _ in range(3)]
+    x1 = torch.randn(2, 5, 768, requires_grad=True)
+    x2 = x1.detach().clone().requires_grad_(True)
+    gs = [torch.randn(2, 5, 768) for _ in range(3)]
+    outs = _FrozenQKV.apply(x1, *[t for m in lin for t in (m.weight.detach(), m.bias.detach())])
+    torch.autograd.backward(outs, gs)
+    ref = [m(x2) for m in lin]
+    torch.autograd.backward(ref, gs)
+    for a, b in zip(outs, ref):
+        assert torch.allclose(a, b, atol=1e-6)
+    assert torch.allclose(x1.grad, x2.grad, atol=1e-5)
