@@ -41,8 +41,11 @@ __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
 // (Phi(x), exp(-x^2 / 2))
 __device__ __forceinline__ void gelu_terms(float x, float& cdf, float& e) {
   const float z = fabsf(x) * 0.70710678118654752f;
-  const float t = __frcp_rn(fmaf(0.3275911f, z, 1.f));
-  e = exp2f(-1.4426950408889634f * z * z);
+  // rcp.approx / ex2.approx (1-2 ulp): the IEEE-rounded forms compile to slow-path calls and ~40
+  // instructions per element
+  float t;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, z, 1.f)));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-1.4426950408889634f * z * z));
   float pl = fmaf(t, 1.061405429f, -1.453152027f);
   pl = fmaf(t, pl, 1.421413741f);
   pl = fmaf(t, pl, -0.284496736f);
@@ -54,27 +57,45 @@ __device__ __forceinline__ void gelu_terms(float x, float& cdf, float& e) {
 template <bool kBwd>
 __global__ void __launch_bounds__(256)
 gelu_kernel(const uint4* __restrict__ x, const uint4* __restrict__ dy, uint4* __restrict__ out, int64_t n_vec) {
-  for (int64_t i = blockIdx.x * 256ll + threadIdx.x; i < n_vec; i += static_cast<int64_t>(gridDim.x) * 256) {
-    float xf[8], o[8];
-    unpack8(x[i], xf);
-    if constexpr (kBwd) {
-      float g[8];
-      unpack8(dy[i], g);
+  // four independent 16-byte loads per thread and trip: with one, a full SM holds only 32 KB in flight and
+  // the kernel streamed at ~3 TB/s
+  constexpr int U = 4;
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * 256;
+  for (int64_t i0 = blockIdx.x * 256ll + threadIdx.x; i0 < n_vec; i0 += U * stride) {
+    uint4 xv[U], gv[U];
 #pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        float cdf, e;
-        gelu_terms(xf[k], cdf, e);
-        o[k] = g[k] * fmaf(xf[k], 0.3989422804014327f * e, cdf);
-      }
-    } else {
-#pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        float cdf, e;
-        gelu_terms(xf[k], cdf, e);
-        o[k] = xf[k] * cdf;
+    for (int u = 0; u < U; ++u) {
+      const int64_t i = i0 + u * stride;
+      if (i < n_vec) {
+        xv[u] = x[i];
+        if constexpr (kBwd) gv[u] = dy[i];
       }
     }
-    out[i] = pack8(o);
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int64_t i = i0 + u * stride;
+      if (i >= n_vec) break;
+      float xf[8], o[8];
+      unpack8(xv[u], xf);
+      if constexpr (kBwd) {
+        float g[8];
+        unpack8(gv[u], g);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          float cdf, e;
+          gelu_terms(xf[k], cdf, e);
+          o[k] = g[k] * fmaf(xf[k], 0.3989422804014327f * e, cdf);
+        }
+      } else {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          float cdf, e;
+          gelu_terms(xf[k], cdf, e);
+          o[k] = xf[k] * cdf;
+        }
+      }
+      out[i] = pack8(o);
+    }
   }
 }
 
@@ -92,6 +113,7 @@ int launch_gelu(bool bwd, const void* x, const void* dy, void* out, int64_t n, i
   if ((rc = device_sm_count(&sms))) return rc;
   const int64_t n_vec = n / 8;
   int64_t blocks = (n_vec + 255) / 256;
+  blocks = (blocks + 3) / 4;                        // four vectors per thread and trip
   if (blocks > 8ll * sms) blocks = 8ll * sms;       // 8 resident 256-thread blocks per SM, grid-stride beyond
   auto st = static_cast<cudaStream_t>(stream);
   if (bwd)
