@@ -209,3 +209,43 @@ def test_fused_layernorm_layer_equals_stock_hf_layer():
     (y1, g1), (y2, g2) = outs
     assert ((y1 - y2).abs().max() / y2.abs().max()).item() < 1e-2
     assert ((g1 - g2).abs().max() / g2.abs().max()).item() < 2e-2
+
+
+def test_graphed_step_with_prefetch_equals_direct_batches():
+    """GraphedTrainStep.prefetch() (next batch staged host->device on a copy stream, consumed by the next
+    call without a batch) == feeding the same batches directly."""
+    from feddat_b200.synthetic import make_vilt_batch
+    from feddat_b200.train.graphed import GraphedTrainStep
+    from feddat_b200.train.prepare import default_args, place_on_gpu, prepare_model
+    from feddat_b200.train.task_trainer import get_polynomial_decay_schedule_with_warmup
+    from feddat_b200.synthetic import to_device
+
+    def build():
+        torch.manual_seed(11)
+        model = prepare_model(default_args(ordered_cl_tasks=["art"], adapter_rank=32), place=False)
+        place_on_gpu(model)
+        tr = build_trainer(model, 1e-3, 20, "art", temp=2.0)
+        for n, p in model.named_parameters():
+            if "adapter_2" in n:
+                p.requires_grad = False
+        wrapped = tr.accelerator.prepare(model)
+        opt = tr.create_optimizer(wrapped)
+        sched = get_polynomial_decay_schedule_with_warmup(opt, 2, 20, lr_end=0, power=1)
+        wrapped.train()
+        return tr, wrapped, opt, sched
+
+    host = [make_vilt_batch(2, 16, 224, 100, seed=70 + i, pin=True) for i in range(5)]
+    example = to_device(host[0], "cuda")
+    tr1, w1, o1, s1 = build()
+    g1 = GraphedTrainStep(tr1, w1, o1, s1, example, warmup=1)
+    direct = [g1(host[i]).item() for i in range(5)]
+    tr2, w2, o2, s2 = build()
+    g2 = GraphedTrainStep(tr2, w2, o2, s2, example, warmup=1)
+    staged = []
+    g2.prefetch(host[0])
+    for i in range(5):
+        loss = g2()
+        if i + 1 < 5:
+            g2.prefetch(host[i + 1])
+        staged.append(loss.item())
+    np.testing.assert_allclose(staged, direct, rtol=2e-3)
