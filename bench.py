@@ -148,7 +148,8 @@ def kernel_rooflines(peaks, device):
         ts = []
         for i in range(iters):
             args_i = sets[(3 + i) % len(sets)]
-            torch.cuda._sleep(200_000)                      # ~100 us: the launch below is queued behind it
+            torch.cuda._sleep(1_000_000)                    # ~0.5 ms: every launch of fn is queued behind it (the
+                                                            # backward path spends ~80 us of host time in allocations, tensor-map encodes and ctypes calls)
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
             fn(*args_i)

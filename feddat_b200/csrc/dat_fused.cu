@@ -443,7 +443,8 @@ dat_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
             if (!kSaved) tmem_ld16(t_p + c * 16, v);
             if (kBwd) tmem_ld16(t_g + c * 16, u);
             const float* bdv = bias_smem + c * 16;
-            tmem_ld_wait();
+            if (!kSaved) tmem_ld_wait16(v);
+            if (kBwd) tmem_ld_wait16(u);
             const int col = c * 16;
             if constexpr (!kBwd) {
 #pragma unroll
@@ -531,7 +532,8 @@ dat_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
           if (tr) FD_TRACE(121, tile_it);
           mbar_wait(bar_res_full(sb), rpar);
           if (tr) FD_TRACE(122, tile_it);
-          tmem_ld_wait();
+          tmem_ld_wait32(v0);
+          tmem_ld_wait32(v1);
           if (j == 1) {
             // the chunk's whole accumulator has been read: hand the D buffer back BEFORE the last
             // half's math, so the MMAs of chunk c + 2 run under it

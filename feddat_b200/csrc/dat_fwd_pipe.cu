@@ -368,7 +368,7 @@ dat_pipe_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
           if (c < c_hi) {
             uint32_t v[16];
             tmem_ld16(t_p + c * 16, v);
-            tmem_ld_wait();
+            tmem_ld_wait16(v);
             if constexpr (!kBwd) {
               const float* bdv = bias_smem + c * 16;
 #pragma unroll
@@ -430,7 +430,8 @@ dat_pipe_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
         uint32_t v0[32], v1[32];
         tmem_ld32(t_src, v0);
         tmem_ld32(t_src + 32, v1);
-        tmem_ld_wait();
+        tmem_ld_wait32(v0);
+        tmem_ld_wait32(v1);
         // the accumulator is in registers: hand the D buffer back before anything else
         tc_fence_before();
         __syncwarp();

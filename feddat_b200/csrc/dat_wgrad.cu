@@ -220,7 +220,7 @@ dat_wgrad_kernel(const __grid_constant__ CUtensorMap tmXk, const __grid_constant
       for (int c = 0; c < NCW / 32; ++c) {
         uint32_t v[32];
         tmem_ld32(tmem + lane_addr + c * 32, v);  // D1: dWu^T
-        tmem_ld_wait();
+        tmem_ld_wait32(v);
         if (valid) {
           float* dst = p.dWu + static_cast<size_t>(col0 + c * 32) * p.ld_dwu + j;
 #pragma unroll
@@ -228,7 +228,7 @@ dat_wgrad_kernel(const __grid_constant__ CUtensorMap tmXk, const __grid_constant
             atomicAdd(dst + static_cast<size_t>(i) * p.ld_dwu, p.scale * __uint_as_float(v[i]));
         }
         tmem_ld32(tmem + lane_addr + NCW + c * 32, v);  // D2: dWd
-        tmem_ld_wait();
+        tmem_ld_wait32(v);
         if (valid) {
           float* dst = p.dWd + static_cast<size_t>(j) * kD + col0 + c * 32;
 #pragma unroll
