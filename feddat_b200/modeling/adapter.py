@@ -123,6 +123,64 @@ class _DatFunction(torch.autograd.Function):
         return (None, dx_total if need_dx else None, dres, *grads)
 
 
+class _DualDatFunction(torch.autograd.Function):
+    """Two DAT modes over the two halves of ONE row-stacked tensor (``Adapter.set_dual``): rows [0, M/2) see
+    the gating pair (adapter_0 | adapter_2, scale 0.5), rows [M/2, M) see adapter_1 alone -- the MKD
+    schedule's passes A/C and B sharing every frozen-backbone launch.  Two kernel launches per direction
+    writing into the halves of one output tensor (no concatenation copies); residual == input.
+
+    inputs: x [M, 768] bf16, then the 8 gating parameters (adapter_0, adapter_2) and the 4 of adapter_1.
+    """
+
+    @staticmethod
+    def forward(ctx, adapter: "Adapter", x, *params):
+        need_bwd = any(ctx.needs_input_grad[1:])
+        half = x.shape[0] // 2
+        specs = ((params[:8], 0.5 * adapter.scaling), (params[8:], 1.0))
+        save_h = need_bwd and adapter._act_code == ops.ACT_RELU
+        y = torch.empty_like(x)
+        ctx.parts = []
+        for i, (ps, scale) in enumerate(specs):
+            (pk, _, _), = adapter._segments(ps, need_bwd=need_bwd)
+            xs = x[i * half:(i + 1) * half]
+            out = ops.dat_forward(xs, xs, pk, scale, adapter._act_code, out=y[i * half:(i + 1) * half],
+                                  save_hidden=save_h)
+            ctx.parts.append((pk, scale, out[1] if save_h else None, [p.requires_grad for p in ps]))
+        ctx.adapter = adapter
+        ctx.save_for_backward(x)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        (x,) = ctx.saved_tensors
+        adapter = ctx.adapter
+        dy = dy.contiguous()
+        need_dx = ctx.needs_input_grad[1]
+        half = x.shape[0] // 2
+        r = adapter.rank
+        dx = torch.empty_like(dy) if need_dx else None
+        grads = []
+        for i, (pk, scale, hid, needs) in enumerate(ctx.parts):
+            sl = slice(i * half, (i + 1) * half)
+            nb = len(needs) // 4
+            trains = [any(needs[4 * b: 4 * b + 4]) for b in range(nb)]
+            lo = next((b * r for b in range(nb) if trains[b]), None)
+            hi = None if lo is None else max((b + 1) * r for b in range(nb) if trains[b])
+            ts = None if lo is None else (lo, hi)
+            _, g = ops.dat_backward(x[sl], dy[sl], pk, scale, adapter._act_code, train_slice=ts, need_dx=need_dx,
+                                    add_dy=True, hidden=hid, dx_out=None if dx is None else dx[sl])
+            part = [None] * len(needs)
+            if g is not None:
+                d_down_w, d_down_b, d_up_w, d_up_b = g
+                for b in range(nb):
+                    if trains[b]:
+                        s0, s1 = b * r - lo, (b + 1) * r - lo
+                        part[4 * b:4 * b + 4] = [d_down_w[s0:s1].contiguous(), d_down_b[s0:s1].contiguous(),
+                                                 d_up_w[:, s0:s1].contiguous(), d_up_b.contiguous()]
+            grads += [gr if nd else None for gr, nd in zip(part, needs)]
+        return (None, dx, *grads)
+
+
 class Adapter(nn.Module):
     """The DAT bottleneck operator (reference adapter.py:16-163)."""
 
@@ -167,6 +225,7 @@ class Adapter(nn.Module):
                 for p in m.parameters():
                     p.requires_grad = False
         self._active_name: Optional[str] = None
+        self._dual = False
 
     # ------------------------------------------------------------------ mode switches (reference API)
     def deactivate_gating(self):
@@ -199,6 +258,18 @@ class Adapter(nn.Module):
                 if m is not None:
                     for p in m.parameters():
                         p.requires_grad = flag
+
+    def set_dual(self, on: bool):
+        """Row-batched MKD mode (TaskTrainer's batched schedule): the first half of the rows goes through the
+        gating pair, the second half through adapter_1 (see _DualDatFunction).  Both adapter_0 and
+        adapter_1 are trainable in this mode; adapter_2 stays frozen."""
+        if on:
+            if not hasattr(self, "adapter_2_down"):
+                raise FeddatError("dual mode needs the three DAT adapters (adapter_0, adapter_1, adapter_2)")
+            if 2 * self.rank > ops.MAX_R_TOTAL:
+                raise FeddatError("dual mode covers ranks up to 128 (gating width 256)")
+            self._set_grad(("adapter_0", "adapter_1"), True)
+        self._dual = bool(on)
 
     # ------------------------------------------------------------------ kernel plumbing
     def _scale(self) -> float:
@@ -264,10 +335,22 @@ class Adapter(nn.Module):
         if not hidden_states.is_cuda:
             raise FeddatError("Adapter.forward: CPU tensors are not supported -- the DAT operator exists "
                               "only as sm_100a CUDA kernels (no fallback)")
-        names = self._active_branch_names()
-        params = self._branch_params(names)
         shape = hidden_states.shape
         out_dtype = hidden_states.dtype
+        if self._dual:
+            if input_tensor is not hidden_states:
+                raise FeddatError("dual mode is defined for sites whose residual is the input (ViLT, ViT)")
+            x = hidden_states.reshape(-1, shape[-1])
+            if x.dtype != torch.bfloat16:
+                x = x.to(torch.bfloat16)
+            x = x.contiguous()
+            if x.shape[0] % 2:
+                raise FeddatError("dual mode needs an even number of rows (two stacked copies of the batch)")
+            params = self._branch_params(("adapter_0", "adapter_2", "adapter_1"))
+            y = _DualDatFunction.apply(self, x, *params).view(shape)
+            return y if out_dtype == torch.bfloat16 else y.to(out_dtype)
+        names = self._active_branch_names()
+        params = self._branch_params(names)
         same = input_tensor is hidden_states
         x = hidden_states.reshape(-1, shape[-1])
         if x.dtype != torch.bfloat16:

@@ -163,6 +163,16 @@ class ViltEncoderWrapper(nn.Module):
         # the pooler reads only the CLS row of the final LayerNorm (per-row op): normalise that row alone
         return self.vilt.pooler(self.vilt.layernorm(hidden[:, 0:1]))
 
+    def _dense_forward_stacked(self, input_ids, token_type_ids, pixel_values):
+        """Two copies of the batch stacked along the batch dimension through ONE pass of the frozen layers
+        (the adapters are in dual mode: each half sees its own DAT branch).  Returns (2 * batch, hidden)."""
+        with torch.no_grad():
+            hidden = self._dense_embeddings(input_ids, token_type_ids, pixel_values)
+            hidden = torch.cat([hidden, hidden], dim=0)
+        for layer in self.vilt.encoder.layer:
+            hidden = layer(hidden, None)[0]
+        return self.vilt.pooler(self.vilt.layernorm(hidden[:, 0:1]))
+
     def forward(self, **encodings: Dict) -> torch.FloatTensor:
         """vilt.py:115-129: returns ``pooler_output`` (batch, hidden)."""
         dense = encodings.pop("dense_masks", False)
@@ -245,6 +255,21 @@ class ViltContinualLearner(nn.Module):
         """The task-head half of ``forward_single_image`` (vilt.py:261-262)."""
         head = self.task_layer[task_key]
         return head(encoder_output.to(head.clf_fc0.weight.dtype))
+
+    def encode_dual(self, **encodings):
+        """Pooled outputs of the gating pass (rows [0, batch)) and of the adapter_1 pass (rows [batch,
+        2 batch)) from ONE stacked forward: (2 batch, hidden).  Needs the dense fast path (all-ones masks)."""
+        if not (encodings.get("dense_masks", False) and self.vilt_encoder.dense_fast_path):
+            raise RuntimeError("encode_dual needs pre-encoded batches with all-ones masks (dense_masks=True)")
+        for a in self._adapters():
+            a.set_dual(True)
+        try:
+            enc = self.vilt_encoder._dense_forward_stacked(encodings["input_ids"], encodings.get("token_type_ids"),
+                                                           encodings["pixel_values"])
+        finally:
+            for a in self._adapters():
+                a.set_dual(False)
+        return enc
 
     def gating_forward_is_reusable(self) -> bool:
         """True when the encoder is a deterministic function of (inputs, adapter_0, adapter_2, frozen

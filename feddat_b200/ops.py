@@ -106,7 +106,7 @@ def dat_forward(x: torch.Tensor, res: torch.Tensor, w: PackedWeights, scale: flo
 
 def dat_backward(x: Optional[torch.Tensor], dy: torch.Tensor, w: PackedWeights, scale: float, act=ACT_RELU,
                  train_slice: Optional[tuple] = None, need_dx: bool = True, add_dy: bool = True,
-                 hidden: Optional[torch.Tensor] = None):
+                 hidden: Optional[torch.Tensor] = None, dx_out: Optional[torch.Tensor] = None):
     """Backward of dat_forward.  Returns (dx | None, grads | None) where grads =
     (d_down_w [rt,d], d_down_b [rt], d_up_w [d,rt], d_up_b [d]) in fp32 for the trainable slice
     ``train_slice = (r_lo, r_hi)`` of the concatenated bottleneck.  ``hidden`` = the H saved by
@@ -126,7 +126,9 @@ def dat_backward(x: Optional[torch.Tensor], dy: torch.Tensor, w: PackedWeights, 
     M, d = dy.shape
     R = w.r_total
     dev = dy.device
-    dx = torch.empty_like(dy) if need_dx else None
+    if dx_out is not None:
+        _check_act2d(dx_out, "dat_backward dx_out")
+    dx = (dx_out if dx_out is not None else torch.empty_like(dy)) if need_dx else None
     h_t = dp_t = None
     rt = 0
     if train_slice is not None:

@@ -59,6 +59,31 @@ def get_polynomial_decay_schedule_with_warmup(optimizer, num_warmup_steps, num_t
               lr_end=lr_end, power=power)
 
 
+def split_step(optimizer, scheduler, first_params):
+    """All gradients of the batched schedule are present at once; apply them as the reference's two
+    optimizer steps would: ``first_params`` (adapter_1) with the CURRENT learning rate, scheduler step,
+    every other parameter with the next learning rate, scheduler step, zero_grad.  AdamW skips parameters
+    whose ``.grad`` is None, and its state (moments, step count) is per parameter."""
+    first = {id(p) for p in first_params}
+    held = []
+    for group in optimizer.param_groups:
+        for p in group["params"]:
+            if p.grad is not None and id(p) not in first:
+                held.append((p, p.grad))
+                p.grad = None
+    optimizer.step()
+    if scheduler is not None:
+        scheduler.step()
+    for p in first_params:
+        p.grad = None
+    for p, g in held:
+        p.grad = g
+    optimizer.step()
+    if scheduler is not None:
+        scheduler.step()
+    optimizer.zero_grad()
+
+
 class TaskTrainer(nn.Module):
 
     def __init__(self, **kwargs):
@@ -69,6 +94,9 @@ class TaskTrainer(nn.Module):
         # adapter_2 + frozen backbone; step B only updates adapter_1 and the head) whenever the
         # encoder has no dropout (ViLT): one grad-enabled forward serves both
         self.reuse_gating_forward = True
+        # Batched schedule (same arithmetic, see _train_step_batched): the gating pass and the adapter_1 pass
+        # run as ONE row-stacked forward and ONE row-stacked backward through the frozen backbone
+        self.batched_passes = True
 
     # ------------------------------------------------------------------ train (task_trainer.py:24-111)
     def train(self, model, er=None, ewc=None, der=None, derpp=None, pnn=None, hat=None):
@@ -146,6 +174,63 @@ class TaskTrainer(nn.Module):
             loss_kl = self.kl_criterion(logits, teacher.clone().detach())
         return (task_loss + loss_kl) / 2, task_loss.detach()
 
+    def _objective_is_fused(self) -> bool:
+        return (isinstance(self.loss_criterion, nn.BCEWithLogitsLoss) and self.loss_criterion.reduction == "mean"
+                and self.kl_criterion is kl_loss and self.loss_criterion.weight is None
+                and self.loss_criterion.pos_weight is None)
+
+    def _train_step_batched(self, model, batch, target, optimizer, scheduler):
+        """The dat branch of train_step (task_trainer.py:280-330) with passes A/C and B batched.
+
+        The reference runs  A: logits_all (gating, no grad) | B: forward adapter_1, L_1, backward, step |
+        C: forward gating, L_0, backward, step.  Facts used: (i) ViLT has no dropout, so C's encoder output
+        equals A's (step B changes neither adapter_0, adapter_2 nor the backbone); (ii) AdamW updates every
+        parameter independently, so "step B" may be split into "task head now, adapter_1 later" as long as
+        each parameter is stepped with the same gradient, the same learning rate and the same step count;
+        (iii) backward through the frozen backbone is linear in the incoming gradient rows.  Hence:
+
+          1. ONE forward over the batch stacked twice: rows [0, B) through the gating pair, rows [B, 2B)
+             through adapter_1 (Adapter.set_dual) -> enc_A, enc_B
+          2. logits_all = head(enc_A) (old head, no grad); L_1 from head(enc_B); backward through the HEAD
+             only (-> head grads, d enc_B); optimizer step of the head with the first learning rate
+          3. L_0 from the UPDATED head(enc_A) and logits_1; backward through the head (-> head grads, d enc_A)
+          4. ONE backward through the encoder with [d enc_A; d enc_B] -> adapter_0 and adapter_1 grads
+          5. step adapter_1 (first learning rate), scheduler step, step adapter_0 + head (second learning
+             rate), scheduler step
+
+        Every parameter receives the updates of the reference schedule; the frozen backbone runs once
+        forward and once backward over 2B rows instead of twice / twice over B rows (fuller GEMM waves,
+        half the launches).  Checked against the reference trainer by tests/test_train_step_gpu.py."""
+        inner = model.module
+        enc = inner.encode_dual(**self.batch2inputs_converter(batch))
+        b = enc.shape[0] // 2
+        leaf = enc.detach().requires_grad_(True)                     # head gradients stop here until step 4
+        enc_a, enc_b = leaf[:b], leaf[b:]
+        with torch.no_grad():
+            logits_all = inner.classify(self.task_key, enc_a)        # (A): old head, gating encoder
+
+        logits_1 = inner.classify(self.task_key, enc_b)              # (B)
+        L_1, _ = self._objective(logits_1, logits_all, target, None)
+        self.accelerator.backward(L_1)                               # head grads + d enc_B (adapters: none yet)
+        optimizer.step()                                             # only the head has gradients
+        optimizer.zero_grad()
+
+        logits_0 = inner.classify(self.task_key, enc_a)              # (C): updated head
+        L_0, loss_0 = self._objective(logits_0, logits_1, target, None)
+        self.accelerator.backward(L_0)                               # head grads + d enc_A
+        enc.backward(leaf.grad)                                      # adapter_0 (rows A) and adapter_1 (rows B)
+
+        a1 = getattr(self, "_a1_params", None)
+        if a1 is None or a1[0] is not model:
+            a1 = self._a1_params = (model, [p for n, p in model.named_parameters() if "adapter_1" in n])
+        split_step(optimizer, scheduler, a1[1])
+
+        inner.activate_gating()                                      # leave the modes as the reference does
+        inner.set_active_adapter("adapter_0")
+        self.last_logits = (logits_all.detach(), logits_1.detach(), logits_0.detach())
+        self.last_objectives = (L_1.detach(), L_0.detach())
+        return loss_0
+
     def train_step(self, model, step, batch, optimizer=None, scheduler=None, hooks=None, epoch=None):
         target = None
         if isinstance(batch, dict) and "target_scores" in batch.keys():
@@ -157,6 +242,10 @@ class TaskTrainer(nn.Module):
         inner = model.module
         reuse = (self.reuse_gating_forward and not albef
                  and getattr(inner, "gating_forward_is_reusable", lambda: False)())
+        if (reuse and self.batched_passes and optimizer is not None and hasattr(inner, "encode_dual")
+                and isinstance(batch, dict) and batch.get("encodings", {}).get("dense_masks", False)
+                and self._objective_is_fused() and 2 * inner._adapters()[0].rank <= ops.MAX_R_TOTAL):
+            return self._train_step_batched(model, batch, target, optimizer, scheduler)
         if reuse:                                                    # (A) + encoder half of (C)
             inner.activate_gating()
             inner.set_active_adapter("adapter_0")

@@ -139,3 +139,37 @@ def test_shared_gating_forward_equals_three_forward_schedule(monkeypatch):
     for (n, p), (_, q) in zip(m_ref.named_parameters(), m_new.named_parameters()):
         assert torch.allclose(p, q, rtol=1e-6, atol=1e-7), n
         assert p.requires_grad == q.requires_grad, n
+
+
+def test_split_step_equals_the_reference_two_optimizer_steps():
+    """The batched MKD schedule's optimizer choreography (head stepped early, then split_step) leaves every
+    parameter exactly where the reference's "step B, scheduler, step C, scheduler" leaves it (AdamW is
+    per-parameter; weight decay and bias correction included)."""
+    import copy
+    from torch.optim.lr_scheduler import LambdaLR
+    from feddat_b200.train.task_trainer import split_step
+    torch.manual_seed(0)
+    base = {"a1": torch.randn(4, 3), "a0": torch.randn(4, 3), "head": torch.randn(5)}
+
+    def make():
+        ps = {k: torch.nn.Parameter(v.clone()) for k, v in base.items()}
+        opt = torch.optim.AdamW([{"params": [ps["a1"], ps["a0"]], "weight_decay": 1e-2},
+                                 {"params": [ps["head"]], "weight_decay": 0.0}], lr=1e-2, betas=(0.9, 0.98))
+        return ps, opt, LambdaLR(opt, lambda e: 1.0 / (1 + e))
+
+    grads = [{k: torch.randn_like(v) for k, v in base.items()} | {"head2": torch.randn(5)} for _ in range(3)]
+    ref, o1, s1 = make()
+    for g in grads:                                        # reference order (task_trainer.py:290-328)
+        ref["a1"].grad, ref["head"].grad = g["a1"].clone(), g["head"].clone()
+        o1.step(); s1.step(); o1.zero_grad()
+        ref["a0"].grad, ref["head"].grad = g["a0"].clone(), g["head2"].clone()
+        o1.step(); s1.step(); o1.zero_grad()
+    new, o2, s2 = make()
+    for g in grads:                                        # batched order
+        new["head"].grad = g["head"].clone()
+        o2.step(); o2.zero_grad()                          # head early, first learning rate
+        new["a1"].grad, new["a0"].grad, new["head"].grad = g["a1"].clone(), g["a0"].clone(), g["head2"].clone()
+        split_step(o2, s2, [new["a1"]])
+    for k in base:
+        assert torch.equal(ref[k], new[k]), k
+    assert s1.last_epoch == s2.last_epoch == 6
