@@ -128,3 +128,35 @@ class BertOutput(nn.Module):
         if hasattr(self, "adapter"):
             return self.adapter.adapter_layer_forward_bert(hidden_states, input_tensor, self.LayerNorm)
         return self.LayerNorm(hidden_states + input_tensor)
+
+
+class AdapterHooks:
+    """Learner-level adapter hooks (reference src/modeling/albef.py:139-167, src/modeling/vilt.py:363-382) for
+    ANY module tree containing ``Adapter`` sites -- ALBEF's 12 ViT blocks + 12 text-encoder + 6 text-decoder
+    output layers, or ViLT's 12 -- found by walking the sub-modules instead of hard-coded attribute paths.
+    Mix into (or wrap) the learner: ``hooks = AdapterHooks(model)``."""
+
+    def __init__(self, root: nn.Module):
+        self._root = root
+
+    def adapters(self):
+        return [m for m in self._root.modules() if isinstance(m, Adapter)]
+
+    def set_active_adapter(self, name):
+        for a in self.adapters():
+            a.set_active_adapter(name)
+
+    def activate_gating(self):
+        for a in self.adapters():
+            a.activate_gating()
+
+    def deactivate_gating(self):
+        for a in self.adapters():
+            a.deactivate_gating()
+
+    def get_param_adapter(self, name):
+        out = []
+        for a in self.adapters():
+            out.append(getattr(a, f"{name}_down").parameters())
+            out.append(getattr(a, f"{name}_up").parameters())
+        return out

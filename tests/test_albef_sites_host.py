@@ -65,3 +65,26 @@ def test_oracle_bert_site_matches_reference_bert_output():
                                                 1e-12, branches, gating)
         want = GOLD[f"bert_output/{mode}/out"]
         assert np.abs(got - want).max() / np.abs(want).max() < 1e-4
+
+
+def test_adapter_hooks_walk_every_site():
+    """AdapterHooks (albef.py:139-167): mode switches reach every Adapter of a mixed ViT / BERT module tree."""
+    from feddat_b200.modeling.albef_sites import AdapterHooks
+    acfg = {"names": NAMES, "device": "cpu", "rank": 16}
+    cfg = types.SimpleNamespace(intermediate_size=3072, hidden_size=768, layer_norm_eps=1e-12, hidden_dropout_prob=0.0,
+                                adapter_config=acfg)
+    tree = nn.ModuleDict({
+        "visual_encoder": nn.ModuleList([Block(dim=768, num_heads=12, qkv_bias=True, adapter_config=acfg) for _ in range(2)]),
+        "text_encoder": nn.ModuleList([BertOutput(cfg) for _ in range(2)]),
+        "text_decoder": nn.ModuleList([BertOutput(cfg)]),
+    })
+    hooks = AdapterHooks(tree)
+    ads = hooks.adapters()
+    assert len(ads) == 5
+    hooks.activate_gating(); hooks.set_active_adapter("adapter_0")
+    assert all(a.gating and a.adapter_0_up.weight.requires_grad and not a.adapter_1_up.weight.requires_grad for a in ads)
+    hooks.deactivate_gating(); hooks.set_active_adapter("adapter_1")
+    assert all((not a.gating) and a._active_name == "adapter_1" and not a.adapter_0_down.bias.requires_grad for a in ads)
+    assert len(hooks.get_param_adapter("adapter_1")) == 10
+    keys = [k for k in tree.state_dict() if "adapter_1" in k]
+    assert len(keys) == 5 * 4 and "visual_encoder.0.adapter.adapter_1_down.weight" in keys
