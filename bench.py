@@ -189,6 +189,69 @@ def kernel_rooflines(peaks, device):
     return out
 
 
+def eager_reference_adapter(peaks, device):
+    """The reference operator itself on this GPU ("the bar is PyTorch-eager (cuBLAS) on the
+    same box"): the arithmetic of reference adapter.py:124-163 as PyTorch eager ops -- fp32 nn.Linear masters
+    under bf16 autocast (what accelerate's mixed precision does to it), the (B, S, 2) tensor of 0.5s built per
+    call, the per-branch unsqueeze-multiply aggregation -- forward and autograd backward, at the same shapes
+    and with the same cold-input rotation as ``kernel_rooflines``.  adapter_0 trains, adapter_2 is frozen
+    (gating); adapter_1 trains (single)."""
+    import torch
+    import torch.nn as nn
+    out = {}
+    g = torch.Generator(device=device).manual_seed(1)
+
+    def lin(i, o):
+        m = nn.Linear(i, o).to(device)
+        with torch.no_grad():
+            m.weight.normal_(0, 0.02, generator=g); m.bias.zero_()
+        return m
+
+    ad = {n: (lin(D, RANK), lin(RANK, D)) for n in ("adapter_0", "adapter_1", "adapter_2")}
+    for m in ad["adapter_2"]:
+        for p in m.parameters():
+            p.requires_grad = False
+    relu = nn.ReLU()
+
+    def fwd(x, gating):
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            if not gating:                                          # adapter.py:125-131
+                down, up = ad["adapter_1"]
+                return x + up(relu(down(x)))
+            ups = [ad[n][1](relu(ad[n][0](x))) for n in ("adapter_0", "adapter_2")]     # :135-141
+            w = (torch.ones(x.shape[0], x.shape[1], 2) * 0.5).to(device)                # :144 (host-built constant)
+            agg = w[:, :, 0].unsqueeze(-1) * ups[0] + w[:, :, 1].unsqueeze(-1) * ups[1]  # :118-122
+            return x + agg * 1.0                                    # :146
+
+    for M in (B * 185, 12 * B * 185):
+        n_sets = max(2, -(-300_000_000 // (2 * M * D * 2)))
+        sets = [(torch.randn(M // 185, 185, D, device=device, generator=g).to(torch.bfloat16),
+                 torch.randn(M // 185, 185, D, device=device, generator=g).to(torch.bfloat16)) for _ in range(n_sets)]
+        for gating in (True, False):
+            tf, tb = [], []
+            for i in range(3 + 10):
+                x, dy = sets[i % n_sets]
+                x = x.clone().requires_grad_(True)
+                torch.cuda._sleep(1_000_000)
+                e = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+                e[0].record()
+                y = fwd(x, gating)
+                e[1].record()
+                y.backward(dy)
+                e[2].record()
+                torch.cuda.synchronize()
+                for m in ad.values():
+                    for mm in m:
+                        mm.zero_grad(set_to_none=True)
+                if i >= 3:
+                    tf.append(e[0].elapsed_time(e[1]) * 1e3); tb.append(e[1].elapsed_time(e[2]) * 1e3)
+            key = "gating" if gating else "single"
+            out[f"fwd_{key}_M{M}"] = round(statistics.mean(tf), 2)
+            out[f"bwd_{key}_M{M}"] = round(statistics.mean(tb), 2)
+        del sets
+    return out
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -266,6 +329,22 @@ def run_ours(args):
 
     for i in range(W):
         step_resident(i)
+    # the round-boundary collective is warmed like every other kernel (the first ncclAllReduce of a
+    # communicator sets up its channels: 22 ms in round 1's N = 8 run) and timed on its own
+    allreduce_us = None
+    if world > 1:
+        for _ in range(2):
+            round_boundary()
+        barrier()
+        ea, eb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ea.record()
+        for _ in range(5):
+            round_boundary()
+        eb.record()
+        torch.cuda.synchronize()
+        t = torch.tensor([ea.elapsed_time(eb) / 5 * 1e3], device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        allreduce_us = round(t.item(), 1)
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
@@ -289,6 +368,11 @@ def run_ours(args):
         value = world * B * K / (ms * 1e-3)
         e2e = world * B * K / (ms_e2e * 1e-3)
         kr = kernel_rooflines(peaks, device)
+        eager = eager_reference_adapter(peaks, device)
+        for name, us in eager.items():
+            if name in kr:
+                kr[name]["eager_reference_us"] = us
+                kr[name]["vs_eager"] = round(us / kr[name]["us"], 2)
         # dominant kernel of the step = the gating backward (pass C: dgrad + wgrad launches)
         dom = kr[f"bwd_gating_M{B * 185}"]
         big = kr[f"bwd_gating_M{12 * B * 185}"]
@@ -299,12 +383,15 @@ def run_ours(args):
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": WORKLOAD, "global_batch": B * world, "clients": world,
                        "step_launch": "eager" if args.eager else "cuda-graph replay of train_step",
+                       "round_boundary": f"one FedAvg allreduce of the flat adapter_1 buffer after the {K} timed steps "
+                                         "(inside the timed region, communicator warmed; allreduce_us = its own time)",
                        "l2": "per-step working set (222 MB bf16 backbone weights + >1 GB activations) exceeds the 126 MB L2; kernel micro-timings rotate through input sets totalling > 2x L2 (no flush writes)",
                        "init": "seeded random ViLT-B/32 (no pretrained weights on the box)"},
             "clocks": clocks,
             "e2e": {"value": round(e2e, 2), "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                     "ms_per_step": round(ms_e2e / K, 3)},
             "gpu_launches": launches,
+            "allreduce_us": allreduce_us,
             "roofline": {"kernel": "dat_bwd gating r=128 (dgrad + wgrad launches), M=5920 rows/site",
                          "bound": "tensor", "achieved": dom["tflops"], "peak": peak, "unit": "TFLOP/s",
                          "frac": round(dom["tflops"] / peak, 4),
@@ -319,7 +406,7 @@ def run_ours(args):
             "kernels": kr,
         }
         if world == 1 and not args.no_cpu_baseline:
-            result["cpu_baseline"] = cpu_reference(steps=1, warmup=0, sample_batch=args.cpu_batch)
+            result["cpu_baseline"] = cpu_reference(steps=2, warmup=1, sample_batch=args.cpu_batch)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -350,7 +437,7 @@ def cpu_reference(steps: int, warmup: int, sample_batch: int):
             times.append(time.time() - t0)
     sec = statistics.median(times)
     return {"value": round(sample_batch / sec, 3), "unit": "samples/s", "cores": cores, "kind": "port",
-            "sample": f"{steps} train_step(s) of batch {sample_batch} (of the workload's 32) at 384x384 / 40 tok, "
+            "sample": f"{steps} train_step(s) (+{warmup} warm-up) of batch {sample_batch} (the workload's is {B}) at 384x384 / 40 tok, "
                       f"rank {RANK}, fp32, torch CPU {cores} threads; median {sec:.2f} s/step",
             "ms_per_step": round(sec * 1e3, 1)}
 
@@ -361,11 +448,11 @@ def run_reference(args):
         return None
     K, W = args.steps, args.warmup
     t0 = time.time()
-    base = cpu_reference(steps=K, warmup=min(W, 1), sample_batch=args.cpu_batch)
+    base = cpu_reference(steps=K, warmup=W, sample_batch=args.cpu_batch)
     return {"impl": "reference", "metric": METRIC, "value": base["value"], "unit": "samples/s",
-            "n_gpus": args.gpus, "steps": K, "warmup": min(W, 1), "ms_per_step": base["ms_per_step"],
+            "n_gpus": args.gpus, "steps": K, "warmup": W, "ms_per_step": base["ms_per_step"],
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "sample": base["sample"]},
+            "config": {"workload": WORKLOAD, "global_batch": args.cpu_batch, "clients": 1, "sample": base["sample"]},
             "cpu_baseline": base,
             "e2e": {"value": base["value"], "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "wall_s": round(time.time() - t0, 1)}
@@ -374,15 +461,19 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--cpu-batch", type=int, default=4, help="batch of the bounded CPU sample")
+    ap.add_argument("--cpu-batch", type=int, default=None,
+                    help="batch of the CPU arm (default: the workload's own 32, so both arms run the same config; "
+                         "4 when more than 30 CPU steps are requested, to stay within minutes)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--eager", action="store_true", help="launch train_step eagerly instead of replaying its CUDA graph")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3
+    if args.cpu_batch is None:
+        args.cpu_batch = B if (args.impl != "reference" or args.steps + args.warmup <= 30) else 4
     res = run_reference(args) if args.impl == "reference" else run_ours(args)
     if res is not None:
         print(json.dumps(res), flush=True)

@@ -11,7 +11,10 @@ from ctypes import POINTER, c_char_p, c_float, c_int, c_int64, c_uint32, c_void_
 from pathlib import Path
 
 _LIB_PATH = Path(__file__).resolve().parent / "lib" / "libfeddat_sm100.so"
+_DBG_LIB_PATH = Path(__file__).resolve().parent / "lib" / "libfeddat_sm100_dbg.so"
 _lib = None
+_dbg_lib = None
+ABI_VERSION = 2      # feddat_abi_version(); bumped whenever include/feddat_b200.h changes
 
 # every symbol include/feddat_b200.h declares (tests check the built library exports all of them)
 EXPORTED_SYMBOLS = (
@@ -23,13 +26,16 @@ EXPORTED_SYMBOLS = (
     "feddat_pack_weights",
     "feddat_mkd_loss",
     "feddat_fedavg",
-    "feddat_probe_gemm",
-    "feddat_debug_set_trace",
-    "feddat_probe_l2bw",
     "feddat_ln_fwd",
     "feddat_ln_bwd",
     "feddat_gelu_fwd",
     "feddat_gelu_bwd",
+)
+# include/feddat_b200_debug.h: only in the -DFEDDAT_DEBUG twin (libfeddat_sm100_dbg.so), tests / scripts
+DEBUG_SYMBOLS = (
+    "feddat_probe_gemm",
+    "feddat_debug_set_trace",
+    "feddat_probe_l2bw",
     "feddat_debug_force_fused_fwd",
     "feddat_probe_pair",
     "feddat_probe_ingest",
@@ -45,16 +51,34 @@ def lib_path() -> Path:
     return _LIB_PATH
 
 
+def _open(path: Path, debug: bool) -> ctypes.CDLL:
+    if not path.exists():
+        if os.environ.get("FEDDAT_NO_AUTOBUILD"):
+            raise FeddatError(f"{path} is missing; run `python -m feddat_b200.build`")
+        from .build import build_library
+        build_library(debug=debug)          # lock file + atomic rename: safe under torchrun
+    return ctypes.CDLL(str(path))
+
+
+def load_debug() -> ctypes.CDLL:
+    """The -DFEDDAT_DEBUG twin: every product entry point (with trace hooks compiled in) plus the probes and
+    debug switches of include/feddat_b200_debug.h.  Tests and scripts only; the package never calls this."""
+    global _dbg_lib
+    if _dbg_lib is None:
+        _dbg_lib = _bind(_open(_DBG_LIB_PATH, True), debug=True)
+    return _dbg_lib
+
+
 def load() -> ctypes.CDLL:
     global _lib
-    if _lib is not None:
-        return _lib
-    if not _LIB_PATH.exists():
-        if os.environ.get("FEDDAT_NO_AUTOBUILD"):
-            raise FeddatError(f"{_LIB_PATH} is missing; run `python -m feddat_b200.build`")
-        from .build import build_library
-        build_library()
-    lib = ctypes.CDLL(str(_LIB_PATH))
+    if os.environ.get("FEDDAT_DEBUG_LIB"):       # scripts/trace_kernel.py: route ops.* through the traced twin
+        return load_debug()
+    if _lib is None:
+        _lib = _bind(_open(_LIB_PATH, False), debug=False)
+    return _lib
+
+
+def _bind(lib: ctypes.CDLL, debug: bool) -> ctypes.CDLL:
     lib.feddat_last_error.restype = c_char_p
     lib.feddat_last_error.argtypes = []
     lib.feddat_abi_version.restype = c_int
@@ -81,11 +105,6 @@ def load() -> ctypes.CDLL:
     lib.feddat_fedavg.restype = c_int
     lib.feddat_fedavg.argtypes = [POINTER(c_void_p), POINTER(c_float), c_int, c_float, c_void_p,
                                   c_int64, c_void_p]
-    lib.feddat_probe_gemm.restype = c_int
-    lib.feddat_probe_gemm.argtypes = [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
-                                      POINTER(c_uint32), c_void_p]
-    lib.feddat_probe_l2bw.restype = c_int
-    lib.feddat_probe_l2bw.argtypes = [c_void_p, c_int, c_int, c_int, c_int, c_void_p]
     lib.feddat_ln_fwd.restype = c_int
     lib.feddat_ln_fwd.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                   c_void_p, c_void_p, c_int64, c_int, c_float, c_int, c_void_p]
@@ -96,6 +115,13 @@ def load() -> ctypes.CDLL:
     lib.feddat_gelu_fwd.argtypes = [c_void_p, c_void_p, c_int64, c_int, c_void_p]
     lib.feddat_gelu_bwd.restype = c_int
     lib.feddat_gelu_bwd.argtypes = [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p]
+    if not debug:
+        return lib
+    lib.feddat_probe_gemm.restype = c_int
+    lib.feddat_probe_gemm.argtypes = [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
+                                      POINTER(c_uint32), c_void_p]
+    lib.feddat_probe_l2bw.restype = c_int
+    lib.feddat_probe_l2bw.argtypes = [c_void_p, c_int, c_int, c_int, c_int, c_void_p]
     lib.feddat_debug_force_fused_fwd.restype = c_int
     lib.feddat_debug_force_fused_fwd.argtypes = [c_int]
     lib.feddat_probe_tilecopy.restype = c_int
@@ -108,7 +134,6 @@ def load() -> ctypes.CDLL:
                                       c_void_p]
     lib.feddat_debug_set_trace.restype = c_int
     lib.feddat_debug_set_trace.argtypes = [c_void_p]
-    _lib = lib
     return lib
 
 

@@ -41,6 +41,9 @@
 //               input is X itself (adaptered_output.py:78), -> bf16 -> TMA store
 #include "dat_kernels.h"
 #include "feddat_b200.h"
+#ifdef FEDDAT_DEBUG
+#include "feddat_b200_debug.h"
+#endif
 #include "host_common.h"
 #include "ptx_sm100.cuh"
 
@@ -82,11 +85,15 @@ struct FusedParams {
 };
 
 // debug timeline (scripts/trace_kernel.py): event e of CTA 0's tile `t` (t < 2) -> trace[t * 128 + e]
+#ifdef FEDDAT_DEBUG
 #define FD_TRACE(ev, t)                                                             \
   do {                                                                              \
     if (p.trace != nullptr && blockIdx.x == 0 && (t) < 2)                           \
       p.trace[(t) * 128 + (ev)] = globaltimer_ns();                                 \
   } while (0)
+#else   // product build: no trace code in the kernels
+#define FD_TRACE(ev, t) do { (void)(t); } while (0)
+#endif
 
 // activation is a template parameter: a run-time switch makes ptxas keep the erff path live in the
 // epilogue-1 inner loop (measured: 6.8 us instead of ~1.5 us per 128 x 256 tile)
@@ -608,7 +615,11 @@ dat_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
 }
 
 
-bool g_force_fused = false;
+#ifdef FEDDAT_DEBUG
+bool g_force_fused = false;       // A/B switch of the debug build (feddat_debug_force_fused_fwd)
+#else
+constexpr bool g_force_fused = false;
+#endif
 
 int launch_fused(bool bwd, const void* X, const void* Res, void* Out, const void* Wd_cat,
                  const void* W2, const void* W1b, FusedParams p, int64_t M, int r_total,
@@ -617,7 +628,7 @@ int launch_fused(bool bwd, const void* X, const void* Res, void* Out, const void
   p.M = static_cast<int>(M);
   p.R = r_total;
   p.num_tiles = static_cast<int>((M + BM - 1) / BM);
-  p.trace = fd::g_trace;
+  p.trace = FD_TRACE_PTR;
   p.w2_3d = (r_total % 64 == 0) ? 1 : 0;
   const size_t max_smem = 227 * 1024 - 1024;  // static smem (barriers) lives in the same budget
   const size_t smem = 1024 + static_cast<size_t>(NS) * STAGE + static_cast<size_t>(NSTG) * SLOT +
@@ -788,6 +799,7 @@ extern "C" int feddat_dat_bwd_dgrad(const void* X, const void* dY, void* dX, con
                       static_cast<cudaStream_t>(stream), "dat_bwd_dgrad");
 }
 
+#ifdef FEDDAT_DEBUG
 // debug / A-B measurement: route every forward through dat_fused_kernel (1) or choose by size (0)
 extern "C" int feddat_debug_force_fused_fwd(int on) {
   fd::g_force_fused = on != 0;
@@ -799,3 +811,4 @@ extern "C" int feddat_debug_set_trace(void* dev_buf) {
   fd::g_trace = static_cast<unsigned long long*>(dev_buf);
   return 0;
 }
+#endif  // FEDDAT_DEBUG

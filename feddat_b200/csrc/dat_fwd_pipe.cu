@@ -74,11 +74,15 @@ struct PipeParams {
   unsigned long long* trace;
 };
 
+#ifdef FEDDAT_DEBUG
 #define FDP_TRACE(ev, t)                                                            \
   do {                                                                              \
     if (p.trace != nullptr && blockIdx.x == 0 && (t) < 2)                           \
       p.trace[(t) * 128 + (ev)] = globaltimer_ns();                                 \
   } while (0)
+#else
+#define FDP_TRACE(ev, t) do { (void)(t); } while (0)
+#endif
 
 template <bool kGelu>
 __device__ __forceinline__ float apply_act(float x) {
@@ -495,7 +499,7 @@ int launch_pipe(bool bwd, const void* A, const void* Res, void* Out, const void*
   p.R = r_total;
   p.num_tiles = static_cast<int>((M + BM - 1) / BM);
   p.w2_3d = (r_total % 64 == 0) ? 1 : 0;
-  p.trace = g_trace;
+  p.trace = FD_TRACE_PTR;
   const size_t max_smem = 227 * 1024 - 1024;
   const size_t smem = 1024 + static_cast<size_t>(NG1) * G1STAGE + static_cast<size_t>(NW2 + NSTG) * SLOT +
                       (r_total + kD) * sizeof(float);

@@ -54,10 +54,14 @@ dat_wgrad_kernel(const __grid_constant__ CUtensorMap tmXk, const __grid_constant
   __shared__ float red_smem[2][8][NCW];     // bias-gradient partials of the 8 row sets (8 KB)
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+#ifdef FEDDAT_DEBUG
 #define WG_TRACE(ev)                                                              \
   do {                                                                            \
     if (p.trace != nullptr && blockIdx.x == 0) p.trace[(ev)] = globaltimer_ns();  \
   } while (0)
+#else
+#define WG_TRACE(ev) do { } while (0)
+#endif
   if (tid == 0) WG_TRACE(200);
   const int chunk = blockIdx.x % NCHUNK, split = blockIdx.x / NCHUNK;
   const int col0 = chunk * NCW;
@@ -282,7 +286,7 @@ extern "C" int feddat_dat_bwd_wgrad(const void* X, const void* dY, const void* H
   p.ld_dwu = ld_dwu;
   p.scale = branch_scale;
   p.dWu = dWu; p.dbu = dbu; p.dWd = dWd; p.dbd = dbd;
-  p.trace = g_trace;
+  p.trace = FD_TRACE_PTR;
   int sms = 0;
   if ((rc = device_sm_count(&sms))) return rc;
   int splits = sms / NCHUNK;

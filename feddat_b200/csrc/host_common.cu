@@ -87,7 +87,9 @@ int make_tmap_bf16_kblocks(CUtensorMap* out, const void* gptr, uint64_t rows, ui
   return FD_OK;
 }
 
+#ifdef FEDDAT_DEBUG
 unsigned long long* g_trace = nullptr;
+#endif
 
 int device_sm_count(int* out) {
   static int cached[64] = {0};

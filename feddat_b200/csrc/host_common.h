@@ -45,8 +45,14 @@ int make_tmap_bf16_2d(CUtensorMap* out, const void* gptr, uint64_t rows, uint64_
 int make_tmap_bf16_kblocks(CUtensorMap* out, const void* gptr, uint64_t rows, uint64_t cols,
                            uint64_t row_stride_elems, uint32_t box_rows, uint32_t box_blocks);
 
-// debug: device buffer of 256 uint64 receiving pipeline timestamps of CTA 0 (NULL = off)
+#ifdef FEDDAT_DEBUG
+// debug build only (libfeddat_sm100_dbg.so): device buffer of 256 uint64 receiving pipeline timestamps of
+// CTA 0 (NULL = off).  The product library carries no process-global mutable state.
 extern unsigned long long* g_trace;
+#define FD_TRACE_PTR fd::g_trace
+#else
+#define FD_TRACE_PTR nullptr
+#endif
 
 int device_sm_count(int* out);
 int check_device_sm100();

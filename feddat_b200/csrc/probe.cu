@@ -2,6 +2,7 @@
 // production kernels rely on (K-major smem, MN-major smem, A from TMEM).  The descriptor strides can
 // be overridden from the host so a single GPU call can sweep encodings.  Test infrastructure for
 // tests/test_probe_gpu.py; not part of the hot path.
+#ifdef FEDDAT_DEBUG   // bring-up / profiling kernels: only in libfeddat_sm100_dbg.so
 #include "host_common.h"
 #include "ptx_sm100.cuh"
 
@@ -549,3 +550,4 @@ extern "C" int feddat_probe_pair(const void* A, const void* B, float* D, int N, 
                                    reps < 1 ? 1 : reps, ns_out));
   return FD_OK;
 }
+#endif  // FEDDAT_DEBUG

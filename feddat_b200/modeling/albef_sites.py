@@ -43,7 +43,7 @@ class Mlp(nn.Module):
 
 
 class Attention(nn.Module):
-    """vit.py:34-75 (``register_hook`` keeps the explicit-softmax path: it needs the attention map)."""
+    """vit.py:34-75: softmax(q k^T * scale) v through SDPA (frozen backbone op)."""
 
     def __init__(self, dim, num_heads=8, qkv_bias=False, qk_scale=None, attn_drop=0.0, proj_drop=0.0):
         super().__init__()
@@ -53,33 +53,16 @@ class Attention(nn.Module):
         self.attn_drop = nn.Dropout(attn_drop)
         self.proj = nn.Linear(dim, dim)
         self.proj_drop = nn.Dropout(proj_drop)
-        self.attn_gradients = None
-        self.attention_map = None
-
-    def save_attn_gradients(self, attn_gradients):
-        self.attn_gradients = attn_gradients
-
-    def get_attn_gradients(self):
-        return self.attn_gradients
-
-    def save_attention_map(self, attention_map):
-        self.attention_map = attention_map
-
-    def get_attention_map(self):
-        return self.attention_map
 
     def forward(self, x, register_hook=False):
         b, n, c = x.shape
         qkv = self.qkv(x).reshape(b, n, 3, self.num_heads, c // self.num_heads).permute(2, 0, 3, 1, 4)
         q, k, v = qkv[0], qkv[1], qkv[2]
         if register_hook:
-            attn = self.attn_drop(((q @ k.transpose(-2, -1)) * self.scale).softmax(dim=-1))
-            self.save_attention_map(attn)
-            attn.register_hook(self.save_attn_gradients)
-            x = attn @ v
-        else:
-            x = F.scaled_dot_product_attention(q, k, v, dropout_p=self.attn_drop.p if self.training else 0.0,
-                                               scale=self.scale)
+            raise NotImplementedError("register_hook (Grad-CAM attention maps, vit.py:48-58,70-72) is a visualisation "
+                                      "aid outside the FedDAT training path")
+        x = F.scaled_dot_product_attention(q, k, v, dropout_p=self.attn_drop.p if self.training else 0.0,
+                                           scale=self.scale)
         x = x.transpose(1, 2).reshape(b, n, c)
         return self.proj_drop(self.proj(x))
 

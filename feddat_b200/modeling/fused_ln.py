@@ -19,11 +19,22 @@ and otherwise calls the stock HF forward, so nothing changes for other configura
 """
 from __future__ import annotations
 
+import logging
 import types
 
 import torch
 
 from .. import ops
+
+_warned = set()
+
+
+def _fallback_once(what: str, why: str) -> None:
+    """A frozen-backbone fast path that silently falls through to stock HF code would hide a performance
+    regression: say so once per cause."""
+    if (what, why) not in _warned:
+        _warned.add((what, why))
+        logging.getLogger("feddat_b200").warning("%s: stock HF path taken (%s)", what, why)
 
 
 class _AddLayerNorm(torch.autograd.Function):
@@ -117,6 +128,10 @@ def _prebias_ok(out_mod, h: torch.Tensor) -> bool:
 def fast_vilt_layer_forward(self, hidden_states, attention_mask=None, output_attentions=False):
     """HF ViltLayer.forward with fused LayerNorms (see module docstring)."""
     if attention_mask is not None or output_attentions or not _usable(self.layernorm_before, hidden_states):
+        _fallback_once("fast_vilt_layer_forward",
+                       "attention mask given" if attention_mask is not None else
+                       "attention maps requested" if output_attentions else
+                       f"activations {hidden_states.dtype} on {hidden_states.device.type} or unfrozen / non-bf16 LayerNorm")
         return type(self).forward(self, hidden_states, attention_mask, output_attentions)
     ln1 = layer_norm(self.layernorm_before, hidden_states)
     attention_output = self.attention(ln1, None, output_attentions=False)[0]
@@ -129,6 +144,8 @@ def fast_vilt_layer_forward(self, hidden_states, attention_mask=None, output_att
         h = torch.addmm(res_b.reshape(-1, res_b.shape[-1]), inter.reshape(-1, inter.shape[-1]), dense.weight.t())
         h = h.view(res_b.shape)
         return (self.output.adapter(h, h),)
+    _fallback_once("fast_vilt_layer_forward", "output dense layer not a frozen bf16 Linear with bias / active dropout: "
+                                               "second residual stays a separate add")
     hidden_states, ln2 = add_layer_norm(self.layernorm_after, attention_output, hidden_states)   # first residual
     layer_output = intermediate(self.intermediate, ln2)
     layer_output = self.output(layer_output, hidden_states)                                     # second residual + DAT

@@ -59,6 +59,8 @@ class _FrozenQKV(torch.autograd.Function):
 def _sdpa_self_attention_forward(self, hidden_states, attention_mask=None, output_attentions=False):
     """softmax(QK^T / sqrt(d)) V of HF ViltSelfAttention, through torch SDPA (frozen backbone op)."""
     if output_attentions:
+        from .fused_ln import _fallback_once
+        _fallback_once("_sdpa_self_attention_forward", "attention maps requested: explicit softmax path")
         return type(self).forward(self, hidden_states, attention_mask, output_attentions)
     b, s, _ = hidden_states.shape
     h, dh = self.num_attention_heads, self.attention_head_size
@@ -149,15 +151,19 @@ class ViltEncoderWrapper(nn.Module):
         return torch.cat([text + tt[0], img + tt[1]], dim=1)
 
     def _dense_forward(self, input_ids, token_type_ids, pixel_values):
+        # The cache only serves the passes of ONE train step (TaskTrainer clears it at the start of every
+        # train / eval step): ``_version`` does not move for ``.data.copy_`` or external writes into a static
+        # input buffer, so the key alone could not tell a refilled buffer from the old batch.
         key = (input_ids.data_ptr(), input_ids._version, pixel_values.data_ptr(), pixel_values._version,
-               tuple(pixel_values.shape))
+               tuple(pixel_values.shape),
+               None if token_type_ids is None else (token_type_ids.data_ptr(), token_type_ids._version))
         if self._embed_cache is not None and self._embed_cache[0] == key:
             hidden = self._embed_cache[1]
         else:
             with torch.no_grad():                       # embeddings are frozen (main.py:138-139)
                 hidden = self._dense_embeddings(input_ids, token_type_ids, pixel_values)
             # keep references to the inputs so their storage (and the key) stays valid
-            self._embed_cache = (key, hidden, input_ids, pixel_values)
+            self._embed_cache = (key, hidden, input_ids, pixel_values, token_type_ids)
         for layer in self.vilt.encoder.layer:
             hidden = layer(hidden, None)[0]
         # the pooler reads only the CLS row of the final LayerNorm (per-row op): normalise that row alone
@@ -270,6 +276,10 @@ class ViltContinualLearner(nn.Module):
             for a in self._adapters():
                 a.set_dual(False)
         return enc
+
+    def new_step(self) -> None:
+        """Called by the trainer at the start of every train / eval step: drops the per-step embedding cache."""
+        self.vilt_encoder._embed_cache = None
 
     def gating_forward_is_reusable(self) -> bool:
         """True when the encoder is a deterministic function of (inputs, adapter_0, adapter_2, frozen

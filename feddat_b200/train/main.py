@@ -92,7 +92,24 @@ def personal_keys(model, names):
     return [n for n in model.state_dict().keys() if any(pn in n for pn in names)]
 
 
-def main(argv=None):
+def grad_flags(model):
+    """``requires_grad`` of every parameter by name.  The reference hands each client a
+    ``copy.deepcopy`` of the SERVER model (main.py:472), so every client starts from the server model's
+    flags -- not from whatever the previous client's last ``train_step`` left behind
+    (``set_active_adapter('adapter_0')`` switches adapter_1 off, adapter.py:71-77).  The resident model
+    replaces the deepcopy, so the server's flags are recorded where the reference would copy them and
+    restored before each client trains."""
+    return {n: p.requires_grad for n, p in model.named_parameters()}
+
+
+def restore_grad_flags(model, flags):
+    for n, p in model.named_parameters():
+        p.requires_grad = flags[n]
+
+
+def main(argv=None, record=None):
+    """``record`` (tests): a dict that receives, per round, the names of the tensors in every client's
+    optimizer, the clients' adapter_1 snapshots and the averaged buffer."""
     args = build_parser().parse_args(argv)
     args.ordered_cl_tasks = resolve_tasks(args.ordered_cl_tasks)
     args.lr = args.lr if args.lr is not None else 1e-4
@@ -122,6 +139,7 @@ def main(argv=None):
         return 0
 
     n_clients = len(args.ordered_cl_tasks)
+    server_flags = grad_flags(model)             # what deepcopy(model) would carry into every client
     for comm_round in range(args.comm_rounds):
         t0 = time.time()
         global_flat = comm.snapshot()
@@ -132,6 +150,7 @@ def main(argv=None):
                 sd = model.state_dict()
                 for n in pkeys:
                     sd[n].copy_(personal[task_key][n])
+            restore_grad_flags(model, server_flags)
             if args.fix_adapter0_optimizer:
                 for n, p in model.named_parameters():
                     if "adapter_0" in n or "adapter_1" in n:
@@ -140,6 +159,8 @@ def main(argv=None):
             trainer = VQATrainerSynthetic(logger, args, task_configs, model_config, device, task_key, out_dir,
                                           client_id=task_num, accelerator=accelerator)
             _, c_model = trainer.train(model, comm_round)            # main.py:485
+            if record is not None:
+                record.setdefault("optimizer_names", {})[(comm_round, task_key)] = list(trainer.last_optimizer_names)
             with torch.no_grad():                                    # main.py:493-503
                 sd = c_model.state_dict()
                 for n in pkeys:
@@ -149,11 +170,18 @@ def main(argv=None):
                         float(trainer.last_loss) if trainer.last_loss is not None else float("nan"))
         with torch.no_grad():                                        # main.py:510, nums = [1, ...] (:455)
             get_average_net_flat(comm, client_flats, [1.0] * len(client_flats), total=float(n_clients))
+        if record is not None:
+            record.setdefault("client_flats", {})[comm_round] = [f.cpu() for f in client_flats]
+            record.setdefault("global_flat", {})[comm_round] = comm.flat.detach().cpu().clone()
         accelerator.wait_for_everyone()
         logger.info("round %d done in %.2f s", comm_round, time.time() - t0)
 
         if comm_round % 5 == 0 or args.comm_rounds - 1 == comm_round:        # main.py:520-558
             sums = torch.zeros(4, device=device)
+            # the reference evaluates the SERVER model: its flags, then the eval's own side effects on them
+            # (task_trainer.py:236-243 ends on set_active_adapter('adapter_1'): adapter_0 stays frozen in
+            # every later round's deepcopy -- SURVEY.md F8)
+            restore_grad_flags(model, server_flags)
             with torch.no_grad():
                 for task_num, task_key in my_clients:
                     sd = model.state_dict()
@@ -163,8 +191,14 @@ def main(argv=None):
                                                   client_id=task_num, accelerator=accelerator)
                     scores = trainer.eval(model)
                     sums += torch.tensor(scores + [1.0], device=device)
+            if not my_clients:           # a rank without clients still mirrors the eval's flag side effects
+                model.set_active_adapter("adapter_0")
+                model.set_active_adapter("adapter_1")
+            server_flags = grad_flags(model)
             if world > 1:
                 dist.all_reduce(sums)
+            if record is not None:
+                record.setdefault("eval_scores", {})[comm_round] = (sums[:3] / sums[3].clamp_min(1)).tolist()
             logger.info("Round %d: Avg test score [gating, adapter_0, adapter_1] = %s", comm_round,
                         [round(v, 2) for v in (sums[:3] / sums[3]).tolist()])
     if world > 1:

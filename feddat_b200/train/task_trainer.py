@@ -97,6 +97,13 @@ class TaskTrainer(nn.Module):
         # Batched schedule (same arithmetic, see _train_step_batched): the gating pass and the adapter_1 pass
         # run as ONE row-stacked forward and ONE row-stacked backward through the frozen backbone
         self.batched_passes = True
+        # tests: ``grad_probe(tag, model)`` is called with every gradient of a pass in place, BEFORE the
+        # optimizer consumes it (tags "B" / "C" in the reference order; "B_head" / "BC" in the batched one)
+        self.grad_probe = None
+
+    def _probe(self, tag, model):
+        if self.grad_probe is not None:
+            self.grad_probe(tag, model)
 
     # ------------------------------------------------------------------ train (task_trainer.py:24-111)
     def train(self, model, er=None, ewc=None, der=None, derpp=None, pnn=None, hat=None):
@@ -114,6 +121,8 @@ class TaskTrainer(nn.Module):
 
         model = self.accelerator.prepare(model)
         optimizer = self.create_optimizer(model, self.args.optimizer_mode)
+        ids = {id(p) for g in optimizer.param_groups for p in g["params"]}
+        self.last_optimizer_names = [n for n, p in model.named_parameters() if id(p) in ids]
         scheduler = get_polynomial_decay_schedule_with_warmup(
             optimizer, num_warmup_steps=int(self.max_steps * self.warmup_ratio),
             num_training_steps=self.max_steps, lr_end=0, power=1)
@@ -212,6 +221,7 @@ class TaskTrainer(nn.Module):
         logits_1 = inner.classify(self.task_key, enc_b)              # (B)
         L_1, _ = self._objective(logits_1, logits_all, target, None)
         self.accelerator.backward(L_1)                               # head grads + d enc_B (adapters: none yet)
+        self._probe("B_head", model)
         optimizer.step()                                             # only the head has gradients
         optimizer.zero_grad()
 
@@ -219,6 +229,7 @@ class TaskTrainer(nn.Module):
         L_0, loss_0 = self._objective(logits_0, logits_1, target, None)
         self.accelerator.backward(L_0)                               # head grads + d enc_A
         enc.backward(leaf.grad)                                      # adapter_0 (rows A) and adapter_1 (rows B)
+        self._probe("BC", model)
 
         a1 = getattr(self, "_a1_params", None)
         if a1 is None or a1[0] is not model:
@@ -240,6 +251,8 @@ class TaskTrainer(nn.Module):
         albef = "albef" in self.args.encoder_name
 
         inner = model.module
+        if hasattr(inner, "new_step"):
+            inner.new_step()                                          # per-step caches (ViLT embedding output)
         reuse = (self.reuse_gating_forward and not albef
                  and getattr(inner, "gating_forward_is_reusable", lambda: False)())
         if (reuse and self.batched_passes and optimizer is not None and hasattr(inner, "encode_dual")
@@ -262,6 +275,7 @@ class TaskTrainer(nn.Module):
         output_1_0, logits_1 = self.forward_pass(model, batch, do_eval=False)
         L_1, _ = self._objective(logits_1, logits_all, target, output_1_0 if albef else None)
         self.accelerator.backward(L_1)
+        self._probe("B", model)
         if optimizer is not None:
             optimizer.step()
             if scheduler is not None:
@@ -276,6 +290,7 @@ class TaskTrainer(nn.Module):
             output_0_0, logits_0 = self.forward_pass(model, batch, do_eval=False)
         L_0, loss_0 = self._objective(logits_0, logits_1, target, output_0_0 if albef else None)
         self.accelerator.backward(L_0)
+        self._probe("C", model)
         if optimizer is not None:
             optimizer.step()
             if scheduler is not None:

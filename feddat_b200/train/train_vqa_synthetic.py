@@ -55,6 +55,8 @@ class VQATrainerSynthetic(TaskTrainer):
         model.eval()
         score, seen = 0.0, 0
         for batch in loader:
+            if hasattr(model, "new_step"):
+                model.new_step()
             logits = self.forward_pass(model, batch, do_eval=True)[1]
             target = batch["target_scores"].to(self.device)
             score += torch.sum(self.compute_score_with_logits(logits.float(), target)).item()

@@ -20,7 +20,7 @@ sys.path.insert(0, str(ROOT))
 def run_probe(a_mode, b_mode, N, K, overrides=None):
     import torch
     from feddat_b200 import _lib
-    lib = _lib.load()
+    lib = _lib.load_debug()
     torch.manual_seed(0)
     A = torch.randn(128, K, device="cuda").to(torch.bfloat16)
     B = torch.randn(N, K, device="cuda").to(torch.bfloat16)
@@ -42,7 +42,7 @@ def run_probe(a_mode, b_mode, N, K, overrides=None):
 def run_pair(N, K, a_tmem, reps=1):
     import torch
     from feddat_b200 import _lib
-    lib = _lib.load()
+    lib = _lib.load_debug()
     torch.manual_seed(0)
     A = torch.randn(256, K, device="cuda").to(torch.bfloat16)
     B = torch.randn(N, K, device="cuda").to(torch.bfloat16)
@@ -65,7 +65,7 @@ def run_pair(N, K, a_tmem, reps=1):
 def run_fwd(R, M, scale, act=0, alias=True):
     import torch
     from feddat_b200 import _lib
-    lib = _lib.load()
+    lib = _lib.load_debug()
     torch.manual_seed(1)
     d = 768
     X = torch.randn(M, d, device="cuda").to(torch.bfloat16)

@@ -8,7 +8,7 @@ ROOT = Path(__file__).resolve().parent.parent
 sys.path.insert(0, str(ROOT))
 from feddat_b200 import _lib  # noqa: E402
 
-lib = _lib.load()
+lib = _lib.load_debug()
 dev = torch.device("cuda", 0)
 n_rows = 32768
 clk = torch.zeros(1, dtype=torch.int64, device=dev)

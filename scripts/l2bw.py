@@ -8,7 +8,7 @@ ROOT = Path(__file__).resolve().parent.parent
 sys.path.insert(0, str(ROOT))
 from feddat_b200 import _lib  # noqa: E402
 
-lib = _lib.load()
+lib = _lib.load_debug()
 dev = torch.device("cuda", 0)
 for n_boxes in (48, 4096):          # 768 KB (weights-like, L2 resident) and 64 MB
     buf = torch.randn(n_boxes * 128, 64, device=dev).to(torch.bfloat16)

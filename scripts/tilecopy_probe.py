@@ -9,7 +9,7 @@ ROOT = Path(__file__).resolve().parent.parent
 sys.path.insert(0, str(ROOT))
 from feddat_b200 import _lib  # noqa: E402
 
-lib = _lib.load()
+lib = _lib.load_debug()
 dev = torch.device("cuda", 0)
 M = 71040 * 4            # 436 MB per tensor: well beyond L2
 src = torch.randn(M, 768, device=dev).to(torch.bfloat16)

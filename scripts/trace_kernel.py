@@ -21,7 +21,7 @@ pk = ops.pack_weights([[torch.randn(r, 768, device=dev, generator=g) * 0.02, tor
                        for _ in range(nb)])
 x = torch.randn(M, 768, device=dev, generator=g).to(torch.bfloat16)
 dy = torch.randn(M, 768, device=dev, generator=g).to(torch.bfloat16)
-lib = _lib.load()
+lib = _lib.load_debug()
 
 
 def run():

@@ -88,3 +88,18 @@ def albef_site_inputs():
 
 def albef_site_gout(shape):
     return np.random.default_rng(99).standard_normal(tuple(shape)).astype(np.float32)
+
+
+def grad_sketch(name, g, cols=8):
+    """Compact fingerprint of a gradient tensor for the step-level goldens: 1-D tensors in full, 2-D tensors
+    as G @ Omega with a seeded N(0, 1) matrix Omega [in_features, cols] (keyed by the parameter name, so both
+    sides of a comparison draw the same Omega).  A random projection preserves relative Frobenius distances
+    in expectation, so comparing sketches bounds the distance of the full gradients."""
+    import zlib
+    g = np.asarray(g, np.float32)
+    if g.ndim < 2:
+        return g.copy()
+    g2 = g.reshape(g.shape[0], -1)
+    rng = np.random.default_rng([77, zlib.crc32(name.encode())])
+    omega = rng.standard_normal((g2.shape[1], cols)).astype(np.float32)
+    return g2 @ omega

@@ -1,0 +1,123 @@
+"""The ``Adapter`` MODULE (autograd node included) against the oracle at the wide ranks of BASELINE
+configs[2] (ALBEF, r = 256) and configs[4] (rank sweep up to r = 512): bottlenecks wider than one launch
+covers (R = r or 2r > 256) run as several segment launches whose partial results the autograd node has to
+stitch (``Adapter._segments``, ``_DatFunction.backward``).  Forward, dX, d(residual) and every trainable
+parameter gradient, single and gating mode, residual == input (ViLT / ViT sites) and residual != input
+(BERT sites, adapter.py:97-116).  GPU only."""
+import numpy as np
+import pytest
+import torch
+
+import oracle
+
+pytestmark = pytest.mark.gpu
+
+BF16_TOL = 1e-2
+
+
+def relerr(a, b):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-30))
+
+
+def bf16(x):
+    return torch.from_numpy(np.asarray(x, np.float32)).to(torch.bfloat16).float().numpy()
+
+
+@pytest.mark.parametrize("same_residual", [True, False], ids=["res_is_x", "res_not_x"])
+@pytest.mark.parametrize("gating", [False, True], ids=["single", "gating"])
+@pytest.mark.parametrize("r", [48, 128, 256, 512])
+def test_adapter_module_matches_oracle(r, gating, same_residual):
+    from feddat_b200.modeling.adapter import Adapter
+    M = 333                                              # 2 full tiles + a ragged one
+    rng = np.random.default_rng(r * 13 + 2 * gating + same_residual)
+    a = Adapter(names=["adapter_0", "adapter_1", "adapter_2"], device="cuda", rank=r)
+    with torch.no_grad():
+        for n, p in a.named_parameters():
+            std = 0.1 if p.dim() == 1 else 0.05
+            p.copy_(torch.from_numpy((rng.standard_normal(tuple(p.shape)) * std).astype(np.float32)))
+    x = rng.standard_normal((3, 111, 768)).astype(np.float32)
+    res = x if same_residual else rng.standard_normal((3, 111, 768)).astype(np.float32)
+    g = rng.standard_normal((3, 111, 768)).astype(np.float32)
+    assert x.shape[0] * x.shape[1] == M
+
+    if gating:
+        a.activate_gating()
+        a.set_active_adapter("adapter_0")                # adapter_0 trains, adapter_2 is frozen
+        names, train = ("adapter_0", "adapter_2"), "adapter_0"
+    else:
+        a.deactivate_gating()
+        a.set_active_adapter("adapter_1")
+        names, train = ("adapter_1",), "adapter_1"
+
+    xd = torch.from_numpy(x).cuda().to(torch.bfloat16).requires_grad_(True)
+    if same_residual:
+        y = a(xd, xd)
+        rd = None
+    else:
+        rd = torch.from_numpy(res).cuda().to(torch.bfloat16).requires_grad_(True)
+        y = a(xd, rd)
+    y.backward(torch.from_numpy(g).cuda().to(torch.bfloat16))
+    torch.cuda.synchronize()
+
+    def branch(n):
+        d, u = getattr(a, f"{n}_down"), getattr(a, f"{n}_up")
+        return (bf16(d.weight.detach().cpu().numpy()), d.bias.detach().cpu().numpy(),
+                bf16(u.weight.detach().cpu().numpy()), u.bias.detach().cpu().numpy())
+
+    brs = [branch(n) for n in names]
+    xr, rr, gr = bf16(x.reshape(M, 768)), bf16(res.reshape(M, 768)), bf16(g.reshape(M, 768))
+    y_or = oracle.adapter_forward(xr, rr, brs, gating)
+    assert relerr(y.detach().float().cpu().numpy().reshape(M, 768), y_or) < 6e-3
+    dx_or, grads_or = oracle.adapter_backward(xr, gr, brs, gating, residual_is_input=same_residual)
+    # rows holding a pre-activation within rounding noise of 0 may take either relu' value
+    # (tests/test_kernels_gpu.py::test_dat_fwd_bwd_full_size_vs_oracle explains the exemption)
+    near = np.zeros(M, bool)
+    for (dw, db, _, _) in brs:
+        near |= (np.abs(xr.astype(np.float64) @ dw.T.astype(np.float64) + db) < 2e-5).any(axis=1)
+    assert near.sum() <= 8
+    dx = xd.grad.float().cpu().numpy().reshape(M, 768)
+    row_err = np.abs(dx - dx_or).max(axis=1) / np.abs(dx_or).max()
+    assert set(np.nonzero(row_err >= BF16_TOL)[0].tolist()) <= set(np.nonzero(near)[0].tolist())
+    if not same_residual:
+        assert torch.equal(rd.grad, torch.from_numpy(g).cuda().to(torch.bfloat16))      # d(residual) = dY
+    ti = names.index(train)
+    d, u = getattr(a, f"{train}_down"), getattr(a, f"{train}_up")
+    for got, want, what in zip((d.weight.grad, d.bias.grad, u.weight.grad, u.bias.grad), grads_or[ti],
+                               ("down.weight", "down.bias", "up.weight", "up.bias")):
+        assert got is not None, what
+        assert relerr(got.cpu().numpy(), want) < 2 * BF16_TOL, what
+    for n in names:
+        if n != train:
+            assert all(p.grad is None for p in getattr(a, f"{n}_down").parameters())
+
+
+@pytest.mark.parametrize("r", [256, 512])
+def test_bert_site_wrapper_wide_rank(r):
+    """adapter_layer_forward_bert (adapter.py:97-116) at the ALBEF rank: LN(ffn + x) -> adapter(residual = ffn)
+    -> LN(. + x), against the oracle's restatement evaluated with the kernel's bf16 operands."""
+    from feddat_b200.modeling.adapter import Adapter
+    rng = np.random.default_rng(r)
+    a = Adapter(names=["adapter_0", "adapter_1", "adapter_2"], device="cuda", rank=r)
+    with torch.no_grad():
+        for n, p in a.named_parameters():
+            p.copy_(torch.from_numpy((rng.standard_normal(tuple(p.shape)) * (0.1 if p.dim() == 1 else 0.05)).astype(np.float32)))
+    a.activate_gating(); a.set_active_adapter("adapter_0")
+    ln = torch.nn.LayerNorm(768, eps=1e-12).cuda()
+    with torch.no_grad():
+        ln.weight.copy_(1 + 0.1 * torch.randn(768, device="cuda")); ln.bias.copy_(0.1 * torch.randn(768, device="cuda"))
+    ffn = rng.standard_normal((2, 25, 768)).astype(np.float32)
+    x = rng.standard_normal((2, 25, 768)).astype(np.float32)
+    # fp32 activations in (LayerNorm in fp32, as the reference under autocast); the operator rounds its own
+    # input and residual to bf16
+    out = a.adapter_layer_forward_bert(torch.from_numpy(ffn).cuda(), torch.from_numpy(x).cuda(), ln)
+
+    def branch(n):
+        d, u = getattr(a, f"{n}_down"), getattr(a, f"{n}_up")
+        return (bf16(d.weight.detach().cpu().numpy()), d.bias.detach().cpu().numpy(),
+                bf16(u.weight.detach().cpu().numpy()), u.bias.detach().cpu().numpy())
+
+    want = oracle.adapter_layer_forward_bert(ffn, x, ln.weight.detach().cpu().numpy().astype(np.float64),
+                                             ln.bias.detach().cpu().numpy().astype(np.float64), 1e-12,
+                                             [branch("adapter_0"), branch("adapter_2")], True)
+    assert relerr(out.detach().float().cpu().numpy(), want) < 2e-2       # two LayerNorms amplify the bf16 rounding of their inputs

@@ -29,9 +29,12 @@ def test_block_keys_and_plain_path():
     assert not plain.adaptered and not hasattr(plain, "adapter")
     x = torch.randn(2, 5, 768)
     y_sdpa = plain(x)
-    y_hook = plain(x, register_hook=True)                 # explicit softmax path keeps the attention map
-    assert torch.allclose(y_sdpa, y_hook, atol=1e-5)
-    assert plain.attn.get_attention_map().shape == (2, 12, 5, 5)
+    # SDPA == the explicit softmax(q k^T * scale) v of vit.py:65-73
+    a = plain.attn
+    qkv = a.qkv(plain.norm1(x)).reshape(2, 5, 3, 12, 64).permute(2, 0, 3, 1, 4)
+    att = ((qkv[0] @ qkv[1].transpose(-2, -1)) * a.scale).softmax(dim=-1)
+    h = x + a.proj((att @ qkv[2]).transpose(1, 2).reshape(2, 5, 768))
+    assert torch.allclose(y_sdpa, h + plain.mlp(plain.norm2(h)), atol=1e-5)
 
 
 def test_bert_output_keys_and_plain_path():

@@ -61,7 +61,7 @@ def ops():
 def test_tcgen05_probe(a_mode, b_mode):
     import ctypes
     from feddat_b200 import _lib
-    lib = _lib.load()
+    lib = _lib.load_debug()
     N, K = 128, 128
     torch.manual_seed(0)
     A = torch.randn(128, K, device="cuda").to(torch.bfloat16)

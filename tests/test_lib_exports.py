@@ -6,8 +6,8 @@ from pathlib import Path
 ROOT = Path(__file__).resolve().parent.parent
 
 
-def header_functions():
-    text = (ROOT / "include" / "feddat_b200.h").read_text()
+def header_functions(name="feddat_b200.h"):
+    text = (ROOT / "include" / name).read_text()
     text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
     return sorted(set(re.findall(r"\b(feddat_[a-z0-9_]+)\s*\(", text)))
 
@@ -20,7 +20,19 @@ def test_library_exports_every_declared_symbol():
     for n in names:
         assert hasattr(lib, n), f"{n} declared in include/feddat_b200.h but not exported"
     assert set(names) == set(_lib.EXPORTED_SYMBOLS)
-    assert lib.feddat_abi_version() == 2
+    assert lib.feddat_abi_version() == _lib.ABI_VERSION
+    # probes / debug switches are NOT in the product library
+    for n in _lib.DEBUG_SYMBOLS:
+        assert not hasattr(lib, n), f"{n} (debug-only) leaked into the product library"
+
+
+def test_debug_twin_exports_product_and_debug_symbols():
+    from feddat_b200 import _lib
+    dbg = _lib.load_debug()
+    names = header_functions("feddat_b200_debug.h")
+    assert set(names) == set(_lib.DEBUG_SYMBOLS)
+    for n in list(names) + header_functions():
+        assert hasattr(dbg, n), n
 
 
 def test_entry_points_fail_loudly_without_a_gpu():
