@@ -185,6 +185,32 @@ def kernel_rooflines(peaks, device):
             out[f"{name}_M{M}"] = {
                 "us": round(t * 1e6, 2), "bound": bound, "tflops": round(flops / t / 1e12, 1),
                 "gbs": round(nbytes / t / 1e9, 1), "frac_of_roofline": round(max(t_tensor, t_hbm) / t, 4)}
+        if M == B * 185:
+            # what the train step actually launches per adapter site (batched MKD schedule): ONE grouped launch
+            # over [gating rows | adapter_1 rows] per direction
+            Mh = M
+            gsets = []
+            for (x, dy, h2, h1), (x1, dy1, _, h1b) in zip(sets[0::2], sets[1::2]):
+                gsets.append((x, dy, h2, x1, dy1, h1b, torch.empty_like(x), torch.empty_like(x1)))
+
+            def g_fwd(x, dy, h2, x1, dy1, h1, y0, y1):
+                ops.dat_forward_grouped([dict(x=x, res=x, w=pk2, scale=0.5, out=y0, save_hidden=True),
+                                         dict(x=x1, res=x1, w=pk1, scale=1.0, out=y1, save_hidden=True)])
+
+            def g_bwd(x, dy, h2, x1, dy1, h1, y0, y1):
+                ops.dat_backward_grouped([dict(x=x, dy=dy, w=pk2, scale=0.5, train_slice=(0, r), hidden=h2, dx_out=y0),
+                                          dict(x=x1, dy=dy1, w=pk1, scale=1.0, train_slice=(0, r), hidden=h1, dx_out=y1)])
+
+            for name, fn, flops, nbytes in (("site_fwd_grouped", g_fwd, 12 * D * r * Mh, 4 * D * 2 * Mh),
+                                            ("site_bwd_grouped", g_bwd, 20 * D * r * Mh, 6 * D * 2 * Mh)):
+                t = timeit(fn, gsets)
+                t_tensor, t_hbm = flops / (peaks["tf_burst"] * 1e12), nbytes / (peaks["hbm_gbs"] * 1e9)
+                out[f"{name}_M{2 * Mh}"] = {
+                    "us": round(t * 1e6, 2), "bound": "tensor" if t_tensor >= t_hbm else "hbm",
+                    "tflops": round(flops / t / 1e12, 1), "gbs": round(nbytes / t / 1e9, 1),
+                    "frac_of_roofline": round(max(t_tensor, t_hbm) / t, 4),
+                    "rows": f"{Mh} gating (R = {2 * r}) + {Mh} adapter_1 (R = {r})"}
+            del gsets
         del sets
     return out
 

@@ -7,14 +7,14 @@ from __future__ import annotations
 
 import ctypes
 import os
-from ctypes import POINTER, c_char_p, c_float, c_int, c_int64, c_uint32, c_void_p
+from ctypes import POINTER, c_char_p, c_float, c_int, c_int64, c_size_t, c_uint32, c_void_p
 from pathlib import Path
 
 _LIB_PATH = Path(__file__).resolve().parent / "lib" / "libfeddat_sm100.so"
 _DBG_LIB_PATH = Path(__file__).resolve().parent / "lib" / "libfeddat_sm100_dbg.so"
 _lib = None
 _dbg_lib = None
-ABI_VERSION = 2      # feddat_abi_version(); bumped whenever include/feddat_b200.h changes
+ABI_VERSION = 3      # feddat_abi_version(); bumped whenever include/feddat_b200.h changes
 
 # every symbol include/feddat_b200.h declares (tests check the built library exports all of them)
 EXPORTED_SYMBOLS = (
@@ -23,7 +23,12 @@ EXPORTED_SYMBOLS = (
     "feddat_dat_fwd",
     "feddat_dat_bwd_dgrad",
     "feddat_dat_bwd_wgrad",
+    "feddat_dat_wgrad_workspace_bytes",
+    "feddat_dat_fwd_grouped",
+    "feddat_dat_bwd_dgrad_grouped",
+    "feddat_dat_bwd_wgrad_grouped",
     "feddat_pack_weights",
+    "feddat_pack_weights_batched",
     "feddat_mkd_loss",
     "feddat_fedavg",
     "feddat_ln_fwd",
@@ -45,6 +50,30 @@ DEBUG_SYMBOLS = (
 
 class FeddatError(RuntimeError):
     pass
+
+
+class DatGroup(ctypes.Structure):
+    """``FeddatDatGroup`` of include/feddat_b200.h."""
+    _fields_ = [("X", c_void_p), ("Res", c_void_p), ("Y", c_void_p), ("dY", c_void_p), ("dX", c_void_p),
+                ("Wd_cat", c_void_p), ("bd_cat", c_void_p), ("Wu_cat", c_void_p), ("bu_cat", c_void_p),
+                ("WuT_cat", c_void_p), ("WdT_cat", c_void_p), ("H_out", c_void_p), ("H_in", c_void_p),
+                ("H_t", c_void_p), ("dP_t", c_void_p), ("ld_t", c_int), ("r_lo", c_int), ("r_hi", c_int),
+                ("M", c_int64), ("r_total", c_int), ("branch_scale", c_float), ("add_dy", c_int)]
+
+
+class WgradGroup(ctypes.Structure):
+    """``FeddatWgradGroup`` of include/feddat_b200.h."""
+    _fields_ = [("X", c_void_p), ("dY", c_void_p), ("H_t", c_void_p), ("dP_t", c_void_p),
+                ("dWu", c_void_p), ("dbu", c_void_p), ("dWd", c_void_p), ("dbd", c_void_p),
+                ("M", c_int64), ("r_t", c_int), ("ld_ht", c_int), ("ld_dwu", c_int), ("branch_scale", c_float)]
+
+
+class PackJob(ctypes.Structure):
+    """``FeddatPackJob`` of include/feddat_b200.h."""
+    _fields_ = [("down_w", c_void_p * 2), ("down_b", c_void_p * 2), ("up_w", c_void_p * 2), ("bu_src", c_void_p * 2),
+                ("n_branch", c_int), ("r", c_int), ("ld_up", c_int),
+                ("Wd_cat", c_void_p), ("WdT_cat", c_void_p), ("Wu_cat", c_void_p), ("WuT_cat", c_void_p),
+                ("bd_cat", c_void_p), ("bu_cat", c_void_p)]
 
 
 def lib_path() -> Path:
@@ -94,11 +123,22 @@ def _bind(lib: ctypes.CDLL, debug: bool) -> ctypes.CDLL:
     lib.feddat_dat_bwd_wgrad.restype = c_int
     lib.feddat_dat_bwd_wgrad.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                          c_void_p, c_void_p, c_int64, c_int, c_int, c_int, c_int,
-                                         c_float, c_int, c_void_p]
+                                         c_float, c_int, c_void_p, c_size_t, c_void_p]
+    lib.feddat_dat_wgrad_workspace_bytes.restype = c_size_t
+    lib.feddat_dat_wgrad_workspace_bytes.argtypes = []
+    lib.feddat_dat_fwd_grouped.restype = c_int
+    lib.feddat_dat_fwd_grouped.argtypes = [POINTER(DatGroup), c_int, c_int, c_int, c_int, c_void_p]
+    lib.feddat_dat_bwd_dgrad_grouped.restype = c_int
+    lib.feddat_dat_bwd_dgrad_grouped.argtypes = [POINTER(DatGroup), c_int, c_int, c_int, c_int, c_void_p]
+    lib.feddat_dat_bwd_wgrad_grouped.restype = c_int
+    lib.feddat_dat_bwd_wgrad_grouped.argtypes = [POINTER(WgradGroup), c_int, c_int, c_int, c_void_p, c_size_t,
+                                                 c_void_p]
     lib.feddat_pack_weights.restype = c_int
     lib.feddat_pack_weights.argtypes = [POINTER(c_void_p), POINTER(c_void_p), POINTER(c_void_p),
                                         POINTER(c_void_p), c_int, c_int, c_int, c_void_p, c_void_p,
                                         c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]
+    lib.feddat_pack_weights_batched.restype = c_int
+    lib.feddat_pack_weights_batched.argtypes = [POINTER(PackJob), c_int, c_int, c_void_p]
     lib.feddat_mkd_loss.restype = c_int
     lib.feddat_mkd_loss.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int,
                                     c_float, c_float, c_float, c_float, c_int64, c_void_p]

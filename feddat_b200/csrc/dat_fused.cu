@@ -39,6 +39,16 @@
 //               for the trainable slice [r_lo, r_hi) also H = act(P + bd) and dP to HBM (wgrad kernel)
 //   GEMM3  dX = dP * Wd_cat              (B operand: WdT_cat, K-major), + dY when the residual
 //               input is X itself (adaptered_output.py:78), -> bf16 -> TMA store
+//
+// GROUPED launches (feddat_dat_fwd_grouped / feddat_dat_bwd_dgrad_grouped): up to two independent row
+// groups, each with its own activations, weights, bottleneck width and scale, share ONE launch -- the MKD
+// schedule's gating rows (adapter_0 | adapter_2, R = 2r, scale .5) and adapter_1 rows (R = r, scale 1) of
+// one adapter site (task_trainer.py:280-330).  Every CTA pair walks "slots": slot -> (group, super-tile,
+// output-column range); all per-group quantities (R, descriptors, biases, tensor maps) are looked up per
+// slot.  A single site of one batch (2 x 47 tiles) thus fills 144 of the 148 SMs in one launch instead of
+// two launches of 144 CTAs that each recompute the hidden three times.
+#include <stdlib.h>
+
 #include "dat_kernels.h"
 #include "feddat_b200.h"
 #ifdef FEDDAT_DEBUG
@@ -66,8 +76,11 @@ constexpr uint32_t W2_KB_BYTES = (N2 / 2) * 128u;  // one k-block [64 rows x 64]
 constexpr uint32_t TM_P = 0;          // TMEM column of P (and of the packed hidden aliasing it)
 constexpr uint32_t TM_D = 256;        // TMEM column of the output ring (and of dH in backward)
 
-struct FusedParams {
-  int M, R, num_tiles, w2_3d, act;
+constexpr int MAX_GROUPS = 2;
+constexpr int BIAS_STRIDE = 256 + kD;   // floats of bias staging per group: bd [256] | scale * bu [768]
+
+struct GroupCfg {
+  int M, R, num_tiles, w2_3d;
   int n_split;            // S: CTA pairs per super-tile, each owning NC2 / S of the output chunks (small M)
   float scale;
   const float* bd;
@@ -81,7 +94,28 @@ struct FusedParams {
   int ld_t;               // row stride (elements) of H_t / dP_t
   const __nv_bfloat16* H_in;   // bwd, saved mode: the forward's hidden [M, R] (no P recompute)
   __nv_bfloat16* H_out;        // fwd: where to save the hidden [M, R] for such a backward, or null
+};
+
+struct FusedParams {
+  GroupCfg g[MAX_GROUPS];
+  int n_groups;
+  int slots0;             // slots of group 0 (= its super-tiles x its column split); group 1 follows
+  int total_slots;
+  int act;
   unsigned long long* trace;  // debug: globaltimer stamps of CTA 0's pipeline events (or null)
+};
+
+// the seven tensor maps of one group
+struct TmapSet {
+  CUtensorMap x, res, y, wd, w2, w2k, w1b;
+};
+
+// slot -> what this CTA pair computes
+struct Slot {
+  int g;        // group
+  int tile0;    // first 128-row tile of the super-tile (this CTA: tile0 + cluster rank)
+  int c_base;   // first 128-column output chunk of this pair
+  int nc2;      // output chunks of this pair
 };
 
 // debug timeline (scripts/trace_kernel.py): event e of CTA 0's tile `t` (t < 2) -> trace[t * 128 + e]
@@ -109,22 +143,20 @@ __device__ __forceinline__ float act_grad(float x) {
          x * 0.3989422804014327f * __expf(-0.5f * x * x);
 }
 
-// Tensor maps:            forward                      backward (kBwd)
-//   tmX   [M, 768]       X                            X
-//   tmRes [M, 768]       residual input               dY  (GEMM1b A operand and the optional +dY)
-//   tmY   [M, 768]       Y                            dX
-//   tmWd  [R, 768]       Wd_cat                       Wd_cat
-//   tmW2  [768, R]       Wu_cat                       WdT_cat      (2-D, one [64 x 64] k-block per box)
-//   tmW2k [768, R]       the same tensor as a 3-D (64, 768, R/64) view: box = all k-blocks of 64 rows
-//   tmW1b [R, 768]       (unused)                     WuT_cat
+// Tensor maps (per group): forward                      backward (kBwd)
+//   x     [M, 768]       X                            X
+//   res   [M, 768]       residual input               dY  (GEMM1b A operand and the optional +dY)
+//   y     [M, 768]       Y                            dX
+//   wd    [R, 768]       Wd_cat                       Wd_cat
+//   w2    [768, R]       Wu_cat                       WdT_cat      (2-D, one [64 x 64] k-block per box)
+//   w2k   [768, R]       the same tensor as a 3-D (64, 768, R/64) view: box = all k-blocks of 64 rows
+//   w1b   [R, 768]       (unused)                     WuT_cat
 // kSaved (backward, ReLU only): the hidden saved by the forward replaces the recompute of P -- no X
 // read, no GEMM1 pass 0; relu'(P) is read off the saved hidden (H > 0).
 template <bool kBwd, bool kGelu, bool kSaved = false>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
-dat_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmRes,
-                 const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmWd,
-                 const __grid_constant__ CUtensorMap tmW2, const __grid_constant__ CUtensorMap tmW2k,
-                 const __grid_constant__ CUtensorMap tmW1b, const FusedParams p) {
+dat_fused_kernel(const __grid_constant__ TmapSet tm0, const __grid_constant__ TmapSet tm1,
+                 const __grid_constant__ FusedParams p) {
   extern __shared__ uint8_t smem_raw[];
   // barriers: stage full/empty, P full, dH full, hidden full, D full/empty x2, staging res/out/empty
   __shared__ __align__(8) uint64_t bars[2 * NS + 3 + 4 + 3 * NSTG];
@@ -132,19 +164,7 @@ dat_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (tid == 0) FD_TRACE(1, 0);      // kernel entry (before barrier init / TMEM alloc / bias staging)
-  const int R = p.R;
-  const int KC2 = (R + 63) / 64;
-  const int nc2 = (kBwd && !p.has_out) ? 0 : NC2 / p.n_split;   // output chunks THIS pair produces
   const uint32_t rank = cluster_ctarank();            // 0 = leader of the CTA pair
-  const int RH = R / 2;                               // rows of a Wd / WuT k-chunk this CTA holds
-  const uint32_t w_half_bytes = static_cast<uint32_t>(RH) * 128u;
-  // epilogue 1 is split between the two epilogue groups by 16-column chunks of P: group A packs
-  // chunks [0, nA), group B chunks [nA, n16).  Each packs IN PLACE over its own columns, so the
-  // hidden's k-step k (16 bottleneck units = 8 packed columns) sits at hidden_col(k)
-  const int n16 = R / 16, nA = (n16 + 1) / 2;
-  auto hidden_col = [&](int k) -> uint32_t {
-    return TM_P + static_cast<uint32_t>(k < nA ? 8 * k : 16 * nA + 8 * (k - nA));
-  };
 
   const uint32_t smem0 = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t stg_base = smem0 + NS * STAGE;
@@ -181,33 +201,47 @@ dat_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
       mbar_init(bar_stg_empty(b), 1);
     }
     fence_mbar_init();
-    tma_prefetch_desc(&tmX);
-    tma_prefetch_desc(&tmRes);
-    tma_prefetch_desc(&tmY);
-    tma_prefetch_desc(&tmWd);
-    tma_prefetch_desc(&tmW2);
-    tma_prefetch_desc(&tmW2k);
-    if (kBwd) tma_prefetch_desc(&tmW1b);
+    for (int g = 0; g < p.n_groups; ++g) {
+      const TmapSet& T = g ? tm1 : tm0;
+      tma_prefetch_desc(&T.x);
+      tma_prefetch_desc(&T.res);
+      tma_prefetch_desc(&T.y);
+      tma_prefetch_desc(&T.wd);
+      tma_prefetch_desc(&T.w2);
+      tma_prefetch_desc(&T.w2k);
+      if (kBwd) tma_prefetch_desc(&T.w1b);
+    }
   }
   if (warp == 2) tmem_alloc_pair(smem_u32(&tmem_base_smem), 512);
   tc_fence_before();
   cluster_sync_all();   // barrier inits + TMEM allocation visible to both CTAs of the pair
   tc_fence_after();
+  // Everything above overlapped the tail of the previous kernel in the stream (programmatic dependent
+  // launch); from here on this kernel reads what that kernel wrote.
+  pdl_wait();
+  pdl_launch_dependents();
   const uint32_t tmem = tmem_base_smem;
   if (tid == 0) FD_TRACE(0, 0);
-  // Few tiles (a single adapter site of one batch: 47 tiles for 148 SMs): S pairs share a super-tile.
-  // Each recomputes the whole hidden (GEMM1 + epilogue 1; the SMs would idle otherwise, the extra X / W
-  // reads hit L2) and produces its own NC2 / S output chunks [c_base, c_base + nc2).
-  const int num_pairs = (p.num_tiles + 1) / 2, pid = blockIdx.x >> 1;
-  const int pair0 = p.n_split > 1 ? pid % num_pairs : pid;
-  const int pair_stride = p.n_split > 1 ? num_pairs : static_cast<int>(gridDim.x >> 1);
-  const int c_base = p.n_split > 1 ? (pid / num_pairs) * nc2 : 0;
-  const int my_tiles = (num_pairs - pair0 + pair_stride - 1) / pair_stride;   // super-tiles of this pair
-  const uint32_t total_chunks = static_cast<uint32_t>(my_tiles) * nc2 * 2;    // 64-column staging chunks
-  constexpr int G1_STAGES = KC1 * (kBwd ? 2 : 1);
-  // this CTA's tile of super-tile `it`: may lie beyond the tensor (odd tile count) -- TMA then
-  // zero-fills the loads and clips the stores, so no role needs a special case
-  auto tile_of = [&](int it) { return 2 * (pair0 + it * pair_stride) + static_cast<int>(rank); };
+
+  // Slots.  Group g contributes (its super-tiles) x (its column split S_g) slots; group 1's slots follow
+  // group 0's.  With few tiles (a single adapter site of one batch: 47 tiles per group for 148 SMs) the
+  // launch has one CTA pair per slot and S_g pairs share a super-tile: each recomputes the whole hidden
+  // (GEMM1 + epilogue 1; the SMs would idle otherwise, the extra X / W reads hit L2) and produces its own
+  // NC2 / S_g output chunks [c_base, c_base + nc2).  With many tiles S_g = 1 and the pairs stride over the
+  // slots.  A CTA's tile may lie beyond the tensor (odd tile count): TMA then zero-fills the loads and
+  // clips the stores, so no role needs a special case.
+  const int pid = blockIdx.x >> 1, n_pairs_launched = static_cast<int>(gridDim.x >> 1);
+  auto decode = [&](int slot) -> Slot {
+    Slot s;
+    s.g = slot >= p.slots0 ? 1 : 0;
+    const int rel = slot - (s.g ? p.slots0 : 0);
+    const GroupCfg& G = p.g[s.g];
+    const int np = (G.num_tiles + 1) / 2;
+    s.nc2 = (kBwd && !G.has_out) ? 0 : NC2 / G.n_split;
+    s.c_base = (rel / np) * s.nc2;
+    s.tile0 = 2 * (rel % np);
+    return s;
+  };
   // every TMA of the pair credits its bytes to the LEADER's stage barrier
   const uint32_t leader_full0 = mapa_u32(bar_slot_full(0), 0);
 
@@ -217,12 +251,17 @@ dat_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
     // each lane issues its own TMA (a lone thread sustains only one TMA per ~170 ns)
     if (lane < 2) {
       uint32_t n = 0;  // ring stages consumed so far (all roles count the same sequence)
-      for (int it = 0; it < my_tiles; ++it) {
-        const uint32_t tile_it = it;
-        const int m0 = tile_of(it) * BM;
+      uint32_t tile_it = 0;
+      for (int slot = pid; slot < p.total_slots; slot += n_pairs_launched, ++tile_it) {
+        const Slot sl = decode(slot);
+        const GroupCfg& G = p.g[sl.g];
+        const TmapSet& T = sl.g ? tm1 : tm0;
+        const int R = G.R, RH = R / 2, KC2 = (R + 63) / 64;
+        const uint32_t w_half_bytes = static_cast<uint32_t>(RH) * 128u;
+        const int m0 = (sl.tile0 + static_cast<int>(rank)) * BM;
         if (lane == 0) FD_TRACE(110, tile_it);
         for (int pass = kSaved ? 1 : 0; pass < (kBwd ? 2 : 1); ++pass) {
-          const CUtensorMap* tm = lane == 0 ? (pass == 0 ? &tmX : &tmRes) : (pass == 0 ? &tmWd : &tmW1b);
+          const CUtensorMap* tm = lane == 0 ? (pass == 0 ? &T.x : &T.res) : (pass == 0 ? &T.wd : &T.w1b);
           const int c1 = lane == 0 ? m0 : static_cast<int>(rank) * RH;
           const uint64_t pol = kEvictLast;   // activations too: they are re-read as the residual
           for (int kc = 0; kc < KC1; ++kc, ++n) {
@@ -236,28 +275,30 @@ dat_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
           }
         }
         if (lane == 0) FD_TRACE(111, tile_it);
-        // Next tile's activations -> L2 now, so that its GEMM1 streams from L2 instead of waiting on
+        // Next slot's activations -> L2 now, so that its GEMM1 streams from L2 instead of waiting on
         // HBM in lock-step with every other SM
-        if (lane == 0 && it + 1 < my_tiles) {
-          const int m1 = tile_of(it + 1) * BM;
+        if (lane == 0 && slot + n_pairs_launched < p.total_slots) {
+          const Slot nx = decode(slot + n_pairs_launched);
+          const TmapSet& TN = nx.g ? tm1 : tm0;
+          const int m1 = (nx.tile0 + static_cast<int>(rank)) * BM;
           for (int kc = 0; kc < KC1; ++kc) {
-            if (!kSaved) tma_prefetch_l2_2d(&tmX, kc * BK, m1);
-            if (kBwd) tma_prefetch_l2_2d(&tmRes, kc * BK, m1);
+            if (!kSaved) tma_prefetch_l2_2d(&TN.x, kc * BK, m1);
+            if (kBwd) tma_prefetch_l2_2d(&TN.res, kc * BK, m1);
           }
         }
         // GEMM2 stages: this CTA's half [64 x R] of the W2 tile of output chunk c (lane 1); lane 0
         // waits along (a parity wait is only meaningful within one lap of the ring)
-        for (int c = 0; c < nc2; ++c, ++n) {
+        for (int c = 0; c < sl.nc2; ++c, ++n) {
           const uint32_t s = n & (NS - 1), par = (n / NS) & 1;
           mbar_wait(bar_slot_empty(s), par ^ 1);
           if (lane == 1) {
             if (rank == 0) mbar_arrive_expect_tx(bar_slot_full(s), 2 * KC2 * W2_KB_BYTES);
-            const int row0 = (c_base + c) * N2 + static_cast<int>(rank) * (N2 / 2);
-            if (p.w2_3d) {   // all k-blocks of the half tile in one box
-              tma_load_3d_pair(smem0 + s * STAGE, &tmW2k, leader_full0 + 8u * s, 0, row0, 0, kEvictLast);
+            const int row0 = (sl.c_base + c) * N2 + static_cast<int>(rank) * (N2 / 2);
+            if (G.w2_3d) {   // all k-blocks of the half tile in one box
+              tma_load_3d_pair(smem0 + s * STAGE, &T.w2k, leader_full0 + 8u * s, 0, row0, 0, kEvictLast);
             } else {
               for (int kb = 0; kb < KC2; ++kb)
-                tma_load_2d_pair(smem0 + s * STAGE + kb * W2_KB_BYTES, &tmW2, leader_full0 + 8u * s,
+                tma_load_2d_pair(smem0 + s * STAGE + kb * W2_KB_BYTES, &T.w2, leader_full0 + 8u * s,
                                  kb * BK, row0, kEvictLast);
             }
           }
@@ -274,10 +315,13 @@ dat_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
     if (rank == 0) {
       uint32_t n = 0;
       uint32_t de[2] = {0, 0};  // uses of each D buffer so far (parity of its "empty" barrier)
-      const uint32_t idesc1 = make_idesc_bf16(2 * BM, R);
       const uint32_t idesc2 = make_idesc_bf16(2 * BM, N2);
-      for (int it = 0; it < my_tiles; ++it) {
-        const uint32_t tile_it = it;
+      uint32_t tile_it = 0;
+      for (int slot = pid; slot < p.total_slots; slot += n_pairs_launched, ++tile_it) {
+        const Slot sl = decode(slot);
+        const int R = p.g[sl.g].R;
+        const int n16 = R / 16, nA = (n16 + 1) / 2;
+        const uint32_t idesc1 = make_idesc_bf16(2 * BM, R);
         for (int pass = kSaved ? 1 : 0; pass < (kBwd ? 2 : 1); ++pass) {
           // pass 0: P = X Wd_cat^T -> [TM_P, +R);  pass 1 (bwd): dH = dY Wu_cat -> [TM_D, +R)
           const uint32_t d_tmem = tmem + (pass == 0 ? TM_P : TM_D);
@@ -313,7 +357,7 @@ dat_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
         // by the next tile's GEMM1 (waited even when no GEMM2/3 follows)
         mbar_wait(bar_h_full, tile_it & 1);
         tc_fence_after();
-        for (int c = 0; c < nc2; ++c, ++n) {
+        for (int c = 0; c < sl.nc2; ++c, ++n) {
           const int b = c & 1;
           mbar_wait(bar_d_empty(b), (de[b] & 1) ^ 1);
           ++de[b];
@@ -345,17 +389,21 @@ dat_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
   } else if (warp == 3) {
     // ------------------------------------------------------------------ residual producer
     if (lane == 0) {
-      const uint32_t per_tile = nc2 * 2;
       uint32_t g = 0;
-      for (int it = 0; it < my_tiles; ++it) {
-        const int m0 = tile_of(it) * BM;
+      uint32_t tile_it = 0;
+      for (int slot = pid; slot < p.total_slots; slot += n_pairs_launched, ++tile_it) {
+        const Slot sl = decode(slot);
+        const TmapSet& T = sl.g ? tm1 : tm0;
+        const bool has_res = p.g[sl.g].has_res != 0;
+        const int m0 = (sl.tile0 + static_cast<int>(rank)) * BM;
+        const uint32_t per_tile = sl.nc2 * 2;
         for (uint32_t c64 = 0; c64 < per_tile; ++c64, ++g) {
           const uint32_t sb = g % NSTG, par = (g / NSTG) & 1;
           mbar_wait(bar_stg_empty(sb), par ^ 1);
-          if (p.has_res) {
+          if (has_res) {
             mbar_arrive_expect_tx(bar_res_full(sb), SLOT);
-            tma_load_2d(stg_base + sb * SLOT, &tmRes, bar_res_full(sb), (c_base * 2 + c64) * 64, m0);
-            FD_TRACE(90 + c64, it);
+            tma_load_2d(stg_base + sb * SLOT, &T.res, bar_res_full(sb), (sl.c_base * 2 + c64) * 64, m0);
+            FD_TRACE(90 + c64, tile_it);
           } else {
             mbar_arrive(bar_res_full(sb));
           }
@@ -366,27 +414,30 @@ dat_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
   } else if (warp == 2) {
     // ------------------------------------------------------------------ store issuer
     if (lane == 0) {
-      const uint32_t per_tile = nc2 * 2;
       uint32_t g = 0;
-      for (int it = 0; it < my_tiles; ++it) {
-        const int m0 = tile_of(it) * BM;
+      uint32_t tile_it = 0;
+      for (int slot = pid; slot < p.total_slots; slot += n_pairs_launched, ++tile_it) {
+        const Slot sl = decode(slot);
+        const TmapSet& T = sl.g ? tm1 : tm0;
+        const int m0 = (sl.tile0 + static_cast<int>(rank)) * BM;
+        const uint32_t per_tile = sl.nc2 * 2;
         for (uint32_t c64 = 0; c64 < per_tile; ++c64, ++g) {
           const uint32_t sb = g % NSTG, par = (g / NSTG) & 1;
           mbar_wait(bar_out_full(sb), par);
           // outputs are never re-read by this kernel: let them leave L2 first
-          tma_store_2d_hint(&tmY, stg_base + sb * SLOT, (c_base * 2 + c64) * 64, m0, kEvictFirst);
+          tma_store_2d_hint(&T.y, stg_base + sb * SLOT, (sl.c_base * 2 + c64) * 64, m0, kEvictFirst);
           tma_store_commit();
-          FD_TRACE(104 + (c64 >> 1), it);
+          FD_TRACE(104 + (c64 >> 1), tile_it);
           if (g > 0) {  // the previous store has finished reading its buffer: recycle it
             tma_store_wait_read<1>();
             mbar_arrive(bar_stg_empty((g - 1) % NSTG));
           }
         }
       }
-      if (total_chunks > 0) {
+      if (g > 0) {
         // smem has been read; kernel completion covers the visibility of the writes themselves
         tma_store_wait_read<0>();
-        mbar_arrive(bar_stg_empty((total_chunks - 1) % NSTG));
+        mbar_arrive(bar_stg_empty((g - 1) % NSTG));
       }
     }
     __syncwarp();
@@ -396,29 +447,43 @@ dat_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
     const uint32_t q = warp & 3;            // TMEM lane quarter this warp may touch
     const uint32_t row = q * 32 + lane;     // tile row == TMEM lane
     const uint32_t lane_addr = (q * 32) << 16;
-    const float scale = p.scale;
-    const bool has_res = p.has_res != 0;
     uint32_t df = 0;  // chunk fills of this group's D buffer so far
     // the MMA issuer lives in the leader CTA: "hidden ready" / "D buffer drained" go to ITS barriers
     const uint32_t leader_h_full = mapa_u32(bar_h_full, 0);
     const uint32_t leader_d_empty = mapa_u32(bar_d_empty(group), 0);
-    const int c_lo = group == 0 ? 0 : nA, c_hi = group == 0 ? nA : n16;
-    const uint32_t w_base = group == 0 ? 0u : static_cast<uint32_t>(16 * nA);   // where its hidden goes
     // Biases -> smem by the 256 epilogue threads, AFTER the cluster sync: the (cold) global reads overlap
-    // GEMM1 instead of delaying every role.  bd as is; bu PRE-SCALED by the branch scale (epilogue 2 is
-    // one FFMA per element).
+    // GEMM1 instead of delaying every role.  Per group: bd as is at [0, R); bu PRE-SCALED by the branch
+    // scale at [256, 256 + 768) (epilogue 2 is one FFMA per element).
     {
       const int et = tid - 128;
-      if (!kSaved)
-        for (int i = et; i < R; i += 256) bias_smem[i] = p.bd[i];
-      if (!kBwd)
-        for (int i = et; i < kD; i += 256) bias_smem[R + i] = p.scale * p.bu[i];
+      for (int g = 0; g < p.n_groups; ++g) {
+        const GroupCfg& G = p.g[g];
+        float* bs = bias_smem + g * BIAS_STRIDE;
+        if (!kSaved)
+          for (int i = et; i < G.R; i += 256) bs[i] = G.bd[i];
+        if (!kBwd)
+          for (int i = et; i < kD; i += 256) bs[256 + i] = G.scale * G.bu[i];
+      }
       named_bar_sync(1, 256);
     }
 
-    for (int it = 0; it < my_tiles; ++it) {
-      const uint32_t tile_it = it;
-      const int m0 = tile_of(it) * BM;
+    uint32_t stg_n = 0;      // 64-column staging chunks of all previous slots
+    uint32_t tile_it = 0;
+    for (int slot = pid; slot < p.total_slots; slot += n_pairs_launched, ++tile_it) {
+      const Slot sl = decode(slot);
+      const GroupCfg& G = p.g[sl.g];
+      const int R = G.R, nc2 = sl.nc2, c_base = sl.c_base;
+      // epilogue 1 is split between the two epilogue groups by 16-column chunks of P: group A packs
+      // chunks [0, nA), group B chunks [nA, n16).  Each packs IN PLACE over its own columns, so the
+      // hidden's k-step k (16 bottleneck units = 8 packed columns) sits at column 8 k (k < nA) or
+      // 16 nA + 8 (k - nA)
+      const int n16 = R / 16, nA = (n16 + 1) / 2;
+      const int c_lo = group == 0 ? 0 : nA, c_hi = group == 0 ? nA : n16;
+      const uint32_t w_base = group == 0 ? 0u : static_cast<uint32_t>(16 * nA);   // where its hidden goes
+      const float scale = G.scale;
+      const bool has_res = G.has_res != 0;
+      const float* bias_g = bias_smem + sl.g * BIAS_STRIDE;
+      const int m0 = (sl.tile0 + static_cast<int>(rank)) * BM;
       {
         // ---------------- epilogue 1: this group's half of P (and dH) -> packed bf16 hidden
         const int grow = m0 + static_cast<int>(row);
@@ -426,11 +491,11 @@ dat_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
         uint32_t wall[8][8];  // forward with H_out: the packed hidden, stored to HBM after GEMM2 is released
         if constexpr (kSaved) {
           // issued BEFORE the wait on GEMM1b: the global-load latency hides under it
-          const uint4* hrow = reinterpret_cast<const uint4*>(p.H_in + static_cast<size_t>(grow) * R);
+          const uint4* hrow = reinterpret_cast<const uint4*>(G.H_in + static_cast<size_t>(grow) * R);
 #pragma unroll
           for (int ci = 0; ci < 8; ++ci) {
             hreg[ci][0] = hreg[ci][1] = make_uint4(0u, 0u, 0u, 0u);
-            if (c_lo + ci < c_hi && grow < p.M) {
+            if (c_lo + ci < c_hi && grow < G.M) {
               hreg[ci][0] = __ldg(hrow + 2 * (c_lo + ci));
               hreg[ci][1] = __ldg(hrow + 2 * (c_lo + ci) + 1);
             }
@@ -449,7 +514,7 @@ dat_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
             uint32_t v[16], u[16], w[8];
             if (!kSaved) tmem_ld16(t_p + c * 16, v);
             if (kBwd) tmem_ld16(t_g + c * 16, u);
-            const float* bdv = bias_smem + c * 16;
+            const float* bdv = bias_g + c * 16;
             if (!kSaved) tmem_ld_wait16(v);
             if (kBwd) tmem_ld_wait16(u);
             const int col = c * 16;
@@ -469,8 +534,8 @@ dat_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
                 const float g1 = (hb[i] & 0x7fff0000u) ? scale * __uint_as_float(u[2 * i + 1]) : 0.f;
                 w[i] = pack_bf16x2(g0, g1);
               }
-              if (p.dP_t != nullptr && c_base == 0 && col >= p.r_lo && col < p.r_hi && grow < p.M) {
-                uint4* gd = reinterpret_cast<uint4*>(p.dP_t + static_cast<size_t>(grow) * p.ld_t + (col - p.r_lo));
+              if (G.dP_t != nullptr && c_base == 0 && col >= G.r_lo && col < G.r_hi && grow < G.M) {
+                uint4* gd = reinterpret_cast<uint4*>(G.dP_t + static_cast<size_t>(grow) * G.ld_t + (col - G.r_lo));
                 gd[0] = make_uint4(w[0], w[1], w[2], w[3]);
                 gd[1] = make_uint4(w[4], w[5], w[6], w[7]);
               }
@@ -484,10 +549,10 @@ dat_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
                                    scale * __uint_as_float(u[2 * i + 1]) * act_grad<kGelu>(p1));
                 hh[i] = pack_bf16x2(apply_act<kGelu>(p0), apply_act<kGelu>(p1));
               }
-              if (p.H_t != nullptr && c_base == 0 && col >= p.r_lo && col < p.r_hi && grow < p.M) {
-                const size_t off = static_cast<size_t>(grow) * p.ld_t + (col - p.r_lo);
-                uint4* hd = reinterpret_cast<uint4*>(p.H_t + off);
-                uint4* gd = reinterpret_cast<uint4*>(p.dP_t + off);
+              if (G.H_t != nullptr && c_base == 0 && col >= G.r_lo && col < G.r_hi && grow < G.M) {
+                const size_t off = static_cast<size_t>(grow) * G.ld_t + (col - G.r_lo);
+                uint4* hd = reinterpret_cast<uint4*>(G.H_t + off);
+                uint4* gd = reinterpret_cast<uint4*>(G.dP_t + off);
                 hd[0] = make_uint4(hh[0], hh[1], hh[2], hh[3]);
                 hd[1] = make_uint4(hh[4], hh[5], hh[6], hh[7]);
                 gd[0] = make_uint4(w[0], w[1], w[2], w[3]);
@@ -506,8 +571,8 @@ dat_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
         if constexpr (!kBwd) {
           // save the hidden for a kSaved backward AFTER GEMM2 has been released: a row-per-thread store
           // is 32 L1 transactions per instruction and must not sit on the tensor pipe's critical path
-          if (p.H_out != nullptr && c_base == 0 && grow < p.M) {
-            uint4* hrow = reinterpret_cast<uint4*>(p.H_out + static_cast<size_t>(grow) * R);
+          if (G.H_out != nullptr && c_base == 0 && grow < G.M) {
+            uint4* hrow = reinterpret_cast<uint4*>(G.H_out + static_cast<size_t>(grow) * R);
 #pragma unroll
             for (int ci = 0; ci < 8; ++ci)
               if (c_lo + ci < c_hi) {
@@ -527,7 +592,7 @@ dat_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
         if (lane == 0 && q == 0) FD_TRACE(42 + 4 * c, tile_it);
 #pragma unroll 1
         for (int j = 0; j < 2; ++j) {
-          const uint32_t g = (tile_it * nc2 + c) * 2 + j;
+          const uint32_t g = stg_n + c * 2 + j;
           const uint32_t sb = g % NSTG, rpar = (g / NSTG) & 1;
           const int col0 = (c_base + c) * N2 + j * 64;
           const uint32_t t_src = tmem + lane_addr + TM_D + b * N2 + j * 64;
@@ -551,7 +616,7 @@ dat_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
           if (tr) FD_TRACE(123, tile_it);
           if (lane == 0 && q == 0) FD_TRACE(43 + 4 * c + j, tile_it);
           const uint32_t sbuf = stg_base + sb * SLOT;
-          const float4* bu4 = reinterpret_cast<const float4*>(bias_smem + R + col0);
+          const float4* bu4 = reinterpret_cast<const float4*>(bias_g + 256 + col0);
           // Two batches of 32 columns: the four residual ld.shared of a batch are issued back to back,
           // then the math (bias loads included) is free code for the scheduler, then the four
           // st.shared.  (asm volatile keeps program order: interleaving load / math / store per 16-byte
@@ -605,6 +670,7 @@ dat_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
         }
         if (lane == 0 && q == 0) FD_TRACE(45 + 4 * c, tile_it);
       }
+      stg_n += static_cast<uint32_t>(nc2) * 2;
     }
   }
 
@@ -621,49 +687,104 @@ bool g_force_fused = false;       // A/B switch of the debug build (feddat_debug
 constexpr bool g_force_fused = false;
 #endif
 
-int launch_fused(bool bwd, const void* X, const void* Res, void* Out, const void* Wd_cat,
-                 const void* W2, const void* W1b, FusedParams p, int64_t M, int r_total,
-                 cudaStream_t st, const char* who) {
+// Programmatic dependent launch is on unless FEDDAT_PDL=0 (read once; an A/B switch for measurements).
+bool pdl_enabled() {
+  static const bool on = [] {
+    const char* e = getenv("FEDDAT_PDL");
+    return !(e && e[0] == '0');
+  }();
+  return on;
+}
+
+// One group's host-side description (the C ABI's FeddatDatGroup, already validated).
+struct HostGroup {
+  const void *X, *Res, *W1, *W2, *W1b;   // W1: Wd_cat (fwd / recompute) or WuT_cat (saved); W2: Wu_cat / WdT_cat
+  void* Out;
+  GroupCfg cfg;
+};
+
+// cost model of the column split: a pair recomputes GEMM1 (~R) and produces 1/S of GEMM2 (~R / S)
+int pick_splits(const HostGroup* hg, int n_groups, int sms, bool allow_split, int* splits) {
+  int best = -1, best_cost = 0, best_ctas = 0;
+  const int smax = allow_split ? 3 : 1;
+  for (int s0 = 1; s0 <= smax; ++s0)
+    for (int s1 = 1; s1 <= (n_groups > 1 ? smax : 1); ++s1) {
+      const int s[2] = {s0, s1};
+      int ctas = 0, cost = 0;
+      for (int g = 0; g < n_groups; ++g) {
+        const int sg = hg[g].cfg.has_out ? s[g] : 1;
+        if (!hg[g].cfg.has_out && s[g] != 1) { ctas = 1 << 30; break; }
+        ctas += 2 * ((hg[g].cfg.num_tiles + 1) / 2) * sg;
+        const int c = hg[g].cfg.R * (sg + 1) / sg;
+        cost = c > cost ? c : cost;
+      }
+      if (ctas > sms) continue;
+      if (best < 0 || cost < best_cost || (cost == best_cost && ctas < best_ctas)) {
+        best = s0 * 4 + s1; best_cost = cost; best_ctas = ctas;
+        splits[0] = s0; splits[1] = s1;
+      }
+    }
+  return best;
+}
+
+int launch_fused(bool bwd, bool saved, int act, HostGroup* hg, int n_groups, cudaStream_t st, const char* who) {
   int rc;
-  p.M = static_cast<int>(M);
-  p.R = r_total;
-  p.num_tiles = static_cast<int>((M + BM - 1) / BM);
+  FusedParams p{};
+  p.n_groups = n_groups;
+  p.act = act;
   p.trace = FD_TRACE_PTR;
-  p.w2_3d = (r_total % 64 == 0) ? 1 : 0;
   const size_t max_smem = 227 * 1024 - 1024;  // static smem (barriers) lives in the same budget
   const size_t smem = 1024 + static_cast<size_t>(NS) * STAGE + static_cast<size_t>(NSTG) * SLOT +
-                      (r_total + kD) * sizeof(float);
-  FD_REQUIRE(smem <= max_smem, FD_ERR_UNSUPPORTED, "%s: shared-memory budget exceeded (R=%d)", who,
-             r_total);
-
-  CUtensorMap tmX, tmRes, tmY, tmWd, tmW2, tmW2k, tmW1b;
-  if ((rc = make_tmap_bf16_2d(&tmX, X, M, kD, kD, BM, 64))) return rc;
-  if ((rc = make_tmap_bf16_2d(&tmRes, Res, M, kD, kD, BM, 64))) return rc;
-  if ((rc = make_tmap_bf16_2d(&tmY, Out ? Out : X, M, kD, kD, BM, 64))) return rc;
-  const uint32_t w_box_rows = r_total / 2;   // each CTA of a pair holds half of every weight tile
-  if ((rc = make_tmap_bf16_2d(&tmWd, Wd_cat, r_total, kD, kD, w_box_rows, 64))) return rc;
-  if ((rc = make_tmap_bf16_2d(&tmW2, W2, kD, r_total, r_total, N2 / 2, 64))) return rc;
-  tmW2k = tmW2;
-  if (p.w2_3d && (rc = make_tmap_bf16_kblocks(&tmW2k, W2, kD, r_total, r_total, N2 / 2, r_total / 64))) return rc;
-  if ((rc = make_tmap_bf16_2d(&tmW1b, W1b ? W1b : Wd_cat, r_total, kD, kD, w_box_rows, 64))) return rc;
+                      MAX_GROUPS * BIAS_STRIDE * sizeof(float);
+  static_assert(1024 + NS * STAGE + NSTG * SLOT + MAX_GROUPS * BIAS_STRIDE * 4 <= 227 * 1024 - 1024, "smem budget");
 
   int sms = 0;
   if ((rc = device_sm_count(&sms))) return rc;
-  const int num_pairs = (p.num_tiles + 1) / 2;
-  p.n_split = 1;
-  if (!(bwd && !p.has_out))
-    for (int sp = 3; sp > 1; --sp)
-      if (2 * num_pairs * sp <= sms) { p.n_split = sp; break; }
-  const int grid = p.n_split > 1 ? 2 * num_pairs * p.n_split
-                                 : 2 * (num_pairs < sms / 2 ? num_pairs : sms / 2);
-  using KernelFn = void (*)(const CUtensorMap, const CUtensorMap, const CUtensorMap,
-                            const CUtensorMap, const CUtensorMap, const CUtensorMap,
-                            const CUtensorMap, const FusedParams);
-  const bool gelu = p.act == FEDDAT_ACT_GELU;
-  const bool saved = bwd && p.H_in != nullptr;
+  int total_pairs = 0;
+  for (int g = 0; g < n_groups; ++g) total_pairs += (hg[g].cfg.num_tiles + 1) / 2;
+  int splits[2] = {1, 1};
+  const bool one_wave = 2 * total_pairs <= sms;
+  if (one_wave) pick_splits(hg, n_groups, sms, true, splits);
+  FD_REQUIRE(one_wave || n_groups == 1, FD_ERR_UNSUPPORTED,
+             "%s: a grouped launch covers at most %d row tiles in total (the caller launches large groups one by one)",
+             who, sms);
+
+  TmapSet tms[MAX_GROUPS];
+  int slots[MAX_GROUPS] = {0, 0};
+  for (int g = 0; g < n_groups; ++g) {
+    GroupCfg& c = hg[g].cfg;
+    c.n_split = splits[g];
+    c.w2_3d = (c.R % 64 == 0) ? 1 : 0;
+    slots[g] = ((c.num_tiles + 1) / 2) * c.n_split;
+    const int64_t M = c.M;
+    const int R = c.R;
+    TmapSet& T = tms[g];
+    if ((rc = make_tmap_bf16_2d(&T.x, hg[g].X, M, kD, kD, BM, 64))) return rc;
+    if ((rc = make_tmap_bf16_2d(&T.res, hg[g].Res, M, kD, kD, BM, 64))) return rc;
+    if ((rc = make_tmap_bf16_2d(&T.y, hg[g].Out ? hg[g].Out : hg[g].X, M, kD, kD, BM, 64))) return rc;
+    const uint32_t w_box_rows = R / 2;   // each CTA of a pair holds half of every weight tile
+    if ((rc = make_tmap_bf16_2d(&T.wd, hg[g].W1, R, kD, kD, w_box_rows, 64))) return rc;
+    if ((rc = make_tmap_bf16_2d(&T.w2, hg[g].W2, kD, R, R, N2 / 2, 64))) return rc;
+    T.w2k = T.w2;
+    if (c.w2_3d && (rc = make_tmap_bf16_kblocks(&T.w2k, hg[g].W2, kD, R, R, N2 / 2, R / 64))) return rc;
+    if ((rc = make_tmap_bf16_2d(&T.w1b, hg[g].W1b ? hg[g].W1b : hg[g].W1, R, kD, kD, w_box_rows, 64))) return rc;
+    p.g[g] = c;
+  }
+  if (n_groups == 1) {
+    tms[1] = tms[0];
+    p.g[1] = p.g[0];
+  }
+  p.slots0 = slots[0];
+  p.total_slots = slots[0] + slots[1];
+  const int pairs_launched = one_wave ? p.total_slots : (p.total_slots < sms / 2 ? p.total_slots : sms / 2);
+  const int grid = 2 * pairs_launched;
+
+  using KernelFn = void (*)(const TmapSet, const TmapSet, const FusedParams);
+  const bool gelu = act == FEDDAT_ACT_GELU;
   KernelFn fn = saved ? dat_fused_kernel<true, false, true>
                 : bwd ? (gelu ? dat_fused_kernel<true, true> : dat_fused_kernel<true, false>)
                       : (gelu ? dat_fused_kernel<false, true> : dat_fused_kernel<false, false>);
+  // idempotent per-device "attribute already set" cache (not state the results depend on)
   static bool configured[3][2][64] = {{{false}}};
   int dev = 0;
   FD_CHECK_CUDA(cudaGetDevice(&dev));
@@ -678,14 +799,16 @@ int launch_fused(bool bwd, const void* X, const void* Res, void* Out, const void
   cfg.blockDim = dim3(NUM_THREADS);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = 2;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
-  FD_CHECK_CUDA(cudaLaunchKernelEx(&cfg, fn, tmX, tmRes, tmY, tmWd, tmW2, tmW2k, tmW1b, p));
+  cfg.numAttrs = pdl_enabled() ? 2 : 1;
+  FD_CHECK_CUDA(cudaLaunchKernelEx(&cfg, fn, tms[0], tms[1], p));
   FD_CHECK_CUDA(cudaGetLastError());
   return FD_OK;
 }
@@ -704,40 +827,165 @@ int check_common(const char* who, int64_t M, int d, int r_total, int act, int dt
   return FD_OK;
 }
 
+int tiles_of(int64_t M) { return static_cast<int>((M + BM - 1) / BM); }
+
+// forward group -> HostGroup
+int fwd_group(const FeddatDatGroup& G, int d, int act, int dtype, HostGroup* out) {
+  FD_REQUIRE(G.X && G.Res && G.Y && G.Wd_cat && G.bd_cat && G.Wu_cat && G.bu_cat, FD_ERR_INVALID,
+             "dat_fwd: null pointer argument");
+  int rc = check_common("dat_fwd", G.M, d, G.r_total, act, dtype);
+  if (rc) return rc;
+  FD_REQUIRE((reinterpret_cast<uintptr_t>(G.H_out) & 15) == 0, FD_ERR_INVALID, "dat_fwd: H_out must be 16-byte aligned");
+  HostGroup h{};
+  h.X = G.X; h.Res = G.Res; h.Out = G.Y; h.W1 = G.Wd_cat; h.W2 = G.Wu_cat; h.W1b = nullptr;
+  h.cfg.M = static_cast<int>(G.M); h.cfg.R = G.r_total; h.cfg.num_tiles = tiles_of(G.M);
+  h.cfg.scale = G.branch_scale; h.cfg.bd = G.bd_cat; h.cfg.bu = G.bu_cat;
+  h.cfg.has_out = 1; h.cfg.has_res = 1;
+  h.cfg.H_out = static_cast<__nv_bfloat16*>(G.H_out);
+  *out = h;
+  return FD_OK;
+}
+
+// backward (dgrad) group -> HostGroup; *saved = saved-hidden mode
+int bwd_group(const FeddatDatGroup& G, int d, int act, int dtype, HostGroup* out, bool* saved) {
+  FD_REQUIRE(G.dY && G.WuT_cat && G.WdT_cat, FD_ERR_INVALID, "dat_bwd_dgrad: null pointer argument");
+  int rc = check_common("dat_bwd_dgrad", G.M, d, G.r_total, act, dtype);
+  if (rc) return rc;
+  if (G.H_in != nullptr) {
+    FD_REQUIRE(act == FEDDAT_ACT_RELU, FD_ERR_UNSUPPORTED,
+               "dat_bwd_dgrad: a saved hidden determines act' only for ReLU; pass H_in = NULL (recompute) for GELU");
+    FD_REQUIRE(G.H_t == nullptr, FD_ERR_INVALID, "dat_bwd_dgrad: H_t is not produced in saved mode (H_in holds it)");
+    FD_REQUIRE((reinterpret_cast<uintptr_t>(G.H_in) & 15) == 0, FD_ERR_INVALID, "dat_bwd_dgrad: H_in must be 16-byte aligned");
+    FD_REQUIRE(G.dX != nullptr || G.dP_t != nullptr, FD_ERR_INVALID, "dat_bwd_dgrad: nothing to compute");
+  } else {
+    FD_REQUIRE(G.X && G.Wd_cat && G.bd_cat, FD_ERR_INVALID, "dat_bwd_dgrad: X, Wd_cat, bd_cat are needed to recompute P");
+    FD_REQUIRE((G.H_t == nullptr) == (G.dP_t == nullptr), FD_ERR_INVALID,
+               "dat_bwd_dgrad: H_t and dP_t must both be given or both be NULL");
+    FD_REQUIRE(G.dX != nullptr || G.H_t != nullptr, FD_ERR_INVALID,
+               "dat_bwd_dgrad: nothing to compute (dX and H_t are both NULL)");
+  }
+  if (G.dP_t) {
+    FD_REQUIRE(G.r_lo >= 0 && G.r_hi > G.r_lo && G.r_hi <= G.r_total && G.r_lo % 16 == 0 && G.r_hi % 16 == 0,
+               FD_ERR_INVALID, "dat_bwd_dgrad: bad trainable slice [%d, %d) of %d", G.r_lo, G.r_hi, G.r_total);
+    FD_REQUIRE(G.ld_t >= G.r_hi - G.r_lo && G.ld_t % 8 == 0, FD_ERR_INVALID, "dat_bwd_dgrad: bad row stride ld_t=%d", G.ld_t);
+    FD_REQUIRE(((reinterpret_cast<uintptr_t>(G.H_t) | reinterpret_cast<uintptr_t>(G.dP_t)) & 15) == 0,
+               FD_ERR_INVALID, "dat_bwd_dgrad: H_t / dP_t must be 16-byte aligned");
+  }
+  *saved = G.H_in != nullptr;
+  HostGroup h{};
+  // saved mode never touches X / Wd_cat: any valid tensor keeps the (unused) tensor maps well formed
+  h.X = *saved ? G.dY : G.X;
+  h.Res = G.dY; h.Out = G.dX;
+  h.W1 = *saved ? G.WuT_cat : G.Wd_cat;
+  h.W2 = G.WdT_cat; h.W1b = G.WuT_cat;
+  h.cfg.M = static_cast<int>(G.M); h.cfg.R = G.r_total; h.cfg.num_tiles = tiles_of(G.M);
+  h.cfg.scale = G.branch_scale;
+  h.cfg.bd = *saved ? nullptr : G.bd_cat;
+  h.cfg.bu = nullptr;
+  h.cfg.has_out = G.dX != nullptr;
+  h.cfg.has_res = (G.dX != nullptr && G.add_dy) ? 1 : 0;
+  h.cfg.r_lo = G.dP_t ? G.r_lo : 0;
+  h.cfg.r_hi = G.dP_t ? G.r_hi : 0;
+  h.cfg.ld_t = G.ld_t;
+  h.cfg.H_t = static_cast<__nv_bfloat16*>(G.H_t);
+  h.cfg.dP_t = static_cast<__nv_bfloat16*>(G.dP_t);
+  h.cfg.H_in = static_cast<const __nv_bfloat16*>(G.H_in);
+  *out = h;
+  return FD_OK;
+}
+
+int fwd_one(const FeddatDatGroup& G, int d, int act, int dtype, cudaStream_t st) {
+  HostGroup h;
+  int rc = fwd_group(G, d, act, dtype, &h);
+  if (rc) return rc;
+  if (G.M == 0) return FD_OK;
+  int sms = 0;
+  if ((rc = device_sm_count(&sms))) return rc;
+  // more super-tiles than CTA pairs: the tile-pipelined kernel (dat_fwd_pipe.cu)
+  if ((h.cfg.num_tiles + 1) / 2 > sms / 2 && !g_force_fused)
+    return launch_dat_fwd_pipe(G.X, G.Res, G.Y, G.Wd_cat, G.bd_cat, G.Wu_cat, G.bu_cat, G.H_out, G.M, G.r_total,
+                               G.branch_scale, act, 2 * (sms / 2), st);
+  return launch_fused(false, false, act, &h, 1, st, "dat_fwd");
+}
+
+int bwd_one(const FeddatDatGroup& G, int d, int act, int dtype, cudaStream_t st) {
+  HostGroup h;
+  bool saved = false;
+  int rc = bwd_group(G, d, act, dtype, &h, &saved);
+  if (rc) return rc;
+  if (G.M == 0) return FD_OK;
+  int sms = 0;
+  if ((rc = device_sm_count(&sms))) return rc;
+  // more super-tiles than CTA pairs: the tile-pipelined kernel (dat_fwd_pipe.cu, kBwd)
+  if (saved && G.dX != nullptr && !g_force_fused && (h.cfg.num_tiles + 1) / 2 > sms / 2)
+    return launch_dat_bwd_pipe(G.dY, G.dX, G.WuT_cat, G.WdT_cat, G.H_in, G.dP_t, G.ld_t, G.r_lo, G.r_hi, G.M,
+                               G.r_total, G.branch_scale, G.add_dy, 2 * (sms / 2), st);
+  return launch_fused(true, saved, act, &h, 1, st, "dat_bwd_dgrad");
+}
+
 }  // namespace
 }  // namespace fd
+
+extern "C" int feddat_dat_fwd_grouped(const FeddatDatGroup* groups, int n_groups, int d, int act, int dtype,
+                                      void* stream) {
+  using namespace fd;
+  int rc = check_device_sm100();
+  if (rc) return rc;
+  FD_REQUIRE(groups != nullptr && n_groups >= 1 && n_groups <= MAX_GROUPS, FD_ERR_INVALID,
+             "dat_fwd_grouped: 1 or 2 groups (got %d)", n_groups);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  int sms = 0;
+  if ((rc = device_sm_count(&sms))) return rc;
+  HostGroup hg[MAX_GROUPS];
+  int pairs = 0, live = 0;
+  for (int g = 0; g < n_groups; ++g) {
+    if ((rc = fwd_group(groups[g], d, act, dtype, &hg[g]))) return rc;
+    pairs += (hg[g].cfg.num_tiles + 1) / 2;
+    live += groups[g].M > 0;
+  }
+  if (n_groups == 1 || live < n_groups || 2 * pairs > sms) {   // too big for one wave (or empty groups): one by one
+    for (int g = 0; g < n_groups; ++g)
+      if ((rc = fwd_one(groups[g], d, act, dtype, st))) return rc;
+    return FD_OK;
+  }
+  return launch_fused(false, false, act, hg, n_groups, st, "dat_fwd_grouped");
+}
+
+extern "C" int feddat_dat_bwd_dgrad_grouped(const FeddatDatGroup* groups, int n_groups, int d, int act, int dtype,
+                                            void* stream) {
+  using namespace fd;
+  int rc = check_device_sm100();
+  if (rc) return rc;
+  FD_REQUIRE(groups != nullptr && n_groups >= 1 && n_groups <= MAX_GROUPS, FD_ERR_INVALID,
+             "dat_bwd_dgrad_grouped: 1 or 2 groups (got %d)", n_groups);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  int sms = 0;
+  if ((rc = device_sm_count(&sms))) return rc;
+  HostGroup hg[MAX_GROUPS];
+  bool saved[MAX_GROUPS] = {false, false};
+  int pairs = 0, live = 0;
+  for (int g = 0; g < n_groups; ++g) {
+    if ((rc = bwd_group(groups[g], d, act, dtype, &hg[g], &saved[g]))) return rc;
+    pairs += (hg[g].cfg.num_tiles + 1) / 2;
+    live += groups[g].M > 0;
+  }
+  const bool same_mode = n_groups == 1 || saved[0] == saved[1];
+  if (n_groups == 1 || live < n_groups || !same_mode || 2 * pairs > sms) {
+    for (int g = 0; g < n_groups; ++g)
+      if ((rc = bwd_one(groups[g], d, act, dtype, st))) return rc;
+    return FD_OK;
+  }
+  return launch_fused(true, saved[0], act, hg, n_groups, st, "dat_bwd_dgrad_grouped");
+}
 
 extern "C" int feddat_dat_fwd(const void* X, const void* Res, void* Y, const void* Wd_cat,
                               const float* bd_cat, const void* Wu_cat, const float* bu_cat,
                               void* H_out, int64_t M, int d, int r_total, float branch_scale, int act,
                               int dtype, void* stream) {
-  using namespace fd;
-  int rc = check_device_sm100();
-  if (rc) return rc;
-  FD_REQUIRE(X && Res && Y && Wd_cat && bd_cat && Wu_cat && bu_cat, FD_ERR_INVALID,
-             "dat_fwd: null pointer argument");
-  if ((rc = check_common("dat_fwd", M, d, r_total, act, dtype))) return rc;
-  if (M == 0) return FD_OK;
-  {
-    // more super-tiles than CTA pairs: the tile-pipelined kernel (dat_fwd_pipe.cu)
-    int sms = 0;
-    if ((rc = device_sm_count(&sms))) return rc;
-    const int64_t num_pairs = ((M + BM - 1) / BM + 1) / 2;
-    FD_REQUIRE((reinterpret_cast<uintptr_t>(H_out) & 15) == 0, FD_ERR_INVALID, "dat_fwd: H_out must be 16-byte aligned");
-    if (num_pairs > sms / 2 && !g_force_fused)
-      return launch_dat_fwd_pipe(X, Res, Y, Wd_cat, bd_cat, Wu_cat, bu_cat, H_out, M, r_total, branch_scale, act,
-                                 2 * (sms / 2), static_cast<cudaStream_t>(stream));
-  }
-  FusedParams p{};
-  p.act = act;
-  p.scale = branch_scale;
-  p.bd = bd_cat;
-  p.bu = bu_cat;
-  p.has_out = 1;
-  p.has_res = 1;
-  p.H_out = static_cast<__nv_bfloat16*>(H_out);
-  return launch_fused(false, X, Res, Y, Wd_cat, Wu_cat, nullptr, p, M, r_total,
-                      static_cast<cudaStream_t>(stream), "dat_fwd");
+  FeddatDatGroup G{};
+  G.X = X; G.Res = Res; G.Y = Y; G.Wd_cat = Wd_cat; G.bd_cat = bd_cat; G.Wu_cat = Wu_cat; G.bu_cat = bu_cat;
+  G.H_out = H_out; G.M = M; G.r_total = r_total; G.branch_scale = branch_scale;
+  return feddat_dat_fwd_grouped(&G, 1, d, act, dtype, stream);
 }
 
 extern "C" int feddat_dat_bwd_dgrad(const void* X, const void* dY, void* dX, const void* Wd_cat,
@@ -745,58 +993,11 @@ extern "C" int feddat_dat_bwd_dgrad(const void* X, const void* dY, void* dX, con
                                     const void* H_in, void* H_t, void* dP_t, int ld_t, int r_lo, int r_hi,
                                     int64_t M, int d, int r_total, float branch_scale, int act, int add_dy,
                                     int dtype, void* stream) {
-  using namespace fd;
-  int rc = check_device_sm100();
-  if (rc) return rc;
-  FD_REQUIRE(dY && WuT_cat && WdT_cat, FD_ERR_INVALID, "dat_bwd_dgrad: null pointer argument");
-  if ((rc = check_common("dat_bwd_dgrad", M, d, r_total, act, dtype))) return rc;
-  if (H_in != nullptr) {
-    FD_REQUIRE(act == FEDDAT_ACT_RELU, FD_ERR_UNSUPPORTED,
-               "dat_bwd_dgrad: a saved hidden determines act' only for ReLU; pass H_in = NULL (recompute) for GELU");
-    FD_REQUIRE(H_t == nullptr, FD_ERR_INVALID, "dat_bwd_dgrad: H_t is not produced in saved mode (H_in holds it)");
-    FD_REQUIRE((reinterpret_cast<uintptr_t>(H_in) & 15) == 0, FD_ERR_INVALID, "dat_bwd_dgrad: H_in must be 16-byte aligned");
-    FD_REQUIRE(dX != nullptr || dP_t != nullptr, FD_ERR_INVALID, "dat_bwd_dgrad: nothing to compute");
-  } else {
-    FD_REQUIRE(X && Wd_cat && bd_cat, FD_ERR_INVALID, "dat_bwd_dgrad: X, Wd_cat, bd_cat are needed to recompute P");
-    FD_REQUIRE((H_t == nullptr) == (dP_t == nullptr), FD_ERR_INVALID,
-               "dat_bwd_dgrad: H_t and dP_t must both be given or both be NULL");
-    FD_REQUIRE(dX != nullptr || H_t != nullptr, FD_ERR_INVALID,
-               "dat_bwd_dgrad: nothing to compute (dX and H_t are both NULL)");
-  }
-  if (dP_t) {
-    FD_REQUIRE(r_lo >= 0 && r_hi > r_lo && r_hi <= r_total && r_lo % 16 == 0 && r_hi % 16 == 0,
-               FD_ERR_INVALID, "dat_bwd_dgrad: bad trainable slice [%d, %d) of %d", r_lo, r_hi,
-               r_total);
-    FD_REQUIRE(ld_t >= r_hi - r_lo && ld_t % 8 == 0, FD_ERR_INVALID, "dat_bwd_dgrad: bad row stride ld_t=%d", ld_t);
-    FD_REQUIRE(((reinterpret_cast<uintptr_t>(H_t) | reinterpret_cast<uintptr_t>(dP_t)) & 15) == 0,
-               FD_ERR_INVALID, "dat_bwd_dgrad: H_t / dP_t must be 16-byte aligned");
-  }
-  if (M == 0) return FD_OK;
-  if (H_in != nullptr && dX != nullptr && !g_force_fused) {
-    // more super-tiles than CTA pairs: the tile-pipelined kernel (dat_fwd_pipe.cu, kBwd)
-    int sms = 0;
-    if ((rc = device_sm_count(&sms))) return rc;
-    const int64_t num_pairs = ((M + BM - 1) / BM + 1) / 2;
-    if (num_pairs > sms / 2)
-      return launch_dat_bwd_pipe(dY, dX, WuT_cat, WdT_cat, H_in, dP_t, ld_t, r_lo, r_hi, M, r_total, branch_scale,
-                                 add_dy, 2 * (sms / 2), static_cast<cudaStream_t>(stream));
-  }
-  FusedParams p{};
-  p.act = act;
-  p.scale = branch_scale;
-  p.bd = H_in ? nullptr : bd_cat;
-  p.bu = nullptr;
-  p.has_out = dX != nullptr;
-  p.has_res = (dX != nullptr && add_dy) ? 1 : 0;
-  p.r_lo = dP_t ? r_lo : 0;
-  p.r_hi = dP_t ? r_hi : 0;
-  p.ld_t = ld_t;
-  p.H_t = static_cast<__nv_bfloat16*>(H_t);
-  p.dP_t = static_cast<__nv_bfloat16*>(dP_t);
-  p.H_in = static_cast<const __nv_bfloat16*>(H_in);
-  // saved mode never touches X / Wd_cat: any valid tensor keeps the (unused) tensor maps well formed
-  return launch_fused(true, H_in ? dY : X, dY, dX, H_in ? WuT_cat : Wd_cat, WdT_cat, WuT_cat, p, M, r_total,
-                      static_cast<cudaStream_t>(stream), "dat_bwd_dgrad");
+  FeddatDatGroup G{};
+  G.X = X; G.dY = dY; G.dX = dX; G.Wd_cat = Wd_cat; G.bd_cat = bd_cat; G.WuT_cat = WuT_cat; G.WdT_cat = WdT_cat;
+  G.H_in = H_in; G.H_t = H_t; G.dP_t = dP_t; G.ld_t = ld_t; G.r_lo = r_lo; G.r_hi = r_hi;
+  G.M = M; G.r_total = r_total; G.branch_scale = branch_scale; G.add_dy = add_dy;
+  return feddat_dat_bwd_dgrad_grouped(&G, 1, d, act, dtype, stream);
 }
 
 #ifdef FEDDAT_DEBUG

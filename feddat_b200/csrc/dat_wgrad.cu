@@ -2,19 +2,29 @@
 // adapter.py:124-163; trainability per adapter.py:71-85).  Inputs are the activations X, dY and the
 // bf16 hidden H_t / pre-activation gradient dP_t slices written by feddat_dat_bwd_dgrad:
 //
-//   dWu [768, r_t] += scale * dY^T H_t        dbu [768] += scale * sum_m dY
-//   dWd [r_t, 768] += dP_t^T  X               dbd [r_t] += sum_m dP_t
+//   dWu [768, r_t] = scale * dY^T H_t        dbu [768] = scale * sum_m dY
+//   dWd [r_t, 768] = dP_t^T  X               dbd [r_t] = sum_m dP_t
 //
 // Both products contract over the token dimension, so every operand is MN-major for tcgen05:
 // the TMA box is [64 rows x 64 columns] of the row-major activation and the UMMA descriptors walk
 // K = rows (128 B apart), MN = columns (contiguous), 64-column blocks `LBO` apart.
 //
-// Grid = 6 column chunks (128 of the 768 model columns) x row splits.  A CTA accumulates
+// Grid = groups x 6 column chunks (128 of the 768 model columns) x row splits, at most one CTA per SM.
+// A CTA accumulates
 //   D1 [r_t(<=128 lanes) x 128] = H_t^T  dY[:, chunk]     (= dWu^T chunk)
 //   D2 [r_t          x 128]    = dP_t^T X [:, chunk]     (= dWd chunk)
-// in TMEM over all its 64-row blocks, and reduces into the fp32 gradients with red.global.add at
-// the end (fp32 atomics: summation order across row splits is not deterministic).  The bias
-// gradients are column sums taken from the same smem stages by the otherwise idle epilogue warps.
+// in TMEM over all its 64-row blocks.  The bias gradients are column sums taken from the same smem
+// stages by the otherwise idle epilogue warps.
+//
+// DETERMINISTIC two-stage reduction across the row splits (round 1 used fp32 atomics: run-to-run
+// different summation order): every CTA stores its partial tiles to a workspace (coalesced float4
+// layout), the S CTAs of one (group, chunk) meet at a counter in global memory -- all CTAs of the launch
+// are co-resident: the grid never exceeds the SM count and a CTA takes a whole SM -- and then each sums
+// 1/S of the tile over the S partials IN SPLIT ORDER and writes the final gradient (no atomics, no
+// zero-initialised outputs).  Up to two groups per launch (the gating rows and the adapter_1 rows of one
+// site, see dat_fused.cu).
+#include <stdlib.h>
+
 #include "feddat_b200.h"
 #include "host_common.h"
 #include "ptx_sm100.cuh"
@@ -32,22 +42,50 @@ constexpr int STAGE = 4 * OPER;          // H, dP, dY, X
 constexpr int WG_STAGES = 3;
 constexpr int NUM_THREADS = 192;
 
-struct WgradParams {
+constexpr int MAX_GROUPS = 2;
+constexpr int TILE_F4 = 2 * 128 * NCW / 4;   // float4s of one CTA's two partial tiles (D1 | D2) = 8192
+constexpr int PART_FLOATS = 2 * 128 * NCW + 2 * NCW;   // + the two bias-gradient partial vectors
+
+struct WgradGroup {
   int M, rt, n_splits, n_rowblocks, a_blocks, a_3d;
   int ld_dwu;
+  int first_cta;       // first CTA of this group in the launch (NCHUNK * n_splits CTAs)
   float scale;
   float* dWu;
   float* dbu;
   float* dWd;
   float* dbd;
+};
+
+struct WgradParams {
+  WgradGroup g[MAX_GROUPS];
+  int n_groups;
+  unsigned int* counters;   // workspace head: [group][chunk][2] = {partials stored, final slices written}
+  float* partials;          // workspace: [CTA][PART_FLOATS]
   unsigned long long* trace;   // debug timeline of CTA 0 (events 200..) or null
 };
 
+struct WgradTmaps {
+  CUtensorMap xk, dyk, h, dp, hk, dpk;
+};
+
+// spin until *ctr >= target (all CTAs of the launch are co-resident; bounded like mbar_wait)
+__device__ __forceinline__ void wait_counter(const unsigned int* ctr, unsigned int target) {
+  const uint64_t t0 = globaltimer_ns();
+  unsigned int v, spins = 0;
+  for (;;) {
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ctr) : "memory");
+    if (v >= target) return;
+    if ((++spins & 0x3ff) == 0 && globaltimer_ns() - t0 > FD_MBAR_TIMEOUT_NS) {
+      printf("[feddat] wgrad split barrier timeout: block %d counter %u / %u\n", blockIdx.x, v, target);
+      __trap();
+    }
+  }
+}
+
 __global__ void __launch_bounds__(NUM_THREADS, 1)
-dat_wgrad_kernel(const __grid_constant__ CUtensorMap tmXk, const __grid_constant__ CUtensorMap tmDYk,
-                 const __grid_constant__ CUtensorMap tmH, const __grid_constant__ CUtensorMap tmDP,
-                 const __grid_constant__ CUtensorMap tmHk, const __grid_constant__ CUtensorMap tmDPk,
-                 const WgradParams p) {
+dat_wgrad_kernel(const __grid_constant__ WgradTmaps tm0, const __grid_constant__ WgradTmaps tm1,
+                 const __grid_constant__ WgradParams pp) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bars[2 * WG_STAGES + 1];
   __shared__ uint32_t tmem_base_smem;
@@ -57,13 +95,18 @@ dat_wgrad_kernel(const __grid_constant__ CUtensorMap tmXk, const __grid_constant
 #ifdef FEDDAT_DEBUG
 #define WG_TRACE(ev)                                                              \
   do {                                                                            \
-    if (p.trace != nullptr && blockIdx.x == 0) p.trace[(ev)] = globaltimer_ns();  \
+    if (pp.trace != nullptr && blockIdx.x == 0) pp.trace[(ev)] = globaltimer_ns();  \
   } while (0)
 #else
 #define WG_TRACE(ev) do { } while (0)
 #endif
+  const int grp = (pp.n_groups > 1 && static_cast<int>(blockIdx.x) >= pp.g[1].first_cta) ? 1 : 0;
+  const WgradGroup& p = pp.g[grp];
+  const WgradTmaps& T = grp ? tm1 : tm0;
+  const CUtensorMap &tmXk = T.xk, &tmDYk = T.dyk, &tmH = T.h, &tmDP = T.dp, &tmHk = T.hk, &tmDPk = T.dpk;
   if (tid == 0) WG_TRACE(200);
-  const int chunk = blockIdx.x % NCHUNK, split = blockIdx.x / NCHUNK;
+  const int rel = static_cast<int>(blockIdx.x) - p.first_cta;
+  const int chunk = rel % NCHUNK, split = rel / NCHUNK;
   const int col0 = chunk * NCW;
   const uint32_t smem0 = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t bar0 = smem_u32(bars);
@@ -89,6 +132,8 @@ dat_wgrad_kernel(const __grid_constant__ CUtensorMap tmXk, const __grid_constant
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  pdl_wait();                         // the prologue above overlapped the previous kernel's tail (PDL)
+  pdl_launch_dependents();
   const uint32_t tmem = tmem_base_smem;
   if (tid == 0) WG_TRACE(201);       // prologue done
   const int ablk = p.a_blocks;  // 1 when r_t <= 64 (second 64-column block of H/dP never loaded)
@@ -194,10 +239,10 @@ dat_wgrad_kernel(const __grid_constant__ CUtensorMap tmXk, const __grid_constant
       ++it_a;
       if (++stage == WG_STAGES) { stage = 0; phase ^= 1; }
     }
-    // eight row-set partials per column -> one sum per column and CTA through smem (one global atomic
-    // per column and CTA, as many-way contended as the weight-gradient reduction: the row splits)
+    // ---- stage 1 of the reduction: this CTA's partials -> workspace
+    float* part = pp.partials + static_cast<size_t>(blockIdx.x) * PART_FLOATS;
     {
-      const bool cta_dbd = (chunk == 0) && p.dbd != nullptr;
+      // eight row-set partials per column -> one sum per column and CTA through smem
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
         red_smem[0][rs][g * 8 + k] = acc_dy[k];
@@ -210,42 +255,89 @@ dat_wgrad_kernel(const __grid_constant__ CUtensorMap tmXk, const __grid_constant
         sdy += red_smem[0][r][t];
         sdp += red_smem[1][r][t];
       }
-      if (do_dbu) atomicAdd(p.dbu + col0 + t, p.scale * sdy);
-      if (cta_dbd && static_cast<int>(t) < p.rt) atomicAdd(p.dbd + t, sdp);
+      part[2 * 128 * NCW + t] = sdy;
+      part[2 * 128 * NCW + NCW + t] = sdp;
     }
-
-    if (split < p.n_rowblocks) {  // this CTA accumulated at least one row block
-      mbar_wait(bar_acc, 0);
-      tc_fence_after();
-      if (tid == 64) WG_TRACE(203);   // accumulators complete
+    mbar_wait(bar_acc, 0);
+    tc_fence_after();
+    if (tid == 64) WG_TRACE(203);   // accumulators complete
+    {
+      // thread j = TMEM lane = bottleneck unit j.  float4 i of the 32-column group c of matrix m goes to
+      // float4 index ((m * 4 + c) * 8 + i) * 128 + j: the 32 lanes of a warp store 512 contiguous bytes
       const uint32_t lane_addr = (q * 32) << 16;
-      const bool valid = static_cast<int>(j) < p.rt;  // lane j = bottleneck unit j
+      float4* dst4 = reinterpret_cast<float4*>(part);
 #pragma unroll 1
-      for (int c = 0; c < NCW / 32; ++c) {
+      for (int mc = 0; mc < 2 * (NCW / 32); ++mc) {
         uint32_t v[32];
-        tmem_ld32(tmem + lane_addr + c * 32, v);  // D1: dWu^T
+        tmem_ld32(tmem + lane_addr + (mc >> 2) * NCW + (mc & 3) * 32, v);
         tmem_ld_wait32(v);
-        if (valid) {
-          float* dst = p.dWu + static_cast<size_t>(col0 + c * 32) * p.ld_dwu + j;
 #pragma unroll
-          for (int i = 0; i < 32; ++i)
-            atomicAdd(dst + static_cast<size_t>(i) * p.ld_dwu, p.scale * __uint_as_float(v[i]));
-        }
-        tmem_ld32(tmem + lane_addr + NCW + c * 32, v);  // D2: dWd
-        tmem_ld_wait32(v);
-        if (valid) {
-          float* dst = p.dWd + static_cast<size_t>(j) * kD + col0 + c * 32;
-#pragma unroll
-          for (int i = 0; i < 32; i += 4)
-            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + i),
-                         "f"(__uint_as_float(v[i])), "f"(__uint_as_float(v[i + 1])),
-                         "f"(__uint_as_float(v[i + 2])), "f"(__uint_as_float(v[i + 3]))
-                         : "memory");
+        for (int i = 0; i < 8; ++i)
+          dst4[(mc * 8 + i) * 128 + j] = make_float4(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]),
+                                                    __uint_as_float(v[4 * i + 2]), __uint_as_float(v[4 * i + 3]));
+      }
+    }
+    __threadfence();
+    named_bar_sync(1, 128);
+    unsigned int* ctr = pp.counters + (grp * NCHUNK + chunk) * 2;
+    // ---- stage 2: wait for the partials of all row splits of this (group, chunk), then sum 1 / S of the
+    // tile over the splits in split order (deterministic) and write the final gradients
+    const int S = p.n_splits;
+    if (t == 0) {
+      atomicAdd(ctr, 1u);
+      wait_counter(ctr, static_cast<unsigned int>(S));
+    }
+    named_bar_sync(1, 128);
+    __threadfence();
+    if (tid == 64) WG_TRACE(204);
+    const float* part0 = pp.partials + static_cast<size_t>(p.first_cta + chunk) * PART_FLOATS;   // split 0
+    const size_t split_stride = static_cast<size_t>(NCHUNK) * PART_FLOATS;
+    const int per = (TILE_F4 + S - 1) / S;
+    const int f_end = (split + 1) * per < TILE_F4 ? (split + 1) * per : TILE_F4;
+    for (int f = split * per + static_cast<int>(t); f < f_end; f += 128) {
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+      const float4* src = reinterpret_cast<const float4*>(part0) + f;
+      for (int sidx = 0; sidx < S; ++sidx) {
+        const float4 v = __ldcg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(src) + sidx * split_stride));
+        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+      }
+      const int jj = f & 127, i = (f >> 7) & 7, c = (f >> 10) & 3, m = f >> 12;
+      if (jj < p.rt) {
+        const int col = col0 + c * 32 + i * 4;
+        if (m == 0) {   // D1 = dWu^T chunk: element (jj, col) -> dWu[col, jj]
+          float* d = p.dWu + static_cast<size_t>(col) * p.ld_dwu + jj;
+          d[0] = p.scale * acc.x;
+          d[p.ld_dwu] = p.scale * acc.y;
+          d[2 * static_cast<size_t>(p.ld_dwu)] = p.scale * acc.z;
+          d[3 * static_cast<size_t>(p.ld_dwu)] = p.scale * acc.w;
+        } else {        // D2 = dWd chunk
+          *reinterpret_cast<float4*>(p.dWd + static_cast<size_t>(jj) * kD + col) = acc;
         }
       }
     }
+    if (split == 0) {   // bias gradients: one CTA per (group, chunk), same fixed order
+      const bool cta_dbd = (chunk == 0) && p.dbd != nullptr;
+      float sdy = 0.f, sdp = 0.f;
+      for (int sidx = 0; sidx < S; ++sidx) {
+        const float* ps = part0 + sidx * split_stride + 2 * 128 * NCW;
+        sdy += __ldcg(ps + t);
+        sdp += __ldcg(ps + NCW + t);
+      }
+      if (do_dbu) p.dbu[col0 + t] = p.scale * sdy;
+      if (cta_dbd && static_cast<int>(t) < p.rt) p.dbd[t] = sdp;
+    }
+    // the last CTA of this (group, chunk) to finish resets the counters for the next launch
+    named_bar_sync(1, 128);
+    if (t == 0) {
+      const unsigned int done = atomicAdd(ctr + 1, 1u);
+      if (done == static_cast<unsigned int>(S) - 1) {
+        ctr[0] = 0u;
+        ctr[1] = 0u;
+        __threadfence();
+      }
+    }
   }
-  if (tid == 64) WG_TRACE(204);       // reductions issued
+  if (tid == 64) WG_TRACE(206);       // reductions done
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem, 256);
@@ -255,60 +347,98 @@ dat_wgrad_kernel(const __grid_constant__ CUtensorMap tmXk, const __grid_constant
 }  // namespace
 }  // namespace fd
 
-extern "C" int feddat_dat_bwd_wgrad(const void* X, const void* dY, const void* H_t,
-                                    const void* dP_t, float* dWu, float* dbu, float* dWd, float* dbd,
-                                    int64_t M, int d, int r_t, int ld_ht, int ld_dwu,
-                                    float branch_scale, int dtype, void* stream) {
-  using namespace fd;
-  int rc = check_device_sm100();
-  if (rc) return rc;
-  FD_REQUIRE(X && dY && H_t && dP_t && dWu && dWd, FD_ERR_INVALID,
+namespace fd {
+namespace {
+
+size_t wgrad_ws_bytes(int sms) {
+  return 1024 + static_cast<size_t>(sms) * PART_FLOATS * sizeof(float);
+}
+
+int check_group(const FeddatWgradGroup& G, int d, int dtype) {
+  FD_REQUIRE(G.X && G.dY && G.H_t && G.dP_t && G.dWu && G.dWd, FD_ERR_INVALID,
              "dat_bwd_wgrad: null pointer argument");
   FD_REQUIRE(dtype == FEDDAT_DTYPE_BF16, FD_ERR_UNSUPPORTED,
              "dat_bwd_wgrad: only bf16 activations are implemented (dtype=%d)", dtype);
   FD_REQUIRE(d == kD, FD_ERR_UNSUPPORTED, "dat_bwd_wgrad: model_dim must be 768 (got %d)", d);
-  FD_REQUIRE(r_t >= 16 && r_t <= 128 && r_t % 16 == 0, FD_ERR_UNSUPPORTED,
+  FD_REQUIRE(G.r_t >= 16 && G.r_t <= 128 && G.r_t % 16 == 0, FD_ERR_UNSUPPORTED,
              "dat_bwd_wgrad: r_t must be a multiple of 16 in [16, 128] (got %d); call once per "
-             "128-wide slice for wider bottlenecks", r_t);
-  FD_REQUIRE(ld_ht >= r_t && ld_ht % 8 == 0 && ld_dwu >= r_t, FD_ERR_INVALID,
-             "dat_bwd_wgrad: bad leading dimensions ld_ht=%d ld_dwu=%d", ld_ht, ld_dwu);
-  FD_REQUIRE((reinterpret_cast<uintptr_t>(dWd) & 15) == 0, FD_ERR_INVALID,
+             "128-wide slice for wider bottlenecks", G.r_t);
+  FD_REQUIRE(G.ld_ht >= G.r_t && G.ld_ht % 8 == 0 && G.ld_dwu >= G.r_t, FD_ERR_INVALID,
+             "dat_bwd_wgrad: bad leading dimensions ld_ht=%d ld_dwu=%d", G.ld_ht, G.ld_dwu);
+  FD_REQUIRE((reinterpret_cast<uintptr_t>(G.dWd) & 15) == 0, FD_ERR_INVALID,
              "dat_bwd_wgrad: dWd must be 16-byte aligned");
-  FD_REQUIRE(M >= 0 && M < (1ll << 31) - 256, FD_ERR_INVALID, "dat_bwd_wgrad: bad row count %lld",
-             (long long)M);
-  if (M == 0) return FD_OK;
+  FD_REQUIRE(G.M >= 1 && G.M < (1ll << 31) - 256, FD_ERR_INVALID, "dat_bwd_wgrad: bad row count %lld",
+             (long long)G.M);
+  return FD_OK;
+}
 
-  WgradParams p{};
-  p.M = static_cast<int>(M);
-  p.rt = r_t;
-  p.n_rowblocks = static_cast<int>((M + KB - 1) / KB);
-  p.a_blocks = r_t > 64 ? 2 : 1;
-  p.ld_dwu = ld_dwu;
-  p.scale = branch_scale;
-  p.dWu = dWu; p.dbu = dbu; p.dWd = dWd; p.dbd = dbd;
-  p.trace = FD_TRACE_PTR;
+}  // namespace
+}  // namespace fd
+
+extern "C" size_t feddat_dat_wgrad_workspace_bytes(void) {
+  int sms = 0;
+  if (fd::device_sm_count(&sms)) return 0;
+  return fd::wgrad_ws_bytes(sms);
+}
+
+extern "C" int feddat_dat_bwd_wgrad_grouped(const FeddatWgradGroup* groups, int n_groups, int d, int dtype,
+                                            void* workspace, size_t ws_bytes, void* stream) {
+  using namespace fd;
+  int rc = check_device_sm100();
+  if (rc) return rc;
+  FD_REQUIRE(groups != nullptr && n_groups >= 1 && n_groups <= MAX_GROUPS, FD_ERR_INVALID,
+             "dat_bwd_wgrad_grouped: 1 or 2 groups (got %d)", n_groups);
   int sms = 0;
   if ((rc = device_sm_count(&sms))) return rc;
-  int splits = sms / NCHUNK;
-  if (splits > p.n_rowblocks) splits = p.n_rowblocks;
-  if (splits < 1) splits = 1;
-  p.n_splits = splits;
+  FD_REQUIRE(workspace != nullptr && ws_bytes >= wgrad_ws_bytes(sms) &&
+                 (reinterpret_cast<uintptr_t>(workspace) & 15) == 0,
+             FD_ERR_INVALID, "dat_bwd_wgrad: workspace of feddat_dat_wgrad_workspace_bytes() = %zu bytes needed "
+             "(16-byte aligned, zero-initialised once)", wgrad_ws_bytes(sms));
 
-  p.a_3d = (r_t % 64 == 0) ? 1 : 0;
-  CUtensorMap tmXk, tmDYk, tmH, tmDP, tmHk, tmDPk;
-  if ((rc = make_tmap_bf16_kblocks(&tmXk, X, M, kD, kD, KB, 2))) return rc;
-  if ((rc = make_tmap_bf16_kblocks(&tmDYk, dY, M, kD, kD, KB, 2))) return rc;
-  if ((rc = make_tmap_bf16_2d(&tmH, H_t, M, r_t, ld_ht, KB, 64))) return rc;
-  if ((rc = make_tmap_bf16_2d(&tmDP, dP_t, M, r_t, ld_ht, KB, 64))) return rc;
-  tmHk = tmH;
-  tmDPk = tmDP;
-  if (p.a_3d) {
-    if ((rc = make_tmap_bf16_kblocks(&tmHk, H_t, M, r_t, ld_ht, KB, r_t / 64))) return rc;
-    if ((rc = make_tmap_bf16_kblocks(&tmDPk, dP_t, M, r_t, ld_ht, KB, r_t / 64))) return rc;
+  WgradParams p{};
+  WgradTmaps tms[MAX_GROUPS];
+  p.n_groups = n_groups;
+  p.counters = static_cast<unsigned int*>(workspace);
+  p.partials = reinterpret_cast<float*>(static_cast<char*>(workspace) + 1024);
+  p.trace = FD_TRACE_PTR;
+  int max_splits = sms / (NCHUNK * n_groups);
+  if (max_splits < 1) max_splits = 1;
+  int ctas = 0;
+  for (int gi = 0; gi < n_groups; ++gi) {
+    const FeddatWgradGroup& G = groups[gi];
+    if ((rc = check_group(G, d, dtype))) return rc;
+    WgradGroup& w = p.g[gi];
+    w.M = static_cast<int>(G.M);
+    w.rt = G.r_t;
+    w.n_rowblocks = static_cast<int>((G.M + KB - 1) / KB);
+    w.a_blocks = G.r_t > 64 ? 2 : 1;
+    w.ld_dwu = G.ld_dwu;
+    w.scale = G.branch_scale;
+    w.dWu = G.dWu; w.dbu = G.dbu; w.dWd = G.dWd; w.dbd = G.dbd;
+    w.n_splits = max_splits < w.n_rowblocks ? max_splits : w.n_rowblocks;
+    w.first_cta = ctas;
+    ctas += NCHUNK * w.n_splits;
+    w.a_3d = (G.r_t % 64 == 0) ? 1 : 0;
+    WgradTmaps& T = tms[gi];
+    if ((rc = make_tmap_bf16_kblocks(&T.xk, G.X, G.M, kD, kD, KB, 2))) return rc;
+    if ((rc = make_tmap_bf16_kblocks(&T.dyk, G.dY, G.M, kD, kD, KB, 2))) return rc;
+    if ((rc = make_tmap_bf16_2d(&T.h, G.H_t, G.M, G.r_t, G.ld_ht, KB, 64))) return rc;
+    if ((rc = make_tmap_bf16_2d(&T.dp, G.dP_t, G.M, G.r_t, G.ld_ht, KB, 64))) return rc;
+    T.hk = T.h;
+    T.dpk = T.dp;
+    if (w.a_3d) {
+      if ((rc = make_tmap_bf16_kblocks(&T.hk, G.H_t, G.M, G.r_t, G.ld_ht, KB, G.r_t / 64))) return rc;
+      if ((rc = make_tmap_bf16_kblocks(&T.dpk, G.dP_t, G.M, G.r_t, G.ld_ht, KB, G.r_t / 64))) return rc;
+    }
   }
+  if (n_groups == 1) {
+    tms[1] = tms[0];
+    p.g[1] = p.g[0];
+  }
+  FD_REQUIRE(ctas <= sms, FD_ERR_UNSUPPORTED, "dat_bwd_wgrad: %d CTAs exceed the %d SMs (co-residency)", ctas, sms);
 
   const size_t smem = 1024 + static_cast<size_t>(WG_STAGES) * STAGE;
-  static bool configured[64] = {false};
+  static bool configured[64] = {false};   // idempotent "attribute already set" cache
   int dev = 0;
   FD_CHECK_CUDA(cudaGetDevice(&dev));
   if (dev >= 64 || !configured[dev]) {
@@ -316,8 +446,30 @@ extern "C" int feddat_dat_bwd_wgrad(const void* X, const void* dY, const void* H
                                        (int)smem));
     if (dev < 64) configured[dev] = true;
   }
-  dat_wgrad_kernel<<<NCHUNK * splits, NUM_THREADS, smem, static_cast<cudaStream_t>(stream)>>>(
-      tmXk, tmDYk, tmH, tmDP, tmHk, tmDPk, p);
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(ctas);
+  cfg.blockDim = dim3(NUM_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = static_cast<cudaStream_t>(stream);
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  const char* e = getenv("FEDDAT_PDL");
+  cfg.numAttrs = (e && e[0] == '0') ? 0 : 1;
+  FD_CHECK_CUDA(cudaLaunchKernelEx(&cfg, dat_wgrad_kernel, tms[0], tms[1], p));
   FD_CHECK_CUDA(cudaGetLastError());
   return FD_OK;
+}
+
+extern "C" int feddat_dat_bwd_wgrad(const void* X, const void* dY, const void* H_t,
+                                    const void* dP_t, float* dWu, float* dbu, float* dWd, float* dbd,
+                                    int64_t M, int d, int r_t, int ld_ht, int ld_dwu,
+                                    float branch_scale, int dtype, void* workspace, size_t ws_bytes,
+                                    void* stream) {
+  if (M == 0) return FEDDAT_OK;
+  FeddatWgradGroup G{};
+  G.X = X; G.dY = dY; G.H_t = H_t; G.dP_t = dP_t; G.dWu = dWu; G.dbu = dbu; G.dWd = dWd; G.dbd = dbd;
+  G.M = M; G.r_t = r_t; G.ld_ht = ld_ht; G.ld_dwu = ld_dwu; G.branch_scale = branch_scale;
+  return feddat_dat_bwd_wgrad_grouped(&G, 1, d, dtype, workspace, ws_bytes, stream);
 }

@@ -108,6 +108,14 @@ int device_sm_count(int* out) {
 
 int check_device_sm100() {
   static int ok[64] = {0};
+  // cuTensorMapEncodeTiled is a DRIVER call and needs a current context on the calling thread.  PyTorch's
+  // autograd threads select their device lazily, so a backward entry point can be the first CUDA call of
+  // its thread: bind the runtime's primary context once per thread.
+  static thread_local bool ctx_bound = false;
+  if (!ctx_bound) {
+    FD_CHECK_CUDA(cudaFree(nullptr));
+    ctx_bound = true;
+  }
   int dev = 0;
   FD_CHECK_CUDA(cudaGetDevice(&dev));
   if (dev < 64 && ok[dev]) return FD_OK;

@@ -44,6 +44,18 @@ __device__ __forceinline__ void setmaxnreg_dec() {
 }
 
 // ----------------------------------------------------------------------------------------------
+// programmatic dependent launch (PDL): a kernel launched with
+// cudaLaunchAttributeProgrammaticStreamSerialization may start while its predecessor in the stream is
+// still draining; everything before pdl_wait() (barrier init, TMEM allocation, tensor-map prefetch)
+// overlaps the predecessor's tail, everything after it sees the predecessor's memory.  No-ops when the
+// kernel was launched without the attribute.
+// ----------------------------------------------------------------------------------------------
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+
+// ----------------------------------------------------------------------------------------------
 // mbarrier
 // ----------------------------------------------------------------------------------------------
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {

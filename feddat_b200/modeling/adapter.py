@@ -41,9 +41,9 @@ class _DatFunction(torch.autograd.Function):
     """
 
     @staticmethod
-    def forward(ctx, adapter: "Adapter", x, res, *params):
-        need_bwd = any(ctx.needs_input_grad[1:])
-        segs = adapter._segments(params, need_bwd=need_bwd)
+    def forward(ctx, adapter: "Adapter", names, x, res, *params):
+        need_bwd = any(ctx.needs_input_grad[2:])
+        segs = adapter._segments(params, need_bwd=need_bwd, key=names)
         same = res is x
         y = None
         # ReLU: keep the hidden (what autograd would save) so that backward skips the recompute of
@@ -70,8 +70,8 @@ class _DatFunction(torch.autograd.Function):
         (x,) = ctx.saved_tensors
         adapter = ctx.adapter
         dy = dy.contiguous()
-        need_dx = ctx.needs_input_grad[1]
-        need_dres = ctx.needs_input_grad[2] and not ctx.same
+        need_dx = ctx.needs_input_grad[2]
+        need_dres = ctx.needs_input_grad[3] and not ctx.same
         r = adapter.rank
         nb = ctx.n_params // 4
         # which branches train (adapter.py:71-85 toggles requires_grad per mode)
@@ -120,14 +120,16 @@ class _DatFunction(torch.autograd.Function):
             if not needs:
                 grads[i] = None
         dres = dy if need_dres else None
-        return (None, dx_total if need_dx else None, dres, *grads)
+        return (None, None, dx_total if need_dx else None, dres, *grads)
 
 
 class _DualDatFunction(torch.autograd.Function):
     """Two DAT modes over the two halves of ONE row-stacked tensor (``Adapter.set_dual``): rows [0, M/2) see
     the gating pair (adapter_0 | adapter_2, scale 0.5), rows [M/2, M) see adapter_1 alone -- the MKD
-    schedule's passes A/C and B sharing every frozen-backbone launch.  Two kernel launches per direction
-    writing into the halves of one output tensor (no concatenation copies); residual == input.
+    schedule's passes A/C and B sharing every frozen-backbone launch.  ONE grouped kernel launch per direction
+    (forward; backward data gradient; backward weight gradients) covers both halves, each half with its own
+    packed weights, bottleneck width and scale, writing into the halves of one output tensor (no
+    concatenation copies); residual == input.
 
     inputs: x [M, 768] bf16, then the 8 gating parameters (adapter_0, adapter_2) and the 4 of adapter_1.
     """
@@ -136,16 +138,17 @@ class _DualDatFunction(torch.autograd.Function):
     def forward(ctx, adapter: "Adapter", x, *params):
         need_bwd = any(ctx.needs_input_grad[1:])
         half = x.shape[0] // 2
-        specs = ((params[:8], 0.5 * adapter.scaling), (params[8:], 1.0))
+        specs = ((params[:8], 0.5 * adapter.scaling, ("adapter_0", "adapter_2")), (params[8:], 1.0, ("adapter_1",)))
         save_h = need_bwd and adapter._act_code == ops.ACT_RELU
         y = torch.empty_like(x)
-        ctx.parts = []
-        for i, (ps, scale) in enumerate(specs):
-            (pk, _, _), = adapter._segments(ps, need_bwd=need_bwd)
+        groups, meta = [], []
+        for i, (ps, scale, key) in enumerate(specs):
+            (pk, _, _), = adapter._segments(ps, need_bwd=need_bwd, key=key)
             xs = x[i * half:(i + 1) * half]
-            out = ops.dat_forward(xs, xs, pk, scale, adapter._act_code, out=y[i * half:(i + 1) * half],
-                                  save_hidden=save_h)
-            ctx.parts.append((pk, scale, out[1] if save_h else None, [p.requires_grad for p in ps]))
+            groups.append(dict(x=xs, res=xs, w=pk, scale=scale, out=y[i * half:(i + 1) * half], save_hidden=save_h))
+            meta.append((pk, scale, [p.requires_grad for p in ps]))
+        outs = ops.dat_forward_grouped(groups, adapter._act_code)
+        ctx.parts = [(pk, scale, h, needs) for (pk, scale, needs), (_, h) in zip(meta, outs)]
         ctx.adapter = adapter
         ctx.save_for_backward(x)
         return y
@@ -159,16 +162,19 @@ class _DualDatFunction(torch.autograd.Function):
         half = x.shape[0] // 2
         r = adapter.rank
         dx = torch.empty_like(dy) if need_dx else None
-        grads = []
+        groups, slices = [], []
         for i, (pk, scale, hid, needs) in enumerate(ctx.parts):
             sl = slice(i * half, (i + 1) * half)
             nb = len(needs) // 4
             trains = [any(needs[4 * b: 4 * b + 4]) for b in range(nb)]
             lo = next((b * r for b in range(nb) if trains[b]), None)
             hi = None if lo is None else max((b + 1) * r for b in range(nb) if trains[b])
-            ts = None if lo is None else (lo, hi)
-            _, g = ops.dat_backward(x[sl], dy[sl], pk, scale, adapter._act_code, train_slice=ts, need_dx=need_dx,
-                                    add_dy=True, hidden=hid, dx_out=None if dx is None else dx[sl])
+            slices.append((lo, hi, trains, nb))
+            groups.append(dict(x=x[sl], dy=dy[sl], w=pk, scale=scale, train_slice=None if lo is None else (lo, hi),
+                               need_dx=need_dx, add_dy=True, hidden=hid, dx_out=None if dx is None else dx[sl]))
+        results = ops.dat_backward_grouped(groups, adapter._act_code)
+        grads = []
+        for (_, g), (lo, hi, trains, nb), (_, _, _, needs) in zip(results, slices, ctx.parts):
             part = [None] * len(needs)
             if g is not None:
                 d_down_w, d_down_b, d_up_w, d_up_b = g
@@ -226,6 +232,9 @@ class Adapter(nn.Module):
                     p.requires_grad = False
         self._active_name: Optional[str] = None
         self._dual = False
+        self._bank = {}                 # branch-name tuple -> segments, packed by refresh_packs()
+        self._bank_store = {}           # persistent operand buffers behind the bank
+        self._bank_valid = False
 
     # ------------------------------------------------------------------ mode switches (reference API)
     def deactivate_gating(self):
@@ -291,43 +300,53 @@ class Adapter(nn.Module):
             out += [d.weight, d.bias, u.weight, u.bias]
         return out
 
-    def _segments(self, params, need_bwd: bool = True):
-        """Packed bf16 operands of the active branches, split into <=256-wide launches.
-
-        Packed afresh on EVERY forward (one ~3 us launch per site): nothing observable from Python
-        tells reliably that a parameter's values changed -- ``torch._fused_adamw_`` does not bump
-        ``Tensor._version`` and neither does the ``state_dict()[k].data.copy_(...)`` idiom the
-        reference round loop uses (main.py:446-450, task_trainer.py:36-41) -- so a cached copy would
-        silently go stale.  Backward reuses the forward's packs through ``ctx.segs``."""
+    def _seg_specs(self, params, need_bwd: bool = True):
+        """Packing jobs of the given branches' parameters, split into <= 256-wide launches:
+        [(ops.PackSpec, first column, width)].  Segments of a wide bottleneck are row / column SLICES of the
+        masters (no copies); the (summed) up bias rides on the first segment only."""
         for p in params:
             if not (p.is_cuda and p.dtype == torch.float32):
                 raise FeddatError("adapter parameters must be fp32 CUDA tensors (fp32 masters; the "
                                   "kernels consume a packed bf16 copy)")
         nb = len(params) // 4
         r = self.rank
+        br = [[params[4 * b + i].detach() for i in range(4)] for b in range(nb)]
+        if nb * r <= ops.MAX_R_TOTAL:
+            return [(ops.PackSpec([b[0] for b in br], [b[1] for b in br], [b[2] for b in br],
+                                  [b[3] for b in br], need_bwd), 0, nb * r)]
+        out, col = [], 0
+        for b in range(nb):
+            dw, db, uw, _ = br[b]
+            for j0 in range(0, r, ops.MAX_R_TOTAL):
+                j1 = min(r, j0 + ops.MAX_R_TOTAL)
+                bu_src = [x[3] for x in br] if col == 0 else [None, None]
+                out.append((ops.PackSpec([dw[j0:j1]], [db[j0:j1]], [uw[:, j0:j1]], bu_src, need_bwd), col, j1 - j0))
+                col += j1 - j0
+        return out
+
+    def _segments(self, params, need_bwd: bool = True, key=None):
+        """Packed bf16 operands of the active branches: [(PackedWeights, first column, width)].
+
+        Inside a train step the trainer has packed every site once (``refresh_packs`` below: ONE launch for
+        all sites and both modes) and the operands are taken from that bank.  Outside -- eval, ad-hoc calls --
+        they are packed afresh on every forward: nothing observable from Python tells reliably that a
+        parameter's values changed (``torch._fused_adamw_`` does not bump ``Tensor._version`` and neither
+        does the ``state_dict()[k].data.copy_(...)`` idiom of the reference round loop, main.py:446-450,
+        task_trainer.py:36-41), so a cache without an owner that knows when weights change would go stale
+        silently.  Backward reuses the forward's packs through ``ctx.segs``."""
+        if self._bank_valid and key is not None and key in self._bank:
+            return self._bank[key]
+        specs = self._seg_specs(params, need_bwd)
         with torch.no_grad():
-            branches = [[params[4 * b + i].detach().contiguous() for i in range(4)] for b in range(nb)]
-            R = nb * r
-            if R <= ops.MAX_R_TOTAL:
-                segs = [(ops.pack_weights(branches, need_bwd=need_bwd), 0, R)]
-            else:
-                segs = []
-                col = 0
-                first = True
-                for b in range(nb):
-                    dw, db, uw, ub = branches[b]
-                    for j0 in range(0, r, ops.MAX_R_TOTAL):
-                        j1 = min(r, j0 + ops.MAX_R_TOTAL)
-                        # bu_cat is the SUM of all branches' up biases: put it on the first segment only
-                        ub_seg = ub if first else torch.zeros_like(ub)
-                        if first and nb == 2:
-                            ub_seg = ub + branches[1][3]
-                        seg = [[dw[j0:j1].contiguous(), db[j0:j1].contiguous(),
-                                uw[:, j0:j1].contiguous(), ub_seg.contiguous()]]
-                        segs.append((ops.pack_weights(seg, need_bwd=need_bwd), col, j1 - j0))
-                        col += j1 - j0
-                        first = False
-        return segs
+            packs = ops.pack_weights_batched([sp for sp, _, _ in specs])
+        return [(pk, c0, w) for pk, (_, c0, w) in zip(packs, specs)]
+
+    def bank_keys(self):
+        """The branch sets a train step uses: the gating pair and adapter_1 alone (task_trainer.py:280-330)."""
+        if not hasattr(self, "adapter_1_down"):
+            return []
+        gate = ("adapter_0", "adapter_2") if hasattr(self, "adapter_2_down") else ("adapter_0", "adapter_1")
+        return [gate, ("adapter_1",)]
 
     # ------------------------------------------------------------------ forward (reference API)
     def forward(self, hidden_states, input_tensor):
@@ -363,7 +382,7 @@ class Adapter(nn.Module):
             if res.dtype != torch.bfloat16:
                 res = res.to(torch.bfloat16)
             res = res.contiguous()
-        y = _DatFunction.apply(self, x, res, *params)
+        y = _DatFunction.apply(self, names, x, res, *params)
         y = y.view(shape)
         return y if out_dtype == torch.bfloat16 else y.to(out_dtype)
 
@@ -388,3 +407,33 @@ class Adapter(nn.Module):
         else:
             hidden_states = hidden_states + input_tensor
         return hidden_states
+
+
+def refresh_packs(adapters: Sequence[Adapter]) -> None:
+    """Packs the operands of every given site for both train-step modes in ONE launch
+    (feddat_pack_weights_batched) into persistent buffers and marks the sites' banks valid.  The trainer calls
+    this at the start of a train step -- every forward of the MKD schedule runs before the optimizer step that
+    changes the branches it reads (task_trainer.py:280-330: pass B updates adapter_1 and the head, pass C
+    adapter_0 and the head; adapter_2 is frozen) -- and ``invalidate_packs`` at its end."""
+    specs, outs, slots = [], [], []
+    with torch.no_grad():
+        for a in adapters:
+            for key in a.bank_keys():
+                segs = a._seg_specs(a._branch_params(key), need_bwd=True)
+                store = a._bank_store.get(key)
+                if store is None:
+                    dev = segs[0][0].down_w[0].device
+                    store = a._bank_store[key] = [ops.alloc_packed(sp.down_w[0].shape[0], len(sp.down_w), a.model_dim, dev)
+                                                  for sp, _, _ in segs]
+                for (sp, c0, w), pk in zip(segs, store):
+                    specs.append(sp); outs.append(pk)
+                slots.append((a, key, [(pk, c0, w) for (_, c0, w), pk in zip(segs, store)]))
+        ops.pack_weights_batched(specs, outs)
+    for a, key, segs in slots:
+        a._bank[key] = segs
+        a._bank_valid = True
+
+
+def invalidate_packs(adapters: Sequence[Adapter]) -> None:
+    for a in adapters:
+        a._bank_valid = False

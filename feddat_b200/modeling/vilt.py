@@ -277,9 +277,18 @@ class ViltContinualLearner(nn.Module):
                 a.set_dual(False)
         return enc
 
-    def new_step(self) -> None:
-        """Called by the trainer at the start of every train / eval step: drops the per-step embedding cache."""
+    def new_step(self, train: bool = False) -> None:
+        """Called by the trainer at the start of every train / eval step: drops the per-step embedding cache;
+        for a train step also packs the bf16 operands of all 12 sites, both modes, in one launch."""
+        from .adapter import refresh_packs
         self.vilt_encoder._embed_cache = None
+        if train:
+            refresh_packs(self._adapters())
+
+    def end_step(self) -> None:
+        """The optimizer has changed the masters: the packed operands are stale from here on."""
+        from .adapter import invalidate_packs
+        invalidate_packs(self._adapters())
 
     def gating_forward_is_reusable(self) -> bool:
         """True when the encoder is a deterministic function of (inputs, adapter_0, adapter_2, frozen

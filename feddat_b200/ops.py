@@ -54,41 +54,86 @@ class PackedWeights:
         return self.r * self.n_branch
 
 
+@dataclass
+class PackSpec:
+    """One packing job (``FeddatPackJob``): per-branch fp32 CUDA tensors.  ``down_w[b]`` [r, d] and
+    ``down_b[b]`` [r] contiguous (a row slice of the master is fine), ``up_w[b]`` [d, r] with unit column
+    stride (a column slice view of the master is fine: its row stride is passed along), ``bu_src`` the up
+    biases summed into ``bu`` (entries may be None)."""
+    down_w: Sequence[torch.Tensor]
+    down_b: Sequence[torch.Tensor]
+    up_w: Sequence[torch.Tensor]
+    bu_src: Sequence[Optional[torch.Tensor]]
+    need_bwd: bool = True
+
+
+def alloc_packed(r: int, nb: int, d: int, device, need_bwd: bool = True) -> PackedWeights:
+    R = nb * r
+    bf = dict(device=device, dtype=torch.bfloat16)
+    return PackedWeights(torch.empty(R, d, **bf), torch.empty(d, R, **bf) if need_bwd else None,
+                         torch.empty(d, R, **bf), torch.empty(R, d, **bf) if need_bwd else None,
+                         torch.empty(R, device=device, dtype=torch.float32),
+                         torch.empty(d, device=device, dtype=torch.float32), r, nb)
+
+
+def pack_weights_batched(specs: Sequence[PackSpec], outs: Optional[Sequence[PackedWeights]] = None):
+    """All ``specs`` in ONE launch (feddat_pack_weights_batched; 24 jobs per launch).  ``outs``: persistent
+    operand sets to overwrite (allocated when None).  Returns the list of PackedWeights."""
+    lib = _lib.load()
+    if not specs:
+        return []
+    d = specs[0].down_w[0].shape[1]
+    dev = specs[0].down_w[0].device
+    res = []
+    jobs = (_lib.PackJob * len(specs))()
+    for i, sp in enumerate(specs):
+        nb = len(sp.down_w)
+        r = sp.down_w[0].shape[0]
+        for b in range(nb):
+            dw, db, uw = sp.down_w[b], sp.down_b[b], sp.up_w[b]
+            ok = (dw.is_cuda and dw.dtype == torch.float32 and dw.is_contiguous() and tuple(dw.shape) == (r, d)
+                  and db.is_cuda and db.dtype == torch.float32 and db.is_contiguous() and tuple(db.shape) == (r,)
+                  and uw.is_cuda and uw.dtype == torch.float32 and tuple(uw.shape) == (d, r) and uw.stride(1) == 1)
+            if not ok:
+                raise _lib.FeddatError(f"pack_weights: job {i} branch {b}: expected fp32 CUDA down_w [{r}, {d}] / down_b "
+                                       f"[{r}] contiguous and up_w [{d}, {r}] with unit column stride, got "
+                                       f"{tuple(dw.shape)} {tuple(db.shape)} {tuple(uw.shape)} strides {uw.stride()}")
+        for t in sp.bu_src:
+            if t is not None and not (t.is_cuda and t.dtype == torch.float32 and t.is_contiguous() and tuple(t.shape) == (d,)):
+                raise _lib.FeddatError(f"pack_weights: job {i}: up biases must be contiguous fp32 CUDA [{d}]")
+        out = outs[i] if outs is not None else alloc_packed(r, nb, d, dev, sp.need_bwd)
+        if out.r != r or out.n_branch != nb:
+            raise _lib.FeddatError("pack_weights: persistent operand set has another shape")
+        j = jobs[i]
+        for b in range(nb):
+            j.down_w[b], j.down_b[b], j.up_w[b] = sp.down_w[b].data_ptr(), sp.down_b[b].data_ptr(), sp.up_w[b].data_ptr()
+        for b, t in enumerate(list(sp.bu_src)[:2]):
+            j.bu_src[b] = None if t is None else t.data_ptr()
+        j.n_branch, j.r, j.ld_up = nb, r, sp.up_w[0].stride(0)
+        if any(u.stride(0) != j.ld_up for u in sp.up_w):
+            raise _lib.FeddatError("pack_weights: the branches of one job must share the up_w row stride")
+        j.Wd_cat, j.Wu_cat = out.wd.data_ptr(), out.wu.data_ptr()
+        j.WdT_cat = None if out.wdT is None or not sp.need_bwd else out.wdT.data_ptr()
+        j.WuT_cat = None if out.wuT is None or not sp.need_bwd else out.wuT.data_ptr()
+        j.bd_cat, j.bu_cat = out.bd.data_ptr(), out.bu.data_ptr()
+        res.append(out)
+    rc = lib.feddat_pack_weights_batched(jobs, len(specs), d, _lib.stream_ptr())
+    _lib.check(rc, "feddat_pack_weights_batched")
+    _count(-(-len(specs) // 24))
+    return res
+
+
 def pack_weights(branches: Sequence[Sequence[torch.Tensor]], need_bwd: bool = True) -> PackedWeights:
     """branches: [(down_w [r,d], down_b [r], up_w [d,r], up_b [d]), ...] fp32 CUDA tensors (1 or 2)."""
-    lib = _lib.load()
-    nb = len(branches)
-    dw0 = branches[0][0]
-    r, d = dw0.shape
-    dev = dw0.device
+    spec = PackSpec([b[0] for b in branches], [b[1] for b in branches], [b[2] for b in branches],
+                    [b[3] for b in branches], need_bwd)
     for b in branches:
-        for t, shp in zip(b, ((r, d), (r,), (d, r), (d,))):
-            if not (t.is_cuda and t.dtype == torch.float32 and t.is_contiguous() and tuple(t.shape) == shp):
-                raise _lib.FeddatError(f"pack_weights: expected contiguous CUDA fp32 {shp}, got "
-                                       f"{tuple(t.shape)} {t.dtype} {t.device}")
-    R = nb * r
-    bf = dict(device=dev, dtype=torch.bfloat16)
-    wd = torch.empty(R, d, **bf)
-    wu = torch.empty(d, R, **bf)
-    wdT = torch.empty(d, R, **bf) if need_bwd else None
-    wuT = torch.empty(R, d, **bf) if need_bwd else None
-    bd = torch.empty(R, device=dev, dtype=torch.float32)
-    bu = torch.empty(d, device=dev, dtype=torch.float32)
-    arr = ctypes.c_void_p * nb
-    tabs = [arr(*[b[i].data_ptr() for b in branches]) for i in range(4)]
-    rc = lib.feddat_pack_weights(tabs[0], tabs[1], tabs[2], tabs[3], nb, r, d, _lib.ptr(wd),
-                                 _lib.ptr(wdT), _lib.ptr(wu), _lib.ptr(wuT), _lib.ptr(bd),
-                                 _lib.ptr(bu), _lib.stream_ptr())
-    _lib.check(rc, "feddat_pack_weights")
-    _count()
-    return PackedWeights(wd, wdT, wu, wuT, bd, bu, r, nb)
+        if not b[2].is_contiguous():
+            raise _lib.FeddatError("pack_weights: expected contiguous CUDA fp32 tensors")
+    return pack_weights_batched([spec])[0]
 
 
-def dat_forward(x: torch.Tensor, res: torch.Tensor, w: PackedWeights, scale: float, act=ACT_RELU,
-                out: Optional[torch.Tensor] = None, save_hidden: bool = False):
-    """Y = res + scale * (act(x Wd^T + bd) Wu^T + bu)   (adapter.py:124-163).  With ``save_hidden`` returns
-    (Y, H) where H [M, r_total] bf16 is the hidden, for a backward that does not recompute it."""
-    lib = _lib.load()
+def _fwd_group(x, res, w, scale, out, save_hidden):
     _check_act2d(x, "dat_forward x")
     _check_act2d(res, "dat_forward res")
     if w.r_total > MAX_R_TOTAL:
@@ -96,12 +141,161 @@ def dat_forward(x: torch.Tensor, res: torch.Tensor, w: PackedWeights, scale: flo
                                "splits such bottlenecks into several launches")
     y = out if out is not None else torch.empty_like(x)
     h = torch.empty(x.shape[0], w.r_total, device=x.device, dtype=torch.bfloat16) if save_hidden else None
-    rc = lib.feddat_dat_fwd(_lib.ptr(x), _lib.ptr(res), _lib.ptr(y), _lib.ptr(w.wd), _lib.ptr(w.bd),
-                            _lib.ptr(w.wu), _lib.ptr(w.bu), _lib.ptr(h), x.shape[0], x.shape[1], w.r_total,
-                            float(scale), act_code(act), DTYPE_BF16, _lib.stream_ptr())
-    _lib.check(rc, "feddat_dat_fwd")
+    g = _lib.DatGroup()
+    g.X, g.Res, g.Y = x.data_ptr(), res.data_ptr(), y.data_ptr()
+    g.Wd_cat, g.bd_cat, g.Wu_cat, g.bu_cat = w.wd.data_ptr(), w.bd.data_ptr(), w.wu.data_ptr(), w.bu.data_ptr()
+    g.H_out = None if h is None else h.data_ptr()
+    g.M, g.r_total, g.branch_scale = x.shape[0], w.r_total, float(scale)
+    return g, y, h
+
+
+def dat_forward_grouped(groups: Sequence[dict], act=ACT_RELU):
+    """Up to two independent row groups in ONE launch (feddat_dat_fwd_grouped): each group is a dict with the
+    arguments of ``dat_forward`` (x, res, w, scale, out=None, save_hidden=False).  Returns [(y, h | None)]."""
+    lib = _lib.load()
+    arr = (_lib.DatGroup * len(groups))()
+    outs = []
+    for i, gr in enumerate(groups):
+        g, y, h = _fwd_group(gr["x"], gr["res"], gr["w"], gr["scale"], gr.get("out"), gr.get("save_hidden", False))
+        arr[i] = g
+        outs.append((y, h))
+    rc = lib.feddat_dat_fwd_grouped(arr, len(groups), groups[0]["x"].shape[1], act_code(act), DTYPE_BF16,
+                                    _lib.stream_ptr())
+    _lib.check(rc, "feddat_dat_fwd_grouped")
     _count()
+    return outs
+
+
+def dat_forward(x: torch.Tensor, res: torch.Tensor, w: PackedWeights, scale: float, act=ACT_RELU,
+                out: Optional[torch.Tensor] = None, save_hidden: bool = False):
+    """Y = res + scale * (act(x Wd^T + bd) Wu^T + bu)   (adapter.py:124-163).  With ``save_hidden`` returns
+    (Y, H) where H [M, r_total] bf16 is the hidden, for a backward that does not recompute it."""
+    (y, h), = dat_forward_grouped([dict(x=x, res=res, w=w, scale=scale, out=out, save_hidden=save_hidden)], act)
     return (y, h) if save_hidden else y
+
+
+_wgrad_ws = {}
+
+
+def wgrad_workspace(device: torch.device) -> torch.Tensor:
+    """Workspace of the deterministic weight-gradient reduction: one per device, zero-initialised once (the
+    kernel leaves its counters at zero).  The process model is one client training per GPU at a time
+    (SURVEY.md section 8e): weight-gradient launches of one device are stream-ordered and share it; launches
+    that could run CONCURRENTLY on one device would need a workspace each (C ABI: feddat_dat_bwd_wgrad)."""
+    key = device.index if device.index is not None else torch.cuda.current_device()
+    ws = _wgrad_ws.get(key)
+    if ws is None:
+        nbytes = int(_lib.load().feddat_dat_wgrad_workspace_bytes())
+        if nbytes == 0:
+            raise _lib.FeddatError("feddat_dat_wgrad_workspace_bytes() failed (no sm_100 device?)")
+        if torch.cuda.is_current_stream_capturing():
+            raise _lib.FeddatError("the weight-gradient workspace must exist before CUDA-graph capture: run one "
+                                   "eager backward on this stream first (GraphedTrainStep's warm-up does)")
+        ws = _wgrad_ws[key] = torch.zeros(nbytes // 4 + 4, device=device, dtype=torch.float32)
+    return ws
+
+
+def dat_backward_grouped(groups: Sequence[dict], act=ACT_RELU):
+    """Backward of up to two row groups: ONE data-gradient launch (feddat_dat_bwd_dgrad_grouped) and ONE
+    weight-gradient launch (feddat_dat_bwd_wgrad_grouped) for all of them.  Each group is a dict with the
+    arguments of ``dat_backward`` (x, dy, w, scale, train_slice=None, need_dx=True, add_dy=True, hidden=None,
+    dx_out=None).  Returns [(dx | None, grads | None)]."""
+    lib = _lib.load()
+    arr = (_lib.DatGroup * len(groups))()
+    info = []
+    n_live = 0
+    d = groups[0]["dy"].shape[1]
+    for gr in groups:
+        x, dy, w, scale = gr.get("x"), gr["dy"], gr["w"], gr["scale"]
+        train_slice, need_dx = gr.get("train_slice"), gr.get("need_dx", True)
+        add_dy, hidden, dx_out = gr.get("add_dy", True), gr.get("hidden"), gr.get("dx_out")
+        _check_act2d(dy, "dat_backward dy")
+        if x is not None:
+            _check_act2d(x, "dat_backward x")
+        if w.wdT is None:
+            raise _lib.FeddatError("dat_backward: weights were packed with need_bwd=False")
+        saved = hidden is not None
+        if saved and act_code(act) != ACT_RELU:
+            raise _lib.FeddatError("dat_backward: a saved hidden determines act' only for ReLU")
+        if x is None and (not saved or train_slice is not None):
+            raise _lib.FeddatError("dat_backward: x is required (recompute mode, or weight gradients)")
+        M = dy.shape[0]
+        R = w.r_total
+        dev = dy.device
+        if dx_out is not None:
+            _check_act2d(dx_out, "dat_backward dx_out")
+        dx = (dx_out if dx_out is not None else torch.empty_like(dy)) if need_dx else None
+        h_t = dp_t = None
+        rt = r_lo = r_hi = ld_t = 0
+        if train_slice is not None:
+            r_lo, r_hi = train_slice
+            rt = r_hi - r_lo
+            if saved:
+                # full-width scratch: only the trainable columns are written / read (row stride R, like H)
+                dp_full = torch.empty(M, R, device=dev, dtype=torch.bfloat16)
+                dp_t = dp_full[:, r_lo:r_hi]
+                h_t = hidden[:, r_lo:r_hi]
+                ld_t = R
+            else:
+                h_t = torch.empty(M, rt, device=dev, dtype=torch.bfloat16)
+                dp_t = torch.empty(M, rt, device=dev, dtype=torch.bfloat16)
+                ld_t = rt
+        if dx is None and dp_t is None:
+            info.append(None)
+            continue
+        g = arr[n_live]
+        g.X, g.dY, g.dX = _lib.ptr(x), dy.data_ptr(), _lib.ptr(dx)
+        g.Wd_cat, g.bd_cat, g.WuT_cat, g.WdT_cat = w.wd.data_ptr(), w.bd.data_ptr(), w.wuT.data_ptr(), w.wdT.data_ptr()
+        g.H_in = _lib.ptr(hidden)
+        g.H_t = None if saved else _lib.ptr(h_t)
+        g.dP_t = _lib.ptr(dp_t)
+        g.ld_t, g.r_lo, g.r_hi = ld_t, r_lo, r_hi
+        g.M, g.r_total, g.branch_scale, g.add_dy = M, R, float(scale), int(add_dy)
+        n_live += 1
+        info.append(dict(x=x, dy=dy, dx=dx, h_t=h_t, dp_t=dp_t, ld_t=ld_t, rt=rt, scale=float(scale), M=M, dev=dev))
+    if n_live:
+        rc = lib.feddat_dat_bwd_dgrad_grouped(arr, n_live, d, act_code(act), DTYPE_BF16, _lib.stream_ptr())
+        _lib.check(rc, "feddat_dat_bwd_dgrad_grouped")
+        _count()
+    # weight gradients: every <= 128-wide slice of every group is one "wgrad group"; two per launch
+    wg, results = [], []
+    for it in info:
+        if it is None:
+            results.append((None, None))
+            continue
+        grads = None
+        if it["rt"] and it["M"] > 0:
+            rt = it["rt"]
+            g = torch.empty(2 * d * rt + rt + d, device=it["dev"], dtype=torch.float32)   # the kernel overwrites
+            d_down_w = g[: rt * d].view(rt, d)
+            d_up_w = g[rt * d: 2 * rt * d].view(d, rt)
+            d_down_b = g[2 * rt * d: 2 * rt * d + rt]
+            d_up_b = g[2 * rt * d + rt:]
+            for j0 in range(0, rt, MAX_R_WGRAD):
+                w_ = min(MAX_R_WGRAD, rt - j0)
+                q = _lib.WgradGroup()
+                q.X, q.dY = it["x"].data_ptr(), it["dy"].data_ptr()
+                q.H_t, q.dP_t = it["h_t"].data_ptr() + 2 * j0, it["dp_t"].data_ptr() + 2 * j0
+                q.dWu, q.dbu = d_up_w.data_ptr() + 4 * j0, (d_up_b.data_ptr() if j0 == 0 else None)
+                q.dWd, q.dbd = d_down_w.data_ptr() + 4 * j0 * d, d_down_b.data_ptr() + 4 * j0
+                q.M, q.r_t, q.ld_ht, q.ld_dwu, q.branch_scale = it["M"], w_, it["ld_t"], rt, it["scale"]
+                wg.append(q)
+            grads = (d_down_w, d_down_b, d_up_w, d_up_b)
+        elif it["rt"]:
+            g = torch.zeros(2 * d * it["rt"] + it["rt"] + d, device=it["dev"], dtype=torch.float32)
+            rt = it["rt"]
+            grads = (g[: rt * d].view(rt, d), g[2 * rt * d: 2 * rt * d + rt], g[rt * d: 2 * rt * d].view(d, rt),
+                     g[2 * rt * d + rt:])
+        results.append((it["dx"], grads))
+    if wg:
+        ws = wgrad_workspace(groups[0]["dy"].device)
+        for i in range(0, len(wg), 2):
+            pair = (_lib.WgradGroup * 2)(*wg[i:i + 2]) if len(wg) - i >= 2 else (_lib.WgradGroup * 1)(wg[i])
+            rc = lib.feddat_dat_bwd_wgrad_grouped(pair, len(pair), d, DTYPE_BF16, _lib.ptr(ws), ws.numel() * 4,
+                                                  _lib.stream_ptr())
+            _lib.check(rc, "feddat_dat_bwd_wgrad_grouped")
+            _count()
+    return results
 
 
 def dat_backward(x: Optional[torch.Tensor], dy: torch.Tensor, w: PackedWeights, scale: float, act=ACT_RELU,
@@ -112,70 +306,8 @@ def dat_backward(x: Optional[torch.Tensor], dy: torch.Tensor, w: PackedWeights, 
     ``train_slice = (r_lo, r_hi)`` of the concatenated bottleneck.  ``hidden`` = the H saved by
     ``dat_forward(save_hidden=True)`` (ReLU): the dgrad kernel then skips the recompute of x Wd^T
     (``x`` is still needed by the weight-gradient kernel when something trains)."""
-    lib = _lib.load()
-    _check_act2d(dy, "dat_backward dy")
-    if x is not None:
-        _check_act2d(x, "dat_backward x")
-    if w.wdT is None:
-        raise _lib.FeddatError("dat_backward: weights were packed with need_bwd=False")
-    saved = hidden is not None
-    if saved and act_code(act) != ACT_RELU:
-        raise _lib.FeddatError("dat_backward: a saved hidden determines act' only for ReLU")
-    if x is None and (not saved or train_slice is not None):
-        raise _lib.FeddatError("dat_backward: x is required (recompute mode, or weight gradients)")
-    M, d = dy.shape
-    R = w.r_total
-    dev = dy.device
-    if dx_out is not None:
-        _check_act2d(dx_out, "dat_backward dx_out")
-    dx = (dx_out if dx_out is not None else torch.empty_like(dy)) if need_dx else None
-    h_t = dp_t = None
-    rt = 0
-    if train_slice is not None:
-        r_lo, r_hi = train_slice
-        rt = r_hi - r_lo
-        if saved:
-            # full-width scratch: only the trainable columns are written / read (row stride R, like H)
-            dp_full = torch.empty(M, R, device=dev, dtype=torch.bfloat16)
-            dp_t = dp_full[:, r_lo:r_hi]
-            h_t = hidden[:, r_lo:r_hi]
-            ld_t = R
-        else:
-            h_t = torch.empty(M, rt, device=dev, dtype=torch.bfloat16)
-            dp_t = torch.empty(M, rt, device=dev, dtype=torch.bfloat16)
-            ld_t = rt
-    else:
-        r_lo = r_hi = 0
-        ld_t = 0
-    if dx is None and dp_t is None:
-        return None, None
-    grads = None
-    if train_slice is not None:
-        f32 = dict(device=dev, dtype=torch.float32)
-        g = torch.zeros(2 * d * rt + rt + d, **f32)          # one memset for all four gradients
-    rc = lib.feddat_dat_bwd_dgrad(_lib.ptr(x), _lib.ptr(dy), _lib.ptr(dx), _lib.ptr(w.wd), _lib.ptr(w.bd),
-                                  _lib.ptr(w.wuT), _lib.ptr(w.wdT), _lib.ptr(hidden),
-                                  None if saved else _lib.ptr(h_t), _lib.ptr(dp_t), ld_t, r_lo,
-                                  r_hi, M, d, R, float(scale), act_code(act), int(add_dy),
-                                  DTYPE_BF16, _lib.stream_ptr())
-    _lib.check(rc, "feddat_dat_bwd_dgrad")
-    _count()
-    if train_slice is not None:
-        d_down_w = g[: rt * d].view(rt, d)
-        d_up_w = g[rt * d: 2 * rt * d].view(d, rt)
-        d_down_b = g[2 * rt * d: 2 * rt * d + rt]
-        d_up_b = g[2 * rt * d + rt:]
-        for j0 in range(0, rt, MAX_R_WGRAD):
-            w_ = min(MAX_R_WGRAD, rt - j0)
-            rc = lib.feddat_dat_bwd_wgrad(
-                _lib.ptr(x), _lib.ptr(dy), ctypes.c_void_p(h_t.data_ptr() + 2 * j0),
-                ctypes.c_void_p(dp_t.data_ptr() + 2 * j0), ctypes.c_void_p(d_up_w.data_ptr() + 4 * j0),
-                _lib.ptr(d_up_b) if j0 == 0 else None, ctypes.c_void_p(d_down_w.data_ptr() + 4 * j0 * d),
-                ctypes.c_void_p(d_down_b.data_ptr() + 4 * j0), M, d, w_, ld_t, rt, float(scale), DTYPE_BF16,
-                _lib.stream_ptr())
-            _lib.check(rc, "feddat_dat_bwd_wgrad")
-            _count()
-        grads = (d_down_w, d_down_b, d_up_w, d_up_b)
+    (dx, grads), = dat_backward_grouped([dict(x=x, dy=dy, w=w, scale=scale, train_slice=train_slice, need_dx=need_dx,
+                                              add_dy=add_dy, hidden=hidden, dx_out=dx_out)], act)
     return dx, grads
 
 

@@ -252,7 +252,14 @@ class TaskTrainer(nn.Module):
 
         inner = model.module
         if hasattr(inner, "new_step"):
-            inner.new_step()                                          # per-step caches (ViLT embedding output)
+            inner.new_step(train=True)          # per-step caches; all sites' bf16 operands packed in one launch
+        try:
+            return self._train_step_dat(model, inner, batch, target, optimizer, scheduler, albef)
+        finally:
+            if hasattr(inner, "end_step"):
+                inner.end_step()
+
+    def _train_step_dat(self, model, inner, batch, target, optimizer, scheduler, albef):
         reuse = (self.reuse_gating_forward and not albef
                  and getattr(inner, "gating_forward_is_reusable", lambda: False)())
         if (reuse and self.batched_passes and optimizer is not None and hasattr(inner, "encode_dual")

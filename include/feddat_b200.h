@@ -74,13 +74,16 @@ int feddat_dat_fwd(const void* X, const void* Res, void* Y, const void* Wd_cat,
  *   unused (may be NULL), relu'(P) = (H_in > 0), H_t must be NULL (stage 2 reads the slice of H_in
  *   itself), dP_t [.., ld_t] is written for the trainable slice.
  *
- * Stage 2, feddat_dat_bwd_wgrad: fp32 accumulate-into (caller zeroes):
- *     dWu [d, r_t] += branch_scale * dY^T H_t                        dbu [d]   += scale * sum_m dY
- *     dWd [r_t, d] += dP_t^T X                                       dbd [r_t] += sum_m dP_t
+ * Stage 2, feddat_dat_bwd_wgrad: fp32, OVERWRITES its outputs (no zero-initialisation needed), bit-wise
+ * reproducible (fixed summation order across the row splits):
+ *     dWu [d, r_t] = branch_scale * dY^T H_t                        dbu [d]   = scale * sum_m dY
+ *     dWd [r_t, d] = dP_t^T X                                       dbd [r_t] = sum_m dP_t
  *   (dP_t already carries branch_scale.)  r_t must be a multiple of 16, <= 128; wider trainable
  *   slices are covered by one call per 128 columns: ld_ht is the row stride (elements) of H_t/dP_t,
  *   ld_dwu the row stride of dWu, so a call can address a column slice of wider arrays.  dbu / dbd
- *   may be NULL (skipped).
+ *   may be NULL (skipped).  `workspace`: feddat_dat_wgrad_workspace_bytes() bytes of device memory,
+ *   16-byte aligned, zero-initialised ONCE by the caller (the kernel leaves its counters at zero), not
+ *   shared by launches that may run concurrently.
  */
 int feddat_dat_bwd_dgrad(const void* X, const void* dY, void* dX, const void* Wd_cat,
                          const float* bd_cat, const void* WuT_cat, const void* WdT_cat,
@@ -90,7 +93,58 @@ int feddat_dat_bwd_dgrad(const void* X, const void* dY, void* dX, const void* Wd
 
 int feddat_dat_bwd_wgrad(const void* X, const void* dY, const void* H_t, const void* dP_t,
                          float* dWu, float* dbu, float* dWd, float* dbd, int64_t M, int d, int r_t,
-                         int ld_ht, int ld_dwu, float branch_scale, int dtype, void* stream);
+                         int ld_ht, int ld_dwu, float branch_scale, int dtype, void* workspace,
+                         size_t ws_bytes, void* stream);
+size_t feddat_dat_wgrad_workspace_bytes(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * Grouped launches: up to two independent row groups -- each with its own activations, packed weights,
+ * bottleneck width and scale -- in ONE kernel launch.  This is the MKD schedule of
+ * TaskTrainer.train_step (task_trainer.py:280-330) at one adapter site when passes A/C (gating pair,
+ * r_total = 2r, scale .5) and B (adapter_1 alone, r_total = r, scale 1) are row-stacked: one launch per
+ * site and direction instead of two, filling the machine without recomputing the hidden per column split.
+ * A group uses the fields of the single-group call of the same direction (forward: X, Res, Y, Wd_cat,
+ * bd_cat, Wu_cat, bu_cat, H_out; backward dgrad: X, dY, dX, Wd_cat, bd_cat, WuT_cat, WdT_cat, H_in, H_t,
+ * dP_t, ld_t, r_lo, r_hi, add_dy) with the same meaning and constraints; unused fields are NULL / 0.  Both
+ * groups of a backward launch must be in the same mode (saved / recompute).  Groups too large for one wave
+ * of CTAs (more than one 128-row tile per SM in total) are launched one by one by the library.
+ * `groups` is a HOST array.
+ */
+typedef struct FeddatDatGroup {
+  const void* X;
+  const void* Res;      /* forward: residual input */
+  void* Y;              /* forward: output */
+  const void* dY;       /* backward */
+  void* dX;             /* backward (nullable) */
+  const void* Wd_cat;
+  const float* bd_cat;
+  const void* Wu_cat;
+  const float* bu_cat;
+  const void* WuT_cat;
+  const void* WdT_cat;
+  void* H_out;          /* forward: hidden to save (nullable) */
+  const void* H_in;     /* backward, saved mode */
+  void* H_t;
+  void* dP_t;
+  int ld_t, r_lo, r_hi;
+  int64_t M;
+  int r_total;
+  float branch_scale;
+  int add_dy;
+} FeddatDatGroup;
+int feddat_dat_fwd_grouped(const FeddatDatGroup* groups, int n_groups, int d, int act, int dtype, void* stream);
+int feddat_dat_bwd_dgrad_grouped(const FeddatDatGroup* groups, int n_groups, int d, int act, int dtype,
+                                 void* stream);
+/* weight gradients of up to two groups in one launch (same fields as feddat_dat_bwd_wgrad) */
+typedef struct FeddatWgradGroup {
+  const void *X, *dY, *H_t, *dP_t;
+  float *dWu, *dbu, *dWd, *dbd;
+  int64_t M;
+  int r_t, ld_ht, ld_dwu;
+  float branch_scale;
+} FeddatWgradGroup;
+int feddat_dat_bwd_wgrad_grouped(const FeddatWgradGroup* groups, int n_groups, int d, int dtype,
+                                 void* workspace, size_t ws_bytes, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Packing of the fp32 master weights of the active branches into the bf16 operands above.
@@ -103,6 +157,25 @@ int feddat_pack_weights(const float* const* down_w, const float* const* down_b,
                         const float* const* up_w, const float* const* up_b, int n_branch, int r,
                         int d, void* Wd_cat, void* WdT_cat, void* Wu_cat, void* WuT_cat,
                         float* bd_cat, float* bu_cat, void* stream);
+
+/* The same packing for several operand sets ("jobs") in ONE launch: a train step packs every adapter site
+ * in both of its modes (gating pair; adapter_1 alone) once, when the weights change, instead of once per
+ * forward.  `jobs` is a HOST array (copied into the kernel parameters; more than 24 jobs run as several
+ * launches).  Per job: up_w[b] may point at a column slice of a wider [d, ld_up] matrix (ld_up = its row
+ * stride in elements, 0 means r) and down_w[b] at a row slice, so a bottleneck wider than one launch
+ * covers is packed segment by segment without copies; bu_cat = bu_src[0] + bu_src[1] (either may be NULL:
+ * the up biases ride on ONE segment only).
+ */
+typedef struct FeddatPackJob {
+  const float* down_w[2];
+  const float* down_b[2];
+  const float* up_w[2];
+  const float* bu_src[2];
+  int n_branch, r, ld_up;
+  void *Wd_cat, *WdT_cat, *Wu_cat, *WuT_cat;
+  float *bd_cat, *bu_cat;
+} FeddatPackJob;
+int feddat_pack_weights_batched(const FeddatPackJob* jobs, int n_jobs, int d, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * MKD head.  Replaces kl_loss (src/train/visionlanguage_tasks/task_trainer.py:506-516) plus the

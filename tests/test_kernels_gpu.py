@@ -384,3 +384,93 @@ def test_gelu_matches_torch(ops, shape):
     exact = 0.5 * x.double() * (1 + torch.erf(x.double() / 2 ** 0.5))
     d = (y.double() - exact).abs()
     assert bool((d <= exact.abs() * 2 ** -8 + 1e-6).all())
+
+
+# ------------------------------------------------------------------------- grouped launches (ABI v3)
+def _rand_branches(rng, r, nb):
+    return [((rng.standard_normal((r, 768)) * 0.05).astype(np.float32), (rng.standard_normal(r) * 0.1).astype(np.float32),
+             (rng.standard_normal((768, r)) * 0.05).astype(np.float32), (rng.standard_normal(768) * 0.1).astype(np.float32))
+            for _ in range(nb)]
+
+
+@pytest.mark.parametrize("M0,M1,r", [(5920, 5920, 128),     # BASELINE configs[1]: one site of the batched MKD schedule
+                                     (333, 130, 64),        # ragged tiles in both groups
+                                     (1, 700, 48),          # R % 64 != 0 (the reference's r = 48), single-row group
+                                     (9000, 5920, 128)])    # 118 tiles: still one wave
+def test_grouped_launch_equals_single_launches(ops, M0, M1, r):
+    """feddat_dat_fwd_grouped / feddat_dat_bwd_dgrad_grouped / feddat_dat_bwd_wgrad_grouped over [gating rows |
+    adapter_1 rows] == the single-group launches: forward, hidden and dX bit for bit (same per-element
+    arithmetic; only the assignment of tiles to CTAs differs), weight gradients up to the summation order
+    across row splits, and everything against the oracle."""
+    rng = np.random.default_rng(M0 * 7 + M1 + r)
+    br2, br1 = _rand_branches(rng, r, 2), _rand_branches(rng, r, 1)
+    pk2, pk1 = ops.pack_weights(dev_branches(br2)), ops.pack_weights(dev_branches(br1))
+    x = rng.standard_normal((M0 + M1, 768)).astype(np.float32)
+    g = rng.standard_normal((M0 + M1, 768)).astype(np.float32)
+    xd, gd = to_dev(x, torch.bfloat16), to_dev(g, torch.bfloat16)
+    y = torch.empty_like(xd)
+    specs = [(slice(0, M0), pk2, 0.5, (0, r)), (slice(M0, M0 + M1), pk1, 1.0, (0, r))]
+    outs = ops.dat_forward_grouped([dict(x=xd[sl], res=xd[sl], w=pk, scale=sc, out=y[sl], save_hidden=True)
+                                    for sl, pk, sc, _ in specs])
+    dx = torch.empty_like(xd)
+    res = ops.dat_backward_grouped([dict(x=xd[sl], dy=gd[sl], w=pk, scale=sc, train_slice=ts, need_dx=True, add_dy=True,
+                                         hidden=h, dx_out=dx[sl]) for (sl, pk, sc, ts), (_, h) in zip(specs, outs)])
+    res_again = ops.dat_backward_grouped([dict(x=xd[sl], dy=gd[sl], w=pk, scale=sc, train_slice=ts, need_dx=True,
+                                               add_dy=True, hidden=h) for (sl, pk, sc, ts), (_, h) in zip(specs, outs)])
+    torch.cuda.synchronize()
+    for (sl, pk, sc, ts), (y_g, h_g), (dx_g, gr_g), (dx_a, gr_a), brs, gating in zip(
+            specs, outs, res, res_again, (br2, br1), (True, False)):
+        y1, h1 = ops.dat_forward(xd[sl], xd[sl], pk, sc, save_hidden=True)
+        dx1, gr1 = ops.dat_backward(xd[sl], gd[sl], pk, sc, train_slice=ts, need_dx=True, add_dy=True, hidden=h1)
+        torch.cuda.synchronize()
+        assert torch.equal(y[sl], y1) and torch.equal(h_g, h1)
+        assert torch.equal(dx[sl], dx1) and torch.equal(dx_a, dx1)
+        for a, b, c in zip(gr_g, gr1, gr_a):
+            assert torch.equal(a, c)                                   # deterministic: run-to-run bit-exact
+            assert relerr(a.cpu().numpy(), b.cpu().numpy()) < 1e-5     # vs the single launch: split count differs
+        xr, gr = bf16_round(x[sl]), bf16_round(g[sl])
+        rb = rounded_branches(brs)
+        assert relerr(y[sl].float().cpu().numpy(), oracle.adapter_forward(xr, xr, rb, gating)) < 6e-3
+        _, grads_or = oracle.adapter_backward(xr, gr, rb, gating, residual_is_input=True)
+        for got, want in zip(gr_g, grads_or[0]):
+            assert relerr(got.cpu().numpy(), want) < 2 * BF16_TOL
+
+
+def test_wgrad_is_bitwise_reproducible(ops):
+    """The two-stage weight-gradient reduction sums the row splits in a fixed order: repeated launches give
+    identical bits (round 1 reduced with fp32 atomics)."""
+    rng = np.random.default_rng(77)
+    r, M = 128, 5920
+    pk = ops.pack_weights(dev_branches(_rand_branches(rng, r, 2)))
+    x = to_dev(rng.standard_normal((M, 768)).astype(np.float32), torch.bfloat16)
+    g = to_dev(rng.standard_normal((M, 768)).astype(np.float32), torch.bfloat16)
+    _, h = ops.dat_forward(x, x, pk, 0.5, save_hidden=True)
+    runs = [ops.dat_backward(x, g, pk, 0.5, train_slice=(0, r), hidden=h)[1] for _ in range(4)]
+    torch.cuda.synchronize()
+    for other in runs[1:]:
+        for a, b in zip(runs[0], other):
+            assert torch.equal(a, b)
+
+
+def test_pack_weights_batched_slices(ops):
+    """feddat_pack_weights_batched: several jobs in one launch, with row / column SLICE views of wide masters
+    (how a bottleneck wider than one launch is packed segment by segment), bias on the first segment only."""
+    g = torch.Generator(device="cuda").manual_seed(5)
+    r = 512
+    dw, db = torch.randn(r, 768, device="cuda", generator=g) * 0.05, torch.randn(r, device="cuda", generator=g)
+    uw, ub = torch.randn(768, r, device="cuda", generator=g) * 0.05, torch.randn(768, device="cuda", generator=g)
+    specs = [ops.PackSpec([dw[j:j + 256]], [db[j:j + 256]], [uw[:, j:j + 256]], [ub if j == 0 else None, None])
+             for j in (0, 256)]
+    small = [torch.randn(32, 768, device="cuda", generator=g), torch.randn(32, device="cuda", generator=g),
+             torch.randn(768, 32, device="cuda", generator=g), torch.randn(768, device="cuda", generator=g)]
+    specs.append(ops.PackSpec([small[0], small[0]], [small[1], small[1]], [small[2], small[2]], [small[3], small[3]]))
+    packs = ops.pack_weights_batched(specs)
+    torch.cuda.synchronize()
+    for pk, j in zip(packs[:2], (0, 256)):
+        assert torch.equal(pk.wd, dw[j:j + 256].to(torch.bfloat16)) and torch.equal(pk.wdT, dw[j:j + 256].t().to(torch.bfloat16).contiguous())
+        assert torch.equal(pk.wu, uw[:, j:j + 256].to(torch.bfloat16).contiguous())
+        assert torch.equal(pk.wuT, uw[:, j:j + 256].t().to(torch.bfloat16).contiguous())
+        assert torch.equal(pk.bd, db[j:j + 256])
+        assert torch.equal(pk.bu, ub if j == 0 else torch.zeros_like(ub))
+    assert torch.equal(packs[2].bu, small[3] + small[3]) and packs[2].r_total == 64
+    assert torch.equal(packs[2].wd, torch.cat([small[0], small[0]]).to(torch.bfloat16))
