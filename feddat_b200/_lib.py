@@ -30,6 +30,7 @@ EXPORTED_SYMBOLS = (
     "feddat_pack_weights",
     "feddat_pack_weights_batched",
     "feddat_mkd_loss",
+    "feddat_mkd_ce_loss",
     "feddat_fedavg",
     "feddat_ln_fwd",
     "feddat_ln_bwd",
@@ -141,7 +142,10 @@ def _bind(lib: ctypes.CDLL, debug: bool) -> ctypes.CDLL:
     lib.feddat_pack_weights_batched.argtypes = [POINTER(PackJob), c_int, c_int, c_void_p]
     lib.feddat_mkd_loss.restype = c_int
     lib.feddat_mkd_loss.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int,
-                                    c_float, c_float, c_float, c_float, c_int64, c_void_p]
+                                    c_float, c_float, c_float, c_float, c_int64, c_void_p, c_void_p]
+    lib.feddat_mkd_ce_loss.restype = c_int
+    lib.feddat_mkd_ce_loss.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int,
+                                       c_int, c_int, c_float, c_float, c_float, c_int, c_void_p, c_void_p]
     lib.feddat_fedavg.restype = c_int
     lib.feddat_fedavg.argtypes = [POINTER(c_void_p), POINTER(c_float), c_int, c_float, c_void_p,
                                   c_int64, c_void_p]

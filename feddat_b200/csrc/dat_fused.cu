@@ -534,11 +534,8 @@ dat_fused_kernel(const __grid_constant__ TmapSet tm0, const __grid_constant__ Tm
                 const float g1 = (hb[i] & 0x7fff0000u) ? scale * __uint_as_float(u[2 * i + 1]) : 0.f;
                 w[i] = pack_bf16x2(g0, g1);
               }
-              if (G.dP_t != nullptr && c_base == 0 && col >= G.r_lo && col < G.r_hi && grow < G.M) {
-                uint4* gd = reinterpret_cast<uint4*>(G.dP_t + static_cast<size_t>(grow) * G.ld_t + (col - G.r_lo));
-                gd[0] = make_uint4(w[0], w[1], w[2], w[3]);
-                gd[1] = make_uint4(w[4], w[5], w[6], w[7]);
-              }
+#pragma unroll
+              for (int i = 0; i < 8; ++i) wall[ci][i] = w[i];   // dP_t goes to HBM after GEMM3 has been released
             } else {
               uint32_t hh[8];
 #pragma unroll
@@ -568,6 +565,20 @@ dat_fused_kernel(const __grid_constant__ TmapSet tm0, const __grid_constant__ Tm
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive_cluster_addr(leader_h_full);
+        if constexpr (kSaved) {
+          // the trainable slice of dP for the weight-gradient kernel: stored AFTER GEMM3 has been released
+          if (G.dP_t != nullptr && c_base == 0 && grow < G.M) {
+#pragma unroll
+            for (int ci = 0; ci < 8; ++ci) {
+              const int col = (c_lo + ci) * 16;
+              if (c_lo + ci < c_hi && col >= G.r_lo && col < G.r_hi) {
+                uint4* gd = reinterpret_cast<uint4*>(G.dP_t + static_cast<size_t>(grow) * G.ld_t + (col - G.r_lo));
+                gd[0] = make_uint4(wall[ci][0], wall[ci][1], wall[ci][2], wall[ci][3]);
+                gd[1] = make_uint4(wall[ci][4], wall[ci][5], wall[ci][6], wall[ci][7]);
+              }
+            }
+          }
+        }
         if constexpr (!kBwd) {
           // save the hidden for a kSaved backward AFTER GEMM2 has been released: a row-per-thread store
           // is 32 L1 transactions per instruction and must not sit on the tensor pipe's critical path

@@ -87,7 +87,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
 dat_wgrad_kernel(const __grid_constant__ WgradTmaps tm0, const __grid_constant__ WgradTmaps tm1,
                  const __grid_constant__ WgradParams pp) {
   extern __shared__ uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t bars[2 * WG_STAGES + 1];
+  __shared__ __align__(8) uint64_t bars[2 * WG_STAGES + 2];
   __shared__ uint32_t tmem_base_smem;
   __shared__ float red_smem[2][8][NCW];     // bias-gradient partials of the 8 row sets (8 KB)
 
@@ -113,6 +113,7 @@ dat_wgrad_kernel(const __grid_constant__ WgradTmaps tm0, const __grid_constant__
   auto bar_full = [&](int s) { return bar0 + 8u * s; };
   auto bar_empty = [&](int s) { return bar0 + 8u * (WG_STAGES + s); };
   const uint32_t bar_acc = bar0 + 8u * (2 * WG_STAGES);
+  const uint32_t bar_red = bar0 + 8u * (2 * WG_STAGES + 1);   // stage-2 reduction: partial slices landed in smem
 
   if (tid == 0) {
     for (int s = 0; s < WG_STAGES; ++s) {
@@ -120,6 +121,7 @@ dat_wgrad_kernel(const __grid_constant__ WgradTmaps tm0, const __grid_constant__
       mbar_init(bar_empty(s), 1 + 4);  // MMA commit + one arrive per aux warp
     }
     mbar_init(bar_acc, 1);
+    mbar_init(bar_red, 1);
     fence_mbar_init();
     tma_prefetch_desc(&tmXk);
     tma_prefetch_desc(&tmDYk);
@@ -261,11 +263,12 @@ dat_wgrad_kernel(const __grid_constant__ WgradTmaps tm0, const __grid_constant__
     mbar_wait(bar_acc, 0);
     tc_fence_after();
     if (tid == 64) WG_TRACE(203);   // accumulators complete
+    // The pipeline stages are free now (every MMA that read them has completed): they stage the partial
+    // tiles.  thread j = TMEM lane = bottleneck unit j; float4 i of the 32-column group c of matrix m goes
+    // to float4 index ((m * 4 + c) * 8 + i) * 128 + j (conflict-free st.shared.v4), then ONE 128 KB bulk
+    // copy moves the CTA's partials to the workspace (row-per-thread st.global took 4 us here).
     {
-      // thread j = TMEM lane = bottleneck unit j.  float4 i of the 32-column group c of matrix m goes to
-      // float4 index ((m * 4 + c) * 8 + i) * 128 + j: the 32 lanes of a warp store 512 contiguous bytes
       const uint32_t lane_addr = (q * 32) << 16;
-      float4* dst4 = reinterpret_cast<float4*>(part);
 #pragma unroll 1
       for (int mc = 0; mc < 2 * (NCW / 32); ++mc) {
         uint32_t v[32];
@@ -273,34 +276,76 @@ dat_wgrad_kernel(const __grid_constant__ WgradTmaps tm0, const __grid_constant__
         tmem_ld_wait32(v);
 #pragma unroll
         for (int i = 0; i < 8; ++i)
-          dst4[(mc * 8 + i) * 128 + j] = make_float4(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]),
-                                                    __uint_as_float(v[4 * i + 2]), __uint_as_float(v[4 * i + 3]));
+          st_shared_v4(smem0 + (((mc * 8 + i) * 128 + j) << 4), v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
       }
     }
-    __threadfence();
+    fence_proxy_async_smem();
+    __threadfence();                 // the two bias partial vectors (plain stores above)
     named_bar_sync(1, 128);
     unsigned int* ctr = pp.counters + (grp * NCHUNK + chunk) * 2;
     // ---- stage 2: wait for the partials of all row splits of this (group, chunk), then sum 1 / S of the
     // tile over the splits in split order (deterministic) and write the final gradients
     const int S = p.n_splits;
-    if (t == 0) {
-      atomicAdd(ctr, 1u);
-      wait_counter(ctr, static_cast<unsigned int>(S));
-    }
-    named_bar_sync(1, 128);
-    __threadfence();
-    if (tid == 64) WG_TRACE(204);
     const float* part0 = pp.partials + static_cast<size_t>(p.first_cta + chunk) * PART_FLOATS;   // split 0
     const size_t split_stride = static_cast<size_t>(NCHUNK) * PART_FLOATS;
     const int per = (TILE_F4 + S - 1) / S;
+    const int f_begin = split * per;
     const int f_end = (split + 1) * per < TILE_F4 ? (split + 1) * per : TILE_F4;
-    for (int f = split * per + static_cast<int>(t); f < f_end; f += 128) {
-      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-      const float4* src = reinterpret_cast<const float4*>(part0) + f;
-      for (int sidx = 0; sidx < S; ++sidx) {
-        const float4 v = __ldcg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(src) + sidx * split_stride));
-        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    const int n_f = f_end > f_begin ? f_end - f_begin : 0;
+    if (t == 0) {
+      bulk_store_1d(part, smem0, TILE_F4 * 16);
+      tma_store_commit();
+      tma_store_wait_all<0>();       // the partials are written (not merely read out of smem)
+      fence_proxy_async_all();
+      __threadfence();
+      atomicAdd(ctr, 1u);
+      wait_counter(ctr, static_cast<unsigned int>(S));
+      __threadfence();
+      fence_proxy_async_all();
+      if (tid == 64) WG_TRACE(204);
+      // this CTA's slice [f_begin, f_end) of every split's partial tile -> smem, one bulk copy per split
+      if (n_f > 0) {
+        mbar_arrive_expect_tx(bar_red, static_cast<uint32_t>(S) * n_f * 16u);
+        for (int sidx = 0; sidx < S; ++sidx)
+          bulk_load_1d(smem0 + static_cast<uint32_t>(sidx) * per * 16u,
+                       part0 + sidx * split_stride + static_cast<size_t>(f_begin) * 4, n_f * 16u, bar_red);
+      } else {
+        mbar_arrive(bar_red);
       }
+    }
+    if (split == 0) {   // bias gradients: one CTA per (group, chunk), fixed order; loads issued together
+      named_bar_sync(2, 128);        // thread 0 has passed the split barrier
+      __threadfence();
+      const bool cta_dbd = (chunk == 0) && p.dbd != nullptr;
+      float vy[24], vp[24];
+#pragma unroll
+      for (int sidx = 0; sidx < 24; ++sidx) {
+        vy[sidx] = vp[sidx] = 0.f;
+        if (sidx < S) {
+          const float* ps = part0 + sidx * split_stride + 2 * 128 * NCW;
+          vy[sidx] = __ldcg(ps + t);
+          vp[sidx] = __ldcg(ps + NCW + t);
+        }
+      }
+      float sdy = 0.f, sdp = 0.f;
+#pragma unroll
+      for (int sidx = 0; sidx < 24; ++sidx) {
+        sdy += vy[sidx];
+        sdp += vp[sidx];
+      }
+      if (do_dbu) p.dbu[col0 + t] = p.scale * sdy;
+      if (cta_dbd && static_cast<int>(t) < p.rt) p.dbd[t] = sdp;
+    }
+    mbar_wait(bar_red, 0);
+    for (int k = static_cast<int>(t); k < n_f; k += 128) {
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 4
+      for (int sidx = 0; sidx < S; ++sidx) {
+        const uint4 u = ld_shared_v4(smem0 + (static_cast<uint32_t>(sidx) * per + k) * 16u);
+        acc.x += __uint_as_float(u.x); acc.y += __uint_as_float(u.y);
+        acc.z += __uint_as_float(u.z); acc.w += __uint_as_float(u.w);
+      }
+      const int f = f_begin + k;
       const int jj = f & 127, i = (f >> 7) & 7, c = (f >> 10) & 3, m = f >> 12;
       if (jj < p.rt) {
         const int col = col0 + c * 32 + i * 4;
@@ -314,17 +359,6 @@ dat_wgrad_kernel(const __grid_constant__ WgradTmaps tm0, const __grid_constant__
           *reinterpret_cast<float4*>(p.dWd + static_cast<size_t>(jj) * kD + col) = acc;
         }
       }
-    }
-    if (split == 0) {   // bias gradients: one CTA per (group, chunk), same fixed order
-      const bool cta_dbd = (chunk == 0) && p.dbd != nullptr;
-      float sdy = 0.f, sdp = 0.f;
-      for (int sidx = 0; sidx < S; ++sidx) {
-        const float* ps = part0 + sidx * split_stride + 2 * 128 * NCW;
-        sdy += __ldcg(ps + t);
-        sdp += __ldcg(ps + NCW + t);
-      }
-      if (do_dbu) p.dbu[col0 + t] = p.scale * sdy;
-      if (cta_dbd && static_cast<int>(t) < p.rt) p.dbd[t] = sdp;
     }
     // the last CTA of this (group, chunk) to finish resets the counters for the next launch
     named_bar_sync(1, 128);

@@ -174,6 +174,20 @@ template <int N>
 __device__ __forceinline__ void tma_store_wait_all() {
   asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory");
 }
+// 1-D bulk copies (no tensor map): shared -> global as part of the thread's bulk async-group, and
+// global -> shared signalling an mbarrier with the byte count.  Sizes and addresses: multiples of 16 bytes.
+__device__ __forceinline__ void bulk_store_1d(void* gdst, uint32_t src_smem, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+               ::"l"(reinterpret_cast<uint64_t>(gdst)), "r"(src_smem), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_load_1d(uint32_t dst_smem, const void* gsrc, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst_smem), "l"(reinterpret_cast<uint64_t>(gsrc)), "r"(bytes), "r"(bar)
+               : "memory");
+}
+// orders async-proxy (TMA / bulk copy) accesses with generic-proxy accesses of this thread, all state spaces
+__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
 // L2 eviction-priority policies (same encodings CUTLASS's TMA::CacheHintSm90 uses)
 constexpr uint64_t kEvictFirst = 0x12F0000000000000ull;
 constexpr uint64_t kEvictLast = 0x14F0000000000000ull;

@@ -332,12 +332,56 @@ def mkd_loss(logits: torch.Tensor, teacher: torch.Tensor, target: Optional[torch
     task_scale = 1.0 / logits.shape[0] if target is not None else 0.0
     loss3 = torch.empty(3, device=logits.device, dtype=torch.float32)
     dlogits = torch.empty_like(logits) if need_grad else None
+    row_ws = torch.empty(max(rows, 1), 2, device=logits.device, dtype=torch.float32)
     rc = lib.feddat_mkd_loss(_lib.ptr(logits), _lib.ptr(teacher), _lib.ptr(target), _lib.ptr(loss3),
                              _lib.ptr(dlogits), rows, C, float(temp), float(kl_weight), float(task_weight),
-                             float(task_scale), batchmean_div, _lib.stream_ptr())
+                             float(task_scale), batchmean_div, _lib.ptr(row_ws), _lib.stream_ptr())
     _lib.check(rc, "feddat_mkd_loss")
-    _count(2)  # memset + kernel
+    _count(2)  # row kernel + fixed-order final sum
     return loss3, dlogits
+
+
+DTYPE_F32 = 1
+
+
+def mkd_ce_loss(scores: torch.Tensor, teacher: torch.Tensor, labels: torch.Tensor, seq_weight: torch.Tensor,
+                temp: float, kl_weight: float = 0.5, task_weight: float = 0.5, need_grad: bool = True):
+    """Fused MKD head of the ALBEF path (feddat_mkd_ce_loss): KL(T) between the decoder logits and the teacher's +
+    the weighted answer cross-entropy, value and d/dscores in one pass.  ``scores``: the UNSHIFTED prediction scores
+    [n_seq, La, C] (bf16 or fp32, contiguous); ``teacher``: [n_seq, La, C] or the shifted [n_seq, La - 1, C], same
+    dtype (a [:, :-1] VIEW of an unshifted tensor is taken as its base); ``labels`` [n_seq, La] int64 with -100 =
+    ignore; ``seq_weight`` [n_seq] fp32 = answer weight / image batch.  Returns (loss3 [total, kl, task], dscores)."""
+    lib = _lib.load()
+    if not (scores.is_cuda and scores.dim() == 3 and scores.is_contiguous()
+            and scores.dtype in (torch.bfloat16, torch.float32)):
+        raise _lib.FeddatError("mkd_ce_loss: scores must be a contiguous CUDA [n_seq, La, C] bf16 / fp32 tensor")
+    n_seq, La, C = scores.shape
+    if teacher.dtype != scores.dtype:
+        teacher = teacher.to(scores.dtype)
+    if (not teacher.is_contiguous() and teacher.dim() == 3 and teacher.shape == (n_seq, La - 1, C)
+            and teacher.stride() == (La * C, C, 1)):
+        La_t = La                       # a [:, :-1] view of an unshifted tensor: address it through its row stride
+    else:
+        teacher = teacher.contiguous()
+        La_t = teacher.shape[1]
+    if teacher.shape[0] != n_seq or teacher.shape[2] != C or La_t not in (La, La - 1):
+        raise _lib.FeddatError(f"mkd_ce_loss: teacher {tuple(teacher.shape)} does not match scores {tuple(scores.shape)}")
+    if not (labels.is_cuda and labels.dtype == torch.int64 and tuple(labels.shape) == (n_seq, La)):
+        raise _lib.FeddatError("mkd_ce_loss: labels must be a CUDA int64 [n_seq, La] tensor")
+    labels = labels.contiguous()
+    seq_weight = seq_weight.to(torch.float32).contiguous()
+    if tuple(seq_weight.shape) != (n_seq,):
+        raise _lib.FeddatError("mkd_ce_loss: seq_weight must be [n_seq]")
+    loss3 = torch.empty(3, device=scores.device, dtype=torch.float32)
+    dscores = torch.empty_like(scores) if need_grad else None
+    row_ws = torch.empty(max(n_seq * La, 1), 2, device=scores.device, dtype=torch.float32)
+    rc = lib.feddat_mkd_ce_loss(_lib.ptr(scores), _lib.ptr(teacher), _lib.ptr(labels), _lib.ptr(seq_weight),
+                                _lib.ptr(loss3), _lib.ptr(dscores), n_seq, La, La_t, C, float(temp), float(kl_weight),
+                                float(task_weight), DTYPE_BF16 if scores.dtype == torch.bfloat16 else DTYPE_F32,
+                                _lib.ptr(row_ws), _lib.stream_ptr())
+    _lib.check(rc, "feddat_mkd_ce_loss")
+    _count(2)
+    return loss3, dscores
 
 
 def fedavg(client_bufs: Sequence[torch.Tensor], nums: Sequence[float], out: torch.Tensor,

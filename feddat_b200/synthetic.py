@@ -77,3 +77,98 @@ class SyntheticVQALoader:
             host = make_vilt_batch(seed=self.seed * 100003 + i, pin=torch.device(self.device).type == "cuda",
                                    **self.args)
             yield to_device(host, self.device, image_dtype=self.image_dtype)
+
+
+# ------------------------------------------------------------------------------------------------ ALBEF
+CLS_ID, SEP_ID, PAD_ID = 101, 102, 0        # bert-base-uncased special tokens
+
+
+def make_albef_batch(batch_size: int, image_size: int = 384, seed: int = 0, client: Optional[int] = None,
+                     q_len: int = 25, a_len: int = 6, vocab: int = 30522, pin: bool = False) -> Dict:
+    """Pre-tokenised ALBEF VQA training batch on the HOST (the collate contract of reference
+    vqa_dataset_crossvqa.py:456-471): images N(0, 1); questions [CLS] ids... [SEP] padded to ``q_len``; k_b in
+    {1, 2, 3} answers per sample ([CLS] a... [SEP], 3..``a_len`` tokens, padded) with weights 1 / k_b.  k_b cycles
+    deterministically so that the number of answer sequences is the same for every batch of a size (static shapes
+    for CUDA-graph replay)."""
+    g = torch.Generator().manual_seed(seed)
+    lo, hi, shift = 1000, vocab, 0.0
+    if client is not None:
+        span = (vocab - 1000) // 8
+        lo, hi = 1000 + span * client, 1000 + span * (client + 1)
+        shift = 0.25 * (client - 3.5)
+    images = torch.randn(batch_size, 3, image_size, image_size, generator=g) + shift
+    q_ids = torch.full((batch_size, q_len), PAD_ID, dtype=torch.int64)
+    q_mask = torch.zeros(batch_size, q_len, dtype=torch.int64)
+    for b in range(batch_size):
+        n = int(torch.randint(6, q_len + 1, (1,), generator=g))
+        q_ids[b, 0], q_ids[b, n - 1] = CLS_ID, SEP_ID
+        q_ids[b, 1:n - 1] = torch.randint(lo, hi, (n - 2,), generator=g)
+        q_mask[b, :n] = 1
+    ks = [1 + (b + seed) % 3 for b in range(batch_size)]
+    n_seq = sum(ks)
+    a_ids = torch.full((n_seq, a_len), PAD_ID, dtype=torch.int64)
+    a_mask = torch.zeros(n_seq, a_len, dtype=torch.int64)
+    weights = torch.empty(n_seq)
+    i = 0
+    for b, k in enumerate(ks):
+        for _ in range(k):
+            n = int(torch.randint(3, a_len + 1, (1,), generator=g))
+            a_ids[i, 0], a_ids[i, n - 1] = CLS_ID, SEP_ID
+            a_ids[i, 1:n - 1] = torch.randint(lo, hi, (n - 2,), generator=g)
+            a_mask[i, :n] = 1
+            weights[i] = 1.0 / k
+            i += 1
+    batch = {"images": images, "question_ids": q_ids, "question_mask": q_mask, "answer_ids": a_ids,
+             "answer_mask": a_mask, "weights": weights, "n": ks, "alpha": 0.0, "train": True}
+    if pin and torch.cuda.is_available():
+        batch = {k: (v.pin_memory() if isinstance(v, torch.Tensor) else v) for k, v in batch.items()}
+    return batch
+
+
+def albef_to_device(batch: Dict, device, image_dtype=torch.bfloat16, non_blocking: bool = True) -> Dict:
+    out = {}
+    for k, v in batch.items():
+        if isinstance(v, torch.Tensor):
+            v = v.to(device, non_blocking=non_blocking)
+            if k == "images" and image_dtype is not None:
+                v = v.to(image_dtype)
+        out[k] = v
+    return out
+
+
+def make_albef_eval_set(num_batches: int, batch_size: int, image_size: int, seed: int, n_answers: int = 96,
+                        a_len: int = 6, q_len: int = 25, vocab: int = 30522):
+    """(answer_list_ids, answer_list_mask, [(images, question_ids, question_mask, gts)]) for the rank_answer
+    evaluation (reference task_trainer.py:157-205: top-k over a fixed answer list, exact match against gts)."""
+    g = torch.Generator().manual_seed(seed)
+    ans = torch.full((n_answers, a_len), PAD_ID, dtype=torch.int64)
+    mask = torch.zeros(n_answers, a_len, dtype=torch.int64)
+    for i in range(n_answers):
+        n = int(torch.randint(3, a_len + 1, (1,), generator=g))
+        ans[i, 0], ans[i, n - 1] = CLS_ID, SEP_ID
+        ans[i, 1:n - 1] = torch.randint(1000, vocab, (n - 2,), generator=g)
+        mask[i, :n] = 1
+    batches = []
+    for j in range(num_batches):
+        tr = make_albef_batch(batch_size, image_size, seed=seed * 977 + j, q_len=q_len, vocab=vocab)
+        gts = torch.randint(0, n_answers, (batch_size, 1), generator=g)
+        batches.append((tr["images"], tr["question_ids"], tr["question_mask"], gts))
+    return ans, mask, batches
+
+
+class SyntheticAlbefLoader:
+    """Deterministic stream of pre-tokenised ALBEF batches for one client."""
+
+    def __init__(self, num_batches: int, batch_size: int, device, image_size=384, seed=0, client=None,
+                 image_dtype=torch.bfloat16):
+        self.num_batches, self.batch_size, self.device = num_batches, batch_size, device
+        self.image_size, self.seed, self.client, self.image_dtype = image_size, seed, client, image_dtype
+
+    def __len__(self):
+        return self.num_batches
+
+    def __iter__(self) -> Iterator[Dict]:
+        for i in range(self.num_batches):
+            host = make_albef_batch(self.batch_size, self.image_size, seed=self.seed * 100003 + i, client=self.client,
+                                    pin=torch.device(self.device).type == "cuda")
+            yield albef_to_device(host, self.device, self.image_dtype)

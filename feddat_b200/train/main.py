@@ -72,6 +72,8 @@ def build_parser():
     p.add_argument("--cuda_graph", action="store_true",
                    help="replay the captured train_step (feddat_b200/train/graphed.py) for full-shape batches")
     p.add_argument("--image_size", type=int, default=384)
+    p.add_argument("--vit_depth", type=int, default=None, help="ALBEF: ViT blocks (default 12; smaller for smoke runs)")
+    p.add_argument("--decoder_layers", type=int, default=None, help="ALBEF: answer-decoder layers (default 6)")
     p.add_argument("--text_len", type=int, default=40)
     p.add_argument("--fix_adapter0_optimizer", action="store_true",
                    help="re-enable adapter_0/adapter_1 requires_grad before each client's optimizer is built; "

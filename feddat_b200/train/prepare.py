@@ -15,8 +15,7 @@ from ..modeling.vilt import create_vilt_continual_learner_model
 
 def prepare_model(args, logger=None, device="cuda", place=True):
     logger = logger or logging.getLogger("feddat_b200")
-    if args.encoder_name != "vilt":
-        raise NotImplementedError("round 1 covers the ViLT family; ALBEF sites reuse the same Adapter")
+    albef = "albef" in args.encoder_name
     model_config = dict(model_configs[args.encoder_name])
     if "dat" not in args.optimizer_mode:
         raise NotImplementedError("only optimizer_mode='dat' is on the FedDAT hot path")
@@ -31,15 +30,29 @@ def prepare_model(args, logger=None, device="cuda", place=True):
     adapter_config["activation"] = getattr(args, "adapter_activation", "relu")
     model_config["adapter_config"] = adapter_config
 
-    model = create_vilt_continual_learner_model(logger=logger, model_name_or_path=args.pretrained_model_name,
-                                                ordered_cl_tasks=args.ordered_cl_tasks,
-                                                model_config=model_config, task_configs=task_configs,
-                                                device=device)
+    if albef:
+        from ..modeling.albef import create_albef_continual_learner_model
+        if getattr(args, "image_size", None):
+            model_config["image_res"] = args.image_size
+        for k in ("vit_depth", "decoder_layers"):                        # reduced-depth models for tests
+            if getattr(args, k, None):
+                model_config[k] = getattr(args, k)
+        if getattr(args, "bert_overrides", None):
+            model_config["bert_config"] = dict(model_config["bert_config"], **args.bert_overrides)
+        model = create_albef_continual_learner_model(logger=logger, model_name_or_path=args.pretrained_model_name,
+                                                     ordered_cl_tasks=args.ordered_cl_tasks, model_config=model_config,
+                                                     task_configs=task_configs, device=device)
+    else:
+        model = create_vilt_continual_learner_model(logger=logger, model_name_or_path=args.pretrained_model_name,
+                                                    ordered_cl_tasks=args.ordered_cl_tasks,
+                                                    model_config=model_config, task_configs=task_configs,
+                                                    device=device)
     model.comm_state_dict_names = []
-    args.personal_params_names = ["task"]                                # main.py:130
+    args.personal_params_names = [".cls."] if albef else ["task"]        # main.py:127-130
     for _, p in model.named_parameters():                                # main.py:138-139
         p.requires_grad = False
-    model.add_adapter()                                                  # main.py:153
+    if not albef:
+        model.add_adapter()                                              # main.py:152-153 (ALBEF builds its sites itself)
     args.personal_params_names += ["adapter_0", "adapter_2"]             # main.py:154
     args.shared_params_names = ["adapter_1"]                             # main.py:155
     for n, p in model.named_parameters():                                # main.py:157-159
@@ -49,7 +62,7 @@ def prepare_model(args, logger=None, device="cuda", place=True):
         if any(sn in n for sn in args.shared_params_names):
             model.comm_state_dict_names.append(n)
     for n, p in model.named_parameters():                                # main.py:248-250
-        if any(pn in n for pn in ["task"]):
+        if "task" in n or ".cls." in n:
             p.requires_grad = True
     if place:
         place_on_gpu(model, device)
@@ -58,6 +71,10 @@ def prepare_model(args, logger=None, device="cuda", place=True):
 
 def place_on_gpu(model, device="cuda"):
     model.to(device)
+    if hasattr(model, "albef_model"):
+        model.albef_model.device = torch.device(device)
+        model.cast_frozen_backbone(torch.bfloat16)
+        return model
     model.device = torch.device(device)
     model.vilt_encoder.device = torch.device(device)
     model.cast_frozen_backbone(torch.bfloat16)

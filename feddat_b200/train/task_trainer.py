@@ -40,6 +40,24 @@ class _MkdLossFunction(torch.autograd.Function):
         return g.to(ctx.in_dtype), None, None, None, None, None
 
 
+class _MkdCeFunction(torch.autograd.Function):
+    """ALBEF objective (task_trainer.py:296-301 with the answer loss of albef_model.py:142-143) as ONE fused
+    launch over the decoder's prediction scores: value and d/dscores (feddat_mkd_ce_loss)."""
+
+    @staticmethod
+    def forward(ctx, scores, teacher, labels, seq_weight, temp, kl_weight, task_weight):
+        loss3, dscores = ops.mkd_ce_loss(scores.contiguous(), teacher, labels, seq_weight, temp, kl_weight, task_weight,
+                                         need_grad=True)
+        ctx.save_for_backward(dscores)
+        ctx.mark_non_differentiable(loss3)
+        return loss3[0], loss3
+
+    @staticmethod
+    def backward(ctx, g_total, _g3):
+        (dscores,) = ctx.saved_tensors
+        return dscores * g_total.to(dscores.dtype), None, None, None, None, None, None
+
+
 def kl_loss(output, target, temp=3):
     """task_trainer.py:506-516: T^2 * KL(softmax(target/T) || softmax(output/T)), 'batchmean'."""
     total, _ = _MkdLossFunction.apply(output, target, None, float(temp), 1.0, 0.0)
@@ -169,6 +187,13 @@ class TaskTrainer(nn.Module):
     def _objective(self, logits, teacher, target, task_loss):
         """(L, task) with L = (task + kl(logits, teacher.detach())) / 2.  Fused BCE+KL launch for the ViLT criterion
         (BCEWithLogits 'mean' * C, train_vqa_crossvqa.py:237); KL kernel + given task loss otherwise."""
+        if hasattr(task_loss, "prediction_scores"):
+            # ALBEF with the deferred answer loss (modeling/albef_model.py LazyAnswerLoss): KL + weighted token CE
+            # + gradient in one pass over the [answers, tokens, 30522] scores
+            lazy = task_loss
+            total, loss3 = _MkdCeFunction.apply(lazy.prediction_scores, teacher.detach(), lazy.labels,
+                                                lazy.weights.float() / lazy.batch_size, float(self.kl_temp), 0.5, 0.5)
+            return total, loss3[2]
         fused = (task_loss is None and isinstance(self.loss_criterion, nn.BCEWithLogitsLoss)
                  and self.loss_criterion.reduction == "mean" and self.kl_criterion is kl_loss
                  and self.loss_criterion.weight is None and self.loss_criterion.pos_weight is None)
@@ -260,6 +285,9 @@ class TaskTrainer(nn.Module):
                 inner.end_step()
 
     def _train_step_dat(self, model, inner, batch, target, optimizer, scheduler, albef):
+        if albef and hasattr(inner, "albef_model"):
+            # fused MKD head whenever the KL criterion is the reference's own kl_loss
+            inner.albef_model.defer_loss = self.kl_criterion is kl_loss
         reuse = (self.reuse_gating_forward and not albef
                  and getattr(inner, "gating_forward_is_reusable", lambda: False)())
         if (reuse and self.batched_passes and optimizer is not None and hasattr(inner, "encode_dual")

@@ -32,6 +32,7 @@ extern "C" {
 #define FEDDAT_ERR_NO_DEVICE (-4)
 
 #define FEDDAT_DTYPE_BF16 0
+#define FEDDAT_DTYPE_F32 1 /* MKD head only: the DAT operator itself is bf16 */
 
 #define FEDDAT_ACT_RELU 0 /* reference default: adapter.py:24 */
 #define FEDDAT_ACT_GELU 1 /* opt-in (BASELINE.json north_star wording) */
@@ -189,11 +190,28 @@ int feddat_pack_weights_batched(const FeddatPackJob* jobs, int n_jobs, int d, vo
  * logits/teacher/target/dlogits: [rows, C] fp32 row-major.  loss_out: 3 floats, device memory,
  * overwritten.  For the reference's ViLT path: batchmean_div = rows, task_scale = 1/rows
  * (mean over rows*C, times C), kl_weight = task_weight = 0.5.
+ * row_ws: [rows, 2] floats of device scratch (per-row kl / task sums; the final sum over rows runs in a fixed
+ * order, so loss_out is bit-wise reproducible).
  */
 int feddat_mkd_loss(const float* logits, const float* teacher, const float* target,
                     float* loss_out, float* dlogits, int64_t rows, int C, float temp,
                     float kl_weight, float task_weight, float task_scale, int64_t batchmean_div,
-                    void* stream);
+                    float* row_ws, void* stream);
+
+/* MKD head of the ALBEF path: kl_loss (task_trainer.py:506-516, the C > 3000 branch) over the decoder logits
+ * plus the answer loss of BertLMHeadModel.forward with reduction='none' (src/modeling/models/xbert.py:1287-1297)
+ * weighted as ALBEF.forward does (src/modeling/models/albef_model.py:142-143), value and gradient in one pass:
+ *     kl   = T^2 / n_seq * sum_{s, p < La-1} KL( softmax(teacher[s,p]/T) || softmax(logits[s,p]/T) )
+ *     task = sum_s seq_weight[s] * sum_{p < La-1, labels[s,p+1] != -100} CE(logits[s,p], labels[s,p+1])
+ *     loss_out = {kl_weight * kl + task_weight * task, kl, task};   dlogits = d loss_out[0] / d logits
+ * logits / dlogits: the UNSHIFTED prediction scores [n_seq, La, C] (position La-1 gets a zero gradient);
+ * teacher: [n_seq, La_teacher, C] with La_teacher = La (unshifted) or La - 1 (the reference's returned
+ * logits[:, :-1] copy); dtype FEDDAT_DTYPE_BF16 or FEDDAT_DTYPE_F32 for all three; labels [n_seq, La] int64;
+ * seq_weight [n_seq] fp32 = answer weight / image batch size; row_ws: [n_seq * La, 2] floats of scratch.
+ */
+int feddat_mkd_ce_loss(const void* logits, const void* teacher, const int64_t* labels, const float* seq_weight,
+                       float* loss_out, void* dlogits, int64_t n_seq, int La, int La_teacher, int C, float temp,
+                       float kl_weight, float task_weight, int dtype, float* row_ws, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * FedAvg of the flat communicated buffer.  Replaces get_average_net (src/train/main.py:50-65):

@@ -9,4 +9,5 @@ import this package; the product (``feddat_b200``) never does and has no CPU fal
 from .dat_oracle import (adapter_backward, adapter_forward, adapter_layer_forward_bert,  # noqa: F401
                          pack_branches)
 from .fedavg_oracle import get_average_net  # noqa: F401
-from .mkd_oracle import bce_with_logits_times_c, kl_loss, mkd_total  # noqa: F401
+from .mkd_oracle import (albef_answer_loss, bce_with_logits_times_c, kl_loss, mkd_ce_total,  # noqa: F401
+                         mkd_total)

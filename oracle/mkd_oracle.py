@@ -47,3 +47,38 @@ def mkd_total(logits, teacher, target, temp=3.0):
     kl, gkl = kl_loss(logits, teacher, temp, with_grad=True)
     task, gtask = bce_with_logits_times_c(logits, target, with_grad=True)
     return (task + kl) / 2.0, kl, task, (gkl + gtask) / 2.0
+
+
+def albef_answer_loss(prediction_scores, labels, weights, batch_size, with_grad=False):
+    """The ALBEF task loss: BertLMHeadModel.forward with reduction='none'
+    (src/modeling/models/xbert.py:1287-1297: scores[:, :-1] against labels[:, 1:], CrossEntropyLoss
+    ignore_index = -100, per-sequence sums) weighted and normalised as ALBEF.forward does
+    (src/modeling/models/albef_model.py:142-143: (weights * loss).sum() / image.size(0))."""
+    s = np.asarray(prediction_scores, np.float64)
+    lab = np.asarray(labels)
+    w = np.asarray(weights, np.float64)
+    shifted, tgt = s[:, :-1, :], lab[:, 1:]
+    logp = _log_softmax(shifted, -1)
+    valid = tgt != -100
+    safe = np.where(valid, tgt, 0)
+    tok = -np.take_along_axis(logp, safe[..., None], axis=-1)[..., 0] * valid
+    loss = float((w * tok.sum(1)).sum() / batch_size)
+    if not with_grad:
+        return loss
+    g = np.exp(logp)
+    np.put_along_axis(g, safe[..., None], np.take_along_axis(g, safe[..., None], axis=-1) - 1.0, axis=-1)
+    g = g * valid[..., None] * (w[:, None, None] / batch_size)
+    grad = np.zeros_like(s)
+    grad[:, :-1, :] = g
+    return loss, grad
+
+
+def mkd_ce_total(prediction_scores, teacher_shifted, labels, weights, batch_size, temp=3.0):
+    """task_trainer.py:296-301 on the ALBEF branch: L = (answer_loss + kl_loss(logits[:, :-1], teacher)) / 2 with
+    logits[:, :-1] what ALBEF.forward returns (albef_model.py:145).  Returns (L, kl, task, dL/dscores)."""
+    s = np.asarray(prediction_scores, np.float64)
+    kl, gkl = kl_loss(s[:, :-1, :], teacher_shifted, temp, with_grad=True)
+    task, gtask = albef_answer_loss(s, labels, weights, batch_size, with_grad=True)
+    grad = gtask / 2.0
+    grad[:, :-1, :] += gkl / 2.0
+    return (task + kl) / 2.0, kl, task, grad

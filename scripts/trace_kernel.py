@@ -1,5 +1,7 @@
 """Timeline of CTA 0's pipeline events inside dat_fused_kernel (debug aid).
-    python scripts/trace_kernel.py [R] [M] [fwd|bwd]"""
+    FEDDAT_DEBUG_LIB=1 python scripts/trace_kernel.py [R] [M] [fwd|bwd|bwdw|gfwd|gbwd]
+(gfwd / gbwd: the grouped launch over [M gating rows (R) | M adapter_1 rows (R / 2)] of one site; the trace hooks
+exist only in the -DFEDDAT_DEBUG twin of the library, hence the environment switch)"""
 import sys
 from pathlib import Path
 
@@ -22,10 +24,22 @@ pk = ops.pack_weights([[torch.randn(r, 768, device=dev, generator=g) * 0.02, tor
 x = torch.randn(M, 768, device=dev, generator=g).to(torch.bfloat16)
 dy = torch.randn(M, 768, device=dev, generator=g).to(torch.bfloat16)
 lib = _lib.load_debug()
+pk1 = ops.pack_weights([[torch.randn(r, 768, device=dev, generator=g) * 0.02, torch.zeros(r, device=dev),
+                         torch.randn(768, r, device=dev, generator=g) * 0.02, torch.zeros(768, device=dev)]])
+x1 = torch.randn(M, 768, device=dev, generator=g).to(torch.bfloat16)
+if mode.startswith("g"):
+    (_, h2), (_, h1) = ops.dat_forward_grouped([dict(x=x, res=x, w=pk, scale=0.5, save_hidden=True),
+                                                dict(x=x1, res=x1, w=pk1, scale=1.0, save_hidden=True)])
 
 
 def run():
-    if mode == "fwd":
+    if mode == "gfwd":
+        ops.dat_forward_grouped([dict(x=x, res=x, w=pk, scale=0.5, save_hidden=True),
+                                 dict(x=x1, res=x1, w=pk1, scale=1.0, save_hidden=True)])
+    elif mode == "gbwd":
+        ops.dat_backward_grouped([dict(x=x, dy=dy, w=pk, scale=0.5, train_slice=(0, r), hidden=h2),
+                                  dict(x=x1, dy=dy, w=pk1, scale=1.0, train_slice=(0, r), hidden=h1)])
+    elif mode == "fwd":
         ops.dat_forward(x, x, pk, 0.5)
     else:
         ops.dat_backward(x, dy, pk, 0.5, train_slice=(0, r) if mode == "bwdw" else None, need_dx=True)
@@ -59,7 +73,7 @@ names.update({120: "E2 c0.0: D full seen", 121: "E2 c0.0: tmem_ld issued", 122: 
               123: "E2 c0.0: tmem_ld done", 124: "E2 c0.0: math + st.shared done", 125: "E2 c0.0: proxy fence done",
               126: "E2 c0.0: arrived"})
 wg = {200: "wgrad: entry", 201: "wgrad: prologue done", 202: "wgrad: all MMAs issued", 203: "wgrad: accumulators complete",
-      204: "wgrad: reductions issued", 205: "wgrad: exit"}
+      204: "wgrad: split barrier passed (all partials stored)", 206: "wgrad: final slices written", 205: "wgrad: exit"}
 for i in range(10):
     wg[210 + i] = f"wgrad: stage {i} loads issued"
     wg[220 + i] = f"wgrad: stage {i} MMAs issued"

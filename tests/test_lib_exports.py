@@ -41,5 +41,5 @@ def test_entry_points_fail_loudly_without_a_gpu():
         return
     from feddat_b200 import _lib
     lib = _lib.load()
-    rc = lib.feddat_mkd_loss(None, None, None, None, None, 1, 100, 3.0, 0.5, 0.5, 1.0, 1, None)
+    rc = lib.feddat_mkd_loss(None, None, None, None, None, 1, 100, 3.0, 0.5, 0.5, 1.0, 1, None, None)
     assert rc != 0 and len(lib.feddat_last_error()) > 0       # an error code, never a silent CPU path
