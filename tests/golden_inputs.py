@@ -103,3 +103,36 @@ def grad_sketch(name, g, cols=8):
     rng = np.random.default_rng([77, zlib.crc32(name.encode())])
     omega = rng.standard_normal((g2.shape[1], cols)).astype(np.float32)
     return g2 @ omega
+
+
+# ------------------------------------------------------------------------------------------------ ALBEF step golden
+ALBEF_GOLDEN_CFG = {
+    "image_res": 64, "vit_depth": 2, "decoder_layers": 1, "distill": False,
+    "bert_config": {"attention_probs_dropout_prob": 0.0, "hidden_act": "gelu", "hidden_dropout_prob": 0.0,
+                    "hidden_size": 768, "initializer_range": 0.02, "intermediate_size": 3072, "layer_norm_eps": 1e-12,
+                    "max_position_embeddings": 512, "num_attention_heads": 12, "num_hidden_layers": 2,
+                    "pad_token_id": 0, "type_vocab_size": 2, "vocab_size": 3200, "fusion_layer": 1,
+                    "encoder_width": 768},
+}
+
+
+def albef_golden_batch(step):
+    """B = 2 images, questions of 8 / 6 tokens (padded to 8), k = [1, 2] answers of 5 / 4 / 3 tokens (padded to 5)."""
+    import torch
+    rng = np.random.default_rng(300 + step)
+    images = torch.from_numpy(rng.standard_normal((2, 3, 64, 64)).astype(np.float32))
+    q = np.zeros((2, 8), np.int64)
+    qm = np.zeros((2, 8), np.int64)
+    for b, n in enumerate((8, 6)):
+        q[b, 0], q[b, n - 1] = 101, 102
+        q[b, 1:n - 1] = rng.integers(1000, 3200, n - 2)
+        qm[b, :n] = 1
+    a = np.zeros((3, 5), np.int64)
+    am = np.zeros((3, 5), np.int64)
+    for i, n in enumerate((5, 4, 3)):
+        a[i, 0], a[i, n - 1] = 101, 102
+        a[i, 1:n - 1] = rng.integers(1000, 3200, n - 2)
+        am[i, :n] = 1
+    return {"images": images, "question_ids": torch.from_numpy(q), "question_mask": torch.from_numpy(qm),
+            "answer_ids": torch.from_numpy(a), "answer_mask": torch.from_numpy(am),
+            "weights": torch.tensor([1.0, 0.5, 0.5]), "n": [1, 2], "alpha": 0.0, "train": True}

@@ -1,0 +1,182 @@
+"""ALBEF path on the GPU (BASELINE configs[2]) against goldens from
+the REFERENCE's own ALBEF.forward + vendored ViT / BERT + Adapter + TaskTrainer.train_step
+(tests/golden/make_albef_step_golden.py; reduced depth, dropout 0, weights filled by parameter name on both
+sides): forward loss / logits in both adapter modes, the three-pass MKD train step with pre-Adam gradients,
+the fused KL + token-CE head against the oracle, rank_answer, and an executed ALBEF round loop.  GPU only."""
+from pathlib import Path
+from types import SimpleNamespace
+
+import numpy as np
+import pytest
+import torch
+
+import oracle
+from tests.golden_inputs import ALBEF_GOLDEN_CFG, albef_golden_batch, fill_params, grad_sketch
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def gold():
+    return np.load(Path(__file__).resolve().parent / "golden" / "albef_step_golden.npz")
+
+
+def fro(a, b):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-30))
+
+
+def build(rank, bf16):
+    from feddat_b200.train.prepare import default_args, place_on_gpu, prepare_model
+    args = default_args(encoder_name="albef_no_distill", ordered_cl_tasks=["art"], adapter_rank=rank,
+                        image_size=ALBEF_GOLDEN_CFG["image_res"], vit_depth=ALBEF_GOLDEN_CFG["vit_depth"],
+                        decoder_layers=ALBEF_GOLDEN_CFG["decoder_layers"], bert_overrides=ALBEF_GOLDEN_CFG["bert_config"])
+    model = prepare_model(args, place=False)
+    fill_params(model, seed=21)
+    sd = model.state_dict()                                         # task_trainer.py:36-45
+    for name in sd:
+        if "adapter_1" in name:
+            sd[name.replace("adapter_1", "adapter_2")].data.copy_(sd[name].data)
+    for n, p in model.named_parameters():
+        if "adapter_2" in n:
+            p.requires_grad = False
+    if bf16:
+        place_on_gpu(model)                                         # the product placement: bf16 frozen backbone
+    else:
+        model.to("cuda")
+        model.albef_model.device = torch.device("cuda")
+    model.train()
+    return model
+
+
+def dev(batch):
+    return {k: (v.cuda() if isinstance(v, torch.Tensor) else v) for k, v in batch.items()}
+
+
+@pytest.mark.parametrize("rank", [64, 256])
+@pytest.mark.parametrize("mode", ["gating", "adapter_1"])
+def test_albef_forward_matches_reference(gold, rank, mode):
+    """fp32 backbone, bf16 DAT operator: loss and decoder logits of reference ALBEF.forward (albef_model.py:69-145)."""
+    model = build(rank, bf16=False)
+    if mode == "gating":
+        model.activate_gating(); model.set_active_adapter("adapter_0")
+    else:
+        model.deactivate_gating(); model.set_active_adapter("adapter_1")
+    with torch.no_grad():
+        loss, logits = model("art", dev(albef_golden_batch(0)))
+    want_loss, want_logits = float(gold[f"r{rank}/fwd/{mode}/loss"]), gold[f"r{rank}/fwd/{mode}/logits"]
+    e_logits = fro(logits.float().cpu().numpy(), want_logits)
+    e_loss = abs(loss.item() - want_loss) / abs(want_loss)
+    print(f"\nALBEF forward r={rank} {mode}: logits rel Frobenius {e_logits:.4f}, loss rel {e_loss:.5f}")
+    assert e_logits < 1e-2 and e_loss < 1e-2
+
+
+@pytest.mark.parametrize("rank", [64, 256])
+def test_albef_train_step_matches_reference_trainer(gold, rank):
+    """The product configuration (bf16 frozen backbone, fp32 adapter / LM-head masters, fused KL + CE head) through
+    TaskTrainer.train_step against the reference trainer's fp32 run: step-0 logits, task losses and pre-Adam
+    gradients of pass B (adapter_1 + LM head) and pass C (adapter_0 + LM head); step-1 losses."""
+    from feddat_b200 import ops
+    from feddat_b200.modeling.albef import convert_batch_to_albef_input_dict
+    from feddat_b200.train.accelerator import Accelerator
+    from feddat_b200.train.task_trainer import TaskTrainer, get_polynomial_decay_schedule_with_warmup
+    model = build(rank, bf16=True)
+    steps, max_steps = (int(v) for v in gold["meta"])
+    tr = TaskTrainer()
+    tr.args = SimpleNamespace(optimizer_mode="dat", encoder_name="albef_no_distill", debug=0)
+    tr.accelerator = Accelerator(device="cuda")
+    tr.device, tr.task_key = torch.device("cuda"), "art"
+    tr.batch2inputs_converter = convert_batch_to_albef_input_dict
+    tr.weight_decay, tr.lr, tr.adam_epsilon, tr.kl_temp = 1e-2, float(gold["lr"]), 1e-8, float(gold["temp"])
+    wrapped = tr.accelerator.prepare(model)
+    opt = tr.create_optimizer(wrapped)
+    assert sum(len(g["params"]) for g in opt.param_groups) == int(gold[f"r{rank}/n_optimizer_tensors"])
+    sched = get_polynomial_decay_schedule_with_warmup(opt, int(max_steps * 0.1), max_steps, lr_end=0, power=1)
+    probes = {}
+    tr.grad_probe = lambda tag, _m: probes.__setitem__(
+        tag, {n: p.grad.detach().float().cpu().numpy() for n, p in model.named_parameters() if p.grad is not None})
+    n0 = ops.launch_count
+    rep = []
+    for step in range(steps):
+        probes.clear()
+        loss_0 = tr.train_step(wrapped, step, dev(albef_golden_batch(step)), opt, sched)
+        torch.cuda.synchronize()
+        want = float(gold[f"r{rank}/step{step}/loss_0"])
+        rep.append((step, "loss_0", abs(loss_0.item() - want) / want))
+        if step == 0:
+            for name, t in zip(("all", "1", "0"), tr.last_logits):
+                rep.append((step, f"logits_{name}", fro(t.float().cpu().numpy(), gold[f"r{rank}/step0/logits_{name}"])))
+            for tag in ("B", "C"):
+                gd = probes[tag]
+                names = {k.split("/sketch/")[1] for k in gold.files if k.startswith(f"r{rank}/step0/grad{tag}/sketch/")}
+                assert set(gd) == names, (tag, sorted(set(gd) ^ names)[:4])
+                num = den = 0.0
+                for n, g in gd.items():
+                    w = gold[f"r{rank}/step0/grad{tag}/sketch/{n}"].astype(np.float64)
+                    num += np.linalg.norm(grad_sketch(n, g).astype(np.float64) - w) ** 2
+                    den += np.linalg.norm(w) ** 2
+                rep.append((step, f"grad{tag} (all tensors)", (num / den) ** 0.5))
+                head = [n for n in gd if ".cls." in n]
+                hn = sum(np.linalg.norm(gd[n]) ** 2 for n in head) ** 0.5
+                hw = sum(float(gold[f"r{rank}/step0/grad{tag}/norm/{n}"]) ** 2 for n in head) ** 0.5
+                rep.append((step, f"grad{tag} LM-head norm", abs(hn - hw) / hw))
+    print(f"\nALBEF train_step r={rank} (bf16 backbone) vs the reference trainer (fp32):")
+    for step, what, e in rep:
+        print(f"  step{step}  {what:28s} {e:.4f}")
+    assert ops.launch_count > n0
+    for step, what, e in rep:
+        if what == "loss_0":
+            assert e < (1e-2 if step == 0 else 5e-2), (step, what, e)
+        elif what.startswith("logits"):
+            assert e < 2e-2, (what, e)
+        else:
+            assert e < 3e-2, (what, e)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("teacher_view", [False, True])
+def test_mkd_ce_loss_vs_oracle(dtype, teacher_view):
+    """feddat_mkd_ce_loss at the ALBEF vocabulary: value and d/dscores against the oracle (pinned to the reference's
+    torch expression by tests/test_albef_host.py), ignore_index rows, shifted-copy and [:, :-1]-view teachers."""
+    from feddat_b200 import ops
+    rng = np.random.default_rng(5)
+    n, La, C, B, T = 7, 5, 30522, 4, 2.0
+    s = (rng.standard_normal((n, La, C)) * 2).astype(np.float32)
+    tfull = (rng.standard_normal((n, La, C)) * 2).astype(np.float32)
+    lab = rng.integers(0, C, (n, La))
+    lab[1, 3:] = -100
+    lab[4, 2:] = -100
+    w = (rng.random(n) + 0.2).astype(np.float32)
+    sd = torch.from_numpy(s).cuda().to(dtype)
+    td = torch.from_numpy(tfull).cuda().to(dtype)
+    teacher = td[:, :-1, :] if teacher_view else td[:, :-1, :].contiguous()
+    loss3, ds = ops.mkd_ce_loss(sd, teacher, torch.from_numpy(lab).cuda(), torch.from_numpy(w).cuda() / B, T)
+    loss3b, dsb = ops.mkd_ce_loss(sd, teacher, torch.from_numpy(lab).cuda(), torch.from_numpy(w).cuda() / B, T)
+    torch.cuda.synchronize()
+    assert torch.equal(loss3, loss3b) and torch.equal(ds, dsb)                  # deterministic
+    L, kl, task, g = oracle.mkd_ce_total(sd.float().cpu().numpy(), td[:, :-1].float().cpu().numpy(), lab, w, B, T)
+    got = loss3.cpu().numpy()
+    tol = 1e-3
+    assert abs(got[0] - L) / abs(L) < tol and abs(got[1] - kl) / abs(kl) < tol and abs(got[2] - task) / abs(task) < tol
+    ge = np.abs(ds.float().cpu().numpy() - g).max() / np.abs(g).max()
+    assert ge < (1e-3 if dtype == torch.float32 else 4e-3), ge                   # bf16: one rounding of the result
+    assert float(ds[:, -1, :].abs().max()) == 0.0                                # the last position has no gradient
+
+
+def test_albef_rank_answer_and_round_loop():
+    """rank_answer (albef_model.py:171-228) through the wrapper's eval branch, and the executed federated round
+    loop with the ALBEF encoder: 1 round x 2 clients + eval, FedAvg of the 5 x 4 adapter_1 tensors."""
+    from feddat_b200.train.main import main
+    rec = {}
+    argv = ["--encoder_name", "albef_no_distill", "--pretrained_model_name", "random", "--climb_data_dir", "synthetic",
+            "--do_train", "--output_dir", "/tmp/feddat_albef_round", "--optimizer_mode", "dat", "--ordered_cl_tasks",
+            "art,abstract", "--comm_round", "1", "--batch_size", "3", "--val_batch_size", "3", "--synthetic_batches", "2",
+            "--image_size", "64", "--vit_depth", "2", "--decoder_layers", "1", "--adapter_rank", "32", "--lr", "1e-3",
+            "--num_epochs", "2", "--adapter_config", "pfeiffer"]
+    assert main(argv, record=rec) == 0
+    flats = [f.numpy() for f in rec["client_flats"][0]]
+    assert len(flats) == 2 and not np.array_equal(flats[0], flats[1])
+    assert np.array_equal(rec["global_flat"][0].numpy(), oracle.get_average_net(flats, [1, 1]))
+    names = rec["optimizer_names"][(0, "art")]
+    assert any("adapter_1" in n for n in names) and any(".cls." in n for n in names)
+    assert all(np.isfinite(v) and 0.0 <= v <= 100.0 for v in rec["eval_scores"][0])
