@@ -399,10 +399,31 @@ def run_ours(args):
             if name in kr:
                 kr[name]["eager_reference_us"] = us
                 kr[name]["vs_eager"] = round(us / kr[name]["us"], 2)
-        # dominant kernel of the step = the gating backward (pass C: dgrad + wgrad launches)
-        dom = kr[f"bwd_gating_M{B * 185}"]
-        big = kr[f"bwd_gating_M{12 * B * 185}"]
-        peak = peaks["tf_burst"]
+        for d_ in ("fwd", "bwd"):                       # the grouped site launch vs the two eager reference calls
+            k_ = f"site_{d_}_grouped_M{2 * B * 185}"
+            if k_ in kr:
+                us = eager[f"{d_}_gating_M{B * 185}"] + eager[f"{d_}_single_M{B * 185}"]
+                kr[k_]["eager_reference_us"] = round(us, 2)
+                kr[k_]["vs_eager"] = round(us / kr[k_]["us"], 2)
+        # Dominant DAT work of the step = the backward of one adapter site in the batched MKD schedule: ONE grouped
+        # data-gradient launch + ONE grouped weight-gradient launch over [5920 gating rows (R = 256) | 5920
+        # adapter_1 rows (R = 128)].  Algorithmic work: 12 d r + 8 d r = 20 d r FLOP per row
+        # pair, 6 d bytes per row (read X, read dY, write dX) -> HBM-bound at the measured peaks.
+        Mh = B * 185
+        dom = kr[f"site_bwd_grouped_M{2 * Mh}"]
+        fwd = kr[f"site_fwd_grouped_M{2 * Mh}"]
+        big = kr[f"bwd_gating_M{12 * Mh}"]
+        alg_bytes, alg_flops = 6 * D * 2 * Mh, 20 * D * RANK * Mh
+        traffic, traffic_src = None, None
+        tp = ROOT / "profiles" / "r2_dat_traffic.json"
+        if tp.exists():
+            tj = json.loads(tp.read_text())
+            k = tj["kernels"]
+            if "site_dgrad_grouped" in k and "site_wgrad_grouped" in k:
+                traffic = sum(k[n]["dram_read_bytes"] + k[n]["dram_write_bytes"] for n in ("site_dgrad_grouped", "site_wgrad_grouped"))
+                traffic_src = "profiles/r2_dat_traffic.json (" + tj["source"] + ")"
+        # share of the DAT kernels in the step, from the launches the step makes (12 sites x fwd / dgrad / wgrad)
+        dat_us = 12 * (fwd["us"] + dom["us"])
         result = {
             "metric": METRIC, "value": round(value, 2), "unit": "samples/s", "n_gpus": world, "steps": K,
             "warmup": W, "ms_per_step": round(ms / K, 3), "higher_is_better": True, "scaling": "weak",
@@ -418,17 +439,23 @@ def run_ours(args):
                     "ms_per_step": round(ms_e2e / K, 3)},
             "gpu_launches": launches,
             "allreduce_us": allreduce_us,
-            "roofline": {"kernel": "dat_bwd gating r=128 (dgrad + wgrad launches), M=5920 rows/site",
-                         "bound": "tensor", "achieved": dom["tflops"], "peak": peak, "unit": "TFLOP/s",
-                         "frac": round(dom["tflops"] / peak, 4),
-                         # dram__bytes_read.sum + dram__bytes_write.sum of the two launches, from the round's
-                         # ncu --set full capture (profiles/r1_dat_kernels_v14_raw.csv: dgrad 12.96 MB + wgrad
-                         # 22.05 MB read, 0 written inside the kernels -- the 18 MB of outputs stay dirty in
-                         # L2); algorithmic bytes = 6 d M = 27.3 MB
-                         "traffic": 35.0e6, "traffic_unit": "bytes per dgrad + wgrad launch pair (ncu)",
-                         "peak_source": f"{peaks['source']} bf16_tflops (burst: kernel timed alone)",
-                         "algorithmic_flops_per_launch": 12 * D * RANK * B * 185,
-                         "steady_state_M71040": {"achieved": big["tflops"], "frac": round(big["tflops"] / peak, 4)}},
+            "roofline": {"kernel": "DAT backward of one adapter site, batched MKD schedule: grouped dgrad launch + grouped "
+                                   f"wgrad launch over {Mh} gating rows (R = {2 * RANK}) + {Mh} adapter_1 rows (R = {RANK})",
+                         "bound": "hbm", "achieved": dom["gbs"], "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                         "frac": round(dom["gbs"] / peaks["hbm_gbs"], 4),
+                         "traffic": traffic, "traffic_unit": "dram read + write bytes of the two launches (ncu --set full)",
+                         "traffic_source": traffic_src,
+                         "algorithmic_bytes_per_launch_pair": alg_bytes, "algorithmic_flops_per_launch_pair": alg_flops,
+                         "tensor_view": {"achieved_tflops": dom["tflops"], "peak": peaks["tf_burst"],
+                                         "frac": round(dom["tflops"] / peaks["tf_burst"], 4)},
+                         "peak_source": f"{peaks['source']} hbm_gbs / bf16_tflops burst (kernels timed alone, CUDA events, cold inputs)",
+                         "us": dom["us"],
+                         "forward_same_site": {"us": fwd["us"], "achieved": fwd["gbs"], "frac": fwd["frac_of_roofline"]},
+                         "fwd_plus_bwd_site": {"us": round(fwd["us"] + dom["us"], 2),
+                                               "frac": round((10 * D * 2 * Mh) / ((fwd["us"] + dom["us"]) * 1e-6) / 1e9 / peaks["hbm_gbs"], 4)},
+                         "dat_us_per_step_from_these": round(dat_us, 1),
+                         "steady_state_M71040": {"kernel": "bwd gating, single group (dat_pipe_kernel + wgrad)",
+                                                 "achieved_tflops": big["tflops"], "frac": round(big["tflops"] / peaks["tf_burst"], 4)}},
             "kernels": kr,
         }
         if world == 1 and not args.no_cpu_baseline:
@@ -440,6 +467,124 @@ def run_ours(args):
 
 
 # ------------------------------------------------------------------------------------------------
+ALBEF_WORKLOAD = ("ALBEF (ViT-B/16 @384 + 12-layer BERT question encoder + 6-layer LM-head answer decoder) + DAT rank-256 "
+                  "bf16, 30 adapter sites, synthetic VQA batch=16 (32 answers x 6 tokens, vocabulary 30522), MKD tau=2.0 "
+                  "(BASELINE configs[2])")
+
+
+def run_albef(args):
+    """``--workload albef``: one TaskTrainer.train_step of the ALBEF path (three forwards, two backwards, two AdamW
+    steps in the reference order -- BERT has dropout, so no pass is shared; eager launch) per step.  An extra line
+    beside the headline ViLT workload; same timing rules."""
+    import torch
+    import torch.distributed as dist
+    from feddat_b200 import ops
+    from feddat_b200.modeling.albef import convert_batch_to_albef_input_dict
+    from feddat_b200.synthetic import albef_to_device, make_albef_batch
+    from feddat_b200.train.accelerator import Accelerator
+    from feddat_b200.train.prepare import default_args, place_on_gpu, prepare_model
+    from feddat_b200.train.task_trainer import TaskTrainer, get_polynomial_decay_schedule_with_warmup
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    device = torch.device("cuda", local_rank)
+    torch.cuda.set_device(device)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+    BA, RA = 16, 256
+    torch.manual_seed(2000)
+    a = default_args(encoder_name="albef_no_distill", ordered_cl_tasks=[f"synth{rank % 8}"], adapter_rank=RA, image_size=384)
+    model = prepare_model(a, place=False)
+    sd = model.state_dict()
+    for name in sd:
+        if "adapter_1" in name:
+            sd[name.replace("adapter_1", "adapter_2")].data.copy_(sd[name].data)
+    for n, p in model.named_parameters():
+        if "adapter_2" in n:
+            p.requires_grad = False
+    place_on_gpu(model, device)
+    tr = TaskTrainer()
+    tr.args = SimpleNamespace(optimizer_mode="dat", encoder_name="albef_no_distill", debug=0)
+    tr.accelerator = Accelerator(device=device)
+    tr.device, tr.task_key = torch.device(device), a.ordered_cl_tasks[0]
+    tr.batch2inputs_converter = convert_batch_to_albef_input_dict
+    tr.weight_decay, tr.lr, tr.adam_epsilon, tr.kl_temp = 1e-2, 1e-4, 1e-8, TEMP
+    wrapped = tr.accelerator.prepare(model)
+    opt = tr.create_optimizer(wrapped)
+    sched = get_polynomial_decay_schedule_with_warmup(opt, 100, 100000, lr_end=0, power=1)
+    wrapped.train()
+    K, W = args.steps, args.warmup
+    host = [make_albef_batch(BA, 384, seed=(2000 + rank) * 1000 + i, client=rank % 8, pin=True) for i in range(min(K + W, 6))]
+    devb = [albef_to_device(b, device) for b in host]
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, n):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(n):
+            fn(i)
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=device)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = t.item()
+        return ms
+
+    for i in range(W):
+        tr.train_step(wrapped, i, devb[i % len(devb)], opt, sched)
+    l0 = ops.launch_count
+    ms = timed(lambda i: tr.train_step(wrapped, i, devb[i % len(devb)], opt, sched), K)
+    launches = ops.launch_count - l0
+    ms_e2e = timed(lambda i: tr.train_step(wrapped, i, albef_to_device(host[i % len(host)], device), opt, sched).item(), K)
+    res = None
+    if rank == 0:
+        h2d = sum(v.numel() * v.element_size() for v in host[0].values() if hasattr(v, "numel"))
+        # the fused MKD head alone, at this workload's logits: 32 answers x 6 tokens x 30522 bf16
+        g = torch.Generator(device=device).manual_seed(0)
+        n_seq, La, Cv = sum(host[0]["n"]), host[0]["answer_ids"].shape[1], 30522
+        sets = [(torch.randn(n_seq, La, Cv, device=device, generator=g).to(torch.bfloat16),
+                 torch.randn(n_seq, La, Cv, device=device, generator=g).to(torch.bfloat16)) for _ in range(24)]
+        lab = devb[0]["answer_ids"].masked_fill(devb[0]["answer_ids"] == 0, -100)
+        sw = devb[0]["weights"] / BA
+        ts = []
+        for i in range(3 + 12):
+            sc, te = sets[i % len(sets)]
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda._sleep(500_000)
+            e0.record()
+            ops.mkd_ce_loss(sc, te[:, :-1], lab, sw, TEMP)
+            e1.record()
+            torch.cuda.synchronize()
+            if i >= 3:
+                ts.append(e0.elapsed_time(e1) * 1e-3)
+        t_head = statistics.mean(ts)
+        head_bytes = 3 * n_seq * La * Cv * 2
+        peaks = read_peaks()
+        res = {"metric": "VQA samples/sec/box (ALBEF+DAT bf16)", "value": round(world * BA * K / (ms * 1e-3), 2),
+               "unit": "samples/s", "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": round(ms / K, 3),
+               "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+               "config": {"workload": ALBEF_WORKLOAD, "global_batch": BA * world, "clients": world,
+                          "step_launch": "eager", "init": "seeded random ALBEF (no checkpoint on the box)"},
+               "e2e": {"value": round(world * BA * K / (ms_e2e * 1e-3), 2), "unit": "samples/s",
+                       "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4, "ms_per_step": round(ms_e2e / K, 3)},
+               "gpu_launches": launches,
+               "kernels": {"mkd_ce_loss": {"us": round(t_head * 1e6, 2), "rows": n_seq * La, "C": Cv, "dtype": "bf16",
+                                           "algorithmic_bytes": head_bytes,
+                                           "gbs": round(head_bytes / t_head / 1e9, 1),
+                                           "frac_of_hbm_peak": round(head_bytes / t_head / 1e9 / peaks["hbm_gbs"], 4)}}}
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return res
+
+
 def cpu_reference(steps: int, warmup: int, sample_batch: int):
     """The reference algorithm (oracle/step_oracle.py, a PyTorch-CPU port pinned to the reference's
     own trainer by tests/test_step_oracle.py) on all host cores: fp32, same model / image / text
@@ -495,11 +640,18 @@ def main():
                          "4 when more than 30 CPU steps are requested, to stay within minutes)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--eager", action="store_true", help="launch train_step eagerly instead of replaying its CUDA graph")
+    ap.add_argument("--workload", default="vilt", choices=["vilt", "albef"],
+                    help="vilt = BASELINE configs[1] (the headline metric); albef = configs[2], an extra line")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3
     if args.cpu_batch is None:
         args.cpu_batch = B if (args.impl != "reference" or args.steps + args.warmup <= 30) else 4
+    if args.workload == "albef" and args.impl == "ours":
+        res = run_albef(args)
+        if res is not None:
+            print(json.dumps(res), flush=True)
+        return
     res = run_reference(args) if args.impl == "reference" else run_ours(args)
     if res is not None:
         print(json.dumps(res), flush=True)

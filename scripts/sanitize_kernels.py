@@ -1,0 +1,63 @@
+"""Small driver for compute-sanitizer (memcheck / racecheck / synccheck) over the DAT kernels:
+    compute-sanitizer --tool memcheck  python scripts/sanitize_kernels.py 1 129 5920 25003
+    compute-sanitizer --tool racecheck python scripts/sanitize_kernels.py 1 129 5920
+Runs, per row count M: single-group forward / saved-mode backward (dat_fused_kernel or dat_pipe_kernel by
+size), the grouped launches over [M gating rows | M adapter_1 rows], the deterministic weight-gradient kernel,
+the batched weight pack and both MKD heads; checks the results against torch so that a sanitizer run is also a
+functional run."""
+import sys
+from pathlib import Path
+
+import torch
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT))
+from feddat_b200 import ops  # noqa: E402
+
+dev = torch.device("cuda", 0)
+g = torch.Generator(device=dev).manual_seed(0)
+r = 64
+
+
+def branches(nb):
+    return [[torch.randn(r, 768, device=dev, generator=g) * 0.05, torch.randn(r, device=dev, generator=g) * 0.1,
+             torch.randn(768, r, device=dev, generator=g) * 0.05, torch.randn(768, device=dev, generator=g) * 0.1]
+            for _ in range(nb)]
+
+
+def ref_fwd(x, brs, scale):
+    up = 0
+    for dw, db, uw, ub in brs:
+        h = torch.relu(x.float() @ dw.to(torch.bfloat16).float().T + db).to(torch.bfloat16).float()
+        up = up + h @ uw.to(torch.bfloat16).float().T + ub
+    return x.float() + (scale * up).to(torch.bfloat16).float()
+
+
+for M in [int(a) for a in sys.argv[1:]] or [129]:
+    b2, b1 = branches(2), branches(1)
+    pk2, pk1 = ops.pack_weights_batched([ops.PackSpec(*[[b[i] for b in bs] for i in range(4)]) for bs in (b2, b1)])
+    x = torch.randn(2 * M, 768, device=dev, generator=g).to(torch.bfloat16)
+    dy = torch.randn(2 * M, 768, device=dev, generator=g).to(torch.bfloat16)
+    y, dx = torch.empty_like(x), torch.empty_like(x)
+    (_, h2), (_, h1) = ops.dat_forward_grouped([dict(x=x[:M], res=x[:M], w=pk2, scale=0.5, out=y[:M], save_hidden=True),
+                                                dict(x=x[M:], res=x[M:], w=pk1, scale=1.0, out=y[M:], save_hidden=True)])
+    res = ops.dat_backward_grouped([dict(x=x[:M], dy=dy[:M], w=pk2, scale=0.5, train_slice=(0, r), hidden=h2, dx_out=dx[:M]),
+                                    dict(x=x[M:], dy=dy[M:], w=pk1, scale=1.0, train_slice=(0, r), hidden=h1, dx_out=dx[M:])])
+    y1, hh = ops.dat_forward(x[:M], x[:M], pk2, 0.5, save_hidden=True)
+    dx1, gr1 = ops.dat_backward(x[:M], dy[:M], pk2, 0.5, train_slice=(0, r), hidden=hh)
+    torch.cuda.synchronize()
+    e_y = ((y[:M].float() - ref_fwd(x[:M], b2, 0.5)).abs().max() / y[:M].float().abs().max()).item()
+    e_y1 = ((y[M:].float() - ref_fwd(x[M:], b1, 1.0)).abs().max() / y[M:].float().abs().max()).item()
+    assert e_y < 1e-2 and e_y1 < 1e-2, (e_y, e_y1)
+    assert torch.equal(y1, y[:M]) and torch.equal(dx1, dx[:M])
+    print(f"M={M}: grouped / single forward + backward ok (fwd err {e_y:.1e} / {e_y1:.1e})")
+
+lg = torch.randn(32, 100, device=dev, generator=g)
+ops.mkd_loss(lg, torch.randn(32, 100, device=dev, generator=g), (torch.rand(32, 100, device=dev, generator=g) < 0.02).float(), 2.0)
+sc = torch.randn(5, 4, 3202, device=dev, generator=g).to(torch.bfloat16)
+lab = torch.randint(0, 3202, (5, 4), device=dev, generator=g)
+lab[1, 2:] = -100
+ops.mkd_ce_loss(sc, torch.randn(5, 4, 3202, device=dev, generator=g).to(torch.bfloat16)[:, :-1], lab,
+                torch.rand(5, device=dev, generator=g), 2.0)
+torch.cuda.synchronize()
+print("mkd heads ok")

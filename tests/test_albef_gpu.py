@@ -128,9 +128,9 @@ def test_albef_train_step_matches_reference_trainer(gold, rank):
         if what == "loss_0":
             assert e < (1e-2 if step == 0 else 5e-2), (step, what, e)
         elif what.startswith("logits"):
-            assert e < 2e-2, (what, e)
+            assert e < 1.5e-2, (what, e)        # measured 0.9e-2 (bf16 backbone vs the fp32 reference run)
         else:
-            assert e < 3e-2, (what, e)
+            assert e < 2e-2, (what, e)          # measured 0.8e-2 .. 1.1e-2
 
 
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
