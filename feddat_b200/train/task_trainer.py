@@ -8,6 +8,7 @@ side effects (detach points, requires_grad toggles, optimizer / scheduler steppe
 """
 from __future__ import annotations
 
+import contextlib
 import os
 from typing import Dict
 
@@ -38,6 +39,14 @@ class _MkdLossFunction(torch.autograd.Function):
         (dlogits,) = ctx.saved_tensors
         g = (dlogits * g_total).view(ctx.shape)
         return g.to(ctx.in_dtype), None, None, None, None, None
+
+
+def _nvtx(name: str):
+    """NVTX range around a phase of the MKD schedule (visible in nsys / ncu --nvtx timelines).
+    A no-op without CUDA."""
+    if torch.cuda.is_available():
+        return torch.cuda.nvtx.range(f"feddat/{name}")
+    return contextlib.nullcontext()
 
 
 class _MkdCeFunction(torch.autograd.Function):
@@ -236,7 +245,8 @@ class TaskTrainer(nn.Module):
         forward and once backward over 2B rows instead of twice / twice over B rows (fuller GEMM waves,
         half the launches).  Checked against the reference trainer by tests/test_train_step_gpu.py."""
         inner = model.module
-        enc = inner.encode_dual(**self.batch2inputs_converter(batch))
+        with _nvtx("batched_fwd_A+B"):
+            enc = inner.encode_dual(**self.batch2inputs_converter(batch))
         b = enc.shape[0] // 2
         leaf = enc.detach().requires_grad_(True)                     # head gradients stop here until step 4
         enc_a, enc_b = leaf[:b], leaf[b:]
@@ -253,7 +263,8 @@ class TaskTrainer(nn.Module):
         logits_0 = inner.classify(self.task_key, enc_a)              # (C): updated head
         L_0, loss_0 = self._objective(logits_0, logits_1, target, None)
         self.accelerator.backward(L_0)                               # head grads + d enc_A
-        enc.backward(leaf.grad)                                      # adapter_0 (rows A) and adapter_1 (rows B)
+        with _nvtx("batched_bwd_C+B"):
+            enc.backward(leaf.grad)                                  # adapter_0 (rows A) and adapter_1 (rows B)
         self._probe("BC", model)
 
         a1 = getattr(self, "_a1_params", None)
@@ -301,15 +312,17 @@ class TaskTrainer(nn.Module):
             with torch.no_grad():
                 logits_all = inner.classify(self.task_key, enc_all)
         else:
-            with torch.no_grad():                                    # (A) :283-287
+            with torch.no_grad(), _nvtx("pass_A_gating_nograd"):     # (A) :283-287
                 model.module.activate_gating()
                 _, logits_all = self.forward_pass(model, batch, do_eval=False)
 
         model.module.deactivate_gating()                             # (B) :290-308
         model.module.set_active_adapter("adapter_1")
-        output_1_0, logits_1 = self.forward_pass(model, batch, do_eval=False)
-        L_1, _ = self._objective(logits_1, logits_all, target, output_1_0 if albef else None)
-        self.accelerator.backward(L_1)
+        with _nvtx("pass_B_adapter1_fwd"):
+            output_1_0, logits_1 = self.forward_pass(model, batch, do_eval=False)
+            L_1, _ = self._objective(logits_1, logits_all, target, output_1_0 if albef else None)
+        with _nvtx("pass_B_adapter1_bwd"):
+            self.accelerator.backward(L_1)
         self._probe("B", model)
         if optimizer is not None:
             optimizer.step()
@@ -324,7 +337,8 @@ class TaskTrainer(nn.Module):
         else:
             output_0_0, logits_0 = self.forward_pass(model, batch, do_eval=False)
         L_0, loss_0 = self._objective(logits_0, logits_1, target, output_0_0 if albef else None)
-        self.accelerator.backward(L_0)
+        with _nvtx("pass_C_gating_bwd"):
+            self.accelerator.backward(L_0)
         self._probe("C", model)
         if optimizer is not None:
             optimizer.step()
