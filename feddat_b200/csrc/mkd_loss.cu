@@ -11,7 +11,10 @@
 //
 // Layout: one warp per row when C <= 2048 (ViLT answer heads: C = 100), one 1024-thread CTA per row otherwise
 // (ALBEF vocabulary: C = 30522).  Two passes over the row: (1) online max / sum-exp of the operands, (2) KL
-// terms, task terms and the gradient; the second pass re-reads the row from L1/L2.  HBM-bound.
+// terms, task terms and the gradient; the second pass re-reads the row from L1/L2.  The byte floor is 2 reads +
+// 1 write of the logits; at the ALBEF batch's size (198 rows x 30 522) the kernel is instruction / MUFU bound
+// instead (six exponentials per element: three running sums and three probabilities; ncu: XU pipe 43 %, 18 M
+// warp instructions, 41 us for 36 MB -- profiles/r2_summary.md).
 //
 // Deterministic: every row's (kl, task) pair goes to a caller-provided workspace and ONE block sums the rows in a
 // fixed order (round 1 accumulated per-CTA partials with float atomics: run-to-run different low bits).
