@@ -36,6 +36,8 @@ EXPORTED_SYMBOLS = (
     "feddat_ln_bwd",
     "feddat_gelu_fwd",
     "feddat_gelu_bwd",
+    "feddat_mlp_fc1_gelu_fwd",
+    "feddat_mlp_fc2_dgelu_bwd",
 )
 # include/feddat_b200_debug.h: only in the -DFEDDAT_DEBUG twin (libfeddat_sm100_dbg.so), tests / scripts
 DEBUG_SYMBOLS = (
@@ -159,6 +161,11 @@ def _bind(lib: ctypes.CDLL, debug: bool) -> ctypes.CDLL:
     lib.feddat_gelu_fwd.argtypes = [c_void_p, c_void_p, c_int64, c_int, c_void_p]
     lib.feddat_gelu_bwd.restype = c_int
     lib.feddat_gelu_bwd.argtypes = [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p]
+    lib.feddat_mlp_fc1_gelu_fwd.restype = c_int
+    lib.feddat_mlp_fc1_gelu_fwd.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int, c_int,
+                                            c_void_p]
+    lib.feddat_mlp_fc2_dgelu_bwd.restype = c_int
+    lib.feddat_mlp_fc2_dgelu_bwd.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int, c_int, c_void_p]
     if not debug:
         return lib
     lib.feddat_probe_gemm.restype = c_int

@@ -15,6 +15,7 @@
 #include <cuda_bf16.h>
 
 #include "feddat_b200.h"
+#include "gelu_math.cuh"
 #include "host_common.h"
 
 namespace fd {
@@ -36,22 +37,6 @@ __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
     w[i] = *reinterpret_cast<uint32_t*>(&t);
   }
   return make_uint4(w[0], w[1], w[2], w[3]);
-}
-
-// (Phi(x), exp(-x^2 / 2))
-__device__ __forceinline__ void gelu_terms(float x, float& cdf, float& e) {
-  const float z = fabsf(x) * 0.70710678118654752f;
-  // rcp.approx / ex2.approx (1-2 ulp): the IEEE-rounded forms compile to slow-path calls and ~40
-  // instructions per element
-  float t;
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, z, 1.f)));
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-1.4426950408889634f * z * z));
-  float pl = fmaf(t, 1.061405429f, -1.453152027f);
-  pl = fmaf(t, pl, 1.421413741f);
-  pl = fmaf(t, pl, -0.284496736f);
-  pl = fmaf(t, pl, 0.254829592f);
-  const float q = 0.5f * t * pl * e;
-  cdf = x >= 0.f ? 1.f - q : q;
 }
 
 template <bool kBwd>

@@ -27,6 +27,7 @@ import torch
 from .. import ops
 
 _warned = set()
+FUSE_MLP_GELU = True      # A/B switch (tests, bench): False = cuBLAS GEMM + streaming GELU kernels
 
 
 def _fallback_once(what: str, why: str) -> None:
@@ -79,6 +80,68 @@ class _Gelu(torch.autograd.Function):
     def backward(ctx, gy):
         (x,) = ctx.saved_tensors
         return ops.gelu_bwd(gy.contiguous(), x)
+
+
+class _FrozenMlp(torch.autograd.Function):
+    """h = res_b + gelu(ln2 W_in^T + b_in) W_out^T for the FROZEN MLP of a ViLT block (HF ViltIntermediate +
+    ViltOutput.dense; res_b already carries the second dense layer's bias).  The exact GELU rides in the epilogue of
+    this repo's tcgen05 GEMM (feddat_mlp_fc1_gelu_fwd) and its derivative in the epilogue of the backward's first
+    GEMM (feddat_mlp_fc2_dgelu_bwd); the two 768-wide products stay cuBLAS.  No weight gradients: everything here
+    is frozen (main.py:138-139)."""
+
+    @staticmethod
+    def forward(ctx, ln2, res_b, w_in, b_in, w_out, w_out_t):
+        shape = res_b.shape
+        pre, act = ops.mlp_fc1_gelu(ln2.reshape(-1, ln2.shape[-1]), w_in, b_in)
+        h = torch.addmm(res_b.reshape(-1, shape[-1]), act, w_out.t())
+        ctx.save_for_backward(pre, w_in, w_out_t)
+        ctx.shape = shape
+        return h.view(shape)
+
+    @staticmethod
+    def backward(ctx, dh):
+        pre, w_in, w_out_t = ctx.saved_tensors
+        dh2 = dh.reshape(-1, dh.shape[-1]).contiguous()
+        dpre = ops.mlp_fc2_dgelu(dh2, w_out_t, pre)
+        d_ln2 = torch.mm(dpre, w_in)
+        return d_ln2.view(*ctx.shape[:-1], w_in.shape[1]), dh, None, None, None, None
+
+
+def _transposed_weight(dense: torch.nn.Linear) -> torch.Tensor:
+    """[in, out] copy of a FROZEN Linear's [out, in] weight (K-major B operand of the backward GEMM), cached on the
+    module and rebuilt when the weight's storage or version changes (load_state_dict, dtype casts)."""
+    w = dense.weight
+    key = (w.data_ptr(), w._version, w.dtype)
+    cached = getattr(dense, "_feddat_wt", None)
+    if cached is None or cached[0] != key:
+        with torch.no_grad():
+            cached = (key, w.detach().t().contiguous())
+        dense._feddat_wt = cached
+    return cached[1]
+
+
+def _bias_f32(dense: torch.nn.Linear) -> torch.Tensor:
+    """fp32 copy of a FROZEN Linear's bias (what the fused epilogue adds to its fp32 accumulator), cached like
+    ``_transposed_weight``."""
+    b = dense.bias
+    key = (b.data_ptr(), b._version, b.dtype)
+    cached = getattr(dense, "_feddat_b32", None)
+    if cached is None or cached[0] != key:
+        with torch.no_grad():
+            cached = (key, b.detach().float().contiguous())
+        dense._feddat_b32 = cached
+    return cached[1]
+
+
+def _mlp_ok(inter_mod, dense: torch.nn.Linear, h: torch.Tensor) -> bool:
+    """The fused GEMM + GELU path: exact-erf GELU, frozen bf16 Linear layers with biases, tile-aligned widths."""
+    act = inter_mod.intermediate_act_fn
+    exact_gelu = type(act).__name__ == "GELUActivation" or (isinstance(act, torch.nn.GELU) and act.approximate == "none")
+    d1 = getattr(inter_mod, "dense", None)
+    return (exact_gelu and isinstance(d1, torch.nn.Linear) and d1.bias is not None and d1.weight.dtype == torch.bfloat16
+            and h.dtype == torch.bfloat16 and h.is_cuda and not d1.weight.requires_grad and not d1.bias.requires_grad
+            and d1.weight.is_contiguous() and dense.weight.is_contiguous()
+            and d1.out_features % 256 == 0 and d1.in_features % 64 == 0 and dense.in_features == d1.out_features)
 
 
 def intermediate(mod, h: torch.Tensor) -> torch.Tensor:
@@ -140,6 +203,13 @@ def fast_vilt_layer_forward(self, hidden_states, attention_mask=None, output_att
         # dense layer's bias pre-added; second residual = the GEMM's beta = 1 epilogue; then the DAT site
         dense = self.output.layer.dense
         res_b, ln2 = add_layer_norm(self.layernorm_after, attention_output, hidden_states, bias2=dense.bias)
+        if FUSE_MLP_GELU and _mlp_ok(self.intermediate, dense, ln2) and ln2.is_contiguous():
+            # first GEMM + exact GELU (and, in backward, the second GEMM's data gradient + GELU') in one kernel each
+            d1 = self.intermediate.dense
+            h = _FrozenMlp.apply(ln2, res_b, d1.weight, _bias_f32(d1), dense.weight, _transposed_weight(dense))
+            return (self.output.adapter(h, h),)
+        _fallback_once("fast_vilt_layer_forward", "MLP not a frozen bf16 768 -> 3072 -> 768 pair with the exact GELU: "
+                                                   "GEMM + streaming GELU kernels")
         inter = intermediate(self.intermediate, ln2)
         h = torch.addmm(res_b.reshape(-1, res_b.shape[-1]), inter.reshape(-1, inter.shape[-1]), dense.weight.t())
         h = h.view(res_b.shape)

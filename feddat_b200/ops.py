@@ -467,3 +467,47 @@ def gelu_bwd(dy: torch.Tensor, x: torch.Tensor) -> torch.Tensor:
                "feddat_gelu_bwd")
     _count()
     return dx
+
+
+def _check_bf16_2d(t: torch.Tensor, name: str) -> None:
+    if not (t.is_cuda and t.dtype == torch.bfloat16 and t.dim() == 2 and t.is_contiguous() and t.data_ptr() % 16 == 0):
+        raise _lib.FeddatError(f"{name}: expected a contiguous 16-byte aligned CUDA bf16 matrix, got {tuple(t.shape)} "
+                               f"{t.dtype} {t.device}")
+
+
+def mlp_fc1_gelu(a: torch.Tensor, w: torch.Tensor, bias: torch.Tensor):
+    """(pre, act) = (a w^T + bias, gelu(pre)) with the exact GELU in the GEMM's epilogue (feddat_mlp_fc1_gelu_fwd).
+    a [M, K], w [N, K] (nn.Linear weight): bf16; bias [N]: fp32 (a widened copy of the frozen bias)."""
+    lib = _lib.load()
+    _check_bf16_2d(a, "mlp_fc1_gelu a")
+    _check_bf16_2d(w, "mlp_fc1_gelu w")
+    M, K = a.shape
+    N = w.shape[0]
+    if w.shape[1] != K or bias.shape != (N,) or bias.dtype != torch.float32 or not bias.is_contiguous():
+        raise _lib.FeddatError("mlp_fc1_gelu: shapes / dtypes of w, bias do not match a")
+    pre = torch.empty(M, N, device=a.device, dtype=torch.bfloat16)
+    act = torch.empty(M, N, device=a.device, dtype=torch.bfloat16)
+    rc = lib.feddat_mlp_fc1_gelu_fwd(_lib.ptr(a), _lib.ptr(w), _lib.ptr(bias), _lib.ptr(pre), _lib.ptr(act), M, N, K,
+                                     DTYPE_BF16, _lib.stream_ptr())
+    _lib.check(rc, "feddat_mlp_fc1_gelu_fwd")
+    _count()
+    return pre, act
+
+
+def mlp_fc2_dgelu(dy: torch.Tensor, w2t: torch.Tensor, pre: torch.Tensor) -> torch.Tensor:
+    """dpre = (dy w2t^T) * gelu'(pre) (feddat_mlp_fc2_dgelu_bwd).  dy [M, K], w2t [N, K] = the transpose of the
+    second dense layer's weight [K, N], pre [M, N]: bf16."""
+    lib = _lib.load()
+    _check_bf16_2d(dy, "mlp_fc2_dgelu dy")
+    _check_bf16_2d(w2t, "mlp_fc2_dgelu w2t")
+    _check_bf16_2d(pre, "mlp_fc2_dgelu pre")
+    M, K = dy.shape
+    N = w2t.shape[0]
+    if w2t.shape[1] != K or tuple(pre.shape) != (M, N):
+        raise _lib.FeddatError("mlp_fc2_dgelu: shapes of w2t / pre do not match dy")
+    out = torch.empty_like(pre)
+    rc = lib.feddat_mlp_fc2_dgelu_bwd(_lib.ptr(dy), _lib.ptr(w2t), _lib.ptr(pre), _lib.ptr(out), M, N, K, DTYPE_BF16,
+                                      _lib.stream_ptr())
+    _lib.check(rc, "feddat_mlp_fc2_dgelu_bwd")
+    _count()
+    return out

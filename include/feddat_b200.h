@@ -249,6 +249,23 @@ int feddat_ln_bwd(const void* dy, const void* dsum, const void* s, const void* w
 int feddat_gelu_fwd(const void* x, void* y, int64_t n, int dtype, void* stream);
 int feddat_gelu_bwd(const void* dy, const void* x, void* dx, int64_t n, int dtype, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * The frozen MLP of the block around each ViLT DAT site with the exact GELU fused into the GEMM epilogue
+ * (HF ViltIntermediate: dense 768 -> 3072 + GELU, feeding the ViltOutput.dense that the reference wraps,
+ * src/modeling/adaptered_output.py:67-79):
+ *   feddat_mlp_fc1_gelu_fwd    pre = A W^T + bias,  act = gelu(pre)                 (both written, bf16)
+ *   feddat_mlp_fc2_dgelu_bwd   dpre = (dY W2T^T) * gelu'(pre)
+ * A, dY: [M, K] bf16 row-major; W, W2T: [N, K] bf16 row-major (K contiguous: W is nn.Linear(K, N).weight, W2T the
+ * TRANSPOSE of ViltOutput.dense.weight [K, N], made once -- the backbone is frozen); bias [N] FP32 (a widened copy
+ * of the frozen bias, made once); pre, act, dpre: [M, N] bf16.  N a multiple of 256, K a multiple of 64, all
+ * pointers 16-byte aligned.  Every output is rounded ONCE, from the fp32 accumulator: act = bf16(gelu(acc + b)),
+ * dpre = bf16(acc * gelu'(pre)) -- one rounding fewer than the unfused sequence, which rounds the GEMM output first.
+ */
+int feddat_mlp_fc1_gelu_fwd(const void* A, const void* W, const void* bias, void* pre_out, void* act_out, int64_t M,
+                            int N, int K, int dtype, void* stream);
+int feddat_mlp_fc2_dgelu_bwd(const void* dY, const void* W2T, const void* pre, void* dpre_out, int64_t M, int N, int K,
+                             int dtype, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
