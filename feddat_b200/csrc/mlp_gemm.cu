@@ -8,8 +8,9 @@
 // ``Adaptered_ViltOutput`` (src/modeling/adaptered_output.py:67-79; the backbone itself is third-party
 // ``transformers.ViltModel``, src/modeling/vilt.py:19,127) and the data gradient that autograd derives for it.
 // Both are [M = 2 x batch x tokens, N = 3072, K = 768] products with K contiguous in both operands.  Unfused,
-// each is a cuBLAS GEMM (47-49 us at M = 11 840) followed by a streaming GELU pass over the [M, 3072] tensor
-// (30 / 36 us, HBM-bound); here the activation rides in the epilogue while the tensor cores run the next tile.
+// each is a cuBLAS GEMM (47-52 us at M = 11 840) followed by a streaming GELU pass over the [M, 3072] tensor
+// (30 / 36 us, HBM-bound); here the activation rides in the epilogue while the tensor cores run the next tile
+// (60-62 us / 63 us for the fused pair of outputs; the bare main loop of this kernel takes 43-45 us).
 //
 // Persistent CTA pairs (cluster of 2, tcgen05 cta_group::2), one 256 x 256 output tile per pair and step:
 //   ring       NS stages of 32 KB: [A k-chunk 128 x 64 | W half k-chunk 128 x 64] per CTA, K-major SW128
@@ -17,18 +18,22 @@
 //   warp 1     tcgen05.mma issuer (leader CTA): M = 256 across the pair, N = 256, fp32 accumulators in TMEM;
 //              TWO accumulator buffers (2 x 256 columns), so the MMAs of tile t + 1 run under the epilogue of t
 //   warp 2     TMEM allocation
-//   warps 4-19 epilogue: SIXTEEN warps, one per (TMEM lane quarter = 32 tile rows) x (64-column chunk of the 256):
-//              tcgen05.ld -> math -> bf16 -> swizzled staging -> TMA store, 32 columns at a time (96 registers).
-//              Every warp owns its [32 rows x 64 columns] slab and ONE 4 KB staging buffer with its own TMA
-//              stores, so no barrier couples the warps.  The epilogue is issue-latency bound (~23 instructions per
-//              element, 6 cycles between instructions of one warp -- ncu of an 8-warp version: IPC 2.0, tensor pipe
-//              52 % active, 8 us per tile against 4.3 us of MMA), hence four epilogue warps per scheduler; shared
-//              memory then goes to the operand ring (4 stages; with 3 the tensor pipe starves), so only one output
-//              per direction is staged: forward writes pre (what the backward needs) straight from registers (each
-//              thread 64 contiguous bytes per step) and act through TMA; backward reads pre straight into registers
-//              and writes dpre through TMA.
-// Rounding points are those of the unfused path: pre = bf16(acc + b), act = bf16(gelu(pre));
-// dpre = bf16(bf16(acc) * gelu'(pre)).
+//   warps 4-19 epilogue: SIXTEEN warps, one per (TMEM lane quarter = 32 tile rows) x (64-column chunk of the 256),
+//              each with ONE private 4 KB staging slab and its own stores, so no barrier couples the warps:
+//              tcgen05.ld (32 columns at a time) -> math in packed fp32 (FFMA2 / FMUL2: ~10 issue slots per element
+//              against ~21 scalar -- an 8-warp scalar epilogue took 8 us per tile against 5.4 us of MMA) -> bf16.
+//     forward  pre goes into the slab and leaves as plain 16-byte stores (eight lanes per 128-byte row segment, so
+//              every store instruction writes four full lines; one row per lane would write 32 half-used sectors);
+//              act waits in 32 registers, then takes the slab and leaves as one TMA store.  The bias is fp32 in
+//              global memory (L1-resident), requested one 8-column step ahead of its use.
+//     backward the saved pre-activations are loaded BEFORE the accumulator wait as full row segments (streaming,
+//              last use), turned into row-per-thread order through the slab, and each thread overwrites its own
+//              chunk with dpre for the TMA store.
+// What bounds it (profiles/r2_summary.md section E): L2 -> SM operand traffic of 256 x 256 tiles is 440 MB per launch
+// (~10 TB/s while the main loop runs); the 73-145 MB of epilogue stores and loads share that path, and each costs
+// about its share (+6 us per [M, 3072] tensor moved).  Math alone is hidden (bwd: +0.4 us).
+// Rounding: every output is rounded once, from fp32: pre = bf16(acc + b), act = bf16(gelu(acc + b)),
+// dpre = bf16(acc * gelu'(pre)).
 #include <stdlib.h>
 
 #include "feddat_b200.h"
@@ -55,13 +60,13 @@ struct GemmParams {
   int M, N, K;
   int m_blocks;          // ceil(M / 256)
   int n_tiles;           // m_blocks * (N / 256)
-  const float* bias;           // fwd: [N], fp32
   __nv_bfloat16* pre_out;      // fwd: [M, N], written from registers
   const __nv_bfloat16* pre_in; // bwd: [M, N], read into registers
+  const float* bias;           // fwd: [N], fp32
 };
 
 struct GemmTmaps {
-  CUtensorMap a, w, out0, out1, pre;   // fwd: out0 = pre, out1 = act;  bwd: out0 = dpre, pre = saved pre-activation
+  CUtensorMap a, w, out0;      // out0: the TMA-stored output (fwd: act, bwd: dpre)
 };
 
 template <bool kBwd>
@@ -168,23 +173,34 @@ mlp_gemm_kernel(const __grid_constant__ GemmTmaps tm, const __grid_constant__ Ge
       const uint32_t b = it & 1, use = it >> 1;
       const int m0 = tile_m0(t) + static_cast<int>(q) * 32, col0 = tile_n0(t) + static_cast<int>(cc) * 64;
       const uint32_t t_src = tmem + lane_addr + b * TN + cc * 64;
-      const int grow = m0 + lane;                    // this thread's row of the [M, N] tensors
-      const bool row_ok = grow < p.M;
-      uint4 pv[2][4];                                // backward: this row's 64 pre-activations, loaded ahead
+      // backward: this warp's [32 rows x 64 columns] of saved pre-activations, loaded ahead of the accumulator as
+      // full 128-byte row segments (eight lanes per row, four rows per instruction; last use -> streaming)
+      const uint32_t j8 = lane & 7, r0 = lane >> 3;
+      uint4 pv[8];
       if constexpr (kBwd) {
-        if (row_ok) {
-          const uint4* src = reinterpret_cast<const uint4*>(p.pre_in + static_cast<size_t>(grow) * p.N + col0);
+        const __nv_bfloat16* src = p.pre_in + static_cast<size_t>(m0 + r0) * p.N + col0 + j8 * 8;
 #pragma unroll
-          for (int c = 0; c < 8; ++c) pv[c >> 2][c & 3] = __ldg(src + c);
-        } else {
-#pragma unroll
-          for (int c = 0; c < 8; ++c) pv[c >> 2][c & 3] = make_uint4(0u, 0u, 0u, 0u);
-        }
+        for (int i = 0; i < 8; ++i)
+          pv[i] = (m0 + static_cast<int>(r0) + 4 * i < p.M)
+                      ? __ldcs(reinterpret_cast<const uint4*>(src + static_cast<size_t>(4 * i) * p.N))
+                      : make_uint4(0u, 0u, 0u, 0u);
+      }
+      const float4* b4 = reinterpret_cast<const float4*>(p.bias + col0);
+      float4 bn0 = make_float4(0.f, 0.f, 0.f, 0.f), bn1 = bn0;
+      if constexpr (!kBwd) {
+        bn0 = __ldg(b4);
+        bn1 = __ldg(b4 + 1);
       }
       mbar_wait(bar_acc_full(b), use & 1);
       tc_fence_after();
       if (lane == 0) tma_store_wait_read<0>();        // this warp's store of the previous tile has left the slab
       __syncwarp();
+      if constexpr (kBwd) {
+        // through the slab into row-per-thread order (the layout of the accumulator in registers)
+#pragma unroll
+        for (int i = 0; i < 8; ++i) st_shared_v4(wbuf + sw128_offset(r0 + 4 * i, j8), pv[i].x, pv[i].y, pv[i].z, pv[i].w);
+        __syncwarp();
+      }
       uint32_t act[kBwd ? 1 : 32];                    // forward: the packed activations wait for the slab
 #pragma unroll
       for (int st = 0; st < 2; ++st) {
@@ -201,11 +217,15 @@ mlp_gemm_kernel(const __grid_constant__ GemmTmaps tm, const __grid_constant__ Ge
         for (int c = 0; c < 4; ++c) {
           uint32_t oo[4];
           if constexpr (!kBwd) {
-            // forward: pre = acc + b -> slab (flushed below with plain stores); act = gelu(pre) -> registers
-            const float4* b4 = reinterpret_cast<const float4*>(p.bias + col0 + st * 32 + c * 8);
-            const float4 b0 = __ldg(b4), b1 = __ldg(b4 + 1);
-            const float2 bb[4] = {make_float2(b0.x, b0.y), make_float2(b0.z, b0.w), make_float2(b1.x, b1.y),
-                                  make_float2(b1.z, b1.w)};
+            // forward: pre = acc + b -> slab (flushed below with plain stores); act = gelu(pre) -> registers.
+            // The bias of the NEXT eight columns is requested before this step's math (an L1 hit still takes ~40
+            // cycles, and 96 registers leave the compiler no room to hoist the loads itself)
+            const float2 bb[4] = {make_float2(bn0.x, bn0.y), make_float2(bn0.z, bn0.w), make_float2(bn1.x, bn1.y),
+                                  make_float2(bn1.z, bn1.w)};
+            if (st * 4 + c < 7) {
+              bn0 = __ldg(b4 + 2 * (st * 4 + c + 1));
+              bn1 = __ldg(b4 + 2 * (st * 4 + c + 1) + 1);
+            }
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
               const int e = c * 8 + 2 * i;
@@ -216,7 +236,8 @@ mlp_gemm_kernel(const __grid_constant__ GemmTmaps tm, const __grid_constant__ Ge
             }
           } else {
             // backward: dpre = acc * gelu'(pre)
-            const uint32_t pw[4] = {pv[st][c].x, pv[st][c].y, pv[st][c].z, pv[st][c].w};
+            const uint4 pq = ld_shared_v4(wbuf + sw128_offset(lane, st * 4 + c));
+            const uint32_t pw[4] = {pq.x, pq.y, pq.z, pq.w};
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
               const int e = c * 8 + 2 * i;
@@ -232,13 +253,12 @@ mlp_gemm_kernel(const __grid_constant__ GemmTmaps tm, const __grid_constant__ Ge
         // pre leaves through plain 16-byte stores, eight lanes per 128-byte row segment (full lines); the slab
         // then takes the activations for the TMA store
         __syncwarp();
-        const uint32_t j = lane & 7, r0 = lane >> 3;
         uint4 row[8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) row[i] = ld_shared_v4(wbuf + sw128_offset(r0 + 4 * i, j));
-        __nv_bfloat16* dst = p.pre_out + static_cast<size_t>(m0 + r0) * p.N + col0 + j * 8;
+        for (int i = 0; i < 8; ++i) row[i] = ld_shared_v4(wbuf + sw128_offset(r0 + 4 * i, j8));
+        __nv_bfloat16* dst = p.pre_out + static_cast<size_t>(m0 + r0) * p.N + col0 + j8 * 8;
 #pragma unroll
-        for (int i = 0; i < 8; ++i)
+        for (int i = 0; i < 8; ++i)   
           if (m0 + static_cast<int>(r0) + 4 * i < p.M) *reinterpret_cast<uint4*>(dst + static_cast<size_t>(4 * i) * p.N) = row[i];
         __syncwarp();
 #pragma unroll
@@ -276,16 +296,14 @@ int launch_mlp_gemm(bool bwd, const void* A, const void* W, const void* bias, co
   p.M = static_cast<int>(M); p.N = N; p.K = K;
   p.m_blocks = static_cast<int>((M + 2 * BM - 1) / (2 * BM));
   p.n_tiles = p.m_blocks * (N / TN);
-  p.bias = static_cast<const float*>(bias);
   p.pre_out = bwd ? nullptr : static_cast<__nv_bfloat16*>(out0);
   p.pre_in = static_cast<const __nv_bfloat16*>(pre_in);
+  p.bias = static_cast<const float*>(bias);
   GemmTmaps tm;
   if ((rc = make_tmap_bf16_2d(&tm.a, A, M, K, K, BM, 64))) return rc;
   if ((rc = make_tmap_bf16_2d(&tm.w, W, N, K, K, TN / 2, 64))) return rc;
   // the TMA-stored output (forward: act, backward: dpre) moves as [32 rows x 64 columns] slabs, one per epilogue warp
   if ((rc = make_tmap_bf16_2d(&tm.out0, bwd ? out0 : out1, M, N, N, 32, 64))) return rc;
-  tm.out1 = tm.out0;
-  tm.pre = tm.out0;
   int sms = 0;
   if ((rc = device_sm_count(&sms))) return rc;
   const int pairs = p.n_tiles < sms / 2 ? p.n_tiles : sms / 2;

@@ -486,9 +486,9 @@ def test_mlp_gemm_gelu_matches_torch(ops, M, N, K):
     g = torch.Generator(device="cuda").manual_seed(M + N + K)
     a = torch.randn(M, K, device="cuda", generator=g).to(torch.bfloat16)
     w = (torch.randn(N, K, device="cuda", generator=g) * 0.05).to(torch.bfloat16)
-    b = (torch.randn(N, device="cuda", generator=g) * 0.1).to(torch.bfloat16).float()  # the kernel takes fp32 bias
-    pre, act = ops.mlp_fc1_gelu(a, w, b)
-    pre_ref = torch.addmm(b, a.float(), w.float().t())
+    b = (torch.randn(N, device="cuda", generator=g) * 0.1).to(torch.bfloat16)
+    pre, act = ops.mlp_fc1_gelu(a, w, b.float())                                      # the kernel takes an fp32 bias
+    pre_ref = torch.addmm(b.float(), a.float(), w.float().t())
     assert relerr(pre.float().cpu().numpy(), pre_ref.cpu().numpy()) < 4e-3            # one bf16 rounding
     assert (pre == pre_ref.to(torch.bfloat16)).float().mean().item() > 0.995           # same bits except rounding ties
     act_ref = torch.nn.functional.gelu(pre_ref)
