@@ -38,6 +38,7 @@ EXPORTED_SYMBOLS = (
     "feddat_gelu_bwd",
     "feddat_mlp_fc1_gelu_fwd",
     "feddat_mlp_fc2_dgelu_bwd",
+    "feddat_attn_fwd",
 )
 # include/feddat_b200_debug.h: only in the -DFEDDAT_DEBUG twin (libfeddat_sm100_dbg.so), tests / scripts
 DEBUG_SYMBOLS = (
@@ -166,6 +167,8 @@ def _bind(lib: ctypes.CDLL, debug: bool) -> ctypes.CDLL:
                                             c_void_p]
     lib.feddat_mlp_fc2_dgelu_bwd.restype = c_int
     lib.feddat_mlp_fc2_dgelu_bwd.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int, c_int, c_void_p]
+    lib.feddat_attn_fwd.restype = c_int
+    lib.feddat_attn_fwd.argtypes = [c_void_p] * 5 + [c_int] * 4 + [c_int64] * 4 + [c_float, c_int, c_void_p]
     if not debug:
         return lib
     lib.feddat_probe_gemm.restype = c_int

@@ -1,0 +1,446 @@
+// Self-attention of the frozen ViLT block that surrounds each DAT site, for SHORT sequences (S <= 256 keys, head
+// dimension 64): softmax(Q K^T * scale) V and its backward, one (batch, head) at a time with the whole key range
+// resident -- no online softmax, no split-K, no fp32 dQ accumulation pass.
+//
+// HF ``ViltSelfAttention`` (transformers; the backbone the reference instantiates in src/modeling/vilt.py:19,127 and
+// runs inside every train_step, src/train/visionlanguage_tasks/task_trainer.py:280-330): query / key / value are the
+// [B * S, 768] outputs of the three projections viewed as [B, S, 12, 64]; the context goes back to [B * S, 768].
+// At the benchmarked shape (B = 2 x 32, S = 185: 40 text + 145 image tokens) the library kernel behind
+// F.scaled_dot_product_attention (cuDNN flash) takes 32 us forward and 64 + 13 + 9 us backward per layer: it is
+// built for long sequences (128 x 128 tiles streamed over the keys, fp32 dQ accumulated across key blocks and
+// converted afterwards, a separate dO . O pass).  Here a row of scores (<= 256 fp32) simply stays in TMEM.
+//
+// Forward, work item = (batch, head, 128-query tile), one persistent CTA per SM, software-pipelined over its items:
+//   control warp  TMA: Q tile [128 x 64], K and V [KP x 64] (3-D tensor maps over [B, S, ld]: rows past S read as
+//                 zero, stores past S are clipped);  tcgen05.mma S = Q K^T (M = 128, N = KP, K = 64, both K-major)
+//                 into one of TWO score buffers in TMEM;  after the softmax: O = P V with P read FROM TMEM (packed
+//                 bf16 pairs written over S's own columns) and V as an MN-major operand.  Q / K of item i + 1 are
+//                 requested as soon as S(i) has completed, V(i + 1) as soon as O(i) has.
+//   warps 0-7     softmax: TWO threads per query row (warps w and w + 4 share a TMEM lane quarter and split the key
+//                 range), the half row (<= 128 scores) is read ONCE into registers -- TMEM reads (~64 B / clock / SM)
+//                 and MUFU are what bound this kernel, a second pass for the maximum would double the former.
+//                 Maximum and sum cross the pair through shared memory and a 64-thread named barrier.  Order per
+//                 thread: softmax(i + 1) BEFORE the output epilogue of item i, so the wait for O(i) = P V is hidden.
+//                 Epilogue: O / sum -> bf16 -> swizzled [32 x 64] slab of the quarter -> its own TMA store.
+#include <stdlib.h>
+
+#include "feddat_b200.h"
+#include "host_common.h"
+#include "ptx_sm100.cuh"
+
+namespace fd {
+namespace {
+
+constexpr int AD = 64;                 // head dimension
+constexpr int AQ = 128;                // query rows per tile (TMEM lanes)
+constexpr int AKMAX = 256;             // keys per (batch, head) at most
+constexpr int ATHREADS = 736;          // 16 softmax + 4 epilogue + MMA issuer + 2 TMA producer warps
+constexpr int A_QBYTES = AQ * 128;     // 16 KB
+constexpr int A_KBYTES = AKMAX * 128;  // 32 KB
+
+struct AttnTmaps {
+  CUtensorMap q, k, v, o;
+};
+struct AttnParams {
+  int B, S, H;
+  int KP;            // keys padded to a multiple of 64
+  int n_mt;          // query tiles per (batch, head)
+  int n_items;
+  int n_buf;         // score / output buffers in TMEM (2 when they fit)
+  float scale_log2e; // scale * log2(e)
+  float* lse;        // [B, H, S]
+  unsigned long long* trace;   // debug twin only: timestamps of CTA 0's first 16 items, [item][event]
+};
+
+#ifdef FEDDAT_DEBUG
+#define AT_TRACE(ev, i)                                                                      \
+  do {                                                                                       \
+    if (p.trace != nullptr && blockIdx.x == 0 && (i) < 16) p.trace[(i) * 16 + (ev)] = globaltimer_ns(); \
+  } while (0)
+#else
+#define AT_TRACE(ev, i) do { (void)(i); } while (0)
+#endif
+
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* tm, uint32_t src_smem, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(tm)), "r"(src_smem), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
+__device__ __forceinline__ float fast_ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float fast_lg2(float x) {
+  float y;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, "
+      "%15, %16};"
+      ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]),
+      "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
+      : "memory");
+}
+
+// kNC = 16-column chunks of scores per thread (KP / 64): its quarter row lives in registers
+template <int kNC>
+__global__ void __launch_bounds__(ATHREADS, 1)
+attn_fwd_kernel(const __grid_constant__ AttnTmaps tm, const __grid_constant__ AttnParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t bars[20];
+  __shared__ uint32_t tmem_base_smem;
+  __shared__ float xmax[2][4][AQ], xsum[2][4][AQ];     // [item parity][column quarter][row]
+  __shared__ float xmc[2][AQ];                         // row maximum * scale * log2(e), for the logsumexp
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t smem0 = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  constexpr int KP = kNC * 64;
+  constexpr uint32_t kv_bytes = static_cast<uint32_t>(KP) * 128u;
+  constexpr uint32_t STAGE = A_QBYTES + 2 * kv_bytes;        // Q tile, K, V of one item
+  constexpr int NSTG = kNC <= 3 ? 3 : 2;                     // operand stages in flight (208 / 176 KB with the staging slabs)
+  auto q_s = [&](uint32_t st) { return smem0 + st * STAGE; };
+  auto k_s = [&](uint32_t st) { return smem0 + st * STAGE + A_QBYTES; };
+  auto v_s = [&](uint32_t st) { return smem0 + st * STAGE + A_QBYTES + kv_bytes; };
+  const uint32_t o_s = smem0 + NSTG * STAGE;
+  const uint32_t bar0 = smem_u32(bars);
+  auto bar_qk = [&](uint32_t st) { return bar0 + 8 * st; };
+  auto bar_v = [&](uint32_t st) { return bar0 + 24 + 8 * st; };
+  auto bar_s = [&](uint32_t sb) { return bar0 + 48 + 8 * sb; };
+  auto bar_p = [&](uint32_t sb) { return bar0 + 64 + 8 * sb; };
+  auto bar_o = [&](uint32_t sb) { return bar0 + 80 + 8 * sb; };
+  auto bar_ofree = [&](uint32_t sb) { return bar0 + 96 + 8 * sb; };   // epilogue warps: O and the row sums are in registers
+  auto bar_qkfree = [&](uint32_t st) { return bar0 + 112 + 8 * st; };  // S(i) has read the stage's Q and K
+  auto bar_vfree = [&](uint32_t st) { return bar0 + 136 + 8 * st; };   // O(i) = P V has read the stage's V
+
+  if (tid == 0) {
+    for (uint32_t st = 0; st < 3; ++st) {
+      mbar_init(bar_qk(st), 1);
+      mbar_init(bar_v(st), 1);
+      mbar_init(bar_qkfree(st), 1);
+      mbar_init(bar_vfree(st), 1);
+    }
+    for (uint32_t sb = 0; sb < 2; ++sb) {
+      mbar_init(bar_s(sb), 1);
+      mbar_init(bar_p(sb), 16);     // one lane of each softmax warp
+      mbar_init(bar_o(sb), 1);
+      mbar_init(bar_ofree(sb), 4);
+    }
+    fence_mbar_init();
+    tma_prefetch_desc(&tm.q);
+    tma_prefetch_desc(&tm.k);
+    tma_prefetch_desc(&tm.v);
+    tma_prefetch_desc(&tm.o);
+  }
+  if (warp == 20) tmem_alloc(smem_u32(&tmem_base_smem), 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  pdl_wait();
+  pdl_launch_dependents();
+  const uint32_t tmem = tmem_base_smem;
+  const uint32_t n_buf = static_cast<uint32_t>(p.n_buf);
+  auto s_col = [&](uint32_t sb) { return sb * KP; };
+  auto o_col = [&](uint32_t sb) { return n_buf * KP + sb * AD; };
+  const int n_mine = (p.n_items - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
+
+  auto item_of = [&](int i) { return static_cast<int>(blockIdx.x) + i * static_cast<int>(gridDim.x); };
+  if (warp == 20) {
+    // ------------------------------------------------------------------ MMA issuer (never waits for its own MMAs)
+    if (lane == 0) {
+      const uint32_t idesc_s = make_idesc_bf16(AQ, KP);
+      const uint32_t idesc_o = make_idesc_bf16(AQ, AD, 0, 1);
+      // S(i) = Q K^T into score buffer i % n_buf.  tcgen05.mma executes in issue order, so S(i) may follow
+      // O(i - n_buf) = P V -- whose P it overwrites -- without waiting for it
+      auto do_s = [&](int i) {
+        const uint32_t sb = static_cast<uint32_t>(i) % n_buf, st = static_cast<uint32_t>(i) % NSTG;
+        mbar_wait(bar_qk(st), (static_cast<uint32_t>(i) / NSTG) & 1);
+        // the epilogue warps have taken O(i - n_buf) and its row sums: buffer sb (scores now, output later) is free
+        if (i >= static_cast<int>(n_buf)) mbar_wait(bar_ofree(sb), ((static_cast<uint32_t>(i) / n_buf) - 1) & 1);
+        tc_fence_after();
+        AT_TRACE(0, i);
+#pragma unroll
+        for (int k = 0; k < AD / 16; ++k)
+          umma_ss(tmem + s_col(sb), desc_kmajor_sw128(q_s(st) + k * 32), desc_kmajor_sw128(k_s(st) + k * 32), idesc_s, k > 0);
+        umma_commit(bar_s(sb));
+        umma_commit(bar_qkfree(st));
+        AT_TRACE(1, i);
+      };
+      // O(i) = P V once the softmax warps have put P in TMEM
+      auto do_pv = [&](int i) {
+        const uint32_t sb = static_cast<uint32_t>(i) % n_buf, par = (static_cast<uint32_t>(i) / n_buf) & 1;
+        const uint32_t st = static_cast<uint32_t>(i) % NSTG;
+        mbar_wait(bar_v(st), (static_cast<uint32_t>(i) / NSTG) & 1);
+        AT_TRACE(2, i);
+        mbar_wait(bar_p(sb), par);
+        tc_fence_after();
+        AT_TRACE(3, i);
+#pragma unroll
+        for (int k = 0; k < KP / 16; ++k)
+          umma_ts(tmem + o_col(sb), tmem + s_col(sb) + k * 8, desc_mnmajor_sw128(v_s(st) + k * 16 * 128, 1024), idesc_o, k > 0);
+        umma_commit(bar_o(sb));
+        umma_commit(bar_vfree(st));
+        AT_TRACE(4, i);
+      };
+      for (int i = 0; i < n_mine; ++i) {
+        if (i >= static_cast<int>(n_buf)) do_pv(i - static_cast<int>(n_buf));   // frees score buffer i % n_buf
+        do_s(i);
+      }
+      for (int i = n_mine > static_cast<int>(n_buf) ? n_mine - static_cast<int>(n_buf) : 0; i < n_mine; ++i) do_pv(i);
+    }
+    __syncwarp();
+  } else if (warp == 21) {
+    // ------------------------------------------------------------------ TMA producer: Q tile and K, NSTG items ahead
+    // (a cold 40 KB load takes ~2 us, as long as a whole item, and issuing it blocks the thread for ~0.6 us)
+    if (lane == 0) {
+      for (int i = 0; i < n_mine; ++i) {
+        const int item = item_of(i), mt = item % p.n_mt, bh = item / p.n_mt, h = bh % p.H, b = bh / p.H;
+        const uint32_t st = static_cast<uint32_t>(i) % NSTG;
+        if (i >= NSTG) mbar_wait(bar_qkfree(st), ((static_cast<uint32_t>(i) / NSTG) - 1) & 1);   // S(i - NSTG) is done
+        mbar_arrive_expect_tx(bar_qk(st), A_QBYTES + kv_bytes);
+        tma_load_3d(q_s(st), &tm.q, bar_qk(st), h * AD, mt * AQ, b);
+        tma_load_3d(k_s(st), &tm.k, bar_qk(st), h * AD, 0, b);
+      }
+    }
+    __syncwarp();
+  } else if (warp == 22) {
+    // ------------------------------------------------------------------ TMA producer: V
+    if (lane == 0) {
+      for (int i = 0; i < n_mine; ++i) {
+        const int item = item_of(i), bh = item / p.n_mt, h = bh % p.H, b = bh / p.H;
+        const uint32_t st = static_cast<uint32_t>(i) % NSTG;
+        if (i >= NSTG) mbar_wait(bar_vfree(st), ((static_cast<uint32_t>(i) / NSTG) - 1) & 1);    // O(i - NSTG) is done
+        mbar_arrive_expect_tx(bar_v(st), kv_bytes);
+        tma_load_3d(v_s(st), &tm.v, bar_v(st), h * AD, 0, b);
+      }
+    }
+    __syncwarp();
+  } else if (warp >= 16) {
+    // ------------------------------------------------------------------ output epilogue: one query row per thread
+    const uint32_t q = warp & 3;
+    const uint32_t row = q * 32 + lane;
+    const uint32_t lane_addr = (q * 32u) << 16;
+    const int S = p.S;
+    const uint32_t slab = o_s + q * 4096u;                     // this warp's [32 x 64] staging slab
+    for (int i = 0; i < n_mine; ++i) {
+      const int item = item_of(i);
+      const int mt = item % p.n_mt, bh = item / p.n_mt, h = bh % p.H, b = bh / p.H;
+      const uint32_t sb = static_cast<uint32_t>(i) % n_buf, par = (static_cast<uint32_t>(i) / n_buf) & 1;
+      const bool live = mt * AQ + static_cast<int>(q) * 32 < S;
+      mbar_wait(bar_o(sb), par);
+      tc_fence_after();
+      if (lane == 0) AT_TRACE(11, i);
+      if (!live) {
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_ofree(sb));
+        continue;
+      }
+      const float sum = (xsum[i & 1][0][row] + xsum[i & 1][1][row]) + (xsum[i & 1][2][row] + xsum[i & 1][3][row]);
+      const float inv = 1.f / sum;
+      if (mt * AQ + static_cast<int>(row) < S)
+        p.lse[(static_cast<size_t>(b) * p.H + h) * S + mt * AQ + row] = (xmc[i & 1][row] + fast_lg2(sum)) * 0.6931471805599453f;
+      const float2 inv2 = make_float2(inv, inv);
+      if (lane == 0) tma_store_wait_read<0>();                 // the slab's previous store has been read
+      __syncwarp();
+#pragma unroll
+      for (int hf = 0; hf < 2; ++hf) {                         // 32 output columns at a time (80 registers per thread)
+        uint32_t v[32];
+        tmem_ld32(tmem + lane_addr + o_col(sb) + hf * 32, v);
+        tmem_ld_wait32(v);
+        if (hf == 1) {
+          // the row sums and the whole output row have been taken: the buffer may be overwritten
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar_ofree(sb));
+        }
+#pragma unroll
+        for (int ch = 0; ch < 4; ++ch) {
+          uint32_t o[4];
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const float2 u = __fmul2_rn(make_float2(__uint_as_float(v[ch * 8 + 2 * k]), __uint_as_float(v[ch * 8 + 2 * k + 1])), inv2);
+            o[k] = pack_bf16x2(u.x, u.y);
+          }
+          st_shared_v4(slab + sw128_offset(lane, hf * 4 + ch), o[0], o[1], o[2], o[3]);
+        }
+      }
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) {
+        tma_store_3d(&tm.o, slab, h * AD, mt * AQ + static_cast<int>(q) * 32, b);
+        tma_store_commit();
+        AT_TRACE(12, i);
+      }
+    }
+    if (lane == 0) tma_store_wait_all<0>();
+  } else {
+    // ------------------------------------------------------------------ softmax: four threads per query row
+    const uint32_t q = warp & 3, cq = warp >> 2;               // TMEM lane quarter, column quarter of the key range
+    const uint32_t row = q * 32 + lane;                        // row of the query tile == TMEM lane
+    const uint32_t lane_addr = (q * 32u) << 16;
+    const int S = p.S;
+    const float c = p.scale_log2e;
+    const int j0 = static_cast<int>(cq) * (KP / 4);            // first key of this thread's quarter row
+
+    for (int i = 0; i < n_mine; ++i) {
+      const int item = static_cast<int>(blockIdx.x) + i * static_cast<int>(gridDim.x);
+      const int mt = item % p.n_mt;
+      const uint32_t sb = static_cast<uint32_t>(i) % n_buf, par = (static_cast<uint32_t>(i) / n_buf) & 1;
+      const bool live = mt * AQ + static_cast<int>(q) * 32 < S;   // warp-uniform: some row of this lane quarter is real
+      mbar_wait(bar_s(sb), par);
+      tc_fence_after();
+      if (tid == 0) AT_TRACE(5, i);
+      if (live) {
+        const uint32_t t_s = tmem + lane_addr + s_col(sb);
+        uint32_t v[kNC][16];
+#pragma unroll
+        for (int ch = 0; ch < kNC; ++ch) tmem_ld16(t_s + j0 + ch * 16, v[ch]);
+        float m = -INFINITY;
+#pragma unroll
+        for (int ch = 0; ch < kNC; ++ch) {
+          tmem_ld_wait16(v[ch]);
+          if (j0 + ch * 16 + 16 <= S) {
+            float m0 = fmaxf(__uint_as_float(v[ch][0]), __uint_as_float(v[ch][1]));
+            float m1 = fmaxf(__uint_as_float(v[ch][2]), __uint_as_float(v[ch][3]));
+#pragma unroll
+            for (int k = 4; k < 16; k += 4) {
+              m0 = fmaxf(m0, fmaxf(__uint_as_float(v[ch][k]), __uint_as_float(v[ch][k + 1])));
+              m1 = fmaxf(m1, fmaxf(__uint_as_float(v[ch][k + 2]), __uint_as_float(v[ch][k + 3])));
+            }
+            m = fmaxf(m, fmaxf(m0, m1));
+          } else {
+#pragma unroll
+            for (int k = 0; k < 16; ++k)
+              if (j0 + ch * 16 + k < S) m = fmaxf(m, __uint_as_float(v[ch][k]));
+          }
+        }
+        if (tid == 0) AT_TRACE(6, i);
+        xmax[i & 1][cq][row] = m;
+        named_bar_sync(2 + q, 128);         // all four quarter rows are in registers: P may overwrite S, maxima are visible
+        m = fmaxf(fmaxf(xmax[i & 1][0][row], xmax[i & 1][1][row]), fmaxf(xmax[i & 1][2][row], xmax[i & 1][3][row]));
+        if (tid == 0) AT_TRACE(7, i);
+        const float mc = m * c;
+        if (cq == 0) xmc[i & 1][row] = mc;
+        const float2 c2 = make_float2(c, c), nmc2 = make_float2(-mc, -mc);
+        float2 acc = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int ch = 0; ch < kNC; ++ch) {
+          uint32_t w[8];
+          const bool full = j0 + ch * 16 + 16 <= S;
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            const float2 a = __ffma2_rn(make_float2(__uint_as_float(v[ch][2 * k]), __uint_as_float(v[ch][2 * k + 1])), c2, nmc2);
+            float2 e = make_float2(fast_ex2(a.x), fast_ex2(a.y));
+            if (!full) {
+              if (j0 + ch * 16 + 2 * k >= S) e.x = 0.f;
+              if (j0 + ch * 16 + 2 * k + 1 >= S) e.y = 0.f;
+            }
+            acc = __fadd2_rn(acc, e);
+            w[k] = pack_bf16x2(e.x, e.y);
+          }
+          tmem_st8(t_s + j0 / 2 + ch * 8, w);
+        }
+        tmem_st_wait();
+        xsum[i & 1][cq][row] = acc.x + acc.y;   // read by the epilogue warp behind bar_p -> MMA -> bar_o
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_p(sb));
+      if (tid == 0) AT_TRACE(8, i);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 20) tmem_dealloc(tmem, 512);
+}
+
+// [B, S, cols] bf16 with token stride `ld` elements, viewed by (column, token, batch); box = [rows x 64 columns]
+int make_tmap_tokens(CUtensorMap* out, const void* gptr, int B, int S, int cols, int64_t ld, uint32_t box_rows) {
+  using PFN = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                           const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                           CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  static PFN enc = nullptr;
+  if (!enc) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    FD_CHECK_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+    FD_REQUIRE(fn != nullptr && qres == cudaDriverEntryPointSuccess, FD_ERR_CUDA,
+               "cuTensorMapEncodeTiled entry point not available");
+    enc = reinterpret_cast<PFN>(fn);
+  }
+  FD_REQUIRE((reinterpret_cast<uintptr_t>(gptr) & 15) == 0 && (ld * 2) % 16 == 0 && cols % AD == 0 && ld >= cols,
+             FD_ERR_INVALID, "attention operand %p: base / token stride %lld not 16-byte aligned or narrower than %d",
+             gptr, (long long)ld, cols);
+  cuuint64_t gdim[3] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(S), static_cast<cuuint64_t>(B)};
+  cuuint64_t gstride[2] = {static_cast<cuuint64_t>(ld) * 2, static_cast<cuuint64_t>(ld) * 2 * S};
+  cuuint32_t box[3] = {AD, box_rows, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(gptr), gdim, gstride, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  FD_REQUIRE(r == CUDA_SUCCESS, FD_ERR_CUDA, "cuTensorMapEncodeTiled (token view) failed (%d) B=%d S=%d ld=%lld", (int)r,
+             B, S, (long long)ld);
+  return FD_OK;
+}
+
+}  // namespace
+}  // namespace fd
+
+extern "C" int feddat_attn_fwd(const void* Q, const void* K, const void* V, void* O, void* LSE, int B, int S, int H,
+                               int D, int64_t ldq, int64_t ldk, int64_t ldv, int64_t ldo, float scale, int dtype,
+                               void* stream) {
+  using namespace fd;
+  int rc = check_device_sm100();
+  if (rc) return rc;
+  FD_REQUIRE(dtype == FEDDAT_DTYPE_BF16, FD_ERR_UNSUPPORTED, "attn_fwd: only bf16 is implemented (dtype=%d)", dtype);
+  FD_REQUIRE(Q && K && V && O && LSE, FD_ERR_INVALID, "attn_fwd: null pointer argument");
+  FD_REQUIRE(D == AD && S >= 1 && S <= AKMAX && H >= 1 && B >= 0, FD_ERR_UNSUPPORTED,
+             "attn_fwd: head dimension %d / sequence length %d outside the short-sequence kernel (D = 64, S <= 256)", D, S);
+  if (B == 0) return FD_OK;
+  AttnParams p{};
+  p.B = B; p.S = S; p.H = H;
+  p.KP = (S + 63) / 64 * 64;
+  p.n_mt = (S + AQ - 1) / AQ;
+  p.n_items = B * H * p.n_mt;
+  p.n_buf = 2 * (p.KP + AD) <= 512 ? 2 : 1;
+  p.scale_log2e = scale * 1.4426950408889634f;
+  p.lse = static_cast<float*>(LSE);
+  p.trace = FD_TRACE_PTR;
+  AttnTmaps tm;
+  if ((rc = make_tmap_tokens(&tm.q, Q, B, S, H * D, ldq, AQ))) return rc;
+  if ((rc = make_tmap_tokens(&tm.k, K, B, S, H * D, ldk, p.KP))) return rc;
+  if ((rc = make_tmap_tokens(&tm.v, V, B, S, H * D, ldv, p.KP))) return rc;
+  if ((rc = make_tmap_tokens(&tm.o, O, B, S, H * D, ldo, 32))) return rc;
+  int sms = 0;
+  if ((rc = device_sm_count(&sms))) return rc;
+  const int nc = p.KP / 64;
+  const size_t stage = A_QBYTES + 2 * static_cast<size_t>(p.KP) * 128;
+  const size_t smem = 1024 + (nc <= 3 ? 3 : 2) * stage + A_QBYTES;
+  using KernelFn = void (*)(const AttnTmaps, const AttnParams);
+  KernelFn fn = nc == 1 ? attn_fwd_kernel<1> : nc == 2 ? attn_fwd_kernel<2> : nc == 3 ? attn_fwd_kernel<3> : attn_fwd_kernel<4>;
+  static bool configured[5][64] = {{false}};
+  int dev = 0;
+  FD_CHECK_CUDA(cudaGetDevice(&dev));
+  if (dev >= 64 || !configured[nc][dev]) {
+    FD_CHECK_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (dev < 64) configured[nc][dev] = true;
+  }
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(p.n_items < sms ? p.n_items : sms);
+  cfg.blockDim = dim3(ATHREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = static_cast<cudaStream_t>(stream);
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  const char* e = getenv("FEDDAT_PDL");
+  cfg.numAttrs = (e && e[0] == '0') ? 0 : 1;
+  FD_CHECK_CUDA(cudaLaunchKernelEx(&cfg, fn, tm, p));
+  FD_CHECK_CUDA(cudaGetLastError());
+  return FD_OK;
+}

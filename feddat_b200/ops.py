@@ -511,3 +511,33 @@ def mlp_fc2_dgelu(dy: torch.Tensor, w2t: torch.Tensor, pre: torch.Tensor) -> tor
     _lib.check(rc, "feddat_mlp_fc2_dgelu_bwd")
     _count()
     return out
+
+
+def _token_view(t: torch.Tensor, what: str):
+    """(B, S, H, D, ld) of a bf16 [B, S, H, D] tensor whose (h, d) are contiguous and whose batch stride is S x the
+    token stride -- a projection output [B * S, H * D] or a column slice of a wider one, viewed per head."""
+    if t.dtype != torch.bfloat16 or not t.is_cuda or t.dim() != 4:
+        raise _lib.FeddatError(f"{what}: expected a 4-D bf16 CUDA tensor [B, S, H, D]")
+    B, S, H, D = t.shape
+    sb, ss, sh, sd = t.stride()
+    if sd != 1 or sh != D or (B > 1 and sb != S * ss) or ss < H * D:
+        raise _lib.FeddatError(f"{what}: strides {t.stride()} are not a [B * S, ld] token layout")
+    return B, S, H, D, ss
+
+
+def attn_fwd(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, scale: float):
+    """(o, lse) = softmax(q k^T scale) v per (batch, head) (feddat_attn_fwd).  q, k, v: [B, S, H, 64] bf16 views with
+    (h, d) contiguous (token stride free); o: [B, S, H, 64] contiguous; lse: [B, H, S] fp32."""
+    lib = _lib.load()
+    B, S, H, D, ldq = _token_view(q, "attn_fwd q")
+    _, _, _, _, ldk = _token_view(k, "attn_fwd k")
+    _, _, _, _, ldv = _token_view(v, "attn_fwd v")
+    if k.shape != q.shape or v.shape != q.shape:
+        raise _lib.FeddatError("attn_fwd: q, k, v shapes differ")
+    o = torch.empty(B, S, H, D, device=q.device, dtype=torch.bfloat16)
+    lse = torch.empty(B, H, S, device=q.device, dtype=torch.float32)
+    rc = lib.feddat_attn_fwd(_lib.ptr(q), _lib.ptr(k), _lib.ptr(v), _lib.ptr(o), _lib.ptr(lse), B, S, H, D, ldq, ldk, ldv,
+                             H * D, float(scale), DTYPE_BF16, _lib.stream_ptr())
+    _lib.check(rc, "feddat_attn_fwd")
+    _count()
+    return o, lse

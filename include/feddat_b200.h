@@ -266,6 +266,17 @@ int feddat_mlp_fc1_gelu_fwd(const void* A, const void* W, const void* bias, void
 int feddat_mlp_fc2_dgelu_bwd(const void* dY, const void* W2T, const void* pre, void* dpre_out, int64_t M, int N, int K,
                              int dtype, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Self-attention of the frozen block around each ViLT DAT site for SHORT sequences (HF ViltSelfAttention, the
+ * backbone of src/modeling/vilt.py:19,127; S <= 256 keys, head dimension 64, no mask, no dropout):
+ *   feddat_attn_fwd   O = softmax(Q K^T * scale) V,  LSE = log sum exp of the scaled scores (natural log)
+ * Q, K, V, O: bf16, element (b, s, h, d) at ((b * S + s) * ld + h * 64 + d) -- the [B * S, H * 64] projection outputs
+ * themselves (ld = 768) or column slices of a fused q/k/v projection (ld = 2304); LSE: [B, H, S] fp32.
+ * Token strides in elements, multiples of 8; bases 16-byte aligned.
+ */
+int feddat_attn_fwd(const void* Q, const void* K, const void* V, void* O, void* LSE, int B, int S, int H, int D,
+                    int64_t ldq, int64_t ldk, int64_t ldv, int64_t ldo, float scale, int dtype, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -534,3 +534,29 @@ def test_fused_mlp_layer_equals_unfused_layer():
 def ops_launches():
     from feddat_b200 import ops as _o
     return _o.launch_count
+
+
+# ------------------------------------------------------------------------- short-sequence attention
+@pytest.mark.parametrize("B,S,H,fused_qkv", [(64, 185, 12, False),     # the benchmarked step: 2 x 32 sequences
+                                             (3, 185, 12, True), (2, 40, 12, False), (5, 128, 4, False),
+                                             (2, 129, 2, True), (1, 1, 1, False), (2, 256, 3, False), (4, 192, 12, True)])
+def test_attn_fwd_matches_torch(ops, B, S, H, fused_qkv):
+    """feddat_attn_fwd against softmax(q k^T / 8) v in fp32 from the same bf16 inputs: output within one bf16
+    rounding of the fp32 result (P is rounded to bf16 for the second product, as in every flash kernel), logsumexp
+    to 1e-3."""
+    g = torch.Generator(device="cuda").manual_seed(B * 1000 + S)
+    D = 64
+    if fused_qkv:
+        qkv = (torch.randn(B * S, 3 * H * D, device="cuda", generator=g) * 1.5).to(torch.bfloat16)
+        q, k, v = (qkv[:, i * H * D:(i + 1) * H * D].view(B, S, H, D) for i in range(3))
+    else:
+        q, k, v = ((torch.randn(B * S, H * D, device="cuda", generator=g) * 1.5).to(torch.bfloat16).view(B, S, H, D)
+                   for _ in range(3))
+    o, lse = ops.attn_fwd(q, k, v, 0.125)
+    qf, kf, vf = (t.float().permute(0, 2, 1, 3) for t in (q, k, v))
+    s = qf @ kf.transpose(-1, -2) * 0.125
+    o_ref = (torch.softmax(s, -1) @ vf).permute(0, 2, 1, 3)
+    lse_ref = torch.logsumexp(s, -1)
+    assert o.shape == (B, S, H, D) and o.is_contiguous()
+    assert relerr(o.float().cpu().numpy(), o_ref.cpu().numpy()) < 8e-3
+    assert (lse - lse_ref).abs().max().item() < 2e-3
