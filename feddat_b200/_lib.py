@@ -39,6 +39,7 @@ EXPORTED_SYMBOLS = (
     "feddat_mlp_fc1_gelu_fwd",
     "feddat_mlp_fc2_dgelu_bwd",
     "feddat_attn_fwd",
+    "feddat_attn_bwd",
 )
 # include/feddat_b200_debug.h: only in the -DFEDDAT_DEBUG twin (libfeddat_sm100_dbg.so), tests / scripts
 DEBUG_SYMBOLS = (
@@ -169,6 +170,8 @@ def _bind(lib: ctypes.CDLL, debug: bool) -> ctypes.CDLL:
     lib.feddat_mlp_fc2_dgelu_bwd.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int, c_int, c_void_p]
     lib.feddat_attn_fwd.restype = c_int
     lib.feddat_attn_fwd.argtypes = [c_void_p] * 5 + [c_int] * 4 + [c_int64] * 4 + [c_float, c_int, c_void_p]
+    lib.feddat_attn_bwd.restype = c_int
+    lib.feddat_attn_bwd.argtypes = [c_void_p] * 9 + [c_int] * 4 + [c_int64] * 8 + [c_float, c_int, c_void_p]
     if not debug:
         return lib
     lib.feddat_probe_gemm.restype = c_int

@@ -541,3 +541,30 @@ def attn_fwd(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, scale: float):
     _lib.check(rc, "feddat_attn_fwd")
     _count()
     return o, lse
+
+
+ATTN_MAX_S_FWD = 256
+ATTN_MAX_S_BWD = 192
+
+
+def attn_bwd(do: torch.Tensor, q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, o: torch.Tensor, lse: torch.Tensor,
+             scale: float):
+    """(dq, dk, dv) of ``attn_fwd`` in one launch (feddat_attn_bwd).  The three gradients are the column slices of ONE
+    [B, S, 3, H, 64] tensor (token stride 3 * H * 64): a fused q/k/v projection's backward can consume it whole."""
+    lib = _lib.load()
+    B, S, H, D, ldq = _token_view(q, "attn_bwd q")
+    _, _, _, _, ldk = _token_view(k, "attn_bwd k")
+    _, _, _, _, ldv = _token_view(v, "attn_bwd v")
+    _, _, _, _, ldo = _token_view(o, "attn_bwd o")
+    _, _, _, _, lddo = _token_view(do, "attn_bwd do")
+    if lse.dtype != torch.float32 or tuple(lse.shape) != (B, H, S) or not lse.is_contiguous():
+        raise _lib.FeddatError("attn_bwd: lse must be a contiguous fp32 [B, H, S] tensor")
+    dqkv = torch.empty(B, S, 3, H, D, device=q.device, dtype=torch.bfloat16)
+    dq, dk, dv = dqkv[:, :, 0], dqkv[:, :, 1], dqkv[:, :, 2]
+    ld = 3 * H * D
+    rc = lib.feddat_attn_bwd(_lib.ptr(do), _lib.ptr(q), _lib.ptr(k), _lib.ptr(v), _lib.ptr(o), _lib.ptr(lse), _lib.ptr(dq),
+                             _lib.ptr(dk), _lib.ptr(dv), B, S, H, D, lddo, ldq, ldk, ldv, ldo, ld, ld, ld, float(scale),
+                             DTYPE_BF16, _lib.stream_ptr())
+    _lib.check(rc, "feddat_attn_bwd")
+    _count()
+    return dq, dk, dv

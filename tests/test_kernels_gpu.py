@@ -560,3 +560,27 @@ def test_attn_fwd_matches_torch(ops, B, S, H, fused_qkv):
     assert o.shape == (B, S, H, D) and o.is_contiguous()
     assert relerr(o.float().cpu().numpy(), o_ref.cpu().numpy()) < 8e-3
     assert (lse - lse_ref).abs().max().item() < 2e-3
+
+
+@pytest.mark.parametrize("B,S,H,fused_qkv", [(64, 185, 12, False), (3, 185, 12, True), (2, 40, 12, False), (5, 128, 4, False),
+                                             (2, 129, 2, True), (1, 1, 1, False), (4, 192, 12, True), (7, 64, 3, False)])
+def test_attn_bwd_matches_torch(ops, B, S, H, fused_qkv):
+    """feddat_attn_bwd against autograd through softmax(q k^T / 8) v in fp32 from the same bf16 inputs (the kernel
+    rounds P and dS to bf16 for the tensor-core products, as every flash backward does)."""
+    g = torch.Generator(device="cuda").manual_seed(B * 1000 + S + 7)
+    D = 64
+    if fused_qkv:
+        qkv = torch.randn(B * S, 3 * H * D, device="cuda", generator=g).to(torch.bfloat16)
+        q, k, v = (qkv[:, i * H * D:(i + 1) * H * D].view(B, S, H, D) for i in range(3))
+    else:
+        q, k, v = (torch.randn(B * S, H * D, device="cuda", generator=g).to(torch.bfloat16).view(B, S, H, D) for _ in range(3))
+    do = torch.randn(B, S, H, D, device="cuda", generator=g).to(torch.bfloat16)
+    o, lse = ops.attn_fwd(q, k, v, 0.125)
+    dq, dk, dv = ops.attn_bwd(do, q, k, v, o, lse, 0.125)
+    qf, kf, vf = (t.float().permute(0, 2, 1, 3).detach().requires_grad_(True) for t in (q, k, v))
+    ref = torch.softmax(qf @ kf.transpose(-1, -2) * 0.125, -1) @ vf
+    ref.backward(do.float().permute(0, 2, 1, 3))
+    for name, got, want in (("dq", dq, qf.grad), ("dk", dk, kf.grad), ("dv", dv, vf.grad)):
+        assert got.shape == (B, S, H, D)
+        err = relerr(got.float().cpu().numpy(), want.permute(0, 2, 1, 3).cpu().numpy())
+        assert err < 1.5e-2, (name, err)
