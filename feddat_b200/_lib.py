@@ -40,6 +40,7 @@ EXPORTED_SYMBOLS = (
     "feddat_mlp_fc2_dgelu_bwd",
     "feddat_attn_fwd",
     "feddat_attn_bwd",
+    "feddat_attn_bwd_workspace_bytes",
 )
 # include/feddat_b200_debug.h: only in the -DFEDDAT_DEBUG twin (libfeddat_sm100_dbg.so), tests / scripts
 DEBUG_SYMBOLS = (
@@ -171,7 +172,10 @@ def _bind(lib: ctypes.CDLL, debug: bool) -> ctypes.CDLL:
     lib.feddat_attn_fwd.restype = c_int
     lib.feddat_attn_fwd.argtypes = [c_void_p] * 5 + [c_int] * 4 + [c_int64] * 4 + [c_float, c_int, c_void_p]
     lib.feddat_attn_bwd.restype = c_int
-    lib.feddat_attn_bwd.argtypes = [c_void_p] * 9 + [c_int] * 4 + [c_int64] * 8 + [c_float, c_int, c_void_p]
+    lib.feddat_attn_bwd.argtypes = [c_void_p] * 9 + [c_int] * 4 + [c_int64] * 8 + [c_float, c_void_p, ctypes.c_size_t, c_int,
+                                    c_void_p]
+    lib.feddat_attn_bwd_workspace_bytes.restype = ctypes.c_size_t
+    lib.feddat_attn_bwd_workspace_bytes.argtypes = [c_int, c_int]
     if not debug:
         return lib
     lib.feddat_probe_gemm.restype = c_int

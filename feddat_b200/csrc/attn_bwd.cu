@@ -17,7 +17,7 @@
 //                split the query range)
 //   warps 16-19  epilogue: delta / lse2 of the NEXT item, dV and dK of each key tile, dQ at the end of the item,
 //                through one [32 x 64] staging slab per warp and TMA stores
-//   warp 20      MMA issuer.  TMEM: X = [0, 192) S^T, then P^T packed in [0, 96) and dS^T packed in [96, 192);
+//   warp 20      MMA issuer.  TMEM: X = [0, 192) S^T, then P^T and dS^T packed over each thread's own score columns;
 //                Y = [192, 384) dP^T, then dV in [192, 256) and dK in [256, 320); dQ accumulators [384, 512).
 //                S^T of the next key tile is issued right behind the MMAs that consume P^T / dS^T (in-order
 //                execution makes that safe), dP^T once the epilogue warps have taken dV / dK out of Y.
@@ -30,24 +30,34 @@
 namespace fd {
 namespace {
 
-constexpr int BTHREADS = 736;
+constexpr int BTHREADS = 768;          // 16 softmax + 4 epilogue + MMA + 2 TMA producer + 1 statistics warp
 constexpr uint32_t X_COL = 0, Y_COL = 192, DQ_COL = 384;
 constexpr uint32_t KT_BYTES = AQ * 128;          // one [128 x 64] operand tile
 
 struct AttnBwdTmaps {
   CUtensorMap q, d_o, k, v;      // loads: Q / dO [QP x 64] per item, K / V [128 x 64] per key tile
-  CUtensorMap dq, dk, dv;        // stores, [32 x 64] boxes
 };
 struct AttnBwdParams {
   int B, S, H;
   int n_kt;          // 128-key tiles per item
   int n_items;       // B * H
   float scale, scale_log2e;
-  const float* lse;  // [B, H, S]
-  const __nv_bfloat16* O;
-  const __nv_bfloat16* dO;
-  int64_t ldo, lddo; // token strides of O and dO in elements
+  const float* stats; // [B * H, 2, 192] fp32 from attn_stats_kernel: lse * log2(e) (+inf past S) | delta (0 past S)
+  __nv_bfloat16* dQ; // the gradients leave through plain, row-segment-coalesced stores
+  __nv_bfloat16* dK;
+  __nv_bfloat16* dV;
+  int64_t lddq, lddk, lddv;
+  unsigned long long* trace;   // debug twin only
 };
+
+#ifdef FEDDAT_DEBUG
+#define AB_TRACE(ev, g)                                                                      \
+  do {                                                                                       \
+    if (p.trace != nullptr && blockIdx.x == 0 && (g) < 16) p.trace[(g) * 16 + (ev)] = globaltimer_ns(); \
+  } while (0)
+#else
+#define AB_TRACE(ev, g) do { (void)(g); } while (0)
+#endif
 
 template <int kNC>   // QP / 64
 __global__ void __launch_bounds__(BTHREADS, 1)
@@ -55,7 +65,9 @@ attn_bwd_kernel(const __grid_constant__ AttnBwdTmaps tm, const __grid_constant__
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bars[20];
   __shared__ uint32_t tmem_base_smem;
-  __shared__ __align__(16) float lse2_s[192], delta_s[192];
+  __shared__ __align__(16) float stats_s[384];           // [lse2 | delta] of the current item, from the statistics kernel
+  float* const lse2_s = stats_s;
+  float* const delta_s = stats_s + 192;
 
   constexpr int QP = kNC * 64;
   constexpr uint32_t QD_BYTES = static_cast<uint32_t>(QP) * 128u;     // Q or dO of one item
@@ -73,8 +85,8 @@ attn_bwd_kernel(const __grid_constant__ AttnBwdTmaps tm, const __grid_constant__
   auto bar_qd_free = [&](uint32_t b) { return bar0 + 16 + 8 * b; };
   auto bar_kv_full = [&](uint32_t s) { return bar0 + 32 + 8 * s; };
   auto bar_kv_free = [&](uint32_t s) { return bar0 + 48 + 8 * s; };
-  const uint32_t bar_st = bar0 + 64, bar_dp = bar0 + 72, bar_pt = bar0 + 80, bar_ds = bar0 + 88, bar_dvk = bar0 + 96,
-                 bar_acc_free = bar0 + 104, bar_dq_free = bar0 + 112, bar_stats = bar0 + 120;
+  const uint32_t bar_st = bar0 + 64, bar_dp = bar0 + 72, bar_ds = bar0 + 88, bar_dvk = bar0 + 96,
+                 bar_acc_free = bar0 + 104, bar_dq_free = bar0 + 112, bar_stats = bar0 + 120, bar_dq_done = bar0 + 128;
 
   if (tid == 0) {
     for (uint32_t i = 0; i < 2; ++i) {
@@ -85,12 +97,12 @@ attn_bwd_kernel(const __grid_constant__ AttnBwdTmaps tm, const __grid_constant__
     }
     mbar_init(bar_st, 1);
     mbar_init(bar_dp, 1);
-    mbar_init(bar_pt, 16);
     mbar_init(bar_ds, 16);
     mbar_init(bar_dvk, 1);
     mbar_init(bar_acc_free, 4);
     mbar_init(bar_dq_free, 4);
-    mbar_init(bar_stats, 4);
+    mbar_init(bar_stats, 1);
+    mbar_init(bar_dq_done, 1);
     fence_mbar_init();
     tma_prefetch_desc(&tm.q);
     tma_prefetch_desc(&tm.d_o);
@@ -114,20 +126,36 @@ attn_bwd_kernel(const __grid_constant__ AttnBwdTmaps tm, const __grid_constant__
 
   if (warp == 20) {
     // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
+    {
+      // the whole warp runs the control flow (waits, address arithmetic) so that descriptors stay in uniform
+      // registers; one elected lane issues
       const uint32_t idesc_t = make_idesc_bf16(AQ, QP);            // S^T, dP^T: both operands K-major
       const uint32_t idesc_v = make_idesc_bf16(AQ, AD, 0, 1);      // dV, dK: A in TMEM, B MN-major
       const uint32_t idesc_q = make_idesc_bf16(AQ, AD, 1, 1);      // dQ: A M-major (dS^T in smem), B MN-major
+      // descriptors differ from tile to tile only in the start-address field (units of 16 bytes, no carry out of
+      // it: every operand lies below 256 KB): one base per operand, then integer adds -- a single thread issues
+      // ~50 MMAs per key tile and descriptor arithmetic was half of its time
+      const uint64_t dk_q0 = desc_kmajor_sw128(q_s(0)), dk_q1 = desc_kmajor_sw128(q_s(1));
+      const uint64_t dk_do0 = desc_kmajor_sw128(do_s(0)), dk_do1 = desc_kmajor_sw128(do_s(1));
+      const uint64_t dm_q0 = desc_mnmajor_sw128(q_s(0), 1024), dm_q1 = desc_mnmajor_sw128(q_s(1), 1024);
+      const uint64_t dm_do0 = desc_mnmajor_sw128(do_s(0), 1024), dm_do1 = desc_mnmajor_sw128(do_s(1), 1024);
+      const uint64_t dk_k0 = desc_kmajor_sw128(k_s(0)), dk_k1 = desc_kmajor_sw128(k_s(1));
+      const uint64_t dk_v0 = desc_kmajor_sw128(v_s(0)), dk_v1 = desc_kmajor_sw128(v_s(1));
+      const uint64_t dm_k0 = desc_mnmajor_sw128(k_s(0), 1024), dm_k1 = desc_mnmajor_sw128(k_s(1), 1024);
+      const uint64_t dm_ds = desc_mnmajor_sw128(ds_s, KT_BYTES);
       uint32_t g = 0;
       auto issue_st = [&](int i, int kt, uint32_t gg) {
         const uint32_t buf = static_cast<uint32_t>(i) & 1, st = gg & 1;
         if (kt == 0) mbar_wait(bar_qd_full(buf), (static_cast<uint32_t>(i) >> 1) & 1);
         mbar_wait(bar_kv_full(st), (gg >> 1) & 1);
         tc_fence_after();
+        if (elect_one()) {
 #pragma unroll
-        for (int k = 0; k < AD / 16; ++k)
-          umma_ss(tmem + X_COL, desc_kmajor_sw128(k_s(st) + k * 32), desc_kmajor_sw128(q_s(buf) + k * 32), idesc_t, k > 0);
-        umma_commit(bar_st);
+          for (int k = 0; k < AD / 16; ++k) umma_ss(tmem + X_COL, (st ? dk_k1 : dk_k0) + 2 * k, (buf ? dk_q1 : dk_q0) + 2 * k, idesc_t, k > 0);
+          umma_commit(bar_st);
+          AB_TRACE(0, gg);
+        }
+        __syncwarp();
       };
       if (n_mine > 0) issue_st(0, 0, 0);
       for (int i = 0; i < n_mine; ++i) {
@@ -137,31 +165,47 @@ attn_bwd_kernel(const __grid_constant__ AttnBwdTmaps tm, const __grid_constant__
           // dP^T = V_t dO^T into Y once the epilogue warps have taken the previous tile's dV / dK out of it
           if (g > 0) mbar_wait(bar_acc_free, (g - 1) & 1);
           tc_fence_after();
+          if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < AD / 16; ++k)
-            umma_ss(tmem + Y_COL, desc_kmajor_sw128(v_s(st) + k * 32), desc_kmajor_sw128(do_s(buf) + k * 32), idesc_t, k > 0);
-          umma_commit(bar_dp);
+            for (int k = 0; k < AD / 16; ++k) umma_ss(tmem + Y_COL, (st ? dk_v1 : dk_v0) + 2 * k, (buf ? dk_do1 : dk_do0) + 2 * k, idesc_t, k > 0);
+            umma_commit(bar_dp);
+            AB_TRACE(1, g);
+          }
+          __syncwarp();
           // P^T and dS^T are in TMEM (X), dS^T also in shared memory; dP^T has been read out of Y
           mbar_wait(bar_ds, g & 1);
-          if (kt == 0 && i > 0) mbar_wait(bar_dq_free, (static_cast<uint32_t>(i) - 1) & 1);   // previous item's dQ is out
           tc_fence_after();
+          if (elect_one()) {
+          AB_TRACE(2, g);
 #pragma unroll
-          for (int k = 0; k < QP / 16; ++k)        // dV_t = P^T dO
-            umma_ts(tmem + Y_COL, tmem + X_COL + k * 8, desc_mnmajor_sw128(do_s(buf) + k * 2048, 1024), idesc_v, k > 0);
+          for (int k = 0; k < QP / 16; ++k)        // dV_t = P^T dO  (16 query rows = 2048 bytes = 128 address units per step)
+            umma_ts(tmem + Y_COL, tmem + X_COL + (k / kNC) * (QP / 4) + (k % kNC) * 8, (buf ? dm_do1 : dm_do0) + 128 * k, idesc_v, k > 0);
 #pragma unroll
           for (int k = 0; k < QP / 16; ++k)        // dK_t = dS^T Q
-            umma_ts(tmem + Y_COL + 64, tmem + X_COL + 96 + k * 8, desc_mnmajor_sw128(q_s(buf) + k * 2048, 1024), idesc_v, k > 0);
+            umma_ts(tmem + Y_COL + 64, tmem + X_COL + (k / kNC) * (QP / 4) + QP / 8 + (k % kNC) * 8, (buf ? dm_q1 : dm_q0) + 128 * k, idesc_v,
+                    k > 0);
+          umma_commit(bar_dvk);
+          }
+          __syncwarp();
+          // S^T of the next key tile overwrites X right behind its two readers (tcgen05.mma executes in order)
+          if (kt + 1 < n_kt) issue_st(i, kt + 1, g + 1);
+          else if (i + 1 < n_mine) issue_st(i + 1, 0, g + 1);
+          if (kt == 0 && i > 0) mbar_wait(bar_dq_free, (static_cast<uint32_t>(i) - 1) & 1);   // previous item's dQ is out
+          tc_fence_after();
+          if (elect_one()) {
           for (int mt = 0; mt < n_mtq; ++mt)       // dQ[128 mt ...] += dS K_t  (M = queries: two 64-query blocks per tile)
 #pragma unroll
             for (int k = 0; k < AQ / 16; ++k)
-              umma_ss(tmem + DQ_COL + mt * 64, desc_mnmajor_sw128(ds_s + mt * 2 * KT_BYTES + k * 2048, KT_BYTES),
-                      desc_mnmajor_sw128(k_s(st) + k * 2048, 1024), idesc_q, !(kt == 0 && k == 0));
-          umma_commit(bar_dvk);
+              umma_ss(tmem + DQ_COL + mt * 64, dm_ds + (mt * 2 * KT_BYTES >> 4) + 128 * k, (st ? dm_k1 : dm_k0) + 128 * k, idesc_q,
+                      !(kt == 0 && k == 0));
           umma_commit(bar_kv_free(st));
-          if (kt == n_kt - 1) umma_commit(bar_qd_free(buf));
-          // S^T of the next key tile overwrites X behind the MMAs that have just been issued
-          if (kt + 1 < n_kt) issue_st(i, kt + 1, g + 1);
-          else if (i + 1 < n_mine) issue_st(i + 1, 0, g + 1);
+          if (kt == n_kt - 1) {
+            umma_commit(bar_qd_free(buf));
+            umma_commit(bar_dq_done);
+          }
+          AB_TRACE(3, g);
+          }
+          __syncwarp();
         }
       }
     }
@@ -195,54 +239,28 @@ attn_bwd_kernel(const __grid_constant__ AttnBwdTmaps tm, const __grid_constant__
       }
     }
     __syncwarp();
+  } else if (warp == 23) {
+    // ------------------------------------------------------------------ statistics: one 1.5 KB bulk copy per item, issued as
+    // soon as the softmax warps are through with the previous item's (its last dS^T is out)
+    // (every phase of bar_ds is waited for in turn: a parity wait cannot tell phase g from phase g - 2)
+    if (lane == 0) {
+      uint32_t g = 0;
+      for (int i = 0; i < n_mine; ++i) {
+        mbar_arrive_expect_tx(bar_stats, 384 * 4);
+        bulk_load_1d(smem_u32(stats_s), p.stats + static_cast<size_t>(item_of(i)) * 384, 384 * 4, bar_stats);
+        for (int kt = 0; kt < n_kt; ++kt, ++g) mbar_wait(bar_ds, g & 1);
+      }
+    }
+    __syncwarp();
   } else if (warp >= 16) {
     // ------------------------------------------------------------------ epilogue warps
     const uint32_t q = warp & 3;
     const uint32_t lane_addr = (q * 32u) << 16;
     const uint32_t slab = slab0 + q * 4096u;
-    const int et = tid - 512;                                  // 0 .. 127
-    // delta[r] = dO[r, :] . O[r, :] and lse2[r] = lse[r] log2(e) of item i for query rows et and et + 128
-    float st_d[2], st_l[2];
-    auto stats_load = [&](int i) {
-      const int bh = item_of(i), h = bh % p.H, b = bh / p.H;
-#pragma unroll
-      for (int u = 0; u < 2; ++u) {
-        const int r = et + u * AQ;
-        st_d[u] = 0.f;
-        st_l[u] = INFINITY;                                    // queries past the sequence: P^T = 2^(-inf) = 0
-        if (r < S) {
-          const uint4* po = reinterpret_cast<const uint4*>(p.O + (static_cast<size_t>(b) * S + r) * p.ldo + h * AD);
-          const uint4* pd = reinterpret_cast<const uint4*>(p.dO + (static_cast<size_t>(b) * S + r) * p.lddo + h * AD);
-          float acc = 0.f;
-#pragma unroll
-          for (int c = 0; c < 8; ++c) {
-            const uint4 a = __ldg(po + c), d = __ldg(pd + c);
-            const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, dw[4] = {d.x, d.y, d.z, d.w};
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              acc = fmaf(__uint_as_float(aw[k] << 16), __uint_as_float(dw[k] << 16), acc);
-              acc = fmaf(__uint_as_float(aw[k] & 0xffff0000u), __uint_as_float(dw[k] & 0xffff0000u), acc);
-            }
-          }
-          st_d[u] = acc;
-          st_l[u] = p.lse[(static_cast<size_t>(b) * p.H + h) * S + r] * 1.4426950408889634f;
-        }
-      }
-    };
-    auto stats_publish = [&]() {
-#pragma unroll
-      for (int u = 0; u < 2; ++u)
-        if (et + u * AQ < 192) {
-          delta_s[et + u * AQ] = st_d[u];
-          lse2_s[et + u * AQ] = st_l[u];
-        }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(bar_stats);
-    };
-    // one [32 x 64] fp32 accumulator block of this lane quarter -> bf16 (x mul) -> slab -> TMA store
-    auto store_block = [&](uint32_t col, float mul, const CUtensorMap* map, int row0, int h, int b, bool arrive_acc) {
-      if (lane == 0) tma_store_wait_read<0>();
-      __syncwarp();
+    // one [32 x 64] fp32 accumulator block of this lane quarter -> x mul -> bf16 -> the warp's slab (row per thread)
+    // -> global memory as full 128-byte row segments, eight lanes per row (four lines per store instruction; a row
+    // per lane would occupy the load / store unit 8 x longer, which the softmax warps' shared-memory traffic feels)
+    auto store_block = [&](uint32_t col, float mul, __nv_bfloat16* base, int64_t ld, int row0, int h, int b, bool arrive_acc) {
       const float2 m2 = make_float2(mul, mul);
 #pragma unroll
       for (int hf = 0; hf < 2; ++hf) {
@@ -265,47 +283,47 @@ attn_bwd_kernel(const __grid_constant__ AttnBwdTmaps tm, const __grid_constant__
           st_shared_v4(slab + sw128_offset(lane, hf * 4 + ch), o[0], o[1], o[2], o[3]);
         }
       }
-      fence_proxy_async_smem();
       __syncwarp();
-      if (lane == 0) {
-        tma_store_3d(map, slab, h * AD, row0, b);
-        tma_store_commit();
+      const uint32_t j8 = lane & 7, r0 = lane >> 3;
+      __nv_bfloat16* dst = base + (static_cast<size_t>(b) * S + row0 + r0) * ld + h * AD + j8 * 8;
+#pragma unroll
+      for (int i2 = 0; i2 < 8; ++i2) {
+        const uint4 t = ld_shared_v4(slab + sw128_offset(r0 + 4 * i2, j8));
+        if (row0 + static_cast<int>(r0) + 4 * i2 < S) *reinterpret_cast<uint4*>(dst + static_cast<size_t>(4 * i2) * ld) = t;
       }
+      __syncwarp();
     };
 
-    if (n_mine > 0) {
-      stats_load(0);
-      stats_publish();
-    }
     uint32_t g = 0;
     for (int i = 0; i < n_mine; ++i) {
       const int bh = item_of(i), h = bh % p.H, b = bh / p.H;
-      if (i + 1 < n_mine) stats_load(i + 1);
       for (int kt = 0; kt < n_kt; ++kt, ++g) {
         mbar_wait(bar_dvk, g & 1);
         tc_fence_after();
-        // the softmax warps are through with this item's delta / lse2 once its last dS^T is out
-        if (kt == n_kt - 1 && i + 1 < n_mine) stats_publish();
+        if (tid == 512) AB_TRACE(9, g);
         const int row0 = kt * AQ + static_cast<int>(q) * 32;
         if (row0 < S) {
-          store_block(Y_COL, 1.f, &tm.dv, row0, h, b, false);
-          store_block(Y_COL + 64, p.scale, &tm.dk, row0, h, b, true);
+          store_block(Y_COL, 1.f, p.dV, p.lddv, row0, h, b, false);
+          store_block(Y_COL + 64, p.scale, p.dK, p.lddk, row0, h, b, true);
+          if (tid == 512) AB_TRACE(10, g);
         } else {
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(bar_acc_free);
         }
         if (kt == n_kt - 1) {
+          mbar_wait(bar_dq_done, i & 1);
+          tc_fence_after();
           for (int mt = 0; mt < n_mtq; ++mt)
             if (mt * AQ + static_cast<int>(q) * 32 < S)
-              store_block(DQ_COL + mt * 64, p.scale, &tm.dq, mt * AQ + static_cast<int>(q) * 32, h, b, false);
+              store_block(DQ_COL + mt * 64, p.scale, p.dQ, p.lddq, mt * AQ + static_cast<int>(q) * 32, h, b, false);
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(bar_dq_free);
+          if (tid == 512) AB_TRACE(11, g);
         }
       }
     }
-    if (lane == 0) tma_store_wait_all<0>();
   } else {
     // ------------------------------------------------------------------ "softmax" warps: four threads per key row
     const uint32_t q = warp & 3, cq = warp >> 2;
@@ -321,6 +339,7 @@ attn_bwd_kernel(const __grid_constant__ AttnBwdTmaps tm, const __grid_constant__
         const bool live = kt * AQ + static_cast<int>(q) * 32 < S;     // warp-uniform: some key of this lane quarter is real
         mbar_wait(bar_st, g & 1);
         tc_fence_after();
+        if (tid == 0) AB_TRACE(5, g);
         uint32_t pk[NQ / 2];                                   // this thread's P^T, bf16 pairs
         if (live) {
           uint32_t v[kNC][16];
@@ -341,37 +360,42 @@ attn_bwd_kernel(const __grid_constant__ AttnBwdTmaps tm, const __grid_constant__
             }
           }
         }
-        // every thread of the lane quarter has its scores in registers: the packed P^T may overwrite X's front
-        named_bar_sync(2 + q, 128);
+        // P^T goes over the FIRST half of this thread's own score columns, dS^T (below) over the second half: no
+        // thread writes a column another one still has to read, so no barrier; the MMAs take one TMEM address per
+        // 16-query step and do not care that the steps are not contiguous
         if (live) {
 #pragma unroll
           for (int ch = 0; ch < kNC; ++ch) {
             uint32_t w[8];
 #pragma unroll
             for (int k = 0; k < 8; ++k) w[k] = pk[ch * 8 + k];
-            tmem_st8(tmem + lane_addr + X_COL + j0 / 2 + ch * 8, w);
+            tmem_st8(tmem + lane_addr + X_COL + j0 + ch * 8, w);
           }
         }
+        if (tid == 0) AB_TRACE(6, g);
         mbar_wait(bar_dp, g & 1);
         tc_fence_after();
+        if (tid == 0) AB_TRACE(7, g);
         if (live) {
+          uint32_t u[2][16];                                   // the next chunk is requested before this one is used
+          tmem_ld16(tmem + lane_addr + Y_COL + j0, u[0]);
 #pragma unroll
           for (int ch = 0; ch < kNC; ++ch) {
-            uint32_t u[16], w[8];
-            tmem_ld16(tmem + lane_addr + Y_COL + j0 + ch * 16, u);
-            tmem_ld_wait16(u);
+            uint32_t w[8];
+            tmem_ld_wait16(u[ch & 1]);
+            if (ch + 1 < kNC) tmem_ld16(tmem + lane_addr + Y_COL + j0 + (ch + 1) * 16, u[(ch + 1) & 1]);
 #pragma unroll
             for (int k4 = 0; k4 < 4; ++k4) {
               const float4 d = *reinterpret_cast<const float4*>(&delta_s[j0 + ch * 16 + k4 * 4]);
               const float2 p0 = unpack_bf16x2(pk[ch * 8 + k4 * 2]), p1 = unpack_bf16x2(pk[ch * 8 + k4 * 2 + 1]);
-              const float2 t0 = __fadd2_rn(make_float2(__uint_as_float(u[k4 * 4]), __uint_as_float(u[k4 * 4 + 1])), make_float2(-d.x, -d.y));
-              const float2 t1 = __fadd2_rn(make_float2(__uint_as_float(u[k4 * 4 + 2]), __uint_as_float(u[k4 * 4 + 3])), make_float2(-d.z, -d.w));
+              const float2 t0 = __fadd2_rn(make_float2(__uint_as_float(u[ch & 1][k4 * 4]), __uint_as_float(u[ch & 1][k4 * 4 + 1])), make_float2(-d.x, -d.y));
+              const float2 t1 = __fadd2_rn(make_float2(__uint_as_float(u[ch & 1][k4 * 4 + 2]), __uint_as_float(u[ch & 1][k4 * 4 + 3])), make_float2(-d.z, -d.w));
               const float2 s0 = __fmul2_rn(p0, t0), s1 = __fmul2_rn(p1, t1);
               w[k4 * 2] = pack_bf16x2(s0.x, s0.y);
               w[k4 * 2 + 1] = pack_bf16x2(s1.x, s1.y);
             }
-            // dS^T: packed over the upper half of X (every S^T value there was read before the barrier above) ...
-            tmem_st8(tmem + lane_addr + X_COL + 96 + j0 / 2 + ch * 8, w);
+            // dS^T: packed over the second half of this thread's own score columns ...
+            tmem_st8(tmem + lane_addr + X_COL + j0 + NQ / 2 + ch * 8, w);
             // ... and into the [keys x queries] shared-memory tile the dQ product reads
             const int qc = j0 + ch * 16;                       // first of these 16 query columns
             const uint32_t blk = ds_s + static_cast<uint32_t>(qc >> 6) * KT_BYTES;
@@ -384,6 +408,7 @@ attn_bwd_kernel(const __grid_constant__ AttnBwdTmaps tm, const __grid_constant__
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_ds);
+        if (tid == 0) AB_TRACE(8, g);
       }
     }
   }
@@ -393,13 +418,50 @@ attn_bwd_kernel(const __grid_constant__ AttnBwdTmaps tm, const __grid_constant__
   if (warp == 20) tmem_dealloc(tmem, 512);
 }
 
+// delta[q] = dO[q, :] . O[q, :] and lse2[q] = lse[q] log2(e) per (batch, head): one thread per query row (a row of O or
+// dO is one 128-byte line), padded to 192 entries with (+inf, 0) so that padded queries get P^T = 0, dS^T = 0
+__global__ void __launch_bounds__(192)
+attn_stats_kernel(const __nv_bfloat16* __restrict__ O, const __nv_bfloat16* __restrict__ dO, const float* __restrict__ lse,
+                  float* __restrict__ stats, int S, int H, int64_t ldo, int64_t lddo) {
+  pdl_wait();
+  pdl_launch_dependents();
+  const int bh = blockIdx.x, h = bh % H, b = bh / H, r = threadIdx.x;
+  float l2 = INFINITY, dl = 0.f;
+  if (r < S) {
+    const uint4* po = reinterpret_cast<const uint4*>(O + (static_cast<size_t>(b) * S + r) * ldo + h * AD);
+    const uint4* pd = reinterpret_cast<const uint4*>(dO + (static_cast<size_t>(b) * S + r) * lddo + h * AD);
+    uint4 a[8], d[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      a[c] = __ldg(po + c);
+      d[c] = __ldg(pd + c);
+    }
+    l2 = __ldg(lse + static_cast<size_t>(bh) * S + r) * 1.4426950408889634f;
+    float acc0 = 0.f, acc1 = 0.f;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      const uint32_t aw[4] = {a[c].x, a[c].y, a[c].z, a[c].w}, dw[4] = {d[c].x, d[c].y, d[c].z, d[c].w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        acc0 = fmaf(__uint_as_float(aw[k] << 16), __uint_as_float(dw[k] << 16), acc0);
+        acc1 = fmaf(__uint_as_float(aw[k] & 0xffff0000u), __uint_as_float(dw[k] & 0xffff0000u), acc1);
+      }
+    }
+    dl = acc0 + acc1;
+  }
+  stats[static_cast<size_t>(bh) * 384 + r] = l2;
+  stats[static_cast<size_t>(bh) * 384 + 192 + r] = dl;
+}
+
 }  // namespace
 }  // namespace fd
+
+extern "C" size_t feddat_attn_bwd_workspace_bytes(int B, int H) { return static_cast<size_t>(B) * H * 384 * sizeof(float); }
 
 extern "C" int feddat_attn_bwd(const void* dO, const void* Q, const void* K, const void* V, const void* O, const void* LSE,
                                void* dQ, void* dK, void* dV, int B, int S, int H, int D, int64_t lddo, int64_t ldq,
                                int64_t ldk, int64_t ldv, int64_t ldo, int64_t lddq, int64_t lddk, int64_t lddv, float scale,
-                               int dtype, void* stream) {
+                               void* workspace, size_t ws_bytes, int dtype, void* stream) {
   using namespace fd;
   int rc = check_device_sm100();
   if (rc) return rc;
@@ -409,26 +471,48 @@ extern "C" int feddat_attn_bwd(const void* dO, const void* Q, const void* K, con
              "attn_bwd: head dimension %d / sequence length %d outside the short-sequence kernel (D = 64, S <= 192)", D, S);
   FD_REQUIRE(ldo % 8 == 0 && lddo % 8 == 0 && ((reinterpret_cast<uintptr_t>(O) | reinterpret_cast<uintptr_t>(dO)) & 15) == 0,
              FD_ERR_INVALID, "attn_bwd: O / dO rows must be 16-byte aligned");
+  FD_REQUIRE(workspace != nullptr && ws_bytes >= feddat_attn_bwd_workspace_bytes(B, H) &&
+                 (reinterpret_cast<uintptr_t>(workspace) & 15) == 0,
+             FD_ERR_INVALID, "attn_bwd: workspace of feddat_attn_bwd_workspace_bytes(B, H) bytes, 16-byte aligned, required");
   if (B == 0) return FD_OK;
+  auto st = static_cast<cudaStream_t>(stream);
+  const char* e = getenv("FEDDAT_PDL");
+  const int n_attr = (e && e[0] == '0') ? 0 : 1;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  {
+    cudaLaunchConfig_t c0{};
+    c0.gridDim = dim3(B * H);
+    c0.blockDim = dim3(192);
+    c0.stream = st;
+    c0.attrs = attr;
+    c0.numAttrs = n_attr;
+    FD_CHECK_CUDA(cudaLaunchKernelEx(&c0, attn_stats_kernel, static_cast<const __nv_bfloat16*>(O),
+                                     static_cast<const __nv_bfloat16*>(dO), static_cast<const float*>(LSE),
+                                     static_cast<float*>(workspace), S, H, ldo, lddo));
+  }
   AttnBwdParams p{};
   p.B = B; p.S = S; p.H = H;
   p.n_kt = (S + AQ - 1) / AQ;
   p.n_items = B * H;
   p.scale = scale;
   p.scale_log2e = scale * 1.4426950408889634f;
-  p.lse = static_cast<const float*>(LSE);
-  p.O = static_cast<const __nv_bfloat16*>(O);
-  p.dO = static_cast<const __nv_bfloat16*>(dO);
-  p.ldo = ldo; p.lddo = lddo;
+  p.stats = static_cast<const float*>(workspace);
+  p.dQ = static_cast<__nv_bfloat16*>(dQ);
+  p.dK = static_cast<__nv_bfloat16*>(dK);
+  p.dV = static_cast<__nv_bfloat16*>(dV);
+  p.lddq = lddq; p.lddk = lddk; p.lddv = lddv;
+  p.trace = FD_TRACE_PTR;
   const int nc = (S + 63) / 64, QP = nc * 64;
   AttnBwdTmaps tm;
   if ((rc = make_tmap_tokens(&tm.q, Q, B, S, H * D, ldq, QP))) return rc;
   if ((rc = make_tmap_tokens(&tm.d_o, dO, B, S, H * D, lddo, QP))) return rc;
   if ((rc = make_tmap_tokens(&tm.k, K, B, S, H * D, ldk, AQ))) return rc;
   if ((rc = make_tmap_tokens(&tm.v, V, B, S, H * D, ldv, AQ))) return rc;
-  if ((rc = make_tmap_tokens(&tm.dq, dQ, B, S, H * D, lddq, 32))) return rc;
-  if ((rc = make_tmap_tokens(&tm.dk, dK, B, S, H * D, lddk, 32))) return rc;
-  if ((rc = make_tmap_tokens(&tm.dv, dV, B, S, H * D, lddv, 32))) return rc;
+  FD_REQUIRE(lddq % 8 == 0 && lddk % 8 == 0 && lddv % 8 == 0 &&
+                 ((reinterpret_cast<uintptr_t>(dQ) | reinterpret_cast<uintptr_t>(dK) | reinterpret_cast<uintptr_t>(dV)) & 15) == 0,
+             FD_ERR_INVALID, "attn_bwd: dQ / dK / dV rows must be 16-byte aligned");
   int sms = 0;
   if ((rc = device_sm_count(&sms))) return rc;
   // Q / dO double-buffered, K / V two stages, dS^T, four slabs (+ one operand tile of slack behind dS^T for the
@@ -447,13 +531,9 @@ extern "C" int feddat_attn_bwd(const void* dO, const void* Q, const void* K, con
   cfg.gridDim = dim3(p.n_items < sms ? p.n_items : sms);
   cfg.blockDim = dim3(BTHREADS);
   cfg.dynamicSmemBytes = smem;
-  cfg.stream = static_cast<cudaStream_t>(stream);
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.stream = st;
   cfg.attrs = attr;
-  const char* e = getenv("FEDDAT_PDL");
-  cfg.numAttrs = (e && e[0] == '0') ? 0 : 1;
+  cfg.numAttrs = n_attr;
   FD_CHECK_CUDA(cudaLaunchKernelEx(&cfg, fn, tm, p));
   FD_CHECK_CUDA(cudaGetLastError());
   return FD_OK;

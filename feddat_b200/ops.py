@@ -562,9 +562,11 @@ def attn_bwd(do: torch.Tensor, q: torch.Tensor, k: torch.Tensor, v: torch.Tensor
     dqkv = torch.empty(B, S, 3, H, D, device=q.device, dtype=torch.bfloat16)
     dq, dk, dv = dqkv[:, :, 0], dqkv[:, :, 1], dqkv[:, :, 2]
     ld = 3 * H * D
+    ws = torch.empty(B * H * 384, device=q.device, dtype=torch.float32)     # per-row statistics of the pre-pass
     rc = lib.feddat_attn_bwd(_lib.ptr(do), _lib.ptr(q), _lib.ptr(k), _lib.ptr(v), _lib.ptr(o), _lib.ptr(lse), _lib.ptr(dq),
                              _lib.ptr(dk), _lib.ptr(dv), B, S, H, D, lddo, ldq, ldk, ldv, ldo, ld, ld, ld, float(scale),
-                             DTYPE_BF16, _lib.stream_ptr())
+                             _lib.ptr(ws), ws.numel() * 4, DTYPE_BF16, _lib.stream_ptr())
+    _count()
     _lib.check(rc, "feddat_attn_bwd")
     _count()
     return dq, dk, dv

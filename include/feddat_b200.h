@@ -276,12 +276,14 @@ int feddat_mlp_fc2_dgelu_bwd(const void* dY, const void* W2T, const void* pre, v
  */
 int feddat_attn_fwd(const void* Q, const void* K, const void* V, void* O, void* LSE, int B, int S, int H, int D,
                     int64_t ldq, int64_t ldk, int64_t ldv, int64_t ldo, float scale, int dtype, void* stream);
-/*   feddat_attn_bwd   dQ, dK, dV of the same attention from dO, the forward's inputs, its output O and LSE, in ONE launch
- *                     (S <= 192).  All nine tensors in the token layout above, each with its own token stride, so the
+/*   feddat_attn_bwd   dQ, dK, dV of the same attention from dO, the forward's inputs, its output O and LSE (S <= 192):
+ *                     a row-statistics pass (delta = dO . O) into the caller's workspace, then ONE fused launch.  All nine tensors in the token layout above, each with its own token stride, so the
  *                     three gradients may be column slices of one [B * S, 3 * H * 64] tensor. */
+size_t feddat_attn_bwd_workspace_bytes(int B, int H);   /* per-row statistics (delta, scaled logsumexp), fp32 */
 int feddat_attn_bwd(const void* dO, const void* Q, const void* K, const void* V, const void* O, const void* LSE, void* dQ,
                     void* dK, void* dV, int B, int S, int H, int D, int64_t lddo, int64_t ldq, int64_t ldk, int64_t ldv,
-                    int64_t ldo, int64_t lddq, int64_t lddk, int64_t lddv, float scale, int dtype, void* stream);
+                    int64_t ldo, int64_t lddq, int64_t lddk, int64_t lddv, float scale, void* workspace, size_t ws_bytes,
+                    int dtype, void* stream);
 
 #ifdef __cplusplus
 }

@@ -27,3 +27,22 @@ t0 = min(x for row in t for x in row if x)
 for i in range(12):
     print(f"item {i}: " + "  ".join(f"{names[e].split(':')[0]}{e}={(t[i][e] - t0) / 1e3:6.2f}" for e in range(13) if t[i][e]))
 print("events:", {e: n for e, n in enumerate(names)})
+
+# ---- backward
+do = torch.randn(B, S, H, D, device=dev, generator=g).to(torch.bfloat16)
+o, lse = ops.attn_fwd(q, k, v, 0.125)
+for _ in range(3):
+    ops.attn_bwd(do, q, k, v, o, lse, 0.125)
+buf.zero_()
+lib.feddat_debug_set_trace(_lib.ptr(buf))
+ops.attn_bwd(do, q, k, v, o, lse, 0.125)
+torch.cuda.synchronize()
+lib.feddat_debug_set_trace(None)
+t = buf.cpu().view(16, 16).tolist()
+names = ["mma: S^T issued", "mma: dP^T issued", "mma: dS^T seen", "mma: dV dK dQ issued", "", "smx: S^T seen", "smx: P^T packed", "smx: dP^T seen",
+         "smx: dS^T out", "epi: dV dK done seen", "epi: dK stored, Y free", "epi: dQ stored"]
+t0 = min(x for row in t for x in row if x)
+print("backward, key tile steps g (two per item):")
+for i in range(12):
+    print(f"g {i}: " + "  ".join(f"{names[e].split(':')[0]}{e}={(t[i][e] - t0) / 1e3:6.2f}" for e in range(12) if t[i][e]))
+print("events:", {e: n for e, n in enumerate(names) if n})
