@@ -56,8 +56,62 @@ class _FrozenQKV(torch.autograd.Function):
         return dx.view(*shape[:-1], wq.shape[1]), None, None, None, None, None, None
 
 
+FUSE_ATTENTION = True      # own short-sequence attention kernels (csrc/attn.cu, attn_bwd.cu) where they apply
+
+
+class _FrozenQKVAttention(torch.autograd.Function):
+    """ctx = softmax(q k^T / sqrt(d)) v with q, k, v the three FROZEN projections of x, for short sequences:
+    ONE [M, 768] x [768, 2304] GEMM (concatenated frozen weights), this repo's attention kernel on column slices of
+    its output (feddat_attn_fwd), and in backward feddat_attn_bwd writing dq | dk | dv into ONE [M, 2304] tensor that
+    a single GEMM against the concatenated weight turns into dx -- instead of 3 GEMMs + cuDNN SDPA forward and
+    3 cuDNN launches + 3 GEMMs backward (HF ViltSelfAttention; reference src/modeling/vilt.py:19,127)."""
+
+    @staticmethod
+    def forward(ctx, x, w_qkv, b_qkv, heads, scale):
+        from .. import ops
+        b, s, d = x.shape
+        qkv = torch.addmm(b_qkv, x.reshape(-1, d), w_qkv.t()).view(b, s, 3, heads, d // heads)
+        o, lse = ops.attn_fwd(qkv[:, :, 0], qkv[:, :, 1], qkv[:, :, 2], scale)
+        ctx.save_for_backward(qkv, o, lse, w_qkv)
+        ctx.scale = scale
+        return o.view(b, s, d)
+
+    @staticmethod
+    def backward(ctx, g):
+        from .. import ops
+        qkv, o, lse, w_qkv = ctx.saved_tensors
+        b, s, _, heads, dh = qkv.shape
+        g = g.contiguous().view(b, s, heads, dh)
+        dqkv = ops.attn_bwd(g, qkv[:, :, 0], qkv[:, :, 1], qkv[:, :, 2], o, lse, ctx.scale, packed=True)
+        dx = torch.mm(dqkv.view(b * s, 3 * heads * dh), w_qkv)
+        return dx.view(b, s, heads * dh), None, None, None, None
+
+
+def _qkv_concat(att):
+    """[2304, 768] weight and [2304] bias of the three frozen projections, cached on the attention module and
+    rebuilt when any of the six tensors changes (load_state_dict, dtype casts)."""
+    ps = (att.query.weight, att.key.weight, att.value.weight, att.query.bias, att.key.bias, att.value.bias)
+    key = tuple((p.data_ptr(), p._version, p.dtype) for p in ps)
+    cached = getattr(att, "_feddat_qkv", None)
+    if cached is None or cached[0] != key:
+        with torch.no_grad():
+            cached = (key, torch.cat([p.detach() for p in ps[:3]], 0).contiguous(),
+                      torch.cat([p.detach() for p in ps[3:]], 0).contiguous())
+        att._feddat_qkv = cached
+    return cached[1], cached[2]
+
+
+def _own_attention_ok(att, x, frozen, needs_grad) -> bool:
+    from .. import ops
+    dh = att.attention_head_size
+    return (FUSE_ATTENTION and frozen and x.is_cuda and x.dtype == torch.bfloat16 and att.query.weight.dtype == torch.bfloat16
+            and dh == 64 and x.dim() == 3 and x.shape[1] <= (ops.ATTN_MAX_S_BWD if needs_grad else ops.ATTN_MAX_S_FWD)
+            and (att.dropout.p == 0.0 or not att.training))
+
+
 def _sdpa_self_attention_forward(self, hidden_states, attention_mask=None, output_attentions=False):
-    """softmax(QK^T / sqrt(d)) V of HF ViltSelfAttention, through torch SDPA (frozen backbone op)."""
+    """softmax(QK^T / sqrt(d)) V of HF ViltSelfAttention: this repo's short-sequence kernels when they apply
+    (``_FrozenQKVAttention``), torch SDPA otherwise (frozen backbone op)."""
     if output_attentions:
         from .fused_ln import _fallback_once
         _fallback_once("_sdpa_self_attention_forward", "attention maps requested: explicit softmax path")
@@ -66,6 +120,14 @@ def _sdpa_self_attention_forward(self, hidden_states, attention_mask=None, outpu
     h, dh = self.num_attention_heads, self.attention_head_size
     mods = (self.query, self.key, self.value)
     frozen = not any(p.requires_grad for m in mods for p in m.parameters()) and all(m.bias is not None for m in mods)
+    if attention_mask is None and _own_attention_ok(self, hidden_states, frozen,
+                                                        hidden_states.requires_grad and torch.is_grad_enabled()):
+        w_qkv, b_qkv = _qkv_concat(self)
+        return (_FrozenQKVAttention.apply(hidden_states.contiguous(), w_qkv, b_qkv, h, 1.0 / math.sqrt(dh)),)
+    if FUSE_ATTENTION and attention_mask is None:
+        from .fused_ln import _fallback_once
+        _fallback_once("_sdpa_self_attention_forward", "sequence longer than the short-sequence attention kernels cover, "
+                       "non-bf16 / unfrozen projections or active dropout: torch SDPA")
     if frozen and hidden_states.requires_grad:
         q, k, v = _FrozenQKV.apply(hidden_states, self.query.weight, self.query.bias, self.key.weight,
                                    self.key.bias, self.value.weight, self.value.bias)

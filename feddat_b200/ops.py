@@ -548,9 +548,10 @@ ATTN_MAX_S_BWD = 192
 
 
 def attn_bwd(do: torch.Tensor, q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, o: torch.Tensor, lse: torch.Tensor,
-             scale: float):
-    """(dq, dk, dv) of ``attn_fwd`` in one launch (feddat_attn_bwd).  The three gradients are the column slices of ONE
-    [B, S, 3, H, 64] tensor (token stride 3 * H * 64): a fused q/k/v projection's backward can consume it whole."""
+             scale: float, packed: bool = False):
+    """(dq, dk, dv) of ``attn_fwd`` (feddat_attn_bwd: a row-statistics pass, then one fused launch).  The three gradients
+    are the column slices of ONE [B, S, 3, H, 64] tensor (token stride 3 * H * 64), returned whole with ``packed``: a
+    fused q/k/v projection's backward can consume it as it is."""
     lib = _lib.load()
     B, S, H, D, ldq = _token_view(q, "attn_bwd q")
     _, _, _, _, ldk = _token_view(k, "attn_bwd k")
@@ -569,4 +570,4 @@ def attn_bwd(do: torch.Tensor, q: torch.Tensor, k: torch.Tensor, v: torch.Tensor
     _count()
     _lib.check(rc, "feddat_attn_bwd")
     _count()
-    return dq, dk, dv
+    return dqkv if packed else (dq, dk, dv)

@@ -584,3 +584,32 @@ def test_attn_bwd_matches_torch(ops, B, S, H, fused_qkv):
         assert got.shape == (B, S, H, D)
         err = relerr(got.float().cpu().numpy(), want.permute(0, 2, 1, 3).cpu().numpy())
         assert err < 1.5e-2, (name, err)
+
+
+def test_own_attention_layer_equals_sdpa_layer():
+    """A ViLT block with the fused q/k/v GEMM + this repo's attention kernels (vilt.FUSE_ATTENTION) == the same block
+    with three projections + torch SDPA: output and input gradient at bf16 tolerance."""
+    from feddat_b200.modeling import vilt as vilt_mod
+    from feddat_b200.train.prepare import default_args, place_on_gpu, prepare_model
+    torch.manual_seed(5)
+    model = prepare_model(default_args(ordered_cl_tasks=["art"], adapter_rank=32), place=False)
+    place_on_gpu(model)
+    model.activate_gating(); model.set_active_adapter("adapter_0")
+    layer = model.vilt_encoder.vilt.encoder.layer[2]
+    h0 = torch.randn(6, 185, 768, device="cuda").to(torch.bfloat16)
+    outs = []
+    for fused in (True, False):
+        vilt_mod.FUSE_ATTENTION = fused
+        try:
+            h = h0.clone().requires_grad_(True)
+            y = layer(h)[0]
+            y.float().square().mean().backward()
+            outs.append((y.detach().float(), h.grad.detach().float()))
+            with torch.no_grad():                                   # forward-only path (eval, pass A of the schedule)
+                y2 = layer(h0)[0]
+            assert ((y2.float() - outs[-1][0]).abs().max() / outs[-1][0].abs().max()).item() < 1e-2
+        finally:
+            vilt_mod.FUSE_ATTENTION = True
+    (y1, g1), (y2, g2) = outs
+    assert ((y1 - y2).abs().max() / y2.abs().max()).item() < 1e-2
+    assert ((g1 - g2).abs().max() / g2.abs().max()).item() < 2e-2
