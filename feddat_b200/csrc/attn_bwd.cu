@@ -418,39 +418,44 @@ attn_bwd_kernel(const __grid_constant__ AttnBwdTmaps tm, const __grid_constant__
   if (warp == 20) tmem_dealloc(tmem, 512);
 }
 
-// delta[q] = dO[q, :] . O[q, :] and lse2[q] = lse[q] log2(e) per (batch, head): one thread per query row (a row of O or
-// dO is one 128-byte line), padded to 192 entries with (+inf, 0) so that padded queries get P^T = 0, dS^T = 0
-__global__ void __launch_bounds__(192)
+// delta[q] = dO[q, :] . O[q, :] and lse2[q] = lse[q] log2(e) per (batch, head), padded to 192 entries with (+inf, 0)
+// so that padded queries get P^T = 0 and dS^T = 0.  Eight lanes per query row (one 16-byte chunk of O and of dO each,
+// i.e. whole 128-byte lines per row), reduced with three shuffles: 256 threads cover 32 rows per pass.
+__global__ void __launch_bounds__(256)
 attn_stats_kernel(const __nv_bfloat16* __restrict__ O, const __nv_bfloat16* __restrict__ dO, const float* __restrict__ lse,
                   float* __restrict__ stats, int S, int H, int64_t ldo, int64_t lddo) {
   pdl_wait();
   pdl_launch_dependents();
-  const int bh = blockIdx.x, h = bh % H, b = bh / H, r = threadIdx.x;
-  float l2 = INFINITY, dl = 0.f;
-  if (r < S) {
-    const uint4* po = reinterpret_cast<const uint4*>(O + (static_cast<size_t>(b) * S + r) * ldo + h * AD);
-    const uint4* pd = reinterpret_cast<const uint4*>(dO + (static_cast<size_t>(b) * S + r) * lddo + h * AD);
-    uint4 a[8], d[8];
+  const int bh = blockIdx.x, h = bh % H, b = bh / H;
+  const int j = threadIdx.x & 7, r0 = threadIdx.x >> 3;
+  uint4 a[6], d[6];
 #pragma unroll
-    for (int c = 0; c < 8; ++c) {
-      a[c] = __ldg(po + c);
-      d[c] = __ldg(pd + c);
+  for (int u = 0; u < 6; ++u) {                // all twelve loads of this thread in flight at once
+    const int r = r0 + 32 * u;
+    a[u] = d[u] = make_uint4(0u, 0u, 0u, 0u);
+    if (r < S) {
+      a[u] = __ldg(reinterpret_cast<const uint4*>(O + (static_cast<size_t>(b) * S + r) * ldo + h * AD) + j);
+      d[u] = __ldg(reinterpret_cast<const uint4*>(dO + (static_cast<size_t>(b) * S + r) * lddo + h * AD) + j);
     }
-    l2 = __ldg(lse + static_cast<size_t>(bh) * S + r) * 1.4426950408889634f;
-    float acc0 = 0.f, acc1 = 0.f;
-#pragma unroll
-    for (int c = 0; c < 8; ++c) {
-      const uint32_t aw[4] = {a[c].x, a[c].y, a[c].z, a[c].w}, dw[4] = {d[c].x, d[c].y, d[c].z, d[c].w};
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        acc0 = fmaf(__uint_as_float(aw[k] << 16), __uint_as_float(dw[k] << 16), acc0);
-        acc1 = fmaf(__uint_as_float(aw[k] & 0xffff0000u), __uint_as_float(dw[k] & 0xffff0000u), acc1);
-      }
-    }
-    dl = acc0 + acc1;
   }
-  stats[static_cast<size_t>(bh) * 384 + r] = l2;
-  stats[static_cast<size_t>(bh) * 384 + 192 + r] = dl;
+#pragma unroll
+  for (int u = 0; u < 6; ++u) {
+    const int r = r0 + 32 * u;
+    const uint32_t aw[4] = {a[u].x, a[u].y, a[u].z, a[u].w}, dw[4] = {d[u].x, d[u].y, d[u].z, d[u].w};
+    float acc = 0.f;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      acc = fmaf(__uint_as_float(aw[k] << 16), __uint_as_float(dw[k] << 16), acc);
+      acc = fmaf(__uint_as_float(aw[k] & 0xffff0000u), __uint_as_float(dw[k] & 0xffff0000u), acc);
+    }
+    acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+    acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+    acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+    if (j == 0) {
+      stats[static_cast<size_t>(bh) * 384 + r] = r < S ? __ldg(lse + static_cast<size_t>(bh) * S + r) * 1.4426950408889634f : INFINITY;
+      stats[static_cast<size_t>(bh) * 384 + 192 + r] = acc;
+    }
+  }
 }
 
 }  // namespace
@@ -484,7 +489,7 @@ extern "C" int feddat_attn_bwd(const void* dO, const void* Q, const void* K, con
   {
     cudaLaunchConfig_t c0{};
     c0.gridDim = dim3(B * H);
-    c0.blockDim = dim3(192);
+    c0.blockDim = dim3(256);
     c0.stream = st;
     c0.attrs = attr;
     c0.numAttrs = n_attr;
