@@ -215,6 +215,67 @@ def kernel_rooflines(peaks, device):
     return out
 
 
+def backbone_kernel_timings(device, batch):
+    """The two own kernels that replaced library ops in the frozen block around each site, next to what they replaced
+    (same shapes as the step: 2 x batch sequences of 185 tokens; CUDA events, rotating input sets):
+    GEMM + exact GELU (feddat_mlp_fc1_gelu_fwd / feddat_mlp_fc2_dgelu_bwd) vs cuBLAS + this repo's streaming GELU, and the
+    short-sequence attention (feddat_attn_fwd / feddat_attn_bwd) vs F.scaled_dot_product_attention (cuDNN flash)."""
+    import torch
+    import torch.nn.functional as F
+    from feddat_b200 import ops
+    g = torch.Generator(device=device).manual_seed(2)
+    Bq, S, H, Dh = 2 * batch, 185, 12, 64
+    M = Bq * S
+    w1 = (torch.randn(4 * D, D, device=device, generator=g) * 0.05).to(torch.bfloat16)
+    b1 = (torch.randn(4 * D, device=device, generator=g) * 0.1).to(torch.bfloat16)
+    w2t = (torch.randn(4 * D, D, device=device, generator=g) * 0.05).to(torch.bfloat16)
+    sets = []
+    for _ in range(5):
+        a, dy, q, k, v, do = (torch.randn(M, D, device=device, generator=g).to(torch.bfloat16) for _ in range(6))
+        sets.append((a, dy, torch.addmm(b1, a, w1.t()), q.view(Bq, S, H, Dh), k.view(Bq, S, H, Dh), v.view(Bq, S, H, Dh),
+                     do.view(Bq, S, H, Dh)))
+    b1f = b1.float()
+
+    def timeit(fn, iters=10):
+        for i in range(3):
+            fn(*sets[i % 5])
+        ts = []
+        for i in range(iters):
+            torch.cuda._sleep(1_000_000)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); fn(*sets[(3 + i) % 5]); e1.record()
+            torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1) * 1e3)
+        return round(sum(ts) / len(ts), 2)
+
+    o_l = [ops.attn_fwd(s_[3], s_[4], s_[5], 0.125) for s_ in sets]
+
+    def sdpa_fb(a, dy, pre, q, k, v, do):
+        q, k, v = (t.detach().permute(0, 2, 1, 3).requires_grad_(True) for t in (q, k, v))
+        F.scaled_dot_product_attention(q, k, v).backward(do.permute(0, 2, 1, 3))
+
+    own = {
+        "mlp_fc1_gelu_fwd": timeit(lambda a, dy, pre, q, k, v, do: ops.mlp_fc1_gelu(a, w1, b1f)),
+        "mlp_fc2_dgelu_bwd": timeit(lambda a, dy, pre, q, k, v, do: ops.mlp_fc2_dgelu(dy, w2t, pre)),
+        "attn_fwd": timeit(lambda a, dy, pre, q, k, v, do: ops.attn_fwd(q, k, v, 0.125)),
+        "attn_bwd": timeit(lambda a, dy, pre, q, k, v, do: ops.attn_bwd(do, q, k, v, o_l[0][0], o_l[0][1], 0.125)),
+    }
+    sdpa_f = timeit(lambda a, dy, pre, q, k, v, do: F.scaled_dot_product_attention(q.permute(0, 2, 1, 3), k.permute(0, 2, 1, 3),
+                                                                                 v.permute(0, 2, 1, 3)))
+    lib = {
+        "mlp_fc1_gelu_fwd": timeit(lambda a, dy, pre, q, k, v, do: ops.gelu_fwd(torch.addmm(b1, a, w1.t()))),
+        "mlp_fc2_dgelu_bwd": timeit(lambda a, dy, pre, q, k, v, do: ops.gelu_bwd(torch.mm(dy, w2t.t()), pre)),
+        "attn_fwd": sdpa_f,
+        "attn_bwd": round(timeit(sdpa_fb) - sdpa_f, 2),
+    }
+    what = {"mlp_fc1_gelu_fwd": "cuBLAS addmm + streaming GELU", "mlp_fc2_dgelu_bwd": "cuBLAS mm + streaming GELU'",
+            "attn_fwd": "F.scaled_dot_product_attention", "attn_bwd": "its autograd backward (fwd + bwd minus fwd)"}
+    shape = {"mlp_fc1_gelu_fwd": f"[{M}, {D}] x [{D}, {4 * D}]", "mlp_fc2_dgelu_bwd": f"[{M}, {D}] x [{D}, {4 * D}]",
+             "attn_fwd": f"B={Bq} S={S} H={H} d={Dh}", "attn_bwd": f"B={Bq} S={S} H={H} d={Dh}"}
+    return {k_: {"us": own[k_], "library_us": lib[k_], "vs_library": round(lib[k_] / own[k_], 2), "library": what[k_],
+                 "shape": shape[k_]} for k_ in own}
+
+
 def eager_reference_adapter(peaks, device):
     """The reference operator itself on this GPU ("the bar is PyTorch-eager (cuBLAS) on the
     same box"): the arithmetic of reference adapter.py:124-163 as PyTorch eager ops -- fp32 nn.Linear masters
@@ -395,6 +456,10 @@ def run_ours(args):
         e2e = world * B * K / (ms_e2e * 1e-3)
         kr = kernel_rooflines(peaks, device)
         eager = eager_reference_adapter(peaks, device)
+        try:
+            kr.update(backbone_kernel_timings(device, B))
+        except Exception as exc:                              # the headline numbers do not depend on this leg
+            kr["backbone_kernels_error"] = repr(exc)[:200]
         for name, us in eager.items():
             if name in kr:
                 kr[name]["eager_reference_us"] = us

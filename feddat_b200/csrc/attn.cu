@@ -35,7 +35,6 @@ namespace {
 constexpr int AKMAX = 256;             // keys per (batch, head) at most
 constexpr int ATHREADS = 736;          // 16 softmax + 4 epilogue + MMA issuer + 2 TMA producer warps
 constexpr int A_QBYTES = AQ * 128;     // 16 KB
-constexpr int A_KBYTES = AKMAX * 128;  // 32 KB
 
 struct AttnTmaps {
   CUtensorMap q, k, v, o;
