@@ -61,3 +61,27 @@ ops.mkd_ce_loss(sc, torch.randn(5, 4, 3202, device=dev, generator=g).to(torch.bf
                 torch.rand(5, device=dev, generator=g), 2.0)
 torch.cuda.synchronize()
 print("mkd heads ok")
+
+
+# ---- the frozen block's own kernels: GEMM + GELU epilogues, short-sequence attention (forward, statistics, backward)
+for M, N, K in ((257, 512, 128), (5920, 3072, 768)):
+    a = torch.randn(M, K, device=dev, generator=g).to(torch.bfloat16)
+    w = (torch.randn(N, K, device=dev, generator=g) * 0.05).to(torch.bfloat16)
+    b = torch.randn(N, device=dev, generator=g) * 0.1
+    pre, act = ops.mlp_fc1_gelu(a, w, b)
+    dpre = ops.mlp_fc2_dgelu(a, w, pre)
+    torch.cuda.synchronize()
+    ref = torch.nn.functional.gelu(torch.addmm(b, a.float(), w.float().t()))
+    e = ((act.float() - ref).abs().max() / ref.abs().max()).item()
+    assert e < 1e-2, e
+    print(f"mlp gemm M={M} N={N} K={K}: ok (act err {e:.1e})")
+for B, S, H in ((2, 185, 3), (8, 185, 12), (3, 64, 2), (2, 129, 1)):
+    q, k, v, do = (torch.randn(B, S, H, 64, device=dev, generator=g).to(torch.bfloat16) for _ in range(4))
+    o, lse = ops.attn_fwd(q, k, v, 0.125)
+    dq, dk, dv = ops.attn_bwd(do, q, k, v, o, lse, 0.125)
+    torch.cuda.synchronize()
+    qf, kf, vf = (t.float().permute(0, 2, 1, 3) for t in (q, k, v))
+    ref = (torch.softmax(qf @ kf.transpose(-1, -2) * 0.125, -1) @ vf).permute(0, 2, 1, 3)
+    e = ((o.float() - ref).abs().max() / ref.abs().max()).item()
+    assert e < 1e-2 and torch.isfinite(dq.float()).all() and torch.isfinite(dk.float()).all() and torch.isfinite(dv.float()).all(), e
+    print(f"attention B={B} S={S} H={H}: forward + backward ok (out err {e:.1e})")
