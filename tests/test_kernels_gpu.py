@@ -613,3 +613,38 @@ def test_own_attention_layer_equals_sdpa_layer():
     (y1, g1), (y2, g2) = outs
     assert ((y1 - y2).abs().max() / y2.abs().max()).item() < 1e-2
     assert ((g1 - g2).abs().max() / g2.abs().max()).item() < 2e-2
+
+
+def test_block_kernels_match_numpy_oracle(ops):
+    """Attention forward / backward and GEMM + GELU / GELU' against the numpy float64 oracle (oracle/block_oracle.py,
+    itself pinned to torch float64 autograd on the CPU) on bf16-rounded inputs."""
+    import oracle
+    rng = np.random.default_rng(3)
+
+    def dev(a, dt=torch.bfloat16):
+        return torch.from_numpy(a).cuda().to(dt).contiguous()
+
+    def bf(a):
+        return torch.from_numpy(a).to(torch.bfloat16).float().numpy()
+
+    B, S, H = 3, 185, 4
+    q, k, v, do = (rng.standard_normal((B, S, H, 64)).astype(np.float32) for _ in range(4))
+    o, lse = ops.attn_fwd(dev(q), dev(k), dev(v), 0.125)
+    dq, dk, dv = ops.attn_bwd(dev(do), dev(q), dev(k), dev(v), o, lse, 0.125)
+    o_or, lse_or = oracle.attention_forward(bf(q), bf(k), bf(v), 0.125)
+    grads_or = oracle.attention_backward(bf(do), bf(q), bf(k), bf(v), 0.125)
+    assert relerr(o.float().cpu().numpy(), o_or) < 8e-3
+    assert np.abs(lse.cpu().numpy() - lse_or).max() < 2e-3
+    for got, want in zip((dq, dk, dv), grads_or):
+        assert relerr(got.float().cpu().numpy(), want) < 1.5e-2
+    M, d = 300, 768
+    a = rng.standard_normal((M, d)).astype(np.float32)
+    w1 = (rng.standard_normal((4 * d, d)) * 0.05).astype(np.float32)
+    b1 = (rng.standard_normal(4 * d) * 0.1).astype(np.float32)
+    w2 = (rng.standard_normal((d, 4 * d)) * 0.05).astype(np.float32)
+    dy = rng.standard_normal((M, d)).astype(np.float32)
+    pre, act = ops.mlp_fc1_gelu(dev(a), dev(w1), dev(b1, torch.float32))
+    dpre = ops.mlp_fc2_dgelu(dev(dy), dev(w2.T.copy()), pre)
+    pre_or, act_or = oracle.mlp_fc1_gelu(bf(a), bf(w1), b1)
+    assert relerr(pre.float().cpu().numpy(), pre_or) < 4e-3 and relerr(act.float().cpu().numpy(), act_or) < 4e-3
+    assert relerr(dpre.float().cpu().numpy(), oracle.mlp_fc2_dgelu(bf(dy), bf(w2), pre.float().cpu().numpy())) < 4e-3
