@@ -41,6 +41,7 @@ EXPORTED_SYMBOLS = (
     "feddat_attn_fwd",
     "feddat_attn_bwd",
     "feddat_attn_bwd_workspace_bytes",
+    "feddat_patchify",
 )
 # include/feddat_b200_debug.h: only in the -DFEDDAT_DEBUG twin (libfeddat_sm100_dbg.so), tests / scripts
 DEBUG_SYMBOLS = (
@@ -174,6 +175,8 @@ def _bind(lib: ctypes.CDLL, debug: bool) -> ctypes.CDLL:
     lib.feddat_attn_bwd.restype = c_int
     lib.feddat_attn_bwd.argtypes = [c_void_p] * 9 + [c_int] * 4 + [c_int64] * 8 + [c_float, c_void_p, ctypes.c_size_t, c_int,
                                     c_void_p]
+    lib.feddat_patchify.restype = c_int
+    lib.feddat_patchify.argtypes = [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]
     lib.feddat_attn_bwd_workspace_bytes.restype = ctypes.c_size_t
     lib.feddat_attn_bwd_workspace_bytes.argtypes = [c_int, c_int]
     if not debug:

@@ -68,6 +68,28 @@ class _AddLayerNorm(torch.autograd.Function):
         return dx, (dx if ctx.has_res else None), None, None, None, None
 
 
+class _LayerNormPass(torch.autograd.Function):
+    """(LayerNorm(x), x) for frozen affine parameters.  The second output IS x: the caller routes the residual stream
+    through it, so both gradients reaching x -- through the LayerNorm and through the residual add further down -- meet
+    in this node's backward and leave as ONE launch (feddat_ln_bwd with ``dsum``) instead of a LayerNorm backward plus
+    autograd's gradient-sum kernel."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, eps):
+        shape = x.shape
+        y, _, mean, rstd, _ = ops.layer_norm_fwd(x.reshape(-1, shape[-1]), None, weight, bias, eps, None)
+        ctx.save_for_backward(x, weight, mean, rstd)
+        return y.view(shape), x.view_as(x)
+
+    @staticmethod
+    def backward(ctx, gy, gx):
+        x, weight, mean, rstd = ctx.saved_tensors
+        d = x.shape[-1]
+        gx2 = None if gx is None else gx.reshape(-1, d).contiguous()
+        dx = ops.layer_norm_bwd(gy.reshape(-1, d).contiguous(), gx2, x.reshape(-1, d), weight, mean, rstd)
+        return dx.view(x.shape), None, None, None
+
+
 class _Gelu(torch.autograd.Function):
     """Exact-erf GELU (HF ViltIntermediate's activation) through feddat_gelu_fwd / feddat_gelu_bwd."""
 
@@ -169,6 +191,13 @@ def layer_norm(ln: torch.nn.LayerNorm, h: torch.Tensor) -> torch.Tensor:
     return ln(h)
 
 
+def layer_norm_pass(ln: torch.nn.LayerNorm, h: torch.Tensor):
+    """(LayerNorm(h), h): take the residual stream from the second value (see ``_LayerNormPass``)."""
+    if _usable(ln, h) and h.requires_grad and torch.is_grad_enabled():
+        return _LayerNormPass.apply(h, ln.weight, ln.bias, ln.eps)
+    return layer_norm(ln, h), h
+
+
 def add_layer_norm(ln: torch.nn.LayerNorm, a: torch.Tensor, b: torch.Tensor, bias2=None):
     """(a + b [+ bias2], LayerNorm(a + b))."""
     if _usable(ln, a) and b.dtype == a.dtype and b.shape == a.shape and b.is_contiguous():
@@ -196,7 +225,7 @@ def fast_vilt_layer_forward(self, hidden_states, attention_mask=None, output_att
                        "attention maps requested" if output_attentions else
                        f"activations {hidden_states.dtype} on {hidden_states.device.type} or unfrozen / non-bf16 LayerNorm")
         return type(self).forward(self, hidden_states, attention_mask, output_attentions)
-    ln1 = layer_norm(self.layernorm_before, hidden_states)
+    ln1, hidden_states = layer_norm_pass(self.layernorm_before, hidden_states)
     attention_output = self.attention(ln1, None, output_attentions=False)[0]
     if _prebias_ok(self.output, hidden_states):
         # first residual + LayerNorm in one launch, which also emits the residual stream with the output

@@ -198,8 +198,13 @@ class ViltEncoderWrapper(nn.Module):
         ps = proj.kernel_size[0]
         b, cin, hh, ww = pixel_values.shape
         h, w = hh // ps, ww // ps
-        px = pixel_values.to(proj.weight.dtype)[:, :, :h * ps, :w * ps]
-        patches = px.reshape(b, cin, h, ps, w, ps).permute(0, 2, 4, 1, 3, 5).reshape(b * h * w, cin * ps * ps)
+        if (pixel_values.is_cuda and proj.weight.dtype == torch.bfloat16 and pixel_values.is_contiguous()
+                and pixel_values.dtype in (torch.float32, torch.bfloat16) and ps % 8 == 0 and ww % 8 == 0):
+            from .. import ops
+            patches = ops.patchify(pixel_values, ps)                  # cut + cast in one pass (csrc/patchify.cu)
+        else:
+            px = pixel_values.to(proj.weight.dtype)[:, :, :h * ps, :w * ps]
+            patches = px.reshape(b, cin, h, ps, w, ps).permute(0, 2, 4, 1, 3, 5).reshape(b * h * w, cin * ps * ps)
         x = F.linear(patches, proj.weight.view(proj.out_channels, -1), proj.bias).view(b, h * w, -1)
         c = x.shape[-1]
         pd = cfg.image_size // cfg.patch_size

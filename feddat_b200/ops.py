@@ -571,3 +571,20 @@ def attn_bwd(do: torch.Tensor, q: torch.Tensor, k: torch.Tensor, v: torch.Tensor
     _lib.check(rc, "feddat_attn_bwd")
     _count()
     return dqkv if packed else (dq, dk, dv)
+
+
+def patchify(pixel_values: torch.Tensor, patch: int) -> torch.Tensor:
+    """[B, C, H, W] fp32 / bf16 -> [B (H // patch) (W // patch), C patch patch] bf16 rows of a stride = kernel convolution
+    (feddat_patchify): cut and cast in one pass.  Trailing rows / columns that do not fill a patch are dropped, as the
+    convolution drops them."""
+    lib = _lib.load()
+    if not (pixel_values.is_cuda and pixel_values.dim() == 4 and pixel_values.is_contiguous()
+            and pixel_values.dtype in (torch.float32, torch.bfloat16)):
+        raise _lib.FeddatError("patchify: expected a contiguous CUDA fp32 / bf16 [B, C, H, W] tensor")
+    B, C, H, W = pixel_values.shape
+    out = torch.empty(B * (H // patch) * (W // patch), C * patch * patch, device=pixel_values.device, dtype=torch.bfloat16)
+    rc = lib.feddat_patchify(_lib.ptr(pixel_values), _lib.ptr(out), B, C, H, W, patch,
+                             DTYPE_F32 if pixel_values.dtype == torch.float32 else DTYPE_BF16, _lib.stream_ptr())
+    _lib.check(rc, "feddat_patchify")
+    _count()
+    return out

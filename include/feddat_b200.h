@@ -285,6 +285,13 @@ int feddat_attn_bwd(const void* dO, const void* Q, const void* K, const void* V,
                     int64_t ldo, int64_t lddq, int64_t lddk, int64_t lddv, float scale, void* workspace, size_t ws_bytes,
                     int dtype, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Patch cut + cast for the ViLT patch embedding (HF ViltPatchEmbeddings: Conv2d(C, 768, kernel ps, stride ps)):
+ * pixel_values [B, C, H, W] (fp32 or bf16, in_dtype) -> patches [B (H/ps) (W/ps), C ps ps] bf16, row = (b, patch row,
+ * patch column), column = (channel, y, x); the embedding is then one GEMM against the weight's [768, C ps ps] view.
+ */
+int feddat_patchify(const void* pixel_values, void* patches, int B, int C, int H, int W, int ps, int in_dtype, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

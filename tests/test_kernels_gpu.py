@@ -648,3 +648,14 @@ def test_block_kernels_match_numpy_oracle(ops):
     pre_or, act_or = oracle.mlp_fc1_gelu(bf(a), bf(w1), b1)
     assert relerr(pre.float().cpu().numpy(), pre_or) < 4e-3 and relerr(act.float().cpu().numpy(), act_or) < 4e-3
     assert relerr(dpre.float().cpu().numpy(), oracle.mlp_fc2_dgelu(bf(dy), bf(w2), pre.float().cpu().numpy())) < 4e-3
+
+
+@pytest.mark.parametrize("B,C,H,W,ps,dt", [(4, 3, 384, 384, 32, torch.float32), (2, 3, 224, 224, 32, torch.bfloat16),
+                                            (3, 3, 200, 232, 32, torch.float32), (1, 1, 16, 8, 8, torch.float32)])
+def test_patchify_equals_reshape_permute(ops, B, C, H, W, ps, dt):
+    """feddat_patchify == cast + reshape / permute of the stride = kernel convolution's input, bit for bit."""
+    g = torch.Generator(device="cuda").manual_seed(H + W)
+    px = torch.randn(B, C, H, W, device="cuda", generator=g).to(dt)
+    h, w = H // ps, W // ps
+    ref = px.to(torch.bfloat16)[:, :, :h * ps, :w * ps].reshape(B, C, h, ps, w, ps).permute(0, 2, 4, 1, 3, 5).reshape(B * h * w, C * ps * ps)
+    assert torch.equal(ops.patchify(px, ps), ref)
