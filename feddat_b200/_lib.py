@@ -14,7 +14,7 @@ _LIB_PATH = Path(__file__).resolve().parent / "lib" / "libfeddat_sm100.so"
 _DBG_LIB_PATH = Path(__file__).resolve().parent / "lib" / "libfeddat_sm100_dbg.so"
 _lib = None
 _dbg_lib = None
-ABI_VERSION = 3      # feddat_abi_version(); bumped whenever include/feddat_b200.h changes
+ABI_VERSION = 4      # feddat_abi_version(); bumped whenever include/feddat_b200.h changes
 
 # every symbol include/feddat_b200.h declares (tests check the built library exports all of them)
 EXPORTED_SYMBOLS = (
@@ -42,6 +42,7 @@ EXPORTED_SYMBOLS = (
     "feddat_attn_bwd",
     "feddat_attn_bwd_workspace_bytes",
     "feddat_patchify",
+    "feddat_adamw_step",
 )
 # include/feddat_b200_debug.h: only in the -DFEDDAT_DEBUG twin (libfeddat_sm100_dbg.so), tests / scripts
 DEBUG_SYMBOLS = (
@@ -73,6 +74,12 @@ class WgradGroup(ctypes.Structure):
     _fields_ = [("X", c_void_p), ("dY", c_void_p), ("H_t", c_void_p), ("dP_t", c_void_p),
                 ("dWu", c_void_p), ("dbu", c_void_p), ("dWd", c_void_p), ("dbd", c_void_p),
                 ("M", c_int64), ("r_t", c_int), ("ld_ht", c_int), ("ld_dwu", c_int), ("branch_scale", c_float)]
+
+
+class AdamwTensor(ctypes.Structure):
+    """FeddatAdamwTensor (include/feddat_b200.h)."""
+    _fields_ = [("param", c_void_p), ("grad", c_void_p), ("exp_avg", c_void_p), ("exp_avg_sq", c_void_p),
+                ("step", c_void_p), ("lr", c_void_p), ("weight_decay", c_float), ("numel", c_int64)]
 
 
 class PackJob(ctypes.Structure):
@@ -175,6 +182,8 @@ def _bind(lib: ctypes.CDLL, debug: bool) -> ctypes.CDLL:
     lib.feddat_attn_bwd.restype = c_int
     lib.feddat_attn_bwd.argtypes = [c_void_p] * 9 + [c_int] * 4 + [c_int64] * 8 + [c_float, c_void_p, ctypes.c_size_t, c_int,
                                     c_void_p]
+    lib.feddat_adamw_step.restype = c_int
+    lib.feddat_adamw_step.argtypes = [POINTER(AdamwTensor), c_int, c_float, c_float, c_float, c_void_p]
     lib.feddat_patchify.restype = c_int
     lib.feddat_patchify.argtypes = [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]
     lib.feddat_attn_bwd_workspace_bytes.restype = ctypes.c_size_t

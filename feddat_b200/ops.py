@@ -588,3 +588,11 @@ def patchify(pixel_values: torch.Tensor, patch: int) -> torch.Tensor:
     _lib.check(rc, "feddat_patchify")
     _count()
     return out
+
+
+def adamw_step(tensors, n: int, beta1: float, beta2: float, eps: float) -> None:
+    """One AdamW step over ``n`` FeddatAdamwTensor entries (a ctypes array built by train.fused_adamw.FusedAdamW)."""
+    lib = _lib.load()
+    rc = lib.feddat_adamw_step(tensors, n, float(beta1), float(beta2), float(eps), _lib.stream_ptr())
+    _lib.check(rc, "feddat_adamw_step")
+    _count(2 * ((n + 47) // 48))

@@ -86,6 +86,9 @@ def get_polynomial_decay_schedule_with_warmup(optimizer, num_warmup_steps, num_t
               lr_end=lr_end, power=power)
 
 
+USE_OWN_ADAMW = True      # csrc/adamw.cu behind train/fused_adamw.py; False = torch.optim.AdamW(fused, capturable)
+
+
 def split_step(optimizer, scheduler, first_params):
     """All gradients of the batched schedule are present at once; apply them as the reference's two
     optimizer steps would: ``first_params`` (adapter_1) with the CURRENT learning rate, scheduler step,
@@ -365,8 +368,11 @@ class TaskTrainer(nn.Module):
             return AdamW(groups, lr=self.lr, eps=self.adam_epsilon, betas=(0.9, 0.98))
         # fused + capturable with a device-tensor lr: same arithmetic, and the two optimizer steps of
         # a train step can live inside a CUDA graph (feddat_b200/train/graphed.py)
-        opt = AdamW(groups, lr=float(self.lr), eps=self.adam_epsilon, betas=(0.9, 0.98), fused=True,
-                    capturable=True)
+        if USE_OWN_ADAMW and all(p.dtype == torch.float32 and p.is_cuda for g in groups for p in g["params"]):
+            from .fused_adamw import FusedAdamW           # same rule and state, this repo's multi-tensor kernel
+            opt = FusedAdamW(groups, lr=float(self.lr), eps=self.adam_epsilon, betas=(0.9, 0.98))
+        else:
+            opt = AdamW(groups, lr=float(self.lr), eps=self.adam_epsilon, betas=(0.9, 0.98), fused=True, capturable=True)
         # per-group lr tensors are installed AFTER construction: ``defaults["lr"]`` must stay a float,
         # the HF polynomial schedule divides by it (lr_init) -- if it aliased the live lr tensor, the
         # warm-up step that sets lr = 0 would turn every later factor into 0/0

@@ -292,6 +292,24 @@ int feddat_attn_bwd(const void* dO, const void* Q, const void* K, const void* V,
  */
 int feddat_patchify(const void* pixel_values, void* patches, int B, int C, int H, int W, int ps, int in_dtype, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * AdamW over the tensors of one optimizer step (torch.optim.AdamW as built by the reference's create_optimizer,
+ * task_trainer.py:477-504; arithmetic of torch's fused kernel, fp32).  Every tensor carries its own device-side step
+ * counter (fp32 scalar, incremented by this call) and a pointer to its group's learning rate on the device, so the
+ * call can live inside a CUDA graph; tensors whose gradient is absent are simply not listed.
+ */
+typedef struct {
+  void* param;            /* fp32 [numel], updated in place */
+  const void* grad;       /* fp32 [numel] */
+  void* exp_avg;          /* fp32 [numel] */
+  void* exp_avg_sq;       /* fp32 [numel] */
+  float* step;            /* device scalar: steps taken so far */
+  const float* lr;        /* device scalar */
+  float weight_decay;
+  int64_t numel;
+} FeddatAdamwTensor;
+int feddat_adamw_step(const FeddatAdamwTensor* tensors, int n, float beta1, float beta2, float eps, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -659,3 +659,38 @@ def test_patchify_equals_reshape_permute(ops, B, C, H, W, ps, dt):
     h, w = H // ps, W // ps
     ref = px.to(torch.bfloat16)[:, :, :h * ps, :w * ps].reshape(B, C, h, ps, w, ps).permute(0, 2, 4, 1, 3, 5).reshape(B * h * w, C * ps * ps)
     assert torch.equal(ops.patchify(px, ps), ref)
+
+
+def test_own_adamw_matches_torch_fused_adamw():
+    """train.fused_adamw.FusedAdamW (feddat_adamw_step) == torch.optim.AdamW(fused=True, capturable=True) over several
+    steps with a moving device-side lr, two weight-decay groups, odd sizes, and a parameter that skips a step."""
+    from feddat_b200.train.fused_adamw import FusedAdamW
+    g = torch.Generator(device="cuda").manual_seed(11)
+    shapes = [(768, 128), (128,), (3129, 1536), (5,), (1, 1), (4097,)]
+
+    def make():
+        ps = [torch.nn.Parameter(torch.randn(*s, device="cuda", generator=torch.Generator(device="cuda").manual_seed(i)))
+              for i, s in enumerate(shapes)]
+        return ps, [{"params": ps[0::2], "weight_decay": 1e-2}, {"params": ps[1::2], "weight_decay": 0.0}]
+
+    pa, ga = make()
+    pb, gb = make()
+    oa = FusedAdamW(ga, lr=1e-3, betas=(0.9, 0.98), eps=1e-8)
+    ob = torch.optim.AdamW(gb, lr=1e-3, betas=(0.9, 0.98), eps=1e-8, fused=True, capturable=True)
+    for o in (oa, ob):
+        for grp in o.param_groups:
+            grp["lr"] = torch.tensor(float(grp["lr"]), device="cuda")
+    for step in range(6):
+        grads = [torch.randn(*s, device="cuda", generator=g) for s in shapes]
+        for ps, o in ((pa, oa), (pb, ob)):
+            for i, (p, gr) in enumerate(zip(ps, grads)):
+                p.grad = None if (i == 3 and step == 2) else gr.clone()
+            for grp in o.param_groups:
+                grp["lr"].fill_(1e-3 * (1 + step) / 3)
+            o.step()
+            o.zero_grad()
+    for a, b in zip(pa, pb):
+        assert torch.allclose(a, b, rtol=2e-6, atol=1e-7), (a - b).abs().max().item()
+    for a, b in zip(pa, pb):
+        assert torch.allclose(oa.state[a]["exp_avg_sq"], ob.state[b]["exp_avg_sq"], rtol=1e-6, atol=1e-12)
+        assert oa.state[a]["step"].item() == ob.state[b]["step"].item()
