@@ -419,41 +419,36 @@ attn_bwd_kernel(const __grid_constant__ AttnBwdTmaps tm, const __grid_constant__
 }
 
 // delta[q] = dO[q, :] . O[q, :] and lse2[q] = lse[q] log2(e) per (batch, head), padded to 192 entries with (+inf, 0)
-// so that padded queries get P^T = 0 and dS^T = 0.  Eight lanes per query row (one 16-byte chunk of O and of dO each,
-// i.e. whole 128-byte lines per row), reduced with three shuffles: 256 threads cover 32 rows per pass.
+// so that padded queries get P^T = 0 and dS^T = 0.  One block per (batch, 8 tokens): it reads the tokens' whole rows of
+// O and dO (all heads: H x 128 contiguous bytes per token -- a per-head walk touches 128 bytes every 1.5 KB and runs at
+// a third of the HBM rate), eight lanes per (token, head), three shuffles.
 __global__ void __launch_bounds__(256)
 attn_stats_kernel(const __nv_bfloat16* __restrict__ O, const __nv_bfloat16* __restrict__ dO, const float* __restrict__ lse,
                   float* __restrict__ stats, int S, int H, int64_t ldo, int64_t lddo) {
   pdl_wait();
   pdl_launch_dependents();
-  const int bh = blockIdx.x, h = bh % H, b = bh / H;
-  const int j = threadIdx.x & 7, r0 = threadIdx.x >> 3;
-  uint4 a[6], d[6];
-#pragma unroll
-  for (int u = 0; u < 6; ++u) {                // all twelve loads of this thread in flight at once
-    const int r = r0 + 32 * u;
-    a[u] = d[u] = make_uint4(0u, 0u, 0u, 0u);
-    if (r < S) {
-      a[u] = __ldg(reinterpret_cast<const uint4*>(O + (static_cast<size_t>(b) * S + r) * ldo + h * AD) + j);
-      d[u] = __ldg(reinterpret_cast<const uint4*>(dO + (static_cast<size_t>(b) * S + r) * lddo + h * AD) + j);
-    }
-  }
-#pragma unroll
-  for (int u = 0; u < 6; ++u) {
-    const int r = r0 + 32 * u;
-    const uint32_t aw[4] = {a[u].x, a[u].y, a[u].z, a[u].w}, dw[4] = {d[u].x, d[u].y, d[u].z, d[u].w};
+  const int b = blockIdx.y, t0 = blockIdx.x * 8;
+  const int j = threadIdx.x & 7;
+  for (int slot = threadIdx.x >> 3; slot < 8 * H; slot += 32) {      // slot = (token of the chunk, head)
+    const int r = t0 + slot / H, h = slot % H;
     float acc = 0.f;
+    if (r < S) {
+      const uint4 a = __ldg(reinterpret_cast<const uint4*>(O + (static_cast<size_t>(b) * S + r) * ldo + h * AD) + j);
+      const uint4 d = __ldg(reinterpret_cast<const uint4*>(dO + (static_cast<size_t>(b) * S + r) * lddo + h * AD) + j);
+      const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, dw[4] = {d.x, d.y, d.z, d.w};
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      acc = fmaf(__uint_as_float(aw[k] << 16), __uint_as_float(dw[k] << 16), acc);
-      acc = fmaf(__uint_as_float(aw[k] & 0xffff0000u), __uint_as_float(dw[k] & 0xffff0000u), acc);
+      for (int k = 0; k < 4; ++k) {
+        acc = fmaf(__uint_as_float(aw[k] << 16), __uint_as_float(dw[k] << 16), acc);
+        acc = fmaf(__uint_as_float(aw[k] & 0xffff0000u), __uint_as_float(dw[k] & 0xffff0000u), acc);
+      }
     }
     acc += __shfl_xor_sync(0xffffffffu, acc, 1);
     acc += __shfl_xor_sync(0xffffffffu, acc, 2);
     acc += __shfl_xor_sync(0xffffffffu, acc, 4);
-    if (j == 0) {
-      stats[static_cast<size_t>(bh) * 384 + r] = r < S ? __ldg(lse + static_cast<size_t>(bh) * S + r) * 1.4426950408889634f : INFINITY;
-      stats[static_cast<size_t>(bh) * 384 + 192 + r] = acc;
+    if (j == 0 && r < 192) {
+      const size_t bh = static_cast<size_t>(b) * H + h;
+      stats[bh * 384 + r] = r < S ? __ldg(lse + bh * S + r) * 1.4426950408889634f : INFINITY;
+      stats[bh * 384 + 192 + r] = acc;
     }
   }
 }
@@ -488,7 +483,7 @@ extern "C" int feddat_attn_bwd(const void* dO, const void* Q, const void* K, con
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   {
     cudaLaunchConfig_t c0{};
-    c0.gridDim = dim3(B * H);
+    c0.gridDim = dim3(192 / 8, B);
     c0.blockDim = dim3(256);
     c0.stream = st;
     c0.attrs = attr;
