@@ -59,8 +59,10 @@ class ALBEFWrapper(nn.Module):
             else:                                                                           # albef.py:56-57
                 question = self._tok(batch["questions"], padding="longest", truncation=True, max_length=25)
                 answer = self._tok(batch["answers"], padding="longest")
+            idx = batch.get("answer_index")
             loss, logits = self.albef(image=images, question=question, answer=answer, train=True, alpha=batch["alpha"],
-                                      k=batch["n"], weights=weights, defer_loss=self.defer_loss)
+                                      k=batch["n"], weights=weights, defer_loss=self.defer_loss,
+                                      answer_index=None if idx is None else idx.to(self.device, non_blocking=True))
             return [loss, logits]
         if pre:
             answer = SimpleNamespace(input_ids=batch["answer_list_ids"].to(self.device),

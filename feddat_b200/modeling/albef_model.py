@@ -391,7 +391,8 @@ class ALBEF(nn.Module):
         self.text_encoder = BertModel(enc, add_pooling_layer=False)
         self.text_decoder = BertLMHeadModel(dec)
 
-    def forward(self, image, question, answer=None, alpha=0, k=None, weights=None, train=True, defer_loss=False):
+    def forward(self, image, question, answer=None, alpha=0, k=None, weights=None, train=True, defer_loss=False,
+                answer_index=None):
         """``question`` / ``answer``: objects with ``input_ids`` and ``attention_mask`` (a tokenizer's BatchEncoding or
         a namespace of tensors).  train: (loss, logits[:, :-1]); eval: rank_answer's (topk_ids, topk_probs)."""
         image_embeds = self.visual_encoder(image)
@@ -402,8 +403,10 @@ class ALBEF(nn.Module):
             return self.rank_answer(question_states, question.attention_mask, answer.input_ids, answer.attention_mask, k)
         answer_targets = answer.input_ids.masked_fill(answer.input_ids == self.pad_token_id, -100)
         # one copy of the question states per answer of that question (albef_model.py:92-98)
-        idx = torch.repeat_interleave(torch.arange(len(k), device=image.device),
-                                      torch.as_tensor(k, device=image.device))
+        # (``answer_index`` = that map as a tensor made with the batch: repeat_interleave over a device tensor of
+        # counts has a data-dependent output size, i.e. a host sync per forward and no CUDA-graph capture)
+        idx = answer_index if answer_index is not None else torch.repeat_interleave(
+            torch.arange(len(k), device=image.device), torch.as_tensor(k, device=image.device))
         scores = self.text_decoder(answer.input_ids, attention_mask=answer.attention_mask,
                                    encoder_hidden_states=question_states[idx],
                                    encoder_attention_mask=question.attention_mask[idx])

@@ -104,7 +104,7 @@ def make_albef_batch(batch_size: int, image_size: int = 384, seed: int = 0, clie
         q_ids[b, 0], q_ids[b, n - 1] = CLS_ID, SEP_ID
         q_ids[b, 1:n - 1] = torch.randint(lo, hi, (n - 2,), generator=g)
         q_mask[b, :n] = 1
-    ks = [1 + (b + seed) % 3 for b in range(batch_size)]
+    ks = [1 + ((b + seed) % batch_size) % 3 for b in range(batch_size)]     # a rotation of one list: constant sum
     n_seq = sum(ks)
     a_ids = torch.full((n_seq, a_len), PAD_ID, dtype=torch.int64)
     a_mask = torch.zeros(n_seq, a_len, dtype=torch.int64)
@@ -119,7 +119,9 @@ def make_albef_batch(batch_size: int, image_size: int = 384, seed: int = 0, clie
             weights[i] = 1.0 / k
             i += 1
     batch = {"images": images, "question_ids": q_ids, "question_mask": q_mask, "answer_ids": a_ids,
-             "answer_mask": a_mask, "weights": weights, "n": ks, "alpha": 0.0, "train": True}
+             "answer_mask": a_mask, "weights": weights, "n": ks, "alpha": 0.0, "train": True,
+             # question of each answer sequence (albef_model.py:92-98 builds it per forward from ``n``)
+             "answer_index": torch.repeat_interleave(torch.arange(batch_size), torch.tensor(ks))}
     if pin and torch.cuda.is_available():
         batch = {k: (v.pin_memory() if isinstance(v, torch.Tensor) else v) for k, v in batch.items()}
     return batch

@@ -163,3 +163,52 @@ class GraphedTrainStep:
         from .. import ops
         ops.launch_count += self.launches_per_step
         return self.loss
+
+
+class GraphedDictStep(GraphedTrainStep):
+    """The same capture / replay for learners whose batch is a FLAT dict of tensors and Python values (the ALBEF
+    path: images, question / answer ids and masks, weights, answer_index; ``n`` / ``alpha`` / ``train`` are Python
+    values and must not change between batches).  No prefetch staging: ``__call__(batch)`` copies the batch's tensors
+    into the static ones (host-pinned or device sources)."""
+
+    def __init__(self, trainer, wrapped_model, optimizer, scheduler, example_batch: Dict, warmup: int = 2,
+                 unused=("n",)):
+        """``unused``: Python-valued batch entries the captured step does not read (ALBEF's per-sample answer counts
+        ``n`` are superseded by the ``answer_index`` tensor) and which may therefore differ between batches."""
+        self._unused = tuple(unused)
+        for g in optimizer.param_groups:
+            if not (isinstance(g["lr"], torch.Tensor) and g["lr"].is_cuda and g.get("capturable", False)):
+                raise ValueError("GraphedDictStep needs an optimizer built by TaskTrainer.create_optimizer on CUDA")
+        self.trainer, self.model, self.opt, self.sched = trainer, wrapped_model, optimizer, scheduler
+        self.static = {k: (v.clone() if isinstance(v, torch.Tensor) else v) for k, v in example_batch.items()}
+        dev = next(v.device for v in self.static.values() if isinstance(v, torch.Tensor))
+        if dev.type != "cuda":
+            raise ValueError("GraphedDictStep: the example batch must live on the GPU")
+        self.lr_buf = torch.zeros(3, device=dev, dtype=torch.float32)
+        self.base_lrs = [float(b) for b in scheduler.base_lrs]
+        self.lmbda = scheduler.lr_lambdas[0]
+        self.graph = None
+        self.loss = None
+        self.launches_per_step = 0
+        self._warm = warmup
+
+    def accepts(self, batch) -> bool:
+        return all((isinstance(v, torch.Tensor) and v.shape == self.static[k].shape)
+                   if isinstance(self.static.get(k), torch.Tensor) else (k in self._unused or v == self.static.get(k))
+                   for k, v in batch.items())
+
+    def _load_batch(self, batch):
+        for k, v in batch.items():
+            if isinstance(v, torch.Tensor):
+                self.static[k].copy_(v, non_blocking=True)
+            elif k not in self._unused and v != self.static[k]:
+                raise ValueError(f"GraphedDictStep: batch[{k!r}] = {v!r} differs from the captured {self.static[k]!r}")
+
+    def _load_staged(self):
+        raise RuntimeError("GraphedDictStep has no prefetch stage: pass the batch to __call__")
+
+    def prefetch(self, batch):
+        raise RuntimeError("GraphedDictStep has no prefetch stage: pass the batch to __call__")
+
+    def _clear_caches(self):
+        pass

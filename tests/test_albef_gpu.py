@@ -180,3 +180,43 @@ def test_albef_rank_answer_and_round_loop():
     names = rec["optimizer_names"][(0, "art")]
     assert any("adapter_1" in n for n in names) and any(".cls." in n for n in names)
     assert all(np.isfinite(v) and 0.0 <= v <= 100.0 for v in rec["eval_scores"][0])
+
+
+def test_albef_graphed_step_equals_eager():
+    """GraphedDictStep (CUDA-graph replay of the ALBEF train_step: three forwards, two backwards, two optimizer steps,
+    fused KL + CE head) == the same steps run eagerly, on batches with different answer-to-question maps.  Dropout is
+    taken out of the comparison (eval-mode dropout modules): graph capture and eager draw different Philox offsets."""
+    from feddat_b200.modeling.albef import convert_batch_to_albef_input_dict
+    from feddat_b200.synthetic import albef_to_device, make_albef_batch
+    from feddat_b200.train.accelerator import Accelerator
+    from feddat_b200.train.graphed import GraphedDictStep
+    from feddat_b200.train.task_trainer import TaskTrainer, get_polynomial_decay_schedule_with_warmup
+    res = ALBEF_GOLDEN_CFG["image_res"]
+    batches = [albef_to_device(make_albef_batch(4, res, seed=40 + i, vocab=ALBEF_GOLDEN_CFG["bert_config"].get("vocab_size", 30522)),
+                               "cuda") for i in range(5)]
+    outs = []
+    for graphed in (False, True):
+        torch.manual_seed(0)
+        model = build(64, bf16=True)
+        for m in model.modules():
+            if isinstance(m, torch.nn.Dropout):
+                m.p = 0.0
+        tr = TaskTrainer()
+        tr.args = SimpleNamespace(optimizer_mode="dat", encoder_name="albef_no_distill", debug=0)
+        tr.accelerator = Accelerator(device="cuda")
+        tr.device, tr.task_key = torch.device("cuda"), "art"
+        tr.batch2inputs_converter = convert_batch_to_albef_input_dict
+        tr.weight_decay, tr.lr, tr.adam_epsilon, tr.kl_temp = 1e-2, 1e-3, 1e-8, 2.0
+        wrapped = tr.accelerator.prepare(model)
+        opt = tr.create_optimizer(wrapped)
+        sched = get_polynomial_decay_schedule_with_warmup(opt, 2, 100, lr_end=0, power=1)
+        step = GraphedDictStep(tr, wrapped, opt, sched, batches[0], warmup=1) if graphed else \
+            (lambda b_: tr.train_step(wrapped, 0, b_, opt, sched))
+        losses = [step(b_).item() for b_ in batches]                 # warm-up step, capture, three replays
+        torch.cuda.synchronize()
+        outs.append((losses, {n: p.detach().float().cpu() for n, p in model.named_parameters() if p.requires_grad}))
+    (l0, p0), (l1, p1) = outs
+    assert all(np.isfinite(l0)) and np.allclose(l0, l1, rtol=2e-3), (l0, l1)
+    num = sum(((p0[n] - p1[n]).double() ** 2).sum().item() for n in p0)
+    den = sum(((p0[n]).double() ** 2).sum().item() for n in p0)
+    assert (num / den) ** 0.5 < 1e-3, (num / den) ** 0.5
