@@ -169,11 +169,15 @@ class TaskTrainer(nn.Module):
                     break
                 if "vilt" not in self.args.encoder_name:
                     batch = self.add_alpha(epoch, batch, step)
-                if getattr(self.args, "cuda_graph", False) and "encodings" in batch:
-                    from .graphed import GraphedTrainStep
-                    if graphed is None:
+                if getattr(self.args, "cuda_graph", False) and isinstance(batch, dict):
+                    from .graphed import GraphedDictStep, GraphedTrainStep
+                    if graphed is None and "encodings" in batch:
                         graphed = GraphedTrainStep(self, model, optimizer, scheduler, batch, warmup=1)
-                    if graphed.accepts(batch):
+                    elif graphed is None and "answer_index" in batch and all(
+                            v.is_cuda for v in batch.values() if isinstance(v, torch.Tensor)):
+                        # ALBEF: pre-tokenised device batches with the answer -> question map as a tensor
+                        graphed = GraphedDictStep(self, model, optimizer, scheduler, batch, warmup=1)
+                    if graphed is not None and graphed.accepts(batch):
                         loss = graphed(batch)
                         continue
                 loss = self.train_step(model, step, batch, optimizer, scheduler, hooks=None, epoch=epoch)

@@ -163,16 +163,18 @@ def test_mkd_ce_loss_vs_oracle(dtype, teacher_view):
     assert float(ds[:, -1, :].abs().max()) == 0.0                                # the last position has no gradient
 
 
-def test_albef_rank_answer_and_round_loop():
+@pytest.mark.parametrize("cuda_graph", [False, True])
+def test_albef_rank_answer_and_round_loop(cuda_graph):
     """rank_answer (albef_model.py:171-228) through the wrapper's eval branch, and the executed federated round
-    loop with the ALBEF encoder: 1 round x 2 clients + eval, FedAvg of the 5 x 4 adapter_1 tensors."""
+    loop with the ALBEF encoder: 1 round x 2 clients + eval, FedAvg of the 5 x 4 adapter_1 tensors; eager and with
+    ``--cuda_graph`` (each client's steps replayed from one captured graph)."""
     from feddat_b200.train.main import main
     rec = {}
-    argv = ["--encoder_name", "albef_no_distill", "--pretrained_model_name", "random", "--climb_data_dir", "synthetic",
+    argv = (["--cuda_graph"] if cuda_graph else []) + ["--encoder_name", "albef_no_distill", "--pretrained_model_name", "random", "--climb_data_dir", "synthetic",
             "--do_train", "--output_dir", "/tmp/feddat_albef_round", "--optimizer_mode", "dat", "--ordered_cl_tasks",
             "art,abstract", "--comm_round", "1", "--batch_size", "3", "--val_batch_size", "3", "--synthetic_batches", "2",
             "--image_size", "64", "--vit_depth", "2", "--decoder_layers", "1", "--adapter_rank", "32", "--lr", "1e-3",
-            "--num_epochs", "2", "--adapter_config", "pfeiffer"]
+            "--num_epochs", "2", "--adapter_config", "pfeiffer", "--synthetic_batches", "4" if cuda_graph else "2"]
     assert main(argv, record=rec) == 0
     flats = [f.numpy() for f in rec["client_flats"][0]]
     assert len(flats) == 2 and not np.array_equal(flats[0], flats[1])
