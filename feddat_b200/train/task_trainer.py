@@ -257,10 +257,11 @@ class TaskTrainer(nn.Module):
         b = enc.shape[0] // 2
         leaf = enc.detach().requires_grad_(True)                     # head gradients stop here until step 4
         enc_a, enc_b = leaf[:b], leaf[b:]
-        with torch.no_grad():
-            logits_all = inner.classify(self.task_key, enc_a)        # (A): old head, gating encoder
-
-        logits_1 = inner.classify(self.task_key, enc_b)              # (B)
+        # (A) and (B) read the SAME (old) head: one call over both halves -- the head is ~25 tiny fp32 launches per
+        # call, launch-bound at batch 32.  Only logits_1 carries a gradient: the A rows are detached going in (their
+        # rows of every head-internal gradient are exact zeros, so the head's parameter gradients are those of pass B)
+        both = inner.classify(self.task_key, torch.cat([enc_a.detach(), enc_b], dim=0))
+        logits_all, logits_1 = both[:b].detach(), both[b:]           # (A): old head, gating encoder;  (B)
         L_1, _ = self._objective(logits_1, logits_all, target, None)
         self.accelerator.backward(L_1)                               # head grads + d enc_B (adapters: none yet)
         self._probe("B_head", model)
