@@ -21,8 +21,10 @@
 // layout), the S CTAs of one (group, chunk) meet at a counter in global memory -- all CTAs of the launch
 // are co-resident: the grid never exceeds the SM count and a CTA takes a whole SM -- and then each sums
 // 1/S of the tile over the S partials IN SPLIT ORDER and writes the final gradient (no atomics, no
-// zero-initialised outputs).  Up to two groups per launch (the gating rows and the adapter_1 rows of one
-// site, see dat_fused.cu).
+// zero-initialised outputs).  Up to 24 groups per launch: the gating rows and the adapter_1 rows of one site
+// (dat_fused.cu), or -- the train step's DEFERRED form -- both groups of ALL twelve sites at the end of the
+// backward pass: 24 groups x 6 chunks = 144 CTAs, every CTA contracts over ALL rows of its (group, chunk), so
+// there are no row splits, no partials and no second stage (n_splits == 1 skips the workspace altogether).
 #include <stdlib.h>
 
 #include "feddat_b200.h"
@@ -42,7 +44,8 @@ constexpr int STAGE = 4 * OPER;          // H, dP, dY, X
 constexpr int WG_STAGES = 3;
 constexpr int NUM_THREADS = 192;
 
-constexpr int MAX_GROUPS = 2;
+constexpr int MAX_GROUPS = 24;
+constexpr int WS_HEADER_BYTES = 4096;    // counters: [MAX_GROUPS][NCHUNK][2] u32 = 1152 B
 constexpr int TILE_F4 = 2 * 128 * NCW / 4;   // float4s of one CTA's two partial tiles (D1 | D2) = 8192
 constexpr int PART_FLOATS = 2 * 128 * NCW + 2 * NCW;   // + the two bias-gradient partial vectors
 
@@ -57,16 +60,17 @@ struct WgradGroup {
   float* dbd;
 };
 
+struct WgradTmaps {
+  CUtensorMap xk, dyk, h, dp;   // h / dp: the 3-D k-block view when a_3d, the plain 2-D view otherwise
+};
+
 struct WgradParams {
+  WgradTmaps tm[MAX_GROUPS];    // 12 KB of tensor maps: kernel parameters may take 32 764 B since CUDA 12.1
   WgradGroup g[MAX_GROUPS];
   int n_groups;
   unsigned int* counters;   // workspace head: [group][chunk][2] = {partials stored, final slices written}
   float* partials;          // workspace: [CTA][PART_FLOATS]
   unsigned long long* trace;   // debug timeline of CTA 0 (events 200..) or null
-};
-
-struct WgradTmaps {
-  CUtensorMap xk, dyk, h, dp, hk, dpk;
 };
 
 // spin until *ctr >= target (all CTAs of the launch are co-resident; bounded like mbar_wait)
@@ -84,8 +88,7 @@ __device__ __forceinline__ void wait_counter(const unsigned int* ctr, unsigned i
 }
 
 __global__ void __launch_bounds__(NUM_THREADS, 1)
-dat_wgrad_kernel(const __grid_constant__ WgradTmaps tm0, const __grid_constant__ WgradTmaps tm1,
-                 const __grid_constant__ WgradParams pp) {
+dat_wgrad_kernel(const __grid_constant__ WgradParams pp) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bars[2 * WG_STAGES + 2];
   __shared__ uint32_t tmem_base_smem;
@@ -100,10 +103,12 @@ dat_wgrad_kernel(const __grid_constant__ WgradTmaps tm0, const __grid_constant__
 #else
 #define WG_TRACE(ev) do { } while (0)
 #endif
-  const int grp = (pp.n_groups > 1 && static_cast<int>(blockIdx.x) >= pp.g[1].first_cta) ? 1 : 0;
+  int grp = 0;
+  for (int i = 1; i < pp.n_groups; ++i)
+    if (static_cast<int>(blockIdx.x) >= pp.g[i].first_cta) grp = i;
   const WgradGroup& p = pp.g[grp];
-  const WgradTmaps& T = grp ? tm1 : tm0;
-  const CUtensorMap &tmXk = T.xk, &tmDYk = T.dyk, &tmH = T.h, &tmDP = T.dp, &tmHk = T.hk, &tmDPk = T.dpk;
+  const WgradTmaps& T = pp.tm[grp];
+  const CUtensorMap &tmXk = T.xk, &tmDYk = T.dyk, &tmH = T.h, &tmDP = T.dp;
   if (tid == 0) WG_TRACE(200);
   const int rel = static_cast<int>(blockIdx.x) - p.first_cta;
   const int chunk = rel % NCHUNK, split = rel / NCHUNK;
@@ -127,8 +132,6 @@ dat_wgrad_kernel(const __grid_constant__ WgradTmaps tm0, const __grid_constant__
     tma_prefetch_desc(&tmDYk);
     tma_prefetch_desc(&tmH);
     tma_prefetch_desc(&tmDP);
-    tma_prefetch_desc(&tmHk);
-    tma_prefetch_desc(&tmDPk);
   }
   if (warp == 1) tmem_alloc(smem_u32(&tmem_base_smem), 256);
   tc_fence_before();
@@ -156,7 +159,7 @@ dat_wgrad_kernel(const __grid_constant__ WgradTmaps tm0, const __grid_constant__
         if (lane == 0) mbar_arrive_expect_tx(bar_full(stage), 2 * ablk * BLK + 2 * OPER);
         if (lane < 2) {
           if (p.a_3d) {
-            tma_load_3d(dst, lane == 0 ? &tmHk : &tmDPk, bar_full(stage), 0, m0, 0);
+            tma_load_3d(dst, lane == 0 ? &tmH : &tmDP, bar_full(stage), 0, m0, 0);
           } else {
             for (int b = 0; b < ablk; ++b)
               tma_load_2d(dst + b * BLK, lane == 0 ? &tmH : &tmDP, bar_full(stage), b * 64, m0);
@@ -241,7 +244,9 @@ dat_wgrad_kernel(const __grid_constant__ WgradTmaps tm0, const __grid_constant__
       ++it_a;
       if (++stage == WG_STAGES) { stage = 0; phase ^= 1; }
     }
-    // ---- stage 1 of the reduction: this CTA's partials -> workspace
+    // ---- stage 1 of the reduction: this CTA's partials -> workspace (not needed without row splits)
+    const int S = p.n_splits;
+    const bool cta_dbd = (chunk == 0) && p.dbd != nullptr;
     float* part = pp.partials + static_cast<size_t>(blockIdx.x) * PART_FLOATS;
     {
       // eight row-set partials per column -> one sum per column and CTA through smem
@@ -257,8 +262,13 @@ dat_wgrad_kernel(const __grid_constant__ WgradTmaps tm0, const __grid_constant__
         sdy += red_smem[0][r][t];
         sdp += red_smem[1][r][t];
       }
-      part[2 * 128 * NCW + t] = sdy;
-      part[2 * 128 * NCW + NCW + t] = sdp;
+      if (S == 1) {
+        if (do_dbu) p.dbu[col0 + t] = p.scale * sdy;
+        if (cta_dbd && static_cast<int>(t) < p.rt) p.dbd[t] = sdp;
+      } else {
+        part[2 * 128 * NCW + t] = sdy;
+        part[2 * 128 * NCW + NCW + t] = sdp;
+      }
     }
     mbar_wait(bar_acc, 0);
     tc_fence_after();
@@ -279,64 +289,67 @@ dat_wgrad_kernel(const __grid_constant__ WgradTmaps tm0, const __grid_constant__
           st_shared_v4(smem0 + (((mc * 8 + i) * 128 + j) << 4), v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
       }
     }
-    fence_proxy_async_smem();
-    __threadfence();                 // the two bias partial vectors (plain stores above)
-    named_bar_sync(1, 128);
     unsigned int* ctr = pp.counters + (grp * NCHUNK + chunk) * 2;
     // ---- stage 2: wait for the partials of all row splits of this (group, chunk), then sum 1 / S of the
-    // tile over the splits in split order (deterministic) and write the final gradients
-    const int S = p.n_splits;
-    const float* part0 = pp.partials + static_cast<size_t>(p.first_cta + chunk) * PART_FLOATS;   // split 0
-    const size_t split_stride = static_cast<size_t>(NCHUNK) * PART_FLOATS;
+    // tile over the splits in split order (deterministic) and write the final gradients.  S == 1: the tile
+    // staged in shared memory IS the sum -- same layout, read in place.
     const int per = (TILE_F4 + S - 1) / S;
     const int f_begin = split * per;
     const int f_end = (split + 1) * per < TILE_F4 ? (split + 1) * per : TILE_F4;
     const int n_f = f_end > f_begin ? f_end - f_begin : 0;
-    if (t == 0) {
-      bulk_store_1d(part, smem0, TILE_F4 * 16);
-      tma_store_commit();
-      tma_store_wait_all<0>();       // the partials are written (not merely read out of smem)
-      fence_proxy_async_all();
-      __threadfence();
-      atomicAdd(ctr, 1u);
-      wait_counter(ctr, static_cast<unsigned int>(S));
-      __threadfence();
-      fence_proxy_async_all();
-      if (tid == 64) WG_TRACE(204);
-      // this CTA's slice [f_begin, f_end) of every split's partial tile -> smem, one bulk copy per split
-      if (n_f > 0) {
-        mbar_arrive_expect_tx(bar_red, static_cast<uint32_t>(S) * n_f * 16u);
-        for (int sidx = 0; sidx < S; ++sidx)
-          bulk_load_1d(smem0 + static_cast<uint32_t>(sidx) * per * 16u,
-                       part0 + sidx * split_stride + static_cast<size_t>(f_begin) * 4, n_f * 16u, bar_red);
-      } else {
-        mbar_arrive(bar_red);
-      }
-    }
-    if (split == 0) {   // bias gradients: one CTA per (group, chunk), fixed order; loads issued together
-      named_bar_sync(2, 128);        // thread 0 has passed the split barrier
-      __threadfence();
-      const bool cta_dbd = (chunk == 0) && p.dbd != nullptr;
-      float vy[24], vp[24];
-#pragma unroll
-      for (int sidx = 0; sidx < 24; ++sidx) {
-        vy[sidx] = vp[sidx] = 0.f;
-        if (sidx < S) {
-          const float* ps = part0 + sidx * split_stride + 2 * 128 * NCW;
-          vy[sidx] = __ldcg(ps + t);
-          vp[sidx] = __ldcg(ps + NCW + t);
+    if (S == 1) {
+      named_bar_sync(1, 128);
+    } else {
+      const float* part0 = pp.partials + static_cast<size_t>(p.first_cta + chunk) * PART_FLOATS;   // split 0
+      const size_t split_stride = static_cast<size_t>(NCHUNK) * PART_FLOATS;
+      fence_proxy_async_smem();
+      __threadfence();                 // the two bias partial vectors (plain stores above)
+      named_bar_sync(1, 128);
+      if (t == 0) {
+        bulk_store_1d(part, smem0, TILE_F4 * 16);
+        tma_store_commit();
+        tma_store_wait_all<0>();       // the partials are written (not merely read out of smem)
+        fence_proxy_async_all();
+        __threadfence();
+        atomicAdd(ctr, 1u);
+        wait_counter(ctr, static_cast<unsigned int>(S));
+        __threadfence();
+        fence_proxy_async_all();
+        if (tid == 64) WG_TRACE(204);
+        // this CTA's slice [f_begin, f_end) of every split's partial tile -> smem, one bulk copy per split
+        if (n_f > 0) {
+          mbar_arrive_expect_tx(bar_red, static_cast<uint32_t>(S) * n_f * 16u);
+          for (int sidx = 0; sidx < S; ++sidx)
+            bulk_load_1d(smem0 + static_cast<uint32_t>(sidx) * per * 16u,
+                         part0 + sidx * split_stride + static_cast<size_t>(f_begin) * 4, n_f * 16u, bar_red);
+        } else {
+          mbar_arrive(bar_red);
         }
       }
-      float sdy = 0.f, sdp = 0.f;
+      if (split == 0) {   // bias gradients: one CTA per (group, chunk), fixed order; loads issued together
+        named_bar_sync(2, 128);        // thread 0 has passed the split barrier
+        __threadfence();
+        float vy[24], vp[24];
 #pragma unroll
-      for (int sidx = 0; sidx < 24; ++sidx) {
-        sdy += vy[sidx];
-        sdp += vp[sidx];
+        for (int sidx = 0; sidx < 24; ++sidx) {
+          vy[sidx] = vp[sidx] = 0.f;
+          if (sidx < S) {
+            const float* ps = part0 + sidx * split_stride + 2 * 128 * NCW;
+            vy[sidx] = __ldcg(ps + t);
+            vp[sidx] = __ldcg(ps + NCW + t);
+          }
+        }
+        float sdy = 0.f, sdp = 0.f;
+#pragma unroll
+        for (int sidx = 0; sidx < 24; ++sidx) {
+          sdy += vy[sidx];
+          sdp += vp[sidx];
+        }
+        if (do_dbu) p.dbu[col0 + t] = p.scale * sdy;
+        if (cta_dbd && static_cast<int>(t) < p.rt) p.dbd[t] = sdp;
       }
-      if (do_dbu) p.dbu[col0 + t] = p.scale * sdy;
-      if (cta_dbd && static_cast<int>(t) < p.rt) p.dbd[t] = sdp;
+      mbar_wait(bar_red, 0);
     }
-    mbar_wait(bar_red, 0);
     for (int k = static_cast<int>(t); k < n_f; k += 128) {
       float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll 4
@@ -360,14 +373,16 @@ dat_wgrad_kernel(const __grid_constant__ WgradTmaps tm0, const __grid_constant__
         }
       }
     }
-    // the last CTA of this (group, chunk) to finish resets the counters for the next launch
-    named_bar_sync(1, 128);
-    if (t == 0) {
-      const unsigned int done = atomicAdd(ctr + 1, 1u);
-      if (done == static_cast<unsigned int>(S) - 1) {
-        ctr[0] = 0u;
-        ctr[1] = 0u;
-        __threadfence();
+    if (S > 1) {
+      // the last CTA of this (group, chunk) to finish resets the counters for the next launch
+      named_bar_sync(1, 128);
+      if (t == 0) {
+        const unsigned int done = atomicAdd(ctr + 1, 1u);
+        if (done == static_cast<unsigned int>(S) - 1) {
+          ctr[0] = 0u;
+          ctr[1] = 0u;
+          __threadfence();
+        }
       }
     }
   }
@@ -385,7 +400,7 @@ namespace fd {
 namespace {
 
 size_t wgrad_ws_bytes(int sms) {
-  return 1024 + static_cast<size_t>(sms) * PART_FLOATS * sizeof(float);
+  return WS_HEADER_BYTES + static_cast<size_t>(sms) * PART_FLOATS * sizeof(float);
 }
 
 int check_group(const FeddatWgradGroup& G, int d, int dtype) {
@@ -421,7 +436,7 @@ extern "C" int feddat_dat_bwd_wgrad_grouped(const FeddatWgradGroup* groups, int 
   int rc = check_device_sm100();
   if (rc) return rc;
   FD_REQUIRE(groups != nullptr && n_groups >= 1 && n_groups <= MAX_GROUPS, FD_ERR_INVALID,
-             "dat_bwd_wgrad_grouped: 1 or 2 groups (got %d)", n_groups);
+             "dat_bwd_wgrad_grouped: 1 to %d groups per launch (got %d)", MAX_GROUPS, n_groups);
   int sms = 0;
   if ((rc = device_sm_count(&sms))) return rc;
   FD_REQUIRE(workspace != nullptr && ws_bytes >= wgrad_ws_bytes(sms) &&
@@ -429,11 +444,12 @@ extern "C" int feddat_dat_bwd_wgrad_grouped(const FeddatWgradGroup* groups, int 
              FD_ERR_INVALID, "dat_bwd_wgrad: workspace of feddat_dat_wgrad_workspace_bytes() = %zu bytes needed "
              "(16-byte aligned, zero-initialised once)", wgrad_ws_bytes(sms));
 
-  WgradParams p{};
-  WgradTmaps tms[MAX_GROUPS];
+  static thread_local WgradParams p;    // 14 KB: kept off the stack of the (autograd) caller thread
+  p = WgradParams{};
+  WgradTmaps* tms = p.tm;
   p.n_groups = n_groups;
   p.counters = static_cast<unsigned int*>(workspace);
-  p.partials = reinterpret_cast<float*>(static_cast<char*>(workspace) + 1024);
+  p.partials = reinterpret_cast<float*>(static_cast<char*>(workspace) + WS_HEADER_BYTES);
   p.trace = FD_TRACE_PTR;
   int max_splits = sms / (NCHUNK * n_groups);
   if (max_splits < 1) max_splits = 1;
@@ -456,18 +472,13 @@ extern "C" int feddat_dat_bwd_wgrad_grouped(const FeddatWgradGroup* groups, int 
     WgradTmaps& T = tms[gi];
     if ((rc = make_tmap_bf16_kblocks(&T.xk, G.X, G.M, kD, kD, KB, 2))) return rc;
     if ((rc = make_tmap_bf16_kblocks(&T.dyk, G.dY, G.M, kD, kD, KB, 2))) return rc;
-    if ((rc = make_tmap_bf16_2d(&T.h, G.H_t, G.M, G.r_t, G.ld_ht, KB, 64))) return rc;
-    if ((rc = make_tmap_bf16_2d(&T.dp, G.dP_t, G.M, G.r_t, G.ld_ht, KB, 64))) return rc;
-    T.hk = T.h;
-    T.dpk = T.dp;
     if (w.a_3d) {
-      if ((rc = make_tmap_bf16_kblocks(&T.hk, G.H_t, G.M, G.r_t, G.ld_ht, KB, G.r_t / 64))) return rc;
-      if ((rc = make_tmap_bf16_kblocks(&T.dpk, G.dP_t, G.M, G.r_t, G.ld_ht, KB, G.r_t / 64))) return rc;
+      if ((rc = make_tmap_bf16_kblocks(&T.h, G.H_t, G.M, G.r_t, G.ld_ht, KB, G.r_t / 64))) return rc;
+      if ((rc = make_tmap_bf16_kblocks(&T.dp, G.dP_t, G.M, G.r_t, G.ld_ht, KB, G.r_t / 64))) return rc;
+    } else {
+      if ((rc = make_tmap_bf16_2d(&T.h, G.H_t, G.M, G.r_t, G.ld_ht, KB, 64))) return rc;
+      if ((rc = make_tmap_bf16_2d(&T.dp, G.dP_t, G.M, G.r_t, G.ld_ht, KB, 64))) return rc;
     }
-  }
-  if (n_groups == 1) {
-    tms[1] = tms[0];
-    p.g[1] = p.g[0];
   }
   FD_REQUIRE(ctas <= sms, FD_ERR_UNSUPPORTED, "dat_bwd_wgrad: %d CTAs exceed the %d SMs (co-residency)", ctas, sms);
 
@@ -491,7 +502,7 @@ extern "C" int feddat_dat_bwd_wgrad_grouped(const FeddatWgradGroup* groups, int 
   cfg.attrs = attr;
   const char* e = getenv("FEDDAT_PDL");
   cfg.numAttrs = (e && e[0] == '0') ? 0 : 1;
-  FD_CHECK_CUDA(cudaLaunchKernelEx(&cfg, dat_wgrad_kernel, tms[0], tms[1], p));
+  FD_CHECK_CUDA(cudaLaunchKernelEx(&cfg, dat_wgrad_kernel, p));
   FD_CHECK_CUDA(cudaGetLastError());
   return FD_OK;
 }

@@ -150,6 +150,7 @@ class _DualDatFunction(torch.autograd.Function):
         outs = ops.dat_forward_grouped(groups, adapter._act_code)
         ctx.parts = [(pk, scale, h, needs) for (pk, scale, needs), (_, h) in zip(meta, outs)]
         ctx.adapter = adapter
+        ctx.params = params            # leaves: the deferred weight-gradient queue assigns their .grad itself
         ctx.save_for_backward(x)
         return y
 
@@ -172,7 +173,8 @@ class _DualDatFunction(torch.autograd.Function):
             slices.append((lo, hi, trains, nb))
             groups.append(dict(x=x[sl], dy=dy[sl], w=pk, scale=scale, train_slice=None if lo is None else (lo, hi),
                                need_dx=need_dx, add_dy=True, hidden=hid, dx_out=None if dx is None else dx[sl]))
-        results = ops.dat_backward_grouped(groups, adapter._act_code)
+        results = ops.dat_backward_grouped(groups, adapter._act_code, allow_defer=True)
+        queue = ops.deferred_queue()     # set: the gradient tensors are filled when the trainer flushes the queue
         grads = []
         for (_, g), (lo, hi, trains, nb), (_, _, _, needs) in zip(results, slices, ctx.parts):
             part = [None] * len(needs)
@@ -181,9 +183,15 @@ class _DualDatFunction(torch.autograd.Function):
                 for b in range(nb):
                     if trains[b]:
                         s0, s1 = b * r - lo, (b + 1) * r - lo
-                        part[4 * b:4 * b + 4] = [d_down_w[s0:s1].contiguous(), d_down_b[s0:s1].contiguous(),
-                                                 d_up_w[:, s0:s1].contiguous(), d_up_b.contiguous()]
-            grads += [gr if nd else None for gr, nd in zip(part, needs)]
+                        part[4 * b:4 * b + 4] = [d_down_w[s0:s1], d_down_b[s0:s1], d_up_w[:, s0:s1], d_up_b]
+            if queue is not None:
+                first = len(grads)
+                for k, (gr, nd) in enumerate(zip(part, needs)):
+                    if nd and gr is not None:
+                        queue.assign(ctx.params[first + k], gr)
+                grads += [None] * len(needs)
+            else:
+                grads += [gr.contiguous() if (nd and gr is not None) else None for gr, nd in zip(part, needs)]
         return (None, dx, *grads)
 
 

@@ -195,9 +195,89 @@ def wgrad_workspace(device: torch.device) -> torch.Tensor:
     return ws
 
 
-def dat_backward_grouped(groups: Sequence[dict], act=ACT_RELU):
+MAX_WGRAD_GROUPS = 24        # groups of one feddat_dat_bwd_wgrad_grouped launch
+
+
+def _launch_wgrad(wg, device) -> None:
+    lib = _lib.load()
+    ws = wgrad_workspace(device)
+    for i in range(0, len(wg), MAX_WGRAD_GROUPS):
+        chunk = wg[i:i + MAX_WGRAD_GROUPS]
+        arr = (_lib.WgradGroup * len(chunk))(*chunk)
+        rc = lib.feddat_dat_bwd_wgrad_grouped(arr, len(chunk), 768, DTYPE_BF16, _lib.ptr(ws), ws.numel() * 4,
+                                              _lib.stream_ptr())
+        _lib.check(rc, "feddat_dat_bwd_wgrad_grouped")
+        _count()
+
+
+class DeferredWgrad:
+    """Weight gradients of a whole backward pass in ONE launch.
+
+    The parameter gradients of an adapter site are not needed before the optimizer step, while its data gradient
+    is on the critical path of back-propagation.  Inside ``with ops.deferred_wgrad() as q:`` every
+    ``dat_backward_grouped`` call launches only its data-gradient kernel and queues its weight-gradient groups
+    (keeping X, dY, the saved hidden and dP alive); ``q.flush()`` -- called by the ``with`` exit -- launches them
+    together (24 groups per launch: 12 ViLT sites x {gating rows, adapter_1 rows} = 144 CTAs, each contracting over
+    ALL rows of its (group, 128-column chunk): no row splits, no partial tiles, no second reduction stage, one
+    launch instead of twelve) and then hands the gradients to the parameters registered with ``assign`` exactly as
+    autograd's AccumulateGrad would (``p.grad = g`` or ``p.grad += g``).  Process-global on purpose: autograd runs
+    CUDA backward nodes on its own thread."""
+
+    def __init__(self):
+        self.groups, self.keep, self.pending = [], [], []
+        self.device = None
+
+    def add(self, wgroups, keep, device) -> None:
+        self.groups += wgroups
+        self.keep.append(keep)
+        self.device = device
+
+    def assign(self, param: torch.Tensor, grad_view: torch.Tensor) -> None:
+        self.pending.append((param, grad_view))
+
+    def flush(self) -> None:
+        if self.groups:
+            _launch_wgrad(self.groups, self.device)
+        with torch.no_grad():
+            for p, g in self.pending:
+                g = g.contiguous()
+                if p.grad is None:
+                    p.grad = g
+                else:
+                    p.grad.add_(g)
+        self.groups, self.keep, self.pending = [], [], []
+
+
+_deferred: Optional[DeferredWgrad] = None
+
+
+def deferred_queue() -> Optional[DeferredWgrad]:
+    return _deferred
+
+
+class deferred_wgrad:
+    """Context manager: see DeferredWgrad."""
+
+    def __enter__(self) -> DeferredWgrad:
+        global _deferred
+        if _deferred is not None:
+            raise _lib.FeddatError("deferred_wgrad() does not nest")
+        _deferred = DeferredWgrad()
+        return _deferred
+
+    def __exit__(self, exc_type, exc, tb):
+        global _deferred
+        q, _deferred = _deferred, None
+        if exc_type is None:
+            q.flush()
+        return False
+
+
+def dat_backward_grouped(groups: Sequence[dict], act=ACT_RELU, allow_defer: bool = False):
     """Backward of up to two row groups: ONE data-gradient launch (feddat_dat_bwd_dgrad_grouped) and ONE
-    weight-gradient launch (feddat_dat_bwd_wgrad_grouped) for all of them.  Each group is a dict with the
+    weight-gradient launch (feddat_dat_bwd_wgrad_grouped) for all of them -- or, inside ``deferred_wgrad()``, the
+    weight-gradient groups of a caller that passes ``allow_defer`` (one that registers the returned gradient
+    tensors with the queue instead of reading them) are queued and those tensors are filled at the flush.  Each group is a dict with the
     arguments of ``dat_backward`` (x, dy, w, scale, train_slice=None, need_dx=True, add_dy=True, hidden=None,
     dx_out=None).  Returns [(dx | None, grads | None)]."""
     lib = _lib.load()
@@ -288,13 +368,13 @@ def dat_backward_grouped(groups: Sequence[dict], act=ACT_RELU):
                      g[2 * rt * d + rt:])
         results.append((it["dx"], grads))
     if wg:
-        ws = wgrad_workspace(groups[0]["dy"].device)
-        for i in range(0, len(wg), 2):
-            pair = (_lib.WgradGroup * 2)(*wg[i:i + 2]) if len(wg) - i >= 2 else (_lib.WgradGroup * 1)(wg[i])
-            rc = lib.feddat_dat_bwd_wgrad_grouped(pair, len(pair), d, DTYPE_BF16, _lib.ptr(ws), ws.numel() * 4,
-                                                  _lib.stream_ptr())
-            _lib.check(rc, "feddat_dat_bwd_wgrad_grouped")
-            _count()
+        dev = groups[0]["dy"].device
+        if _deferred is not None and allow_defer:
+            wgrad_workspace(dev)       # exists before any capture
+            _deferred.add(wg, (info, results, [gr.get("hidden") for gr in groups]), dev)
+        else:
+            for i in range(0, len(wg), 2):      # the groups of one site: two per launch (row splits fill the SMs)
+                _launch_wgrad(wg[i:i + 2], dev)
     return results
 
 

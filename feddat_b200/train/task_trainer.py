@@ -86,6 +86,7 @@ def get_polynomial_decay_schedule_with_warmup(optimizer, num_warmup_steps, num_t
               lr_end=lr_end, power=power)
 
 
+DEFER_WGRAD = True        # batched schedule: all sites' weight gradients in ONE launch after the backward (ops.DeferredWgrad)
 USE_OWN_ADAMW = True      # csrc/adamw.cu behind train/fused_adamw.py; False = torch.optim.AdamW(fused, capturable)
 
 
@@ -271,7 +272,9 @@ class TaskTrainer(nn.Module):
         logits_0 = inner.classify(self.task_key, enc_a)              # (C): updated head
         L_0, loss_0 = self._objective(logits_0, logits_1, target, None)
         self.accelerator.backward(L_0)                               # head grads + d enc_A
-        with _nvtx("batched_bwd_C+B"):
+        # the sites' weight gradients are not needed before step 5: the backward queues them and ONE launch at
+        # its end computes all of them (ops.DeferredWgrad)
+        with _nvtx("batched_bwd_C+B"), (ops.deferred_wgrad() if DEFER_WGRAD else contextlib.nullcontext()):
             enc.backward(leaf.grad)                                  # adapter_0 (rows A) and adapter_1 (rows B)
         self._probe("BC", model)
 

@@ -124,3 +124,56 @@ def test_bert_site_wrapper_wide_rank(r):
                                              ln.bias.detach().cpu().numpy().astype(np.float64), 1e-12,
                                              [branch("adapter_0"), branch("adapter_2")], True)
     assert relerr(out.detach().float().cpu().numpy(), want) < 2e-2       # two LayerNorms amplify the bf16 rounding of their inputs
+
+
+def test_dual_mode_deferred_weight_gradients():
+    """Several sites in dual mode (TaskTrainer's batched schedule) chained like encoder blocks: with
+    ``ops.deferred_wgrad()`` around the backward, the data gradient is bit-identical, every parameter gets the
+    gradient of the plain autograd run (one launch over all sites, no row splits: summation order differs), the
+    frozen adapter_2 gets none, and a second deferred backward ACCUMULATES into .grad as autograd would."""
+    from feddat_b200 import ops
+    from feddat_b200.modeling.adapter import Adapter
+    g = torch.Generator(device="cuda").manual_seed(11)
+    sites = []
+    for _ in range(4):
+        a = Adapter(names=["adapter_0", "adapter_1", "adapter_2"], device="cuda", rank=64)
+        with torch.no_grad():
+            for p in a.parameters():
+                p.copy_(torch.randn(p.shape, device="cuda", generator=g) * (0.1 if p.dim() == 1 else 0.05))
+        a.set_dual(True)
+        sites.append(a)
+    x0 = torch.randn(2 * 333, 768, device="cuda", generator=g).to(torch.bfloat16)
+    dy = torch.randn(2 * 333, 768, device="cuda", generator=g).to(torch.bfloat16)
+
+    def run(defer, times=1):
+        for a in sites:
+            a.zero_grad(set_to_none=True)
+        for _ in range(times):
+            x = x0.clone().requires_grad_(True)
+            h = x
+            for a in sites:
+                h = a(h, h)
+            if defer:
+                with ops.deferred_wgrad():
+                    h.backward(dy)
+            else:
+                h.backward(dy)
+        torch.cuda.synchronize()
+        return x.grad.clone(), {n: (None if p.grad is None else p.grad.clone())
+                                for i, a in enumerate(sites) for n, p in ((f"{i}.{k}", v) for k, v in a.named_parameters())}
+
+    dx_ref, ref = run(False)
+    dx_def, got = run(True)
+    assert torch.equal(dx_ref, dx_def)
+    assert ref.keys() == got.keys()
+    for n in ref:
+        if "adapter_2" in n:
+            assert ref[n] is None and got[n] is None
+        else:
+            assert got[n].shape == ref[n].shape and got[n].is_contiguous()
+            assert relerr(got[n].cpu().numpy(), ref[n].cpu().numpy()) < 1e-5, n
+    _, twice = run(True, times=2)
+    for n in ref:
+        if ref[n] is not None:
+            assert relerr(twice[n].cpu().numpy(), 2 * got[n].cpu().numpy()) < 1e-6, n
+    assert ops.deferred_queue() is None

@@ -452,6 +452,61 @@ def test_wgrad_is_bitwise_reproducible(ops):
             assert torch.equal(a, b)
 
 
+@pytest.mark.parametrize("n_sites,M,r", [(12, 5920, 128),   # BASELINE configs[1]: 24 groups x 6 chunks = 144 CTAs, no row splits
+                                         (13, 333, 64),     # 26 groups: two launches; ragged row blocks
+                                         (3, 700, 48),      # r_t % 64 != 0: 2-D hidden boxes; 6 groups -> 4 row splits each
+                                         (5, 1, 16)])       # single-row groups
+def test_deferred_wgrad_equals_per_site_launches(ops, n_sites, M, r):
+    """ops.deferred_wgrad(): the weight gradients of all sites of a backward pass from ONE launch (up to 24
+    groups) == the per-site launches up to the summation order over rows; the data gradient is untouched;
+    repeated flushes are bit-identical; one site against the oracle."""
+    rng = np.random.default_rng(n_sites * 1000 + M + r)
+    sites = []
+    for _ in range(n_sites):
+        br2, br1 = _rand_branches(rng, r, 2), _rand_branches(rng, r, 1)
+        pk2, pk1 = ops.pack_weights(dev_branches(br2)), ops.pack_weights(dev_branches(br1))
+        x = rng.standard_normal((2 * M, 768)).astype(np.float32)
+        g = rng.standard_normal((2 * M, 768)).astype(np.float32)
+        xd, gd = to_dev(x, torch.bfloat16), to_dev(g, torch.bfloat16)
+        specs = [(slice(0, M), pk2, 0.5, (0, r)), (slice(M, 2 * M), pk1, 1.0, (0, r))]
+        y = torch.empty_like(xd)
+        outs = ops.dat_forward_grouped([dict(x=xd[sl], res=xd[sl], w=pk, scale=sc, out=y[sl], save_hidden=True)
+                                        for sl, pk, sc, _ in specs])
+        sites.append((x, g, xd, gd, specs, outs, (br2, br1)))
+
+    def backward_all(defer):
+        def run():
+            return [ops.dat_backward_grouped(
+                [dict(x=xd[sl], dy=gd[sl], w=pk, scale=sc, train_slice=ts, need_dx=True, add_dy=True, hidden=h)
+                 for (sl, pk, sc, ts), (_, h) in zip(specs, outs)], allow_defer=True)
+                for (_, _, xd, gd, specs, outs, _) in sites]
+        if not defer:
+            return run()
+        with ops.deferred_wgrad() as q:
+            res = run()
+            assert len(q.groups) == 2 * n_sites
+        return res
+
+    n0 = ops.launch_count
+    deferred = backward_all(True)
+    assert ops.launch_count - n0 == n_sites + (2 * n_sites + 23) // 24     # one dgrad per site + the flush
+    again = backward_all(True)
+    direct = backward_all(False)
+    torch.cuda.synchronize()
+    for site_d, site_a, site_i in zip(deferred, again, direct):
+        for (dx_d, gr_d), (dx_a, gr_a), (dx_i, gr_i) in zip(site_d, site_a, site_i):
+            assert torch.equal(dx_d, dx_i)
+            for a, b, c in zip(gr_d, gr_a, gr_i):
+                assert torch.equal(a, b)
+                assert relerr(a.cpu().numpy(), c.cpu().numpy()) < 1e-5
+    x, g, _, _, specs, _, brs = sites[-1]
+    for (sl, _, _, _), (_, gr_d), br, gating in zip(specs, deferred[-1], brs, (True, False)):
+        _, grads_or = oracle.adapter_backward(bf16_round(x[sl]), bf16_round(g[sl]), rounded_branches(br), gating,
+                                              residual_is_input=True)
+        for got, want in zip(gr_d, grads_or[0]):
+            assert relerr(got.cpu().numpy(), want) < 2 * BF16_TOL
+
+
 def test_pack_weights_batched_slices(ops):
     """feddat_pack_weights_batched: several jobs in one launch, with row / column SLICE views of wide masters
     (how a bottleneck wider than one launch is packed segment by segment), bias on the first segment only."""
