@@ -105,10 +105,19 @@ struct FusedParams {
   unsigned long long* trace;  // debug: globaltimer stamps of CTA 0's pipeline events (or null)
 };
 
-// the seven tensor maps of one group
+// the nine tensor maps of one group
 struct TmapSet {
-  CUtensorMap x, res, y, wd, w2, w2k, w1b;
+  CUtensorMap x, res, y, wd, w2, w2k, w1b, h, dp;
 };
+
+// Epilogue 1 splits the R / 16 sixteen-column chunks of P between the two epilogue groups: group A packs
+// chunks [0, nA), group B the rest.  nA is rounded up to a multiple of four (64 columns) so that both groups'
+// shares start at a 64-column boundary: the packed hidden also travels through the 64-column staging buffers
+// (saved by the forward / loaded and turned into dP by the backward with TMA, see "hidden chunks" below).
+__host__ __device__ __forceinline__ int split_a(int n16) {
+  const int a = (((n16 + 1) / 2) + 3) & ~3;
+  return a < n16 ? a : n16;
+}
 
 // slot -> what this CTA pair computes
 struct Slot {
@@ -125,8 +134,15 @@ struct Slot {
     if (p.trace != nullptr && blockIdx.x == 0 && (t) < 2)                           \
       p.trace[(t) * 128 + (ev)] = globaltimer_ns();                                 \
   } while (0)
+// the same for BOTH CTAs of pair 0: event ev of CTA rank c -> trace[t * 128 + ev + 8 c]
+#define FD_TRACE_PAIR(ev, t)                                                        \
+  do {                                                                              \
+    if (p.trace != nullptr && blockIdx.x < 2 && (t) < 2)                            \
+      p.trace[(t) * 128 + (ev) + 8 * blockIdx.x] = globaltimer_ns();                \
+  } while (0)
 #else   // product build: no trace code in the kernels
 #define FD_TRACE(ev, t) do { (void)(t); } while (0)
+#define FD_TRACE_PAIR(ev, t) do { (void)(t); } while (0)
 #endif
 
 // activation is a template parameter: a run-time switch makes ptxas keep the erff path live in the
@@ -151,6 +167,16 @@ __device__ __forceinline__ float act_grad(float x) {
 //   w2    [768, R]       Wu_cat                       WdT_cat      (2-D, one [64 x 64] k-block per box)
 //   w2k   [768, R]       the same tensor as a 3-D (64, 768, R/64) view: box = all k-blocks of 64 rows
 //   w1b   [R, 768]       (unused)                     WuT_cat
+//   h     [M, R]         H_out (hidden to save)       H_in (saved hidden)      box [128 x 64]
+//   dp    [M, r_t]       (unused)                     dP_t (trainable slice, row stride ld_t)
+// HIDDEN CHUNKS.  The staging ring (NSTG buffers of [128 rows x 64 columns]) carries, per tile, first the
+// ceil(R / 64) chunks of the hidden and then the output chunks.  Forward with H_out: epilogue 1 writes the packed
+// hidden into the buffers next to its tcgen05.st and the store issuer TMA-stores them.  Saved-hidden backward:
+// the residual producer TMA-loads the H_in chunks, epilogue 1 reads relu' from them, writes dP back IN PLACE
+// and the store issuer stores the chunks of the trainable slice.  (Row-per-thread global loads / stores of
+// these tiles are 32 sectors per instruction: 4 096 LSU transactions per CTA that sat in the SM's in-order
+// memory pipeline in front of every mbarrier operation of the producer and MMA warps -- 2.6 us between
+// "hidden packed" and the first GEMM2 MMA in the forward, 2.9 us on GEMM1b in the backward.)
 // kSaved (backward, ReLU only): the hidden saved by the forward replaces the recompute of P -- no X
 // read, no GEMM1 pass 0; relu'(P) is read off the saved hidden (H > 0).
 template <bool kBwd, bool kGelu, bool kSaved = false>
@@ -210,6 +236,8 @@ dat_fused_kernel(const __grid_constant__ TmapSet tm0, const __grid_constant__ Tm
       tma_prefetch_desc(&T.w2);
       tma_prefetch_desc(&T.w2k);
       if (kBwd) tma_prefetch_desc(&T.w1b);
+      if (!kBwd || kSaved) tma_prefetch_desc(&T.h);
+      if (kSaved) tma_prefetch_desc(&T.dp);
     }
   }
   if (warp == 2) tmem_alloc_pair(smem_u32(&tmem_base_smem), 512);
@@ -241,6 +269,14 @@ dat_fused_kernel(const __grid_constant__ TmapSet tm0, const __grid_constant__ Tm
     s.c_base = (rel / np) * s.nc2;
     s.tile0 = 2 * (rel % np);
     return s;
+  };
+  // hidden chunks of a slot in the staging sequence: total, and group A's share
+  auto hidden_chunks = [&](const Slot& sl, int& nhA) -> int {
+    const GroupCfg& G = p.g[sl.g];
+    const bool on = kBwd ? kSaved : (G.H_out != nullptr && sl.c_base == 0);
+    const int n16 = G.R / 16, nA = split_a(n16);
+    nhA = on ? (nA + 3) / 4 : 0;
+    return on ? nhA + (n16 - nA + 3) / 4 : 0;
   };
   // every TMA of the pair credits its bytes to the LEADER's stage barrier
   const uint32_t leader_full0 = mapa_u32(bar_slot_full(0), 0);
@@ -320,7 +356,7 @@ dat_fused_kernel(const __grid_constant__ TmapSet tm0, const __grid_constant__ Tm
       for (int slot = pid; slot < p.total_slots; slot += n_pairs_launched, ++tile_it) {
         const Slot sl = decode(slot);
         const int R = p.g[sl.g].R;
-        const int n16 = R / 16, nA = (n16 + 1) / 2;
+        const int n16 = R / 16, nA = split_a(n16);
         const uint32_t idesc1 = make_idesc_bf16(2 * BM, R);
         for (int pass = kSaved ? 1 : 0; pass < (kBwd ? 2 : 1); ++pass) {
           // pass 0: P = X Wd_cat^T -> [TM_P, +R);  pass 1 (bwd): dH = dY Wu_cat -> [TM_D, +R)
@@ -357,6 +393,7 @@ dat_fused_kernel(const __grid_constant__ TmapSet tm0, const __grid_constant__ Tm
         // by the next tile's GEMM1 (waited even when no GEMM2/3 follows)
         mbar_wait(bar_h_full, tile_it & 1);
         tc_fence_after();
+        if (lane == 0) FD_TRACE(24, tile_it);
         for (int c = 0; c < sl.nc2; ++c, ++n) {
           const int b = c & 1;
           mbar_wait(bar_d_empty(b), (de[b] & 1) ^ 1);
@@ -397,6 +434,18 @@ dat_fused_kernel(const __grid_constant__ TmapSet tm0, const __grid_constant__ Tm
         const bool has_res = p.g[sl.g].has_res != 0;
         const int m0 = (sl.tile0 + static_cast<int>(rank)) * BM;
         const uint32_t per_tile = sl.nc2 * 2;
+        int nhA;
+        const int nh = hidden_chunks(sl, nhA);
+        for (int j = 0; j < nh; ++j, ++g) {      // hidden chunks: loaded (saved backward) or just granted (forward)
+          const uint32_t sb = g % NSTG, par = (g / NSTG) & 1;
+          mbar_wait(bar_stg_empty(sb), par ^ 1);
+          if constexpr (kSaved) {
+            mbar_arrive_expect_tx(bar_res_full(sb), SLOT);
+            tma_load_2d(stg_base + sb * SLOT, &T.h, bar_res_full(sb), j * 64, m0);
+          } else {
+            mbar_arrive(bar_res_full(sb));
+          }
+        }
         for (uint32_t c64 = 0; c64 < per_tile; ++c64, ++g) {
           const uint32_t sb = g % NSTG, par = (g / NSTG) & 1;
           mbar_wait(bar_stg_empty(sb), par ^ 1);
@@ -421,6 +470,24 @@ dat_fused_kernel(const __grid_constant__ TmapSet tm0, const __grid_constant__ Tm
         const TmapSet& T = sl.g ? tm1 : tm0;
         const int m0 = (sl.tile0 + static_cast<int>(rank)) * BM;
         const uint32_t per_tile = sl.nc2 * 2;
+        int nhA;
+        const int nh = hidden_chunks(sl, nhA);
+        const GroupCfg& G = p.g[sl.g];
+        for (int j = 0; j < nh; ++j, ++g) {      // hidden chunks: H_out (forward) / dP_t of the trainable slice
+          const uint32_t sb = g % NSTG, par = (g / NSTG) & 1;
+          mbar_wait(bar_out_full(sb), par);
+          if constexpr (!kBwd) {
+            tma_store_2d_hint(&T.h, stg_base + sb * SLOT, j * 64, m0, kEvictFirst);
+          } else {
+            if (G.dP_t != nullptr && sl.c_base == 0 && j * 64 < G.r_hi && j * 64 + 64 > G.r_lo)
+              tma_store_2d_hint(&T.dp, stg_base + sb * SLOT, j * 64 - G.r_lo, m0, kEvictLast);
+          }
+          tma_store_commit();                    // (an empty group when nothing was stored: same bookkeeping)
+          if (g > 0) {
+            tma_store_wait_read<1>();
+            mbar_arrive(bar_stg_empty((g - 1) % NSTG));
+          }
+        }
         for (uint32_t c64 = 0; c64 < per_tile; ++c64, ++g) {
           const uint32_t sb = g % NSTG, par = (g / NSTG) & 1;
           mbar_wait(bar_out_full(sb), par);
@@ -477,30 +544,19 @@ dat_fused_kernel(const __grid_constant__ TmapSet tm0, const __grid_constant__ Tm
       // chunks [0, nA), group B chunks [nA, n16).  Each packs IN PLACE over its own columns, so the
       // hidden's k-step k (16 bottleneck units = 8 packed columns) sits at column 8 k (k < nA) or
       // 16 nA + 8 (k - nA)
-      const int n16 = R / 16, nA = (n16 + 1) / 2;
+      const int n16 = R / 16, nA = split_a(n16);
       const int c_lo = group == 0 ? 0 : nA, c_hi = group == 0 ? nA : n16;
       const uint32_t w_base = group == 0 ? 0u : static_cast<uint32_t>(16 * nA);   // where its hidden goes
       const float scale = G.scale;
       const bool has_res = G.has_res != 0;
       const float* bias_g = bias_smem + sl.g * BIAS_STRIDE;
       const int m0 = (sl.tile0 + static_cast<int>(rank)) * BM;
+      int nhA;
+      const int nh = hidden_chunks(sl, nhA);
       {
         // ---------------- epilogue 1: this group's half of P (and dH) -> packed bf16 hidden
         const int grow = m0 + static_cast<int>(row);
-        uint4 hreg[8][2];     // kSaved: this row's saved hidden, all of the group's chunks
-        uint32_t wall[8][8];  // forward with H_out: the packed hidden, stored to HBM after GEMM2 is released
-        if constexpr (kSaved) {
-          // issued BEFORE the wait on GEMM1b: the global-load latency hides under it
-          const uint4* hrow = reinterpret_cast<const uint4*>(G.H_in + static_cast<size_t>(grow) * R);
-#pragma unroll
-          for (int ci = 0; ci < 8; ++ci) {
-            hreg[ci][0] = hreg[ci][1] = make_uint4(0u, 0u, 0u, 0u);
-            if (c_lo + ci < c_hi && grow < G.M) {
-              hreg[ci][0] = __ldg(hrow + 2 * (c_lo + ci));
-              hreg[ci][1] = __ldg(hrow + 2 * (c_lo + ci) + 1);
-            }
-          }
-        }
+        const uint32_t hg0 = stg_n + (group == 0 ? 0u : static_cast<uint32_t>(nhA));   // its first hidden chunk
         if (!kSaved) mbar_wait(bar_p_full, tile_it & 1);
         if (kBwd) mbar_wait(bar_g_full, tile_it & 1);
         tc_fence_after();
@@ -512,9 +568,19 @@ dat_fused_kernel(const __grid_constant__ TmapSet tm0, const __grid_constant__ Tm
           const int c = c_lo + ci;
           if (c < c_hi) {
             uint32_t v[16], u[16], w[8];
+            // the 64-column staging buffer this 16-column chunk belongs to (forward with H_out: to fill; saved
+            // backward: holding the saved hidden)
+            const uint32_t hgi = hg0 + (ci >> 2);
+            const uint32_t hbuf = stg_base + (hgi % NSTG) * SLOT;
+            if (nh > 0 && (ci & 3) == 0) mbar_wait(bar_res_full(hgi % NSTG), (hgi / NSTG) & 1);
             if (!kSaved) tmem_ld16(t_p + c * 16, v);
             if (kBwd) tmem_ld16(t_g + c * 16, u);
             const float* bdv = bias_g + c * 16;
+            uint4 h0 = make_uint4(0u, 0u, 0u, 0u), h1 = h0;
+            if constexpr (kSaved) {
+              h0 = ld_shared_v4(hbuf + sw128_offset(row, 2 * (ci & 3)));
+              h1 = ld_shared_v4(hbuf + sw128_offset(row, 2 * (ci & 3) + 1));
+            }
             if (!kSaved) tmem_ld_wait16(v);
             if (kBwd) tmem_ld_wait16(u);
             const int col = c * 16;
@@ -523,19 +589,14 @@ dat_fused_kernel(const __grid_constant__ TmapSet tm0, const __grid_constant__ Tm
               for (int i = 0; i < 8; ++i)
                 w[i] = pack_bf16x2(apply_act<kGelu>(__uint_as_float(v[2 * i]) + bdv[2 * i]),
                                    apply_act<kGelu>(__uint_as_float(v[2 * i + 1]) + bdv[2 * i + 1]));
-#pragma unroll
-              for (int i = 0; i < 8; ++i) wall[ci][i] = w[i];
             } else if constexpr (kSaved) {
-              const uint32_t hb[8] = {hreg[ci][0].x, hreg[ci][0].y, hreg[ci][0].z, hreg[ci][0].w,
-                                      hreg[ci][1].x, hreg[ci][1].y, hreg[ci][1].z, hreg[ci][1].w};
+              const uint32_t hb[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
 #pragma unroll
               for (int i = 0; i < 8; ++i) {      // relu'(P) == (H > 0); H is never negative
                 const float g0 = (hb[i] & 0x00007fffu) ? scale * __uint_as_float(u[2 * i]) : 0.f;
                 const float g1 = (hb[i] & 0x7fff0000u) ? scale * __uint_as_float(u[2 * i + 1]) : 0.f;
                 w[i] = pack_bf16x2(g0, g1);
               }
-#pragma unroll
-              for (int i = 0; i < 8; ++i) wall[ci][i] = w[i];   // dP_t goes to HBM after GEMM3 has been released
             } else {
               uint32_t hh[8];
 #pragma unroll
@@ -559,39 +620,24 @@ dat_fused_kernel(const __grid_constant__ TmapSet tm0, const __grid_constant__ Tm
             // the target columns lie inside a P chunk of THIS group that it has already read (or, in
             // saved mode, in the unused P region)
             tmem_st8(t_p + w_base + (c - c_lo) * 8, w);
+            if (nh > 0) {
+              // the same 16 columns into the staging buffer (forward: the hidden to save; saved backward: dP over
+              // the hidden it was derived from -- each thread rewrites only what it has read itself)
+              st_shared_v4(hbuf + sw128_offset(row, 2 * (ci & 3)), w[0], w[1], w[2], w[3]);
+              st_shared_v4(hbuf + sw128_offset(row, 2 * (ci & 3) + 1), w[4], w[5], w[6], w[7]);
+              if ((ci & 3) == 3 || c == c_hi - 1) {     // the buffer's last chunk of this group: hand it to the store issuer
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar_out_full(hgi % NSTG));
+              }
+            }
           }
         }
         tmem_st_wait();
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive_cluster_addr(leader_h_full);
-        if constexpr (kSaved) {
-          // the trainable slice of dP for the weight-gradient kernel: stored AFTER GEMM3 has been released
-          if (G.dP_t != nullptr && c_base == 0 && grow < G.M) {
-#pragma unroll
-            for (int ci = 0; ci < 8; ++ci) {
-              const int col = (c_lo + ci) * 16;
-              if (c_lo + ci < c_hi && col >= G.r_lo && col < G.r_hi) {
-                uint4* gd = reinterpret_cast<uint4*>(G.dP_t + static_cast<size_t>(grow) * G.ld_t + (col - G.r_lo));
-                gd[0] = make_uint4(wall[ci][0], wall[ci][1], wall[ci][2], wall[ci][3]);
-                gd[1] = make_uint4(wall[ci][4], wall[ci][5], wall[ci][6], wall[ci][7]);
-              }
-            }
-          }
-        }
-        if constexpr (!kBwd) {
-          // save the hidden for a kSaved backward AFTER GEMM2 has been released: a row-per-thread store
-          // is 32 L1 transactions per instruction and must not sit on the tensor pipe's critical path
-          if (G.H_out != nullptr && c_base == 0 && grow < G.M) {
-            uint4* hrow = reinterpret_cast<uint4*>(G.H_out + static_cast<size_t>(grow) * R);
-#pragma unroll
-            for (int ci = 0; ci < 8; ++ci)
-              if (c_lo + ci < c_hi) {
-                hrow[2 * (c_lo + ci)] = make_uint4(wall[ci][0], wall[ci][1], wall[ci][2], wall[ci][3]);
-                hrow[2 * (c_lo + ci) + 1] = make_uint4(wall[ci][4], wall[ci][5], wall[ci][6], wall[ci][7]);
-              }
-          }
-        }
+        if (lane == 0) FD_TRACE_PAIR(70 + (warp - 4), tile_it);     // this warp's half-quarter of the hidden is packed
         if (tid == 128) FD_TRACE(41, tile_it);
       }
       // ---------------- epilogue 2: this group's output chunks (c = group, group + 2, group + 4)
@@ -603,7 +649,7 @@ dat_fused_kernel(const __grid_constant__ TmapSet tm0, const __grid_constant__ Tm
         if (lane == 0 && q == 0) FD_TRACE(42 + 4 * c, tile_it);
 #pragma unroll 1
         for (int j = 0; j < 2; ++j) {
-          const uint32_t g = stg_n + c * 2 + j;
+          const uint32_t g = stg_n + nh + c * 2 + j;
           const uint32_t sb = g % NSTG, rpar = (g / NSTG) & 1;
           const int col0 = (c_base + c) * N2 + j * 64;
           const uint32_t t_src = tmem + lane_addr + TM_D + b * N2 + j * 64;
@@ -681,7 +727,7 @@ dat_fused_kernel(const __grid_constant__ TmapSet tm0, const __grid_constant__ Tm
         }
         if (lane == 0 && q == 0) FD_TRACE(45 + 4 * c, tile_it);
       }
-      stg_n += static_cast<uint32_t>(nc2) * 2;
+      stg_n += static_cast<uint32_t>(nh + nc2 * 2);
     }
   }
 
@@ -779,6 +825,13 @@ int launch_fused(bool bwd, bool saved, int act, HostGroup* hg, int n_groups, cud
     T.w2k = T.w2;
     if (c.w2_3d && (rc = make_tmap_bf16_kblocks(&T.w2k, hg[g].W2, kD, R, R, N2 / 2, R / 64))) return rc;
     if ((rc = make_tmap_bf16_2d(&T.w1b, hg[g].W1b ? hg[g].W1b : hg[g].W1, R, kD, kD, w_box_rows, 64))) return rc;
+    // hidden chunks through the staging ring: H_out (forward), H_in and the dP_t slice (saved backward)
+    const void* hid = bwd ? static_cast<const void*>(c.H_in) : static_cast<const void*>(c.H_out);
+    T.h = T.x;
+    T.dp = T.x;
+    if (hid != nullptr && (rc = make_tmap_bf16_2d(&T.h, hid, M, R, R, BM, 64))) return rc;
+    if (saved && c.dP_t != nullptr &&
+        (rc = make_tmap_bf16_2d(&T.dp, c.dP_t, M, c.r_hi - c.r_lo, c.ld_t, BM, 64))) return rc;
     p.g[g] = c;
   }
   if (n_groups == 1) {

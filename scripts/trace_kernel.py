@@ -69,6 +69,9 @@ for c in range(6):
     names[104 + c] = f"store: chunk{c}.x issued"
 for k in range(12):
     names[90 + k] = f"res: load c64={k} issued"
+for c in range(2):
+    for w in range(8):
+        names[70 + 8 * c + w] = f"E1: CTA {c} warp {4 + w} (group {'AB'[w >> 2]}) hidden packed"
 names.update({120: "E2 c0.0: D full seen", 121: "E2 c0.0: tmem_ld issued", 122: "E2 c0.0: residual ready",
               123: "E2 c0.0: tmem_ld done", 124: "E2 c0.0: math + st.shared done", 125: "E2 c0.0: proxy fence done",
               126: "E2 c0.0: arrived"})
