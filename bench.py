@@ -160,6 +160,8 @@ def kernel_rooflines(peaks, device):
 
     for M in (B * 185, 12 * B * 185):
         n_sets = max(2, -(-300_000_000 // (2 * M * D * 2)))
+        if M == B * 185:
+            n_sets = max(n_sets, 24)                        # 12 sites x 2 row groups for the deferred weight gradients
         pk2, pk1 = mk(RANK, 2), mk(RANK, 1)
         r = RANK
         sets = []
@@ -201,8 +203,18 @@ def kernel_rooflines(peaks, device):
                 ops.dat_backward_grouped([dict(x=x, dy=dy, w=pk2, scale=0.5, train_slice=(0, r), hidden=h2, dx_out=y0),
                                           dict(x=x1, dy=dy1, w=pk1, scale=1.0, train_slice=(0, r), hidden=h1, dx_out=y1)])
 
+            def g_dgrad(*a):
+                # what a site's backward launches inside the train step: the data gradient only -- the weight
+                # gradients of all sites are ONE launch after the backward pass (ops.DeferredWgrad)
+                with ops.deferred_wgrad() as q:
+                    ops.dat_backward_grouped([dict(x=a[0], dy=a[1], w=pk2, scale=0.5, train_slice=(0, r), hidden=a[2], dx_out=a[6]),
+                                              dict(x=a[3], dy=a[4], w=pk1, scale=1.0, train_slice=(0, r), hidden=a[5], dx_out=a[7])],
+                                             allow_defer=True)
+                    q.groups, q.keep = [], []
+
             for name, fn, flops, nbytes in (("site_fwd_grouped", g_fwd, 12 * D * r * Mh, 4 * D * 2 * Mh),
-                                            ("site_bwd_grouped", g_bwd, 20 * D * r * Mh, 6 * D * 2 * Mh)):
+                                            ("site_bwd_grouped", g_bwd, 20 * D * r * Mh, 6 * D * 2 * Mh),
+                                            ("site_dgrad_grouped", g_dgrad, 12 * D * r * Mh, 4 * D * 2 * Mh)):
                 t = timeit(fn, gsets)
                 t_tensor, t_hbm = flops / (peaks["tf_burst"] * 1e12), nbytes / (peaks["hbm_gbs"] * 1e9)
                 out[f"{name}_M{2 * Mh}"] = {
@@ -210,6 +222,34 @@ def kernel_rooflines(peaks, device):
                     "tflops": round(flops / t / 1e12, 1), "gbs": round(nbytes / t / 1e9, 1),
                     "frac_of_roofline": round(max(t_tensor, t_hbm) / t, 4),
                     "rows": f"{Mh} gating (R = {2 * r}) + {Mh} adapter_1 (R = {r})"}
+            # the deferred weight-gradient launch over 12 sites (24 groups x 6 column chunks = 144 CTAs, no row
+            # splits): 12 data-gradient launches queue their groups, the flush is timed alone (0.5 GB of X / dY / H /
+            # dP: cold by construction)
+            n_sites = min(12, len(gsets))
+            ts = []
+            for it in range(6):
+                with ops.deferred_wgrad() as q:
+                    for a in gsets[:n_sites]:
+                        ops.dat_backward_grouped([dict(x=a[0], dy=a[1], w=pk2, scale=0.5, train_slice=(0, r), hidden=a[2], dx_out=a[6]),
+                                                  dict(x=a[3], dy=a[4], w=pk1, scale=1.0, train_slice=(0, r), hidden=a[5], dx_out=a[7])],
+                                                 allow_defer=True)
+                    torch.cuda._sleep(1_000_000)
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    e0.record()
+                    q.flush()
+                    e1.record()
+                    torch.cuda.synchronize()
+                if it >= 2:
+                    ts.append(e0.elapsed_time(e1) * 1e-3)
+            t = statistics.mean(ts)
+            wbytes = n_sites * 2 * Mh * (2 * D + 2 * r) * 2         # X, dY, H_t, dP_t of both row groups
+            wflops = n_sites * 2 * Mh * 4 * D * r
+            out[f"wgrad_deferred_{n_sites}sites"] = {
+                "us": round(t * 1e6, 2), "us_per_site": round(t * 1e6 / n_sites, 2), "bound": "hbm",
+                "tflops": round(wflops / t / 1e12, 1), "gbs": round(wbytes / t / 1e9, 1),
+                "frac_of_roofline": round(wbytes / t / 1e9 / peaks["hbm_gbs"], 4),
+                "bytes": "X, dY (768 columns) + H_t, dP_t (128 columns) of both row groups of every site, read once",
+                "grid": f"{2 * n_sites} groups x 6 column chunks, one CTA each over all {Mh} rows"}
             del gsets
         del sets
     return out
@@ -470,25 +510,32 @@ def run_ours(args):
                 us = eager[f"{d_}_gating_M{B * 185}"] + eager[f"{d_}_single_M{B * 185}"]
                 kr[k_]["eager_reference_us"] = round(us, 2)
                 kr[k_]["vs_eager"] = round(us / kr[k_]["us"], 2)
-        # Dominant DAT work of the step = the backward of one adapter site in the batched MKD schedule: ONE grouped
-        # data-gradient launch + ONE grouped weight-gradient launch over [5920 gating rows (R = 256) | 5920
-        # adapter_1 rows (R = 128)].  Algorithmic work: 12 d r + 8 d r = 20 d r FLOP per row
-        # pair, 6 d bytes per row (read X, read dY, write dX) -> HBM-bound at the measured peaks.
+        # Dominant DAT work of the step = the backward of one adapter site in the batched MKD schedule, as the step
+        # launches it: ONE grouped data-gradient launch per site over [5920 gating rows (R = 256) | 5920 adapter_1
+        # rows (R = 128)] + that site's 1/12 share of the ONE deferred weight-gradient launch over all 12 sites.
+        # Algorithmic work: 12 d r + 8 d r = 20 d r FLOP per row pair, 6 d bytes per row
+        # (read X, read dY, write dX) -> HBM-bound at the measured peaks.
         Mh = B * 185
-        dom = kr[f"site_bwd_grouped_M{2 * Mh}"]
+        pair = kr[f"site_bwd_grouped_M{2 * Mh}"]            # dgrad + per-site wgrad launch (the non-deferred form)
+        dg = kr[f"site_dgrad_grouped_M{2 * Mh}"]
+        wg = kr["wgrad_deferred_12sites"]
         fwd = kr[f"site_fwd_grouped_M{2 * Mh}"]
         big = kr[f"bwd_gating_M{12 * Mh}"]
         alg_bytes, alg_flops = 6 * D * 2 * Mh, 20 * D * RANK * Mh
+        bwd_us = round(dg["us"] + wg["us_per_site"], 2)
+        bwd_gbs = round(alg_bytes / (bwd_us * 1e-6) / 1e9, 1)
+        bwd_tf = round(alg_flops / (bwd_us * 1e-6) / 1e12, 1)
         traffic, traffic_src = None, None
         tp = ROOT / "profiles" / "r2_dat_traffic.json"
         if tp.exists():
             tj = json.loads(tp.read_text())
             k = tj["kernels"]
-            if "site_dgrad_grouped" in k and "site_wgrad_grouped" in k:
-                traffic = sum(k[n]["dram_read_bytes"] + k[n]["dram_write_bytes"] for n in ("site_dgrad_grouped", "site_wgrad_grouped"))
+            if "site_dgrad_grouped" in k and "wgrad_deferred_12sites" in k:
+                traffic = (k["site_dgrad_grouped"]["dram_read_bytes"] + k["site_dgrad_grouped"]["dram_write_bytes"]
+                           + (k["wgrad_deferred_12sites"]["dram_read_bytes"] + k["wgrad_deferred_12sites"]["dram_write_bytes"]) / 12)
                 traffic_src = "profiles/r2_dat_traffic.json (" + tj["source"] + ")"
-        # share of the DAT kernels in the step, from the launches the step makes (12 sites x fwd / dgrad / wgrad)
-        dat_us = 12 * (fwd["us"] + dom["us"])
+        # share of the DAT kernels in the step, from the launches the step makes (12 x fwd, 12 x dgrad, 1 x wgrad)
+        dat_us = 12 * (fwd["us"] + dg["us"]) + wg["us"]
         result = {
             "metric": METRIC, "value": round(value, 2), "unit": "samples/s", "n_gpus": world, "steps": K,
             "warmup": W, "ms_per_step": round(ms / K, 3), "higher_is_better": True, "scaling": "weak",
@@ -504,20 +551,25 @@ def run_ours(args):
                     "ms_per_step": round(ms_e2e / K, 3)},
             "gpu_launches": launches,
             "allreduce_us": allreduce_us,
-            "roofline": {"kernel": "DAT backward of one adapter site, batched MKD schedule: grouped dgrad launch + grouped "
-                                   f"wgrad launch over {Mh} gating rows (R = {2 * RANK}) + {Mh} adapter_1 rows (R = {RANK})",
-                         "bound": "hbm", "achieved": dom["gbs"], "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                         "frac": round(dom["gbs"] / peaks["hbm_gbs"], 4),
-                         "traffic": traffic, "traffic_unit": "dram read + write bytes of the two launches (ncu --set full)",
+            "roofline": {"kernel": "DAT backward of one adapter site as the batched MKD schedule launches it: ONE grouped dgrad "
+                                   f"launch over {Mh} gating rows (R = {2 * RANK}) + {Mh} adapter_1 rows (R = {RANK}), plus the "
+                                   "site's 1/12 share of the ONE deferred wgrad launch over all 12 sites",
+                         "bound": "hbm", "achieved": bwd_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                         "frac": round(bwd_gbs / peaks["hbm_gbs"], 4),
+                         "traffic": traffic,
+                         "traffic_unit": "dram read + write bytes: the site's dgrad launch + 1/12 of the 12-site wgrad launch (ncu --set full)",
                          "traffic_source": traffic_src,
-                         "algorithmic_bytes_per_launch_pair": alg_bytes, "algorithmic_flops_per_launch_pair": alg_flops,
-                         "tensor_view": {"achieved_tflops": dom["tflops"], "peak": peaks["tf_burst"],
-                                         "frac": round(dom["tflops"] / peaks["tf_burst"], 4)},
+                         "algorithmic_bytes_per_site": alg_bytes, "algorithmic_flops_per_site": alg_flops,
+                         "tensor_view": {"achieved_tflops": bwd_tf, "peak": peaks["tf_burst"],
+                                         "frac": round(bwd_tf / peaks["tf_burst"], 4)},
                          "peak_source": f"{peaks['source']} hbm_gbs / bf16_tflops burst (kernels timed alone, CUDA events, cold inputs)",
-                         "us": dom["us"],
+                         "us": bwd_us,
+                         "parts": {"dgrad_launch_us": dg["us"], "wgrad_12site_launch_us": wg["us"],
+                                   "wgrad_launch_gbs": wg["gbs"], "wgrad_launch_frac": wg["frac_of_roofline"]},
+                         "per_site_launch_pair_us": pair["us"],
                          "forward_same_site": {"us": fwd["us"], "achieved": fwd["gbs"], "frac": fwd["frac_of_roofline"]},
-                         "fwd_plus_bwd_site": {"us": round(fwd["us"] + dom["us"], 2),
-                                               "frac": round((10 * D * 2 * Mh) / ((fwd["us"] + dom["us"]) * 1e-6) / 1e9 / peaks["hbm_gbs"], 4)},
+                         "fwd_plus_bwd_site": {"us": round(fwd["us"] + bwd_us, 2),
+                                               "frac": round((10 * D * 2 * Mh) / ((fwd["us"] + bwd_us) * 1e-6) / 1e9 / peaks["hbm_gbs"], 4)},
                          "dat_us_per_step_from_these": round(dat_us, 1),
                          "steady_state_M71040": {"kernel": "bwd gating, single group (dat_pipe_kernel + wgrad)",
                                                  "achieved_tflops": big["tflops"], "frac": round(big["tflops"] / peaks["tf_burst"], 4)}},
@@ -537,28 +589,15 @@ ALBEF_WORKLOAD = ("ALBEF (ViT-B/16 @384 + 12-layer BERT question encoder + 6-lay
                   "(BASELINE configs[2])")
 
 
-def run_albef(args):
-    """``--workload albef``: one TaskTrainer.train_step of the ALBEF path (three forwards, two backwards, two AdamW
-    steps in the reference order -- BERT has dropout, so no pass is shared; eager launch) per step.  An extra line
-    beside the headline ViLT workload; same timing rules."""
+def build_albef_client(rank: int, device, batch: int = 16, rank_r: int = 256):
+    """Model + trainer of one ALBEF client (BASELINE configs[2]: full depth, rank 256, random init, seeded)."""
     import torch
-    import torch.distributed as dist
-    from feddat_b200 import ops
     from feddat_b200.modeling.albef import convert_batch_to_albef_input_dict
-    from feddat_b200.synthetic import albef_to_device, make_albef_batch
     from feddat_b200.train.accelerator import Accelerator
     from feddat_b200.train.prepare import default_args, place_on_gpu, prepare_model
     from feddat_b200.train.task_trainer import TaskTrainer, get_polynomial_decay_schedule_with_warmup
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    device = torch.device("cuda", local_rank)
-    torch.cuda.set_device(device)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=device)
-    BA, RA = 16, 256
     torch.manual_seed(2000)
-    a = default_args(encoder_name="albef_no_distill", ordered_cl_tasks=[f"synth{rank % 8}"], adapter_rank=RA, image_size=384)
+    a = default_args(encoder_name="albef_no_distill", ordered_cl_tasks=[f"synth{rank % 8}"], adapter_rank=rank_r, image_size=384)
     model = prepare_model(a, place=False)
     sd = model.state_dict()
     for name in sd:
@@ -578,6 +617,26 @@ def run_albef(args):
     opt = tr.create_optimizer(wrapped)
     sched = get_polynomial_decay_schedule_with_warmup(opt, 100, 100000, lr_end=0, power=1)
     wrapped.train()
+    return tr, wrapped, opt, sched
+
+
+def run_albef(args):
+    """``--workload albef``: one TaskTrainer.train_step of the ALBEF path (three forwards, two backwards, two AdamW
+    steps in the reference order -- BERT has dropout, so no pass is shared) per step, replayed from a CUDA graph.
+    An extra line beside the headline ViLT workload; same timing rules."""
+    import torch
+    import torch.distributed as dist
+    from feddat_b200 import ops
+    from feddat_b200.synthetic import albef_to_device, make_albef_batch
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    device = torch.device("cuda", local_rank)
+    torch.cuda.set_device(device)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+    BA, RA = 16, 256
+    tr, wrapped, opt, sched = build_albef_client(rank, device, BA, RA)
     K, W = args.steps, args.warmup
     host = [make_albef_batch(BA, 384, seed=(2000 + rank) * 1000 + i, client=rank % 8, pin=True) for i in range(min(K + W, 6))]
     devb = [albef_to_device(b, device) for b in host]

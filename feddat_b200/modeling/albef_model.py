@@ -29,8 +29,12 @@ from typing import Dict, Optional
 import torch
 import torch.nn as nn
 import torch.nn.functional as F
+from torch.nn.attention import SDPBackend, sdpa_kernel
 
 from .albef_sites import BertOutput, Block
+
+# torch SDPA backend of the BERT-side attention calls with <= 128 queries and keys (None = torch's own choice)
+SMALL_ATTENTION_BACKEND = SDPBackend.EFFICIENT_ATTENTION
 
 # reference src/configs/model_configs.py:40-60
 CONFIG_BERT = {
@@ -153,7 +157,15 @@ class BertSelfAttention(nn.Module):
             self._heads(self.value(kv.to(hidden_states.dtype)))
         if mask is not None:
             mask = mask.to(q.dtype)
-        ctx = F.scaled_dot_product_attention(q, k, v, attn_mask=mask, dropout_p=self.dropout.p if self.training else 0.0)
+        p_drop = self.dropout.p if self.training else 0.0
+        if SMALL_ATTENTION_BACKEND is not None and q.is_cuda and q.shape[2] <= 128 and k.shape[2] <= 128:
+            # a few dozen tokens per sequence (questions <= 25, answers ~6): cuDNN's flash kernels with a mask and
+            # dropout take 47-64 us per call here, the memory-efficient backend 15-17 us (fwd + bwd: 80-107 -> 34-37;
+            # scripts/sdpa_backends_albef.py) -- 90 forward and 60 backward calls per train step
+            with sdpa_kernel(SMALL_ATTENTION_BACKEND):
+                ctx = F.scaled_dot_product_attention(q, k, v, attn_mask=mask, dropout_p=p_drop)
+        else:
+            ctx = F.scaled_dot_product_attention(q, k, v, attn_mask=mask, dropout_p=p_drop)
         b, _, s, _ = ctx.shape
         return ctx.transpose(1, 2).reshape(b, s, -1)
 
@@ -278,10 +290,10 @@ class BertModel(nn.Module):
         x = self.embeddings(input_ids)
         ext = self.extended_attention_mask(attention_mask, is_decoder, x.dtype)
         enc_ext = None
-        if encoder_hidden_states is not None:
-            if encoder_attention_mask is None:
-                encoder_attention_mask = torch.ones(encoder_hidden_states.shape[:2], device=x.device)
-            # transformers' invert_attention_mask: a large negative number on masked keys
+        if encoder_hidden_states is not None and encoder_attention_mask is not None:
+            # transformers' invert_attention_mask: a large negative number on masked keys.  No mask given = every
+            # encoder position visible (the reference builds an all-ones mask, xbert.py:1030-1040, whose additive form
+            # is all zeros): nothing is added, and the attention kernel runs without a mask operand
             enc_ext = (1.0 - encoder_attention_mask[:, None, None, :].to(x.dtype)) * -10000.0
         return self.encoder(x, ext, encoder_hidden_states, enc_ext, mode=mode)
 
@@ -396,7 +408,8 @@ class ALBEF(nn.Module):
         """``question`` / ``answer``: objects with ``input_ids`` and ``attention_mask`` (a tokenizer's BatchEncoding or
         a namespace of tensors).  train: (loss, logits[:, :-1]); eval: rank_answer's (topk_ids, topk_probs)."""
         image_embeds = self.visual_encoder(image)
-        image_atts = torch.ones(image_embeds.shape[:-1], dtype=torch.long, device=image.device)
+        # albef_model.py:95-96 builds an all-ones image mask; "no mask" is the same attention (see BertModel.forward)
+        image_atts = None
         question_states = self.text_encoder(question.input_ids, attention_mask=question.attention_mask,
                                             encoder_hidden_states=image_embeds, encoder_attention_mask=image_atts)
         if not train:

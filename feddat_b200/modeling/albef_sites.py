@@ -13,9 +13,12 @@ sm_100a kernels behind ``Adapter``.
                      (adapter.py:97-116; the residual handed to the operator is the FFN output, not
                      the operator's input).
 
-The attention / MLP / LayerNorm parts are frozen backbone and stay PyTorch ops (SDPA for the
-softmax(QK^T)V product); the full ALBEF model wrapper (tokenizer, cross-attention fusion, LM head) is
-not on the DAT hot path and is not rebuilt here.
+The frozen block around the ViT site runs on this repo's kernels when its preconditions hold (bf16 CUDA activations,
+frozen bf16 parameters, no dropout -- ``Block._fast_forward``): LayerNorm-before and "first residual + LayerNorm-after"
+as one launch each (feddat_ln_fwd / feddat_ln_bwd), the 768 -> 3072 GEMM with the exact GELU in its epilogue and the
+backward's GELU' in its first GEMM (feddat_mlp_fc1_gelu_fwd / feddat_mlp_fc2_dgelu_bwd), "fc2 + bias + second
+residual" as one GEMM.  The 577-token softmax(QK^T)V stays torch SDPA (cuDNN; the own attention kernels cover
+sequences up to 256 keys); stock PyTorch modules otherwise.
 """
 from __future__ import annotations
 
@@ -24,6 +27,8 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from .adapter import Adapter
+
+FAST_BLOCK = True      # A/B switch (tests, bench): False = the stock PyTorch modules of the ViT block
 
 
 class Mlp(nn.Module):
@@ -56,8 +61,10 @@ class Attention(nn.Module):
 
     def forward(self, x, register_hook=False):
         b, n, c = x.shape
-        qkv = self.qkv(x).reshape(b, n, 3, self.num_heads, c // self.num_heads).permute(2, 0, 3, 1, 4)
-        q, k, v = qkv[0], qkv[1], qkv[2]
+        # unbind + transpose (views): autograd's backward is ONE stack into the [b, n, 3, heads, hd] layout the qkv
+        # GEMM's data gradient reads -- indexing qkv[0], qkv[1], qkv[2] costs three zero-fills, three slice copies and
+        # two full-size adds per block and backward pass
+        q, k, v = (t.transpose(1, 2) for t in self.qkv(x).view(b, n, 3, self.num_heads, c // self.num_heads).unbind(2))
         if register_hook:
             raise NotImplementedError("register_hook (Grad-CAM attention maps, vit.py:48-58,70-72) is a visualisation "
                                       "aid outside the FedDAT training path")
@@ -88,11 +95,38 @@ class Block(nn.Module):
             self.adapter = Adapter(**adapter_config, model_dim=dim)
 
     def forward(self, x, register_hook=False):
+        if FAST_BLOCK and not register_hook and self._fast_ok(x):
+            return self._fast_forward(x)
         x = x + self.attn(self.norm1(x), register_hook=register_hook)
         x = x + self.mlp(self.norm2(x))
         if self.adaptered:
             x = self.adapter(x, x)                               # vit.py:107: residual IS the input
         return x
+
+    def _fast_ok(self, x) -> bool:
+        from . import fused_ln
+        fc1, fc2 = self.mlp.fc1, self.mlp.fc2
+        frozen = not any(p.requires_grad for m in (self.norm1, self.norm2, fc1, fc2) for p in m.parameters())
+        no_drop = not self.training or (self.mlp.drop.p == 0.0 and self.attn.proj_drop.p == 0.0)
+        return (frozen and no_drop and isinstance(self.norm1, nn.LayerNorm) and isinstance(self.norm2, nn.LayerNorm)
+                and fused_ln._usable(self.norm1, x) and fused_ln._usable(self.norm2, x)
+                and isinstance(self.mlp.act, nn.GELU) and self.mlp.act.approximate == "none"
+                and fc1.bias is not None and fc2.bias is not None and fc1.weight.dtype == torch.bfloat16
+                and fc2.weight.dtype == torch.bfloat16 and fc1.weight.is_contiguous() and fc2.weight.is_contiguous()
+                and fc1.out_features % 256 == 0 and fc1.in_features % 64 == 0 and fc2.in_features == fc1.out_features)
+
+    def _fast_forward(self, x):
+        """The same block (vit.py:99-110) on the fused kernels of modeling/fused_ln.py -- see the module docstring."""
+        from . import fused_ln
+        fc1, fc2 = self.mlp.fc1, self.mlp.fc2
+        ln1, x = fused_ln.layer_norm_pass(self.norm1, x)
+        attn = self.attn(ln1)
+        res_b, ln2 = fused_ln.add_layer_norm(self.norm2, attn, x, bias2=fc2.bias)
+        h = fused_ln._FrozenMlp.apply(ln2, res_b, fc1.weight, fused_ln._bias_f32(fc1), fc2.weight,
+                                      fused_ln._transposed_weight(fc2))
+        if self.adaptered:
+            h = self.adapter(h, h)                               # vit.py:107: residual IS the input
+        return h
 
 
 class BertOutput(nn.Module):

@@ -135,3 +135,63 @@ def test_bert_output_site_matches_reference(golden, mode):
         return bout(h, x), {"x": x}
 
     check(golden, f"bert_output/{mode}", build, call)
+
+
+@pytest.mark.parametrize("mode", ["single_adapter_1", "gating"])
+def test_vit_block_fast_path_equals_stock_modules(mode):
+    """albef_sites.Block on the fused kernels (LayerNorm launches, GEMM + GELU / GELU' epilogues, fc2 + bias +
+    residual as one GEMM; ``Block._fast_forward``) against the same bf16 block on stock PyTorch modules: output,
+    input gradient and adapter gradients at the bf16 bar.  16 x 577 tokens (the ALBEF ViT's shape at 384 x 384)."""
+    import copy
+
+    from feddat_b200.modeling import albef_sites
+    from feddat_b200.modeling.albef_sites import Block
+    torch.manual_seed(3)
+    blk = Block(768, 12, 4.0, qkv_bias=True, norm_layer=lambda d: torch.nn.LayerNorm(d, eps=1e-6),
+                adapter_config=dict(names=["adapter_0", "adapter_1", "adapter_2"], device="cuda", rank=64)).cuda()
+    with torch.no_grad():
+        for n, p in blk.named_parameters():
+            if "adapter" in n:
+                p.copy_(torch.randn_like(p) * (0.1 if p.dim() == 1 else 0.05))
+            elif "norm" in n:
+                p.add_(0.1 * torch.randn_like(p))
+    for n, p in blk.named_parameters():
+        if "adapter" not in n:
+            p.requires_grad = False
+            p.data = p.data.to(torch.bfloat16)
+    if mode == "gating":
+        blk.adapter.activate_gating(); blk.adapter.set_active_adapter("adapter_0")
+    else:
+        blk.adapter.deactivate_gating(); blk.adapter.set_active_adapter("adapter_1")
+    blk.train()
+    x0 = torch.randn(4, 577, 768, device="cuda").to(torch.bfloat16)
+    gy = torch.randn(4, 577, 768, device="cuda").to(torch.bfloat16)
+
+    def run(fast, fp32=False):
+        albef_sites.FAST_BLOCK = fast
+        try:
+            b = copy.deepcopy(blk)
+            if fp32:            # the same block with fp32 frozen parameters and activations: the yardstick
+                for n, p in b.named_parameters():
+                    if "adapter" not in n:
+                        p.data = p.data.float()
+            x = (x0.float() if fp32 else x0.clone()).requires_grad_(True)
+            assert b._fast_ok(x) == (not fp32)
+            y = b(x)
+            y.backward(gy.float() if fp32 else gy)
+            torch.cuda.synchronize()
+            grads = {n: p.grad.float().cpu().numpy() for n, p in b.named_parameters() if p.grad is not None}
+            return y.detach().float().cpu().numpy(), x.grad.float().cpu().numpy(), grads
+        finally:
+            albef_sites.FAST_BLOCK = True
+
+    y_f, dx_f, g_f = run(True)
+    y_s, dx_s, g_s = run(False)
+    y_r, dx_r, g_r = run(False, fp32=True)
+    # two bf16 evaluations of one block differ by their rounding points: each is held against the fp32 block, and the
+    # fused path may not be further from it than the stock bf16 modules are (plus a quarter of the bar)
+    for got, stock, ref, bar in ((y_f, y_s, y_r, BF16_TOL), (dx_f, dx_s, dx_r, 2 * BF16_TOL)):
+        assert relerr(got, ref) < bar and relerr(got, ref) < relerr(stock, ref) + bar / 4, (relerr(got, ref), relerr(stock, ref))
+    assert set(g_f) == set(g_s) == set(g_r) and len(g_f) == 4
+    for n in g_f:
+        assert relerr(g_f[n], g_r[n]) < 2 * BF16_TOL and relerr(g_f[n], g_r[n]) < relerr(g_s[n], g_r[n]) + BF16_TOL / 2, n
