@@ -14,7 +14,7 @@ _LIB_PATH = Path(__file__).resolve().parent / "lib" / "libfeddat_sm100.so"
 _DBG_LIB_PATH = Path(__file__).resolve().parent / "lib" / "libfeddat_sm100_dbg.so"
 _lib = None
 _dbg_lib = None
-ABI_VERSION = 4      # feddat_abi_version(); bumped whenever include/feddat_b200.h changes
+ABI_VERSION = 5      # feddat_abi_version(); bumped whenever include/feddat_b200.h changes
 
 # every symbol include/feddat_b200.h declares (tests check the built library exports all of them)
 EXPORTED_SYMBOLS = (

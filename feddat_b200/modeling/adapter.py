@@ -33,6 +33,9 @@ def init_bert_weights(module):
         module.bias.data.zero_()
 
 
+_PENDING = object()      # marks a parameter gradient that the deferred weight-gradient queue will deliver
+
+
 class _DatFunction(torch.autograd.Function):
     """y = res + scale * (act(x Wd^T + bd) Wu^T + bu) over the concatenated active branches.
 
@@ -62,6 +65,7 @@ class _DatFunction(torch.autograd.Function):
         ctx.same = same
         ctx.n_params = len(params)
         ctx.param_needs = [p.requires_grad for p in params]
+        ctx.params = params            # leaves: the deferred weight-gradient queue assigns their .grad itself
         ctx.save_for_backward(x)
         return y
 
@@ -78,6 +82,13 @@ class _DatFunction(torch.autograd.Function):
         branch_trains = [any(ctx.param_needs[4 * b: 4 * b + 4]) for b in range(nb)]
         grads: List[Optional[torch.Tensor]] = [None] * ctx.n_params
         dx_total = None
+        # Deferred weight gradients (ops.DeferredWgrad: the trainer computes all sites' gradients in a few launches
+        # after the backward pass) when every trained branch lies whole inside one segment, so that its gradient
+        # tensors are plain views of one launch's outputs (true for every width the train step uses: a branch is
+        # only cut when r > 256)
+        queue = ops.deferred_queue()
+        defer = queue is not None and all(
+            not branch_trains[b] or any(c0 <= b * r and (b + 1) * r <= c0 + w for _, c0, w in ctx.segs) for b in range(nb))
         for si, (pk, col0, width) in enumerate(ctx.segs):
             # trainable slice of this segment in concatenated-bottleneck coordinates
             lo, hi = None, None
@@ -88,7 +99,8 @@ class _DatFunction(torch.autograd.Function):
                     hi = b1 if hi is None else max(hi, b1)
             ts = None if lo is None else (lo - col0, hi - col0)
             dx, g = ops.dat_backward(x, dy, pk, ctx.scale, adapter._act_code, train_slice=ts,
-                                     need_dx=need_dx, add_dy=(ctx.same and si == 0), hidden=ctx.hs[si])
+                                     need_dx=need_dx, add_dy=(ctx.same and si == 0), hidden=ctx.hs[si],
+                                     allow_defer=defer)
             if dx is not None:
                 dx_total = dx if dx_total is None else dx_total + dx
             if g is not None:
@@ -102,7 +114,11 @@ class _DatFunction(torch.autograd.Function):
                     full = (p0 == 0 and p1 == r)
 
                     def put(idx, piece, shape, sl):
-                        if full:
+                        if defer:                 # filled at the flush, handed to .grad there
+                            if ctx.param_needs[idx]:
+                                queue.assign(ctx.params[idx], piece)
+                            grads[idx] = _PENDING
+                        elif full:
                             grads[idx] = piece.contiguous() if grads[idx] is None else grads[idx] + piece
                         else:
                             if grads[idx] is None:
@@ -115,9 +131,12 @@ class _DatFunction(torch.autograd.Function):
                     if si == 0 or grads[4 * b + 3] is None:
                         # d_up_b is the same column sum of dY for every segment: take it once
                         if grads[4 * b + 3] is None:
-                            grads[4 * b + 3] = d_up_b.contiguous()
+                            if defer:
+                                put(4 * b + 3, d_up_b, None, None)
+                            else:
+                                grads[4 * b + 3] = d_up_b.contiguous()
         for i, needs in enumerate(ctx.param_needs):
-            if not needs:
+            if not needs or grads[i] is _PENDING:
                 grads[i] = None
         dres = dy if need_dres else None
         return (None, None, dx_total if need_dx else None, dres, *grads)

@@ -237,6 +237,9 @@ class DeferredWgrad:
 
     def flush(self) -> None:
         if self.groups:
+            # every CTA of a launch walks ALL rows of its group: launch groups of similar size together (ALBEF: 9 232-row
+            # ViT sites next to 400-row text sites would all wait for the longest)
+            self.groups.sort(key=lambda q: -int(q.M))
             _launch_wgrad(self.groups, self.device)
         with torch.no_grad():
             for p, g in self.pending:
@@ -380,14 +383,15 @@ def dat_backward_grouped(groups: Sequence[dict], act=ACT_RELU, allow_defer: bool
 
 def dat_backward(x: Optional[torch.Tensor], dy: torch.Tensor, w: PackedWeights, scale: float, act=ACT_RELU,
                  train_slice: Optional[tuple] = None, need_dx: bool = True, add_dy: bool = True,
-                 hidden: Optional[torch.Tensor] = None, dx_out: Optional[torch.Tensor] = None):
+                 hidden: Optional[torch.Tensor] = None, dx_out: Optional[torch.Tensor] = None,
+                 allow_defer: bool = False):
     """Backward of dat_forward.  Returns (dx | None, grads | None) where grads =
     (d_down_w [rt,d], d_down_b [rt], d_up_w [d,rt], d_up_b [d]) in fp32 for the trainable slice
     ``train_slice = (r_lo, r_hi)`` of the concatenated bottleneck.  ``hidden`` = the H saved by
     ``dat_forward(save_hidden=True)`` (ReLU): the dgrad kernel then skips the recompute of x Wd^T
     (``x`` is still needed by the weight-gradient kernel when something trains)."""
     (dx, grads), = dat_backward_grouped([dict(x=x, dy=dy, w=w, scale=scale, train_slice=train_slice, need_dx=need_dx,
-                                              add_dy=add_dy, hidden=hidden, dx_out=dx_out)], act)
+                                              add_dy=add_dy, hidden=hidden, dx_out=dx_out)], act, allow_defer=allow_defer)
     return dx, grads
 
 

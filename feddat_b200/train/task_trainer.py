@@ -87,6 +87,12 @@ def get_polynomial_decay_schedule_with_warmup(optimizer, num_warmup_steps, num_t
 
 
 DEFER_WGRAD = True        # batched schedule: all sites' weight gradients in ONE launch after the backward (ops.DeferredWgrad)
+
+
+def _deferred():
+    return ops.deferred_wgrad() if DEFER_WGRAD else contextlib.nullcontext()
+
+
 USE_OWN_ADAMW = True      # csrc/adamw.cu behind train/fused_adamw.py; False = torch.optim.AdamW(fused, capturable)
 
 
@@ -274,7 +280,7 @@ class TaskTrainer(nn.Module):
         self.accelerator.backward(L_0)                               # head grads + d enc_A
         # the sites' weight gradients are not needed before step 5: the backward queues them and ONE launch at
         # its end computes all of them (ops.DeferredWgrad)
-        with _nvtx("batched_bwd_C+B"), (ops.deferred_wgrad() if DEFER_WGRAD else contextlib.nullcontext()):
+        with _nvtx("batched_bwd_C+B"), _deferred():
             enc.backward(leaf.grad)                                  # adapter_0 (rows A) and adapter_1 (rows B)
         self._probe("BC", model)
 
@@ -332,7 +338,7 @@ class TaskTrainer(nn.Module):
         with _nvtx("pass_B_adapter1_fwd"):
             output_1_0, logits_1 = self.forward_pass(model, batch, do_eval=False)
             L_1, _ = self._objective(logits_1, logits_all, target, output_1_0 if albef else None)
-        with _nvtx("pass_B_adapter1_bwd"):
+        with _nvtx("pass_B_adapter1_bwd"), _deferred():      # all sites' weight gradients after the backward pass
             self.accelerator.backward(L_1)
         self._probe("B", model)
         if optimizer is not None:
@@ -348,7 +354,7 @@ class TaskTrainer(nn.Module):
         else:
             output_0_0, logits_0 = self.forward_pass(model, batch, do_eval=False)
         L_0, loss_0 = self._objective(logits_0, logits_1, target, output_0_0 if albef else None)
-        with _nvtx("pass_C_gating_bwd"):
+        with _nvtx("pass_C_gating_bwd"), _deferred():
             self.accelerator.backward(L_0)
         self._probe("C", model)
         if optimizer is not None:

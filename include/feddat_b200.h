@@ -136,7 +136,11 @@ typedef struct FeddatDatGroup {
 int feddat_dat_fwd_grouped(const FeddatDatGroup* groups, int n_groups, int d, int act, int dtype, void* stream);
 int feddat_dat_bwd_dgrad_grouped(const FeddatDatGroup* groups, int n_groups, int d, int act, int dtype,
                                  void* stream);
-/* weight gradients of up to two groups in one launch (same fields as feddat_dat_bwd_wgrad) */
+/* Weight gradients of 1 .. 24 groups in one launch (same fields as feddat_dat_bwd_wgrad).  The launch has
+ * groups x 6 column chunks x row splits CTAs, never more than one per SM: two groups = one adapter site of the batched
+ * MKD schedule with 12 row splits and the two-stage reduction; 24 groups = BOTH row groups of ALL twelve ViLT sites
+ * at the end of a backward pass (the deferred form, task_trainer.py:311-328 needs the gradients only at
+ * optimizer.step()): one CTA per (group, chunk) contracts over all rows, no splits, no workspace traffic. */
 typedef struct FeddatWgradGroup {
   const void *X, *dY, *H_t, *dP_t;
   float *dWu, *dbu, *dWd, *dbd;

@@ -177,3 +177,59 @@ def test_dual_mode_deferred_weight_gradients():
         if ref[n] is not None:
             assert relerr(twice[n].cpu().numpy(), 2 * got[n].cpu().numpy()) < 1e-6, n
     assert ops.deferred_queue() is None
+
+
+@pytest.mark.parametrize("r,gating", [(64, False), (64, True), (256, False), (256, True), (512, True)])
+def test_reference_order_deferred_weight_gradients(r, gating):
+    """``_DatFunction`` (single / gating mode, residual != input, bottlenecks of one, two and -- r = 512 -- four segment
+    launches) under ``ops.deferred_wgrad()``: same dX / d(residual) bit for bit, same parameter gradients as the plain
+    autograd run.  At r = 512 a branch is cut across segments and the node must fall back to immediate launches."""
+    from feddat_b200 import ops
+    from feddat_b200.modeling.adapter import Adapter
+    g = torch.Generator(device="cuda").manual_seed(r + gating)
+    sites = []
+    for _ in range(3):
+        a = Adapter(names=["adapter_0", "adapter_1", "adapter_2"], device="cuda", rank=r)
+        with torch.no_grad():
+            for p in a.parameters():
+                p.copy_(torch.randn(p.shape, device="cuda", generator=g) * (0.1 if p.dim() == 1 else 0.05))
+        if gating:
+            a.activate_gating(); a.set_active_adapter("adapter_0")
+        else:
+            a.deactivate_gating(); a.set_active_adapter("adapter_1")
+        sites.append(a)
+    x0 = torch.randn(4, 100, 768, device="cuda", generator=g).to(torch.bfloat16)
+    r0 = torch.randn(4, 100, 768, device="cuda", generator=g).to(torch.bfloat16)
+    dy = torch.randn(4, 100, 768, device="cuda", generator=g).to(torch.bfloat16)
+
+    def run(defer):
+        for a in sites:
+            a.zero_grad(set_to_none=True)
+        x, res = x0.clone().requires_grad_(True), r0.clone().requires_grad_(True)
+        h = x
+        for a in sites:
+            h = a(h, res)
+        n0 = ops.launch_count
+        if defer:
+            with ops.deferred_wgrad() as q:
+                h.backward(dy)
+                queued = len(q.groups)
+        else:
+            h.backward(dy)
+            queued = 0
+        torch.cuda.synchronize()
+        grads = {f"{i}.{n}": (None if p.grad is None else p.grad.clone()) for i, a in enumerate(sites) for n, p in a.named_parameters()}
+        return x.grad.clone(), res.grad.clone(), grads, queued, ops.launch_count - n0
+
+    dx_r, dr_r, ref, _, n_ref = run(False)
+    dx_d, dr_d, got, queued, n_def = run(True)
+    assert torch.equal(dx_r, dx_d) and torch.equal(dr_r, dr_d)
+    assert queued == (0 if r == 512 else 3 * max(1, r // 128))
+    assert n_def < n_ref or r == 512
+    trained = "adapter_0" if gating else "adapter_1"
+    for n in ref:
+        if trained in n:
+            assert got[n] is not None and got[n].is_contiguous() and got[n].shape == ref[n].shape
+            assert relerr(got[n].cpu().numpy(), ref[n].cpu().numpy()) < 1e-5, n
+        else:
+            assert ref[n] is None and got[n] is None, n
