@@ -64,6 +64,14 @@ class Accelerator:
         return torch.cat(outs, dim=0)
 
     def wait_for_everyone(self):
+        """accelerate's barrier over the processes that run ONE client's training (reference task_trainer.py:107, called
+        from inside ``TaskTrainer.train``).  Here a client lives on exactly one process, so there
+        is nobody to wait for -- and it must NOT be a barrier over all ranks: ranks hold different numbers of clients
+        (5 domain clients on 2 GPUs = 3 + 2), so a global barrier per client leaves the ranks one collective apart and
+        the job hangs until the NCCL watchdog aborts it."""
+
+    def barrier_all_ranks(self):
+        """The round boundary: every rank has trained its clients (feddat_b200/train/main.py)."""
         if self.num_processes > 1 and dist.is_initialized():
             dist.barrier()
 

@@ -175,7 +175,7 @@ def main(argv=None, record=None):
         if record is not None:
             record.setdefault("client_flats", {})[comm_round] = [f.cpu() for f in client_flats]
             record.setdefault("global_flat", {})[comm_round] = comm.flat.detach().cpu().clone()
-        accelerator.wait_for_everyone()
+        accelerator.barrier_all_ranks()
         logger.info("round %d done in %.2f s", comm_round, time.time() - t0)
 
         if comm_round % 5 == 0 or args.comm_rounds - 1 == comm_round:        # main.py:520-558

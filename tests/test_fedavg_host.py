@@ -91,3 +91,34 @@ def test_two_rank_allreduce_average_matches_single_process():
     want = oracle.get_average_net(all_clients, [1] * 5)
     assert np.array_equal(ret[0], ret[1])                       # every rank holds the same global adapter
     np.testing.assert_allclose(ret[0], want, rtol=1e-6, atol=1e-7)   # summation order differs across ranks
+
+
+def _uneven_worker(rank, world, port, ret):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from feddat_b200.train.accelerator import Accelerator
+    acc = Accelerator(device="cpu")
+    server = Tiny()
+    flat = fa.FlatCommBuffer(server, fa.comm_state_dict_names(server))
+    fa.ops.fedavg = _oracle_fedavg
+    n_clients = 5
+    for _round in range(2):
+        mine = [c for c in range(n_clients) if c % world == rank]             # 3 clients on rank 0, 2 on rank 1
+        for _c in mine:
+            acc.wait_for_everyone()       # what TaskTrainer.train calls once per CLIENT (task_trainer.py:107)
+        fa.get_average_net_flat(flat, [torch.full_like(flat.flat, float(c)) for c in mine], [1.0] * len(mine),
+                                total=float(n_clients))
+        acc.barrier_all_ranks()
+    ret[rank] = float(flat.flat[0])
+    dist.destroy_process_group()
+
+
+def test_uneven_client_counts_do_not_desynchronise_the_ranks():
+    """5 clients on 2 ranks (the default ``src/train_vilt.sh`` task list on 2 GPUs): the per-client
+    ``wait_for_everyone`` inside ``TaskTrainer.train`` is local to the client's process, so the ranks meet only at the
+    round boundary.  (As a global barrier it left the ranks one collective apart: a hang until the NCCL watchdog.)"""
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_uneven_worker, args=(2, port, ret), nprocs=2, join=True)
+    assert ret[0] == ret[1] == 2.0                       # mean of clients 0 .. 4
