@@ -140,9 +140,15 @@ struct Slot {
     if (p.trace != nullptr && blockIdx.x < 2 && (t) < 2)                            \
       p.trace[(t) * 128 + (ev) + 8 * blockIdx.x] = globaltimer_ns();                \
   } while (0)
+// entry / exit stamps of EVERY CTA (launch ramp and tail skew): trace[256 + 2 * blockIdx.x + which]
+#define FD_TRACE_CTA(which)                                                         \
+  do {                                                                              \
+    if (p.trace != nullptr && blockIdx.x < 384) p.trace[256 + 2 * blockIdx.x + (which)] = globaltimer_ns(); \
+  } while (0)
 #else   // product build: no trace code in the kernels
 #define FD_TRACE(ev, t) do { (void)(t); } while (0)
 #define FD_TRACE_PAIR(ev, t) do { (void)(t); } while (0)
+#define FD_TRACE_CTA(which) do { } while (0)
 #endif
 
 // activation is a template parameter: a run-time switch makes ptxas keep the erff path live in the
@@ -190,6 +196,7 @@ dat_fused_kernel(const __grid_constant__ TmapSet tm0, const __grid_constant__ Tm
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (tid == 0) FD_TRACE(1, 0);      // kernel entry (before barrier init / TMEM alloc / bias staging)
+  if (tid == 0) FD_TRACE_CTA(0);
   const uint32_t rank = cluster_ctarank();            // 0 = leader of the CTA pair
 
   const uint32_t smem0 = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -735,6 +742,7 @@ dat_fused_kernel(const __grid_constant__ TmapSet tm0, const __grid_constant__ Tm
   cluster_sync_all();   // the partner's smem / barriers / TMEM stay valid until both CTAs are done
   if (warp == 2) tmem_dealloc_pair(tmem, 512);
   if (tid == 64) FD_TRACE(2, 0);     // CTA exit
+  if (tid == 64) FD_TRACE_CTA(1);
 }
 
 

@@ -423,14 +423,16 @@ class Adapter(nn.Module):
     def pre_forward(self, hidden_states, input_tensor, layer_norm):
         residual = hidden_states                                # adapter.py:104 residual_before_ln
         if layer_norm:
-            hidden_states = layer_norm(hidden_states + input_tensor)
+            from .fused_ln import layer_norm_of_sum             # add + LayerNorm in one launch where it applies
+            hidden_states = layer_norm_of_sum(layer_norm, hidden_states, input_tensor)
         else:
             hidden_states = hidden_states + input_tensor
         return hidden_states, residual
 
     def post_forward(self, hidden_states, input_tensor, layer_norm):
         if layer_norm:
-            hidden_states = layer_norm(hidden_states + input_tensor)
+            from .fused_ln import layer_norm_of_sum
+            hidden_states = layer_norm_of_sum(layer_norm, hidden_states, input_tensor)
         else:
             hidden_states = hidden_states + input_tensor
         return hidden_states

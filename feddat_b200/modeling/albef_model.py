@@ -32,7 +32,9 @@ import torch.nn.functional as F
 from torch.nn.attention import SDPBackend, sdpa_kernel
 
 from .albef_sites import BertOutput, Block
+from .fused_ln import layer_norm_of_sum
 
+FUSE_PROJECTIONS = True      # frozen q | k | v (self-attention) and k | v (cross-attention) projections as one GEMM
 # torch SDPA backend of the BERT-side attention calls with <= 128 queries and keys (None = torch's own choice)
 SMALL_ATTENTION_BACKEND = SDPBackend.EFFICIENT_ATTENTION
 
@@ -150,11 +152,39 @@ class BertSelfAttention(nn.Module):
         b, s, _ = x.shape
         return x.view(b, s, self.num_attention_heads, self.attention_head_size).transpose(1, 2)
 
+    def _cat(self, mods, tag):
+        """Concatenated weight / bias of FROZEN projections that read the same tensor (q | k | v of a self-attention,
+        k | v of a cross-attention): one GEMM instead of two or three, and in backward one GEMM over the stacked
+        gradient instead of one per projection plus the adds.  Cached on the module; rebuilt when a tensor changes."""
+        ps = [m.weight for m in mods] + [m.bias for m in mods]
+        key = tuple((p.data_ptr(), p._version, p.dtype) for p in ps)
+        cached = getattr(self, "_feddat_cat_" + tag, None)
+        if cached is None or cached[0] != key:
+            with torch.no_grad():
+                n = len(mods)
+                cached = (key, torch.cat([p.detach() for p in ps[:n]], 0).contiguous(),
+                          torch.cat([p.detach() for p in ps[n:]], 0).contiguous())
+            setattr(self, "_feddat_cat_" + tag, cached)
+        return cached[1], cached[2]
+
     def forward(self, hidden_states, attention_mask=None, encoder_hidden_states=None, encoder_attention_mask=None):
         kv = hidden_states if encoder_hidden_states is None else encoder_hidden_states
         mask = attention_mask if encoder_hidden_states is None else encoder_attention_mask
-        q, k, v = self._heads(self.query(hidden_states)), self._heads(self.key(kv.to(hidden_states.dtype))), \
-            self._heads(self.value(kv.to(hidden_states.dtype)))
+        heads, hd = self.num_attention_heads, self.attention_head_size
+        frozen = FUSE_PROJECTIONS and not any(p.requires_grad for m in (self.query, self.key, self.value) for p in m.parameters())
+        if frozen and encoder_hidden_states is None:
+            w, b = self._cat((self.query, self.key, self.value), "qkv")
+            bs, sq, _ = hidden_states.shape
+            q, k, v = (t.transpose(1, 2) for t in F.linear(hidden_states, w, b).view(bs, sq, 3, heads, hd).unbind(2))
+        elif frozen:
+            w, b = self._cat((self.key, self.value), "kv")
+            kv = kv.to(hidden_states.dtype)
+            bs, sk, _ = kv.shape
+            q = self._heads(self.query(hidden_states))
+            k, v = (t.transpose(1, 2) for t in F.linear(kv, w, b).view(bs, sk, 2, heads, hd).unbind(2))
+        else:
+            q, k, v = self._heads(self.query(hidden_states)), self._heads(self.key(kv.to(hidden_states.dtype))), \
+                self._heads(self.value(kv.to(hidden_states.dtype)))
         if mask is not None:
             mask = mask.to(q.dtype)
         p_drop = self.dropout.p if self.training else 0.0
@@ -180,7 +210,7 @@ class BertSelfOutput(nn.Module):
         self.dropout = nn.Dropout(config.hidden_dropout_prob)
 
     def forward(self, hidden_states, input_tensor):
-        return self.LayerNorm(self.dropout(self.dense(hidden_states)) + input_tensor)
+        return layer_norm_of_sum(self.LayerNorm, self.dropout(self.dense(hidden_states)), input_tensor)
 
 
 class BertAttention(nn.Module):

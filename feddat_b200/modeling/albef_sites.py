@@ -144,7 +144,8 @@ class BertOutput(nn.Module):
         hidden_states = self.dropout(self.dense(hidden_states))
         if hasattr(self, "adapter"):
             return self.adapter.adapter_layer_forward_bert(hidden_states, input_tensor, self.LayerNorm)
-        return self.LayerNorm(hidden_states + input_tensor)
+        from .fused_ln import layer_norm_of_sum
+        return layer_norm_of_sum(self.LayerNorm, hidden_states, input_tensor)
 
 
 class AdapterHooks:

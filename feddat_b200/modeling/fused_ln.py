@@ -207,6 +207,15 @@ def add_layer_norm(ln: torch.nn.LayerNorm, a: torch.Tensor, b: torch.Tensor, bia
     return (s if bias2 is None else s + bias2), ln(s)
 
 
+def layer_norm_of_sum(ln, a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
+    """LayerNorm(a + b) -- the post-LN form of BERT's output blocks (xbert.py:350-361, 428-445) and of the DAT wrapper
+    around them (adapter.py:97-116) -- as ONE launch where the kernels apply, ``ln(a + b)`` otherwise."""
+    if (isinstance(ln, torch.nn.LayerNorm) and _usable(ln, a) and b.dtype == a.dtype and b.shape == a.shape
+            and b.is_contiguous()):
+        return _AddLayerNorm.apply(a, b, ln.weight, ln.bias, ln.eps, None)[0]
+    return ln(a + b)
+
+
 def _prebias_ok(out_mod, h: torch.Tensor) -> bool:
     """The "dense + bias + residual" of Adaptered_ViltOutput can be ONE GEMM (beta = 1 epilogue) when its
     dense layer is frozen bf16 with a bias and its dropout is the identity."""

@@ -47,7 +47,7 @@ def run():
 
 for _ in range(3):
     run()
-buf = torch.zeros(256, dtype=torch.int64, device=dev)
+buf = torch.zeros(1024, dtype=torch.int64, device=dev)      # 256 events of CTA 0 + entry / exit stamps of every CTA
 lib.feddat_debug_set_trace(_lib.ptr(buf))
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 e0.record(); run(); e1.record()
@@ -91,3 +91,16 @@ for tile in range(2):
     ev = [(t[tile * 128 + e] - t0, e) for e in range(128) if t[tile * 128 + e] != 0]
     for dt, e in sorted(ev):
         print(f"tile{tile} {dt / 1e3:9.2f} us  {names.get(e, e)}")
+
+ctas = [(t[256 + 2 * b], t[257 + 2 * b]) for b in range(384) if t[256 + 2 * b]]
+if ctas:
+    first = min(a for a, _ in ctas)
+    ent = sorted((a - first) / 1e3 for a, _ in ctas)
+    ext = sorted((b - first) / 1e3 for _, b in ctas)
+    dur = sorted((b - a) / 1e3 for a, b in ctas)
+    q = lambda v, f: v[min(len(v) - 1, int(f * len(v)))]      # noqa: E731
+    print(f"{len(ctas)} CTAs: entry min/median/max {ent[0]:.2f} / {q(ent, .5):.2f} / {ent[-1]:.2f} us after the first; "
+          f"exit min/median/max {ext[0]:.2f} / {q(ext, .5):.2f} / {ext[-1]:.2f} us; "
+          f"CTA time min/median/max {dur[0]:.2f} / {q(dur, .5):.2f} / {dur[-1]:.2f} us")
+    slow = sorted(range(len(ctas)), key=lambda i: -(ctas[i][1] - first))[:6]
+    print("last to exit:", [(i, round((ctas[i][0] - first) / 1e3, 2), round((ctas[i][1] - first) / 1e3, 2)) for i in slow])
