@@ -52,6 +52,37 @@ for M in [int(a) for a in sys.argv[1:]] or [129]:
     assert torch.equal(y1, y[:M]) and torch.equal(dx1, dx[:M])
     print(f"M={M}: grouped / single forward + backward ok (fwd err {e_y:.1e} / {e_y1:.1e})")
 
+# ---- deferred weight gradients: 13 sites x 2 row groups = 26 groups -> one 24-group launch (no row splits) + one
+# 2-group launch (row splits, two-stage reduction), against the per-site launches
+Md = 333
+sites = []
+for _ in range(13):
+    b2, b1 = branches(2), branches(1)
+    pk2, pk1 = ops.pack_weights_batched([ops.PackSpec(*[[b[i] for b in bs] for i in range(4)]) for bs in (b2, b1)])
+    x = torch.randn(2 * Md, 768, device=dev, generator=g).to(torch.bfloat16)
+    dy = torch.randn(2 * Md, 768, device=dev, generator=g).to(torch.bfloat16)
+    (_, h2), (_, h1) = ops.dat_forward_grouped([dict(x=x[:Md], res=x[:Md], w=pk2, scale=0.5, save_hidden=True),
+                                                dict(x=x[Md:], res=x[Md:], w=pk1, scale=1.0, save_hidden=True)])
+    sites.append((x, dy, pk2, pk1, h2, h1))
+
+
+def site_bwd(s_):
+    x, dy, pk2, pk1, h2, h1 = s_
+    return ops.dat_backward_grouped([dict(x=x[:Md], dy=dy[:Md], w=pk2, scale=0.5, train_slice=(0, r), hidden=h2),
+                                     dict(x=x[Md:], dy=dy[Md:], w=pk1, scale=1.0, train_slice=(0, r), hidden=h1)],
+                                    allow_defer=True)
+
+
+with ops.deferred_wgrad():
+    deferred = [site_bwd(s_) for s_ in sites]
+direct = [site_bwd(s_) for s_ in sites]
+torch.cuda.synchronize()
+for a_, b_ in zip(deferred, direct):
+    for (_, ga), (_, gb) in zip(a_, b_):
+        for ta, tb in zip(ga, gb):
+            assert ((ta - tb).abs().max() / tb.abs().max().clamp_min(1e-20)).item() < 1e-5
+print("deferred weight gradients (26 groups): ok")
+
 lg = torch.randn(32, 100, device=dev, generator=g)
 ops.mkd_loss(lg, torch.randn(32, 100, device=dev, generator=g), (torch.rand(32, 100, device=dev, generator=g) < 0.02).float(), 2.0)
 sc = torch.randn(5, 4, 3202, device=dev, generator=g).to(torch.bfloat16)
