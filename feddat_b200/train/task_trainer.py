@@ -93,6 +93,12 @@ def _deferred():
     return ops.deferred_wgrad() if DEFER_WGRAD else contextlib.nullcontext()
 
 
+# The task head (fp32 masters: Linear 768 -> 1536, LayerNorm, GELU, Linear 1536 -> labels on 32 / 64 pooled rows) runs its
+# matmuls on TF32 tensor cores inside a train step: fp32 storage and accumulation, 10-bit-mantissa products -- the
+# precision of the reference's own head under accelerate's fp16 autocast (task_trainer.py:50-63), above the bf16 of the
+# rest of the step.  As fp32 SIMT GEMMs the ~13 launch-bound head matmuls cost 0.09 ms per step (scripts/ab_step.py:
+# 6.21 -> 6.11 ms).  False = strict fp32 matmuls.
+HEAD_TF32 = True
 USE_OWN_ADAMW = True      # csrc/adamw.cu behind train/fused_adamw.py; False = torch.optim.AdamW(fused, capturable)
 
 
@@ -306,9 +312,12 @@ class TaskTrainer(nn.Module):
         inner = model.module
         if hasattr(inner, "new_step"):
             inner.new_step(train=True)          # per-step caches; all sites' bf16 operands packed in one launch
+        tf32 = torch.backends.cuda.matmul.allow_tf32
+        torch.backends.cuda.matmul.allow_tf32 = tf32 or HEAD_TF32
         try:
             return self._train_step_dat(model, inner, batch, target, optimizer, scheduler, albef)
         finally:
+            torch.backends.cuda.matmul.allow_tf32 = tf32
             if hasattr(inner, "end_step"):
                 inner.end_step()
 
