@@ -36,6 +36,7 @@ class ALBEFWrapper(nn.Module):
         self.device = device
         self.tokenizer = tokenizer
         self.defer_loss = False            # set by the trainer: fused MKD head instead of the in-model loss
+        self.image_embeds = None           # set by the trainer: the visual encoder's output, computed once for two passes
 
     def _tok(self, texts, **kw):
         if self.tokenizer is None:
@@ -43,10 +44,18 @@ class ALBEFWrapper(nn.Module):
                                "question_ids / answer_ids tensors instead of strings")
         return self.tokenizer(texts, return_tensors="pt", **kw).to(self.device)
 
-    def forward(self, batch) -> List:
+    def _images(self, batch):
         images = batch["images"].to(self.device, non_blocking=True)
         if images.dtype != torch.bfloat16 and next(self.albef.visual_encoder.parameters()).dtype == torch.bfloat16:
             images = images.to(torch.bfloat16)
+        return images
+
+    def encode_image(self, batch):
+        """The visual encoder alone (albef_model.py:71), in whatever adapter mode is active."""
+        return self.albef.visual_encoder(self._images(batch))
+
+    def forward(self, batch) -> List:
+        images = self._images(batch)
         pre = "question_ids" in batch
         if pre:
             question = SimpleNamespace(input_ids=batch["question_ids"].to(self.device),
@@ -62,7 +71,8 @@ class ALBEFWrapper(nn.Module):
             idx = batch.get("answer_index")
             loss, logits = self.albef(image=images, question=question, answer=answer, train=True, alpha=batch["alpha"],
                                       k=batch["n"], weights=weights, defer_loss=self.defer_loss,
-                                      answer_index=None if idx is None else idx.to(self.device, non_blocking=True))
+                                      answer_index=None if idx is None else idx.to(self.device, non_blocking=True),
+                                      image_embeds=self.image_embeds)
             return [loss, logits]
         if pre:
             answer = SimpleNamespace(input_ids=batch["answer_list_ids"].to(self.device),
@@ -111,11 +121,20 @@ class ALBEFContinualLearner(nn.Module):
         return self.albef_model(batch)
 
     # ------------------------------------------------------------------ B200 setup helpers / per-step hooks
+    def image_forward_is_reusable(self) -> bool:
+        """True when the visual encoder is a deterministic function of (image, adapter_0, adapter_2, frozen ViT): no
+        active dropout in it (ALBEF's ViT is built with drop = attn_drop = drop_path = 0, albef_model.py:24-28).  The
+        MKD schedule's passes A and C then share ONE ViT forward -- step B changes adapter_1 and the LM head only --
+        while the BERT towers (dropout 0.1) run once per pass as in the reference."""
+        vit = self.albef_model.albef.visual_encoder
+        return not any(isinstance(m, nn.Dropout) and m.p > 0.0 and m.training for m in vit.modules())
+
     def new_step(self, train: bool = False) -> None:
         if train:
             refresh_packs(self._adapters())          # all 30 sites, both modes: ONE pack launch per train step
 
     def end_step(self) -> None:
+        self.albef_model.image_embeds = None
         invalidate_packs(self._adapters())
 
     def cast_frozen_backbone(self, dtype=torch.bfloat16):

@@ -434,10 +434,13 @@ class ALBEF(nn.Module):
         self.text_decoder = BertLMHeadModel(dec)
 
     def forward(self, image, question, answer=None, alpha=0, k=None, weights=None, train=True, defer_loss=False,
-                answer_index=None):
+                answer_index=None, image_embeds=None):
         """``question`` / ``answer``: objects with ``input_ids`` and ``attention_mask`` (a tokenizer's BatchEncoding or
-        a namespace of tensors).  train: (loss, logits[:, :-1]); eval: rank_answer's (topk_ids, topk_probs)."""
-        image_embeds = self.visual_encoder(image)
+        a namespace of tensors).  train: (loss, logits[:, :-1]); eval: rank_answer's (topk_ids, topk_probs).
+        ``image_embeds``: the visual encoder's output for ``image`` when the caller already has it (the MKD schedule's
+        passes A and C see the same image through the same gating adapters: TaskTrainer runs the ViT once for both)."""
+        if image_embeds is None:
+            image_embeds = self.visual_encoder(image)
         # albef_model.py:95-96 builds an all-ones image mask; "no mask" is the same attention (see BertModel.forward)
         image_atts = None
         question_states = self.text_encoder(question.input_ids, attention_mask=question.attention_mask,

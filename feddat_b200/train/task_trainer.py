@@ -327,6 +327,7 @@ class TaskTrainer(nn.Module):
             inner.albef_model.defer_loss = self.kl_criterion is kl_loss
         reuse = (self.reuse_gating_forward and not albef
                  and getattr(inner, "gating_forward_is_reusable", lambda: False)())
+        img = None                # ALBEF: the gating ViT forward shared by passes A and C
         if (reuse and self.batched_passes and optimizer is not None and hasattr(inner, "encode_dual")
                 and isinstance(batch, dict) and batch.get("encodings", {}).get("dense_masks", False)
                 and self._objective_is_fused() and 2 * inner._adapters()[0].rank <= ops.MAX_R_TOTAL):
@@ -338,9 +339,21 @@ class TaskTrainer(nn.Module):
             with torch.no_grad():
                 logits_all = inner.classify(self.task_key, enc_all)
         else:
+            # ALBEF: passes A and C see the same image through the same gating adapters and its ViT has no dropout, so
+            # ONE grad-enabled ViT forward serves both (3 -> 2 ViT forwards per step; the BERT towers have dropout
+            # and run once per pass).  The modes are set as pass C sets them (:311-312).
+            if (albef and self.reuse_gating_forward and hasattr(inner, "albef_model")
+                    and getattr(inner, "image_forward_is_reusable", lambda: False)()):
+                inner.activate_gating()
+                inner.set_active_adapter("adapter_0")
+                with _nvtx("pass_AC_vit_fwd"):
+                    img = inner.albef_model.encode_image(self.batch2inputs_converter(batch))
+                inner.albef_model.image_embeds = img.detach()
             with torch.no_grad(), _nvtx("pass_A_gating_nograd"):     # (A) :283-287
                 model.module.activate_gating()
                 _, logits_all = self.forward_pass(model, batch, do_eval=False)
+            if img is not None:
+                inner.albef_model.image_embeds = None
 
         model.module.deactivate_gating()                             # (B) :290-308
         model.module.set_active_adapter("adapter_1")
@@ -361,7 +374,11 @@ class TaskTrainer(nn.Module):
         if reuse:       # same pooled output as a fresh forward (bit-identical), head re-applied after step B
             output_0_0, logits_0 = enc_all, inner.classify(self.task_key, enc_all)
         else:
+            if img is not None:
+                inner.albef_model.image_embeds = img                 # pass A's ViT output, with its graph
             output_0_0, logits_0 = self.forward_pass(model, batch, do_eval=False)
+            if img is not None:
+                inner.albef_model.image_embeds = None
         L_0, loss_0 = self._objective(logits_0, logits_1, target, output_0_0 if albef else None)
         with _nvtx("pass_C_gating_bwd"), _deferred():
             self.accelerator.backward(L_0)

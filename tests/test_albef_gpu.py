@@ -222,3 +222,47 @@ def test_albef_graphed_step_equals_eager():
     num = sum(((p0[n] - p1[n]).double() ** 2).sum().item() for n in p0)
     den = sum(((p0[n]).double() ** 2).sum().item() for n in p0)
     assert (num / den) ** 0.5 < 1e-3, (num / den) ** 0.5
+
+
+def test_albef_shared_vit_forward_equals_separate_forwards():
+    """Passes A and C of the MKD schedule share ONE ViT forward (no dropout in ALBEF's ViT; step B changes adapter_1 and
+    the LM head only): with the same dropout seed for the BERT towers the step gives bit-identical logits, losses and
+    pre-Adam gradients with ``reuse_gating_forward`` on and off (TaskTrainer._train_step_dat)."""
+    from feddat_b200.modeling.albef import convert_batch_to_albef_input_dict
+    from feddat_b200.train.accelerator import Accelerator
+    from feddat_b200.train.task_trainer import TaskTrainer, get_polynomial_decay_schedule_with_warmup
+
+    def run(reuse):
+        model = build(64, bf16=True)
+        assert model.image_forward_is_reusable()
+        tr = TaskTrainer()
+        tr.args = SimpleNamespace(optimizer_mode="dat", encoder_name="albef_no_distill", debug=0)
+        tr.accelerator = Accelerator(device="cuda")
+        tr.device, tr.task_key = torch.device("cuda"), "art"
+        tr.batch2inputs_converter = convert_batch_to_albef_input_dict
+        tr.weight_decay, tr.lr, tr.adam_epsilon, tr.kl_temp = 1e-2, 1e-4, 1e-8, 2.0
+        tr.reuse_gating_forward = reuse
+        wrapped = tr.accelerator.prepare(model)
+        wrapped.train()
+        opt = tr.create_optimizer(wrapped)
+        sched = get_polynomial_decay_schedule_with_warmup(opt, 1, 10, lr_end=0, power=1)
+        probes = {}
+        tr.grad_probe = lambda tag, _m: probes.__setitem__(
+            tag, {n: p.grad.detach().clone() for n, p in model.named_parameters() if p.grad is not None})
+        out = []
+        for step in range(2):
+            torch.manual_seed(100 + step)
+            loss = tr.train_step(wrapped, step, dev(albef_golden_batch(step)), opt, sched)
+            torch.cuda.synchronize()
+            out.append((loss.detach().clone(), [t.clone() for t in tr.last_logits], dict(probes)))
+        return out
+
+    for (la, lga, pa), (lb, lgb, pb) in zip(run(True), run(False)):
+        assert torch.equal(la, lb)
+        for a, b in zip(lga, lgb):
+            assert torch.equal(a, b)
+        assert pa.keys() == pb.keys()
+        for tag in pa:
+            assert pa[tag].keys() == pb[tag].keys()
+            for n in pa[tag]:
+                assert torch.equal(pa[tag][n], pb[tag][n]), (tag, n)
