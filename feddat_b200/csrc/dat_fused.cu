@@ -110,6 +110,15 @@ struct TmapSet {
   CUtensorMap x, res, y, wd, w2, w2k, w1b, h, dp;
 };
 
+// Epilogue 1 splits the R / 16 sixteen-column chunks of P between the two epilogue groups: group A packs
+// chunks [0, nA), group B the rest.  nA is rounded up to a multiple of four (64 columns) so that both groups'
+// shares start at a 64-column boundary: the packed hidden also travels through the 64-column staging buffers
+// (saved by the forward / loaded and turned into dP by the backward with TMA, see "hidden chunks" below).
+__host__ __device__ __forceinline__ int split_a(int n16) {
+  const int a = (((n16 + 1) / 2) + 3) & ~3;
+  return a < n16 ? a : n16;
+}
+
 // slot -> what this CTA pair computes
 struct Slot {
   int g;        // group

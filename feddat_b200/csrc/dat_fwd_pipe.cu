@@ -96,15 +96,11 @@ __device__ __forceinline__ float apply_act(float x) {
 //   tmY          Y                  dX
 //   tmWd         Wd_cat             WuT_cat     (GEMM1 B operand, [R, 768])
 //   tmW2 / k     Wu_cat             WdT_cat     (GEMM2 B operand, [768, R])
-//   tmH          H_out [M, R]       H_in [M, R] (hidden chunks through the staging ring, see dat_fused.cu)
-//   tmDP         (unused)           dP_t slice [M, r_t], row stride ld_t
-// Per tile the staging ring carries first the ceil(R / 64) hidden chunks, then the twelve output chunks.
 template <bool kBwd, bool kGelu>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 dat_pipe_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmRes,
                     const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmWd,
                     const __grid_constant__ CUtensorMap tmW2, const __grid_constant__ CUtensorMap tmW2k,
-                    const __grid_constant__ CUtensorMap tmH, const __grid_constant__ CUtensorMap tmDP,
                     const PipeParams p) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bars[2 * NG1 + 2 * NW2 + 3 + 4 + 3 * NSTG];
@@ -114,11 +110,7 @@ dat_pipe_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
   if (tid == 0) FDP_TRACE(1, 0);
   const int R = p.R;
   const int KC2 = (R + 63) / 64;
-  const int n16 = R / 16, nA = split_a(n16);
-  // hidden chunks per tile in the staging sequence (group A's, total): forward only when the hidden is saved
-  const bool h_on = kBwd || p.H_out != nullptr;
-  const int nhA = h_on ? (nA + 3) / 4 : 0;
-  const int nh = h_on ? nhA + (n16 - nA + 3) / 4 : 0;
+  const int n16 = R / 16, nA = (n16 + 1) / 2;
   const uint32_t rank = cluster_ctarank();
   const int RH = R / 2;
   const uint32_t w_half_bytes = static_cast<uint32_t>(RH) * 128u;
@@ -172,8 +164,6 @@ dat_pipe_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
     tma_prefetch_desc(&tmWd);
     tma_prefetch_desc(&tmW2);
     tma_prefetch_desc(&tmW2k);
-    tma_prefetch_desc(&tmH);
-    if (kBwd) tma_prefetch_desc(&tmDP);
   }
   if (warp == 2) tmem_alloc_pair(smem_u32(&tmem_base_smem), 512);
   tc_fence_before();
@@ -277,20 +267,10 @@ dat_pipe_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
   } else if (warp == 3) {
     // ------------------------------------------------------------------ residual + W2 producer
     if (lane == 0) {
-      uint32_t g = 0, gs = 0;     // W2 tiles / staging chunks so far
+      uint32_t g = 0;
       for (int it = 0; it < my_tiles; ++it) {
         const int m0 = tile_of(it) * BM;
-        for (int j = 0; j < nh; ++j, ++gs) {      // hidden chunks: loaded (backward) or just granted (forward)
-          const uint32_t sb = gs % NSTG, par = (gs / NSTG) & 1;
-          mbar_wait(bar_stg_empty(sb), par ^ 1);
-          if constexpr (kBwd) {
-            mbar_arrive_expect_tx(bar_res_full(sb), SLOT);
-            tma_load_2d(stg_base + sb * SLOT, &tmH, bar_res_full(sb), j * 64, m0);
-          } else {
-            mbar_arrive(bar_res_full(sb));
-          }
-        }
-        for (int c = 0; c < NC2; ++c, ++g, ++gs) {
+        for (int c = 0; c < NC2; ++c, ++g) {
           {   // W2 tile of chunk c: this CTA's 32 rows, every k-block
             const uint32_t s = g % NW2, par = (g / NW2) & 1;
             mbar_wait(bar_w2_empty(s), par ^ 1);
@@ -305,7 +285,7 @@ dat_pipe_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
             }
           }
           {   // residual chunk c
-            const uint32_t sb = gs % NSTG, par = (gs / NSTG) & 1;
+            const uint32_t sb = g % NSTG, par = (g / NSTG) & 1;
             mbar_wait(bar_stg_empty(sb), par ^ 1);
             if (!kBwd || p.has_res) {
               mbar_arrive_expect_tx(bar_res_full(sb), SLOT);
@@ -322,24 +302,9 @@ dat_pipe_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
     // ------------------------------------------------------------------ store issuer
     if (lane == 0) {
       uint32_t g = 0;
-      const uint32_t total = static_cast<uint32_t>(my_tiles) * (NC2 + nh);
+      const uint32_t total = static_cast<uint32_t>(my_tiles) * NC2;
       for (int it = 0; it < my_tiles; ++it) {
         const int m0 = tile_of(it) * BM;
-        for (int j = 0; j < nh; ++j, ++g) {       // hidden chunks: H_out (forward) / dP_t of the trainable slice
-          const uint32_t sb = g % NSTG, par = (g / NSTG) & 1;
-          mbar_wait(bar_out_full(sb), par);
-          if constexpr (!kBwd) {
-            tma_store_2d_hint(&tmH, stg_base + sb * SLOT, j * 64, m0, kEvictFirst);
-          } else {
-            if (p.dP_t != nullptr && j * 64 < p.r_hi && j * 64 + 64 > p.r_lo)
-              tma_store_2d_hint(&tmDP, stg_base + sb * SLOT, j * 64 - p.r_lo, m0, kEvictLast);
-          }
-          tma_store_commit();
-          if (g > 0) {
-            tma_store_wait_read<1>();
-            mbar_arrive(bar_stg_empty((g - 1) % NSTG));
-          }
-        }
         for (int c = 0; c < NC2; ++c, ++g) {
           const uint32_t sb = g % NSTG, par = (g / NSTG) & 1;
           mbar_wait(bar_out_full(sb), par);
@@ -382,61 +347,80 @@ dat_pipe_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
       const int grow = tile_of(it) * BM + static_cast<int>(row);
       {
         // ---------------- epilogue 1: this group's half of P -> packed bf16 hidden in H
-        const uint32_t hg0 = tile_it * (NC2 + nh) + (group == 0 ? 0u : static_cast<uint32_t>(nhA));
+        uint4 hreg[8][2];         // kBwd: this row's saved hidden (issued before the wait on GEMM1)
+        if constexpr (kBwd) {
+          const uint4* hrow = reinterpret_cast<const uint4*>(p.H_in + static_cast<size_t>(grow) * R);
+#pragma unroll
+          for (int ci = 0; ci < 8; ++ci) {
+            hreg[ci][0] = hreg[ci][1] = make_uint4(0u, 0u, 0u, 0u);
+            if (c_lo + ci < c_hi && grow < p.M) {
+              hreg[ci][0] = __ldg(hrow + 2 * (c_lo + ci));
+              hreg[ci][1] = __ldg(hrow + 2 * (c_lo + ci) + 1);
+            }
+          }
+        }
         mbar_wait(bar_p_full, tile_it & 1);
         if (it > 0) mbar_wait(bar_h_free, (tile_it - 1) & 1);   // GEMM2 of the previous tile has read H
         tc_fence_after();
         if (tid == 128) FDP_TRACE(40, tile_it);
         const uint32_t t_p = tmem + lane_addr + TM_P;
         const uint32_t t_h = tmem + lane_addr + TM_H;
+        uint32_t wall[8][8];      // the group's packed hidden / dP, kept for the (deferred) global store
 #pragma unroll
         for (int ci = 0; ci < 8; ++ci) {
           const int c = c_lo + ci;
           if (c < c_hi) {
-            uint32_t v[16], w[8];
-            const uint32_t hgi = hg0 + (ci >> 2);
-            const uint32_t hbuf = stg_base + (hgi % NSTG) * SLOT;
-            if (nh > 0 && (ci & 3) == 0) mbar_wait(bar_res_full(hgi % NSTG), (hgi / NSTG) & 1);
+            uint32_t v[16];
             tmem_ld16(t_p + c * 16, v);
-            uint4 h0 = make_uint4(0u, 0u, 0u, 0u), h1 = h0;
-            if constexpr (kBwd) {
-              h0 = ld_shared_v4(hbuf + sw128_offset(row, 2 * (ci & 3)));
-              h1 = ld_shared_v4(hbuf + sw128_offset(row, 2 * (ci & 3) + 1));
-            }
             tmem_ld_wait16(v);
             if constexpr (!kBwd) {
               const float* bdv = bias_smem + c * 16;
 #pragma unroll
               for (int i = 0; i < 8; ++i)
-                w[i] = pack_bf16x2(apply_act<kGelu>(__uint_as_float(v[2 * i]) + bdv[2 * i]),
-                                   apply_act<kGelu>(__uint_as_float(v[2 * i + 1]) + bdv[2 * i + 1]));
+                wall[ci][i] = pack_bf16x2(apply_act<kGelu>(__uint_as_float(v[2 * i]) + bdv[2 * i]),
+                                          apply_act<kGelu>(__uint_as_float(v[2 * i + 1]) + bdv[2 * i + 1]));
             } else {
-              const uint32_t hb[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
+              const uint32_t hb[8] = {hreg[ci][0].x, hreg[ci][0].y, hreg[ci][0].z, hreg[ci][0].w,
+                                      hreg[ci][1].x, hreg[ci][1].y, hreg[ci][1].z, hreg[ci][1].w};
 #pragma unroll
               for (int i = 0; i < 8; ++i) {      // relu'(P) == (H > 0); H is never negative
                 const float g0 = (hb[i] & 0x00007fffu) ? scale * __uint_as_float(v[2 * i]) : 0.f;
                 const float g1 = (hb[i] & 0x7fff0000u) ? scale * __uint_as_float(v[2 * i + 1]) : 0.f;
-                w[i] = pack_bf16x2(g0, g1);
+                wall[ci][i] = pack_bf16x2(g0, g1);
               }
             }
-            tmem_st8(t_h + c * 8, w);
-            if (nh > 0) {
-              // forward: the hidden to save; backward: dP written over the hidden it was derived from (each thread
-              // rewrites only what it has read itself) -- the store issuer TMA-stores the buffer
-              st_shared_v4(hbuf + sw128_offset(row, 2 * (ci & 3)), w[0], w[1], w[2], w[3]);
-              st_shared_v4(hbuf + sw128_offset(row, 2 * (ci & 3) + 1), w[4], w[5], w[6], w[7]);
-              if ((ci & 3) == 3 || c == c_hi - 1) {
-                fence_proxy_async_smem();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(bar_out_full(hgi % NSTG));
-              }
-            }
+            tmem_st8(t_h + c * 8, wall[ci]);
           }
         }
         tmem_st_wait();
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive_cluster_addr(leader_h_full);
+        // global stores AFTER GEMM2 has been released (a row-per-thread store is 32 L1 transactions per
+        // instruction): forward saves the hidden, backward the trainable slice of dP for the wgrad kernel
+        if constexpr (!kBwd) {
+          if (p.H_out != nullptr && grow < p.M) {
+            uint4* hrow = reinterpret_cast<uint4*>(p.H_out + static_cast<size_t>(grow) * R);
+#pragma unroll
+            for (int ci = 0; ci < 8; ++ci)
+              if (c_lo + ci < c_hi) {
+                hrow[2 * (c_lo + ci)] = make_uint4(wall[ci][0], wall[ci][1], wall[ci][2], wall[ci][3]);
+                hrow[2 * (c_lo + ci) + 1] = make_uint4(wall[ci][4], wall[ci][5], wall[ci][6], wall[ci][7]);
+              }
+          }
+        } else {
+          if (p.dP_t != nullptr && grow < p.M) {
+#pragma unroll
+            for (int ci = 0; ci < 8; ++ci) {
+              const int col = (c_lo + ci) * 16;
+              if (c_lo + ci < c_hi && col >= p.r_lo && col < p.r_hi) {
+                uint4* gd = reinterpret_cast<uint4*>(p.dP_t + static_cast<size_t>(grow) * p.ld_t + (col - p.r_lo));
+                gd[0] = make_uint4(wall[ci][0], wall[ci][1], wall[ci][2], wall[ci][3]);
+                gd[1] = make_uint4(wall[ci][4], wall[ci][5], wall[ci][6], wall[ci][7]);
+              }
+            }
+          }
+        }
         if (tid == 128) FDP_TRACE(41, tile_it);
       }
       // ---------------- epilogue 2: output chunks c == group (mod 2), 64 columns each
@@ -444,7 +428,7 @@ dat_pipe_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
         mbar_wait(bar_d_full(group), df & 1);
         ++df;
         tc_fence_after();
-        const uint32_t g = tile_it * (NC2 + nh) + nh + c;
+        const uint32_t g = tile_it * NC2 + c;
         const uint32_t sb = g % NSTG, rpar = (g / NSTG) & 1;
         const uint32_t t_src = tmem + lane_addr + TM_D + group * N2;
         uint32_t v0[32], v1[32];
@@ -530,15 +514,9 @@ int launch_pipe(bool bwd, const void* A, const void* Res, void* Out, const void*
   tmW2k = tmW2;
   if (p.w2_3d && (rc = make_tmap_bf16_kblocks(&tmW2k, W2, kD, r_total, r_total, N2 / 2, r_total / 64)))
     return rc;
-  // hidden chunks through the staging ring: H_out (forward), H_in and the dP_t slice (backward)
-  CUtensorMap tmH = tmX, tmDP = tmX;
-  const void* hid = bwd ? static_cast<const void*>(p.H_in) : static_cast<const void*>(p.H_out);
-  if (hid != nullptr && (rc = make_tmap_bf16_2d(&tmH, hid, M, r_total, r_total, BM, 64))) return rc;
-  if (bwd && p.dP_t != nullptr && (rc = make_tmap_bf16_2d(&tmDP, p.dP_t, M, p.r_hi - p.r_lo, p.ld_t, BM, 64))) return rc;
 
   using KernelFn = void (*)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap,
-                            const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap,
-                            const PipeParams);
+                            const CUtensorMap, const CUtensorMap, const PipeParams);
   KernelFn fn = bwd ? dat_pipe_kernel<true, false> : (gelu ? dat_pipe_kernel<false, true> : dat_pipe_kernel<false, false>);
   static bool configured[3][64] = {{false}};
   int dev = 0;
@@ -560,7 +538,7 @@ int launch_pipe(bool bwd, const void* A, const void* Res, void* Out, const void*
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  FD_CHECK_CUDA(cudaLaunchKernelEx(&cfg, fn, tmX, tmRes, tmY, tmWd, tmW2, tmW2k, tmH, tmDP, p));
+  FD_CHECK_CUDA(cudaLaunchKernelEx(&cfg, fn, tmX, tmRes, tmY, tmWd, tmW2, tmW2k, p));
   FD_CHECK_CUDA(cudaGetLastError());
   return FD_OK;
 }
