@@ -51,8 +51,47 @@ class ClockSampler:
 
     def __init__(self, gpu_index: int):
         self.gpu, self.rows, self.proc = gpu_index, [], None
+        self.nvml, self.handle, self.samples, self._stop = None, None, [], False
+
+    # NVML in a thread (a sample every ~4 ms: a 20-step timed region is only 0.12 s, the nvidia-smi loop below delivers
+    # one line per 100 ms); the nvidia-smi loop stays as the fallback when pynvml is not importable
+    def _start_nvml(self) -> bool:
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            idx = self.gpu
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            if vis:
+                try:
+                    idx = int(vis.split(",")[self.gpu])
+                except (ValueError, IndexError):
+                    idx = self.gpu
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(idx)
+            pynvml.nvmlDeviceGetClockInfo(self.handle, pynvml.NVML_CLOCK_SM)
+            self.nvml = pynvml
+        except Exception:  # noqa: BLE001
+            self.nvml = None
+            return False
+        threading.Thread(target=self._pump_nvml, daemon=True).start()
+        return True
+
+    def _pump_nvml(self):
+        n = self.nvml
+        while not self._stop:
+            try:
+                mhz = n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM)
+                try:
+                    why = n.nvmlDeviceGetCurrentClocksEventReasons(self.handle)
+                except Exception:  # noqa: BLE001
+                    why = n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle)
+                self.samples.append((time.time(), mhz, why))
+            except Exception:  # noqa: BLE001
+                break
+            time.sleep(0.004)
 
     def start(self):
+        if self._start_nvml():
+            return
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
                                           "-lms", "100", "-i", str(self.gpu)], stdout=subprocess.PIPE,
@@ -65,7 +104,26 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.rows.append((time.time(), [c.strip() for c in line.split(",")]))
 
+    def _stop_nvml(self, t0, t1):
+        n = self.nvml
+        self._stop = True
+        rows = [r for r in self.samples if t0 <= r[0] <= t1] or self.samples
+        bits = {"hw_slowdown": getattr(n, "nvmlClocksEventReasonHwSlowdown", 0x8),
+                "hw_thermal_slowdown": getattr(n, "nvmlClocksEventReasonHwThermalSlowdown", 0x40),
+                "sw_thermal_slowdown": getattr(n, "nvmlClocksEventReasonSwThermalSlowdown", 0x20),
+                "sw_power_cap": getattr(n, "nvmlClocksEventReasonSwPowerCap", 0x4)}
+        reasons = sorted(name for name, bit in bits.items() if any(r[2] & bit for r in rows))
+        try:
+            mx = float(n.nvmlDeviceGetMaxClockInfo(self.handle, n.NVML_CLOCK_SM))
+        except Exception:  # noqa: BLE001
+            mx = None
+        sm = [float(r[1]) for r in rows]
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx, "reasons": reasons,
+                "samples": len(sm), "source": "nvml, one sample per ~4 ms inside the timed region"}
+
     def stop(self, t0, t1):
+        if self.nvml is not None:
+            return self._stop_nvml(t0, t1)
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
@@ -82,7 +140,7 @@ class ClockSampler:
                 if len(r) > col and r[col].lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "source": "nvidia-smi -lms 100"}
 
 
 # ------------------------------------------------------------------------------------------------
