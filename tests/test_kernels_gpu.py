@@ -237,6 +237,27 @@ def test_dat_backward_without_dx_and_frozen_only(ops):
         assert relerr(a.cpu().numpy(), b.cpu().numpy()) < 1e-5
 
 
+@pytest.mark.parametrize("M,r", [(40001, 128), (25003, 64), (19000, 48)])
+def test_saved_backward_without_dx_many_tiles(ops, M, r):
+    """The saved-hidden backward of a FIRST site (no dX: nothing trainable upstream) at row counts where every CTA pair
+    of dat_fused_kernel walks several tiles -- per tile the staging ring then carries only the hidden chunks (TMA load
+    of H_in, dP written in place, TMA store of the trainable slice).  Its weight gradients must equal, bit for bit,
+    those of the variant that also computes dX (the tile-pipelined kernel at these sizes): same dP, same wgrad launch.
+    Repeated, because a mis-ordered hand-off in such a ring shows up as a timing-dependent hang or corruption."""
+    rng = np.random.default_rng(M + r)
+    pk = ops.pack_weights(dev_branches(_rand_branches(rng, r, 2)))
+    x = to_dev(rng.standard_normal((M, 768)).astype(np.float32), torch.bfloat16)
+    g = to_dev(rng.standard_normal((M, 768)).astype(np.float32), torch.bfloat16)
+    _, h = ops.dat_forward(x, x, pk, 0.5, save_hidden=True)
+    _, want = ops.dat_backward(x, g, pk, 0.5, train_slice=(0, r), need_dx=True, add_dy=True, hidden=h)
+    for _ in range(5):
+        dx, got = ops.dat_backward(x, g, pk, 0.5, train_slice=(0, r), need_dx=False, hidden=h)
+        torch.cuda.synchronize()
+        assert dx is None
+        for a, b in zip(got, want):
+            assert torch.equal(a, b)
+
+
 def test_unsupported_shapes_fail_loudly(ops):
     from feddat_b200._lib import FeddatError
     x = torch.zeros(4, 768, device="cuda", dtype=torch.float32)
